@@ -1,0 +1,165 @@
+"""The BEAST.base half of the oracle is 'parity unpinned' (no reference source, no reference test).
+It is therefore checked against independent mathematics: scipy.linalg.expm for P(t), brute-force
+enumeration of internal states on small trees, and the JC69 closed form."""
+import itertools
+import math
+
+import numpy as np
+import pytest
+from scipy.linalg import expm
+
+import oracle
+from starbeast2_b200 import synth
+from starbeast2_b200.newick import parse_newick
+from starbeast2_b200.problem import (SUBST_EIGEN, SUBST_HKY, Locus, const_pattern_mask, gtr_eigen_params, hky_params)
+
+
+def hky_q(kappa, pi):
+    q = np.array([[0, 1, kappa, 1], [1, 0, 1, kappa], [kappa, 1, 0, 1], [1, kappa, 1, 0]], float) * np.asarray(pi)[None, :]
+    np.fill_diagonal(q, -q.sum(1))
+    return q / -(np.asarray(pi) * np.diag(q)).sum()
+
+
+def gtr_q(r, pi):
+    ac, ag, at, cg, ct, gt = r
+    q = np.array([[0, ac, ag, at], [ac, 0, cg, ct], [ag, cg, 0, gt], [at, ct, gt, 0]], float) * np.asarray(pi)[None, :]
+    np.fill_diagonal(q, -q.sum(1))
+    return q / -(np.asarray(pi) * np.diag(q)).sum()
+
+
+@pytest.mark.parametrize("d", [0.0, 1e-6, 0.01, 0.3, 2.5, 40.0])
+def test_hky_matrix_matches_expm(d):
+    pi = np.array([0.30, 0.20, 0.20, 0.30])
+    got = oracle.hky_matrix(2.7, pi, d)
+    np.testing.assert_allclose(got, expm(hky_q(2.7, pi) * d), rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("d", [0.0, 0.01, 0.3, 2.5])
+def test_eigen_matrix_matches_expm(d):
+    pi = np.array([0.28, 0.22, 0.21, 0.29])
+    r = (1, 3, 0.8, 1.2, 3.5, 1)
+    sp = gtr_eigen_params(r, pi)
+    got = oracle.eigen_matrix(sp[0:4], sp[4:20], sp[20:36], d)
+    np.testing.assert_allclose(got, expm(gtr_q(r, pi) * d), rtol=0, atol=1e-13)
+
+
+def brute_force_logl(locus, branch_rates, q):
+    t = locus.tree
+    G, nT = locus.n_nodes, locus.n_tips
+    pi = locus.subst_params[1:5] if locus.subst_kind == SUBST_HKY else locus.subst_params[36:40]
+    internals = list(range(nT, G))
+    total = 0.0
+    pat_ll = []
+    for p in range(locus.n_pat):
+        lk = 0.0
+        for c in range(locus.n_cat):
+            P = {i: expm(q * (t.height[t.parent[i]] - t.height[i]) * branch_rates[i] * locus.cat_rates[c])
+                 for i in range(G) if t.parent[i] >= 0}
+            s = 0.0
+            for assign in itertools.product(range(4), repeat=len(internals)):
+                st = dict(zip(internals, assign))
+                w = pi[st[t.root]]
+                for i in range(G):
+                    if t.parent[i] < 0:
+                        continue
+                    if i < nT:
+                        x = locus.tip_states[i, p]
+                        if x < 4:
+                            w *= P[i][st[t.parent[i]], x]
+                    else:
+                        w *= P[i][st[t.parent[i]], st[i]]
+                s += w
+            lk += locus.cat_props[c] * s
+        pat_ll.append(math.log(lk))
+        total += math.log(lk) * locus.weights[p]
+    return total, np.array(pat_ll)
+
+
+@pytest.mark.parametrize("kind,ncat", [("hky", 1), ("hky", 3), ("gtr", 2)])
+def test_tree_likelihood_matches_brute_force(kind, ncat):
+    rng = np.random.default_rng(5)
+    tree, labels = parse_newick("(((a:0.1,b:0.2):0.15,c:0.3):0.05,(d:0.22,e:0.07):0.4);", adjust_tip_heights=False)
+    nT = 5
+    pats = rng.integers(0, 4, size=(nT, 12)).astype(np.uint8)
+    pats[1, 3] = 4   # missing
+    pats[:, 5] = 2   # constant column
+    pats[0, 7] = 4
+    pats[4, 7] = 4
+    w = rng.integers(1, 5, size=12).astype(np.int32)
+    pi = np.array([0.30, 0.20, 0.20, 0.30])
+    if kind == "hky":
+        sk, spar, q = SUBST_HKY, hky_params(2.0, pi), hky_q(2.0, pi)
+    else:
+        r = (1, 3, 0.8, 1.2, 3.5, 1)
+        sk, spar, q = SUBST_EIGEN, gtr_eigen_params(r, pi), gtr_q(r, pi)
+    cat_rates = synth.discrete_gamma_rates(0.5, ncat) * 1.3
+    loc = Locus(tree=tree, tip_states=pats, weights=w, tip_species=np.zeros(nT, np.int32), subst_kind=sk,
+                subst_params=spar, cat_rates=cat_rates, cat_props=np.full(ncat, 1.0 / ncat))
+    br = rng.uniform(0.5, 2.0, size=tree.n_nodes)
+    want, want_pat = brute_force_logl(loc, br, q)
+    for mode in (0, 1, 2):
+        got, det = oracle.tree_likelihood(loc, br, use_scaling=mode, want_details=True)
+        assert got == pytest.approx(want, rel=1e-12)
+        np.testing.assert_allclose(det["pattern_logl"], want_pat, rtol=1e-12)
+
+
+def test_jc69_two_tip_closed_form():
+    # two tips, distance d: same state 1/4(1/4+3/4 e^{-4d/3}), different 1/4(1/4-1/4 e^{-4d/3})
+    tree, _ = parse_newick("(a:0.35,b:0.35);")
+    loc = Locus(tree=tree, tip_states=np.array([[0, 0], [0, 1]], np.uint8), weights=np.array([3, 2], np.int32),
+                tip_species=np.zeros(2, np.int32), subst_params=hky_params(1.0, [0.25] * 4))
+    d = 0.7
+    e = math.exp(-4 * d / 3)
+    want = 3 * math.log(0.25 * (0.25 + 0.75 * e)) + 2 * math.log(0.25 * (0.25 - 0.25 * e))
+    assert oracle.tree_likelihood(loc, np.ones(3)) == pytest.approx(want, rel=1e-13)
+
+
+def test_scaling_rescues_underflow():
+    # a deep caterpillar with many sites per pattern product: unscaled underflows to -inf, lazy scaling recovers
+    import sys
+    sys.setrecursionlimit(10000)
+    rng = np.random.default_rng(11)
+    n = 640
+    nw = "t0:1.0"
+    for i in range(1, n):
+        nw = f"({nw},t{i}:{1.0 + i}):1.0"
+    tree, labels = parse_newick(nw + ";", taxa=[f"t{i}" for i in range(n)], adjust_tip_heights=False)
+    pats = rng.integers(0, 4, size=(n, 6)).astype(np.uint8)
+    loc = Locus(tree=tree, tip_states=pats, weights=np.ones(6, np.int32), tip_species=np.zeros(n, np.int32),
+                subst_params=hky_params(2.0, [0.3, 0.2, 0.2, 0.3]))
+    br = np.ones(tree.n_nodes)
+    assert oracle.tree_likelihood(loc, br, use_scaling=0) == -math.inf
+    lazy = oracle.tree_likelihood(loc, br, use_scaling=2)
+    always = oracle.tree_likelihood(loc, br, use_scaling=1)
+    assert math.isfinite(lazy) and lazy == pytest.approx(always, rel=1e-12)
+
+
+def test_pinv_constant_patterns():
+    tree, _ = parse_newick("((a:0.1,b:0.1):0.1,c:0.2);")
+    pats = np.array([[0, 1, 4], [0, 2, 3], [0, 1, 3]], np.uint8)
+    assert list(const_pattern_mask(pats)) == [1, 0, 8]
+    loc = Locus(tree=tree, tip_states=pats, weights=np.ones(3, np.int32), tip_species=np.zeros(3, np.int32),
+                subst_params=hky_params(2.0, [0.3, 0.2, 0.2, 0.3]), p_inv=0.2,
+                cat_rates=np.array([1.25]), cat_props=np.array([0.8]))
+    ll, det = oracle.tree_likelihood(loc, np.ones(5), want_details=True)
+    loc0 = Locus(tree=tree, tip_states=pats, weights=np.ones(3, np.int32), tip_species=np.zeros(3, np.int32),
+                 subst_params=hky_params(2.0, [0.3, 0.2, 0.2, 0.3]), cat_rates=np.array([1.25]), cat_props=np.array([1.0]))
+    _, det0 = oracle.tree_likelihood(loc0, np.ones(5), want_details=True)
+    # pattern 0 is constant in A: L = 0.8*L0 + 0.2*pi_A ; pattern 1 is variable: L = 0.8*L0
+    assert math.exp(det["pattern_logl"][0]) == pytest.approx(0.8 * math.exp(det0["pattern_logl"][0]) + 0.2 * 0.3, rel=1e-13)
+    assert math.exp(det["pattern_logl"][1]) == pytest.approx(0.8 * math.exp(det0["pattern_logl"][1]), rel=1e-13)
+
+
+def test_posterior_driver_consistent_with_pieces():
+    pb = synth.make_problem("C3", n_loci=3, n_sites=60)
+    res = oracle.posterior(pb, n_threads=2)
+    assert math.isfinite(res.total)
+    for l, loc in enumerate(pb.loci):
+        emb = oracle.gene_tree_update(loc.tree, loc.tip_species, pb.species)
+        assert emb.compatible
+        rates = oracle.starbeast_clock(loc.clock_rate, pb.species_rates, emb.occupancy)
+        assert oracle.tree_likelihood(loc, rates) == pytest.approx(res.per_locus_lik[l], rel=1e-14)
+        coal = sum(oracle.lwcr_branch_logp(b, pb.species, pb.pop_a, pb.pop_b, loc.ploidy, emb.coalescent_times(b), emb.n[b], emb.k[b])
+                   for b in range(pb.species.n_nodes))
+        assert coal == pytest.approx(res.per_locus_coal[l], rel=1e-13)
+    assert res.total == pytest.approx(res.coalescent + res.likelihood)
