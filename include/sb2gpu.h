@@ -1,0 +1,168 @@
+/*
+ * sb2gpu.h -- C ABI of libsb2gpu.so, the B200 (sm_100a) multi-locus likelihood engine that sits
+ * behind StarBEAST2's own plugin classes.
+ *
+ * The entry points are what a JNI (or Panama FFM) shim for the reference's hot path binds; each one
+ * cites the reference interface it replaces (paths relative to /root/reference).  Conventions:
+ *   - plain pointers and sizes only; the caller owns every pointer; the engine copies inputs before
+ *     returning and writes outputs into caller buffers; no callbacks; no global state besides the handle;
+ *   - return 0 = OK, <0 = error code, message via sb2_last_error();
+ *   - NOT thread-safe: one caller (the reference runs its MCMC single-threaded,
+ *     tutorial/StarBEAST2-tutorial.tex:419 "threads: 1");
+ *   - every array is indexed by the *current* BEAST node number: leaves 0..tips-1, root = last node
+ *     (StarBeastClock.java:60,72; LinearWithConstantRoot.java:42-44);
+ *   - numerical failure is reported the way the reference does it: -INFINITY in the output
+ *     (GeneTree.java:175-178), never an error code.
+ *   - there is no CPU fallback: every call fails with SB2_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SB2GPU_H
+#define SB2GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB2_API __attribute__((visibility("default")))
+
+typedef struct sb2_engine sb2_engine;
+
+enum { SB2_OK = 0, SB2_ERR_ARG = -1, SB2_ERR_STATE = -2, SB2_ERR_CUDA = -3, SB2_ERR_NOMEM = -4 };
+
+/* substitution model kinds: HKY.getTransitionProbabilities / GeneralSubstitutionModel (BEAST.base; named at
+ * tutorial/CanisPhylogeny/Canis-Phylogeny.xml:688, fxtemplates/sbSubstModels.xml:75-215) */
+enum { SB2_SUBST_HKY = 0, SB2_SUBST_EIGEN = 1 };
+/* branch-rate model kinds: StrictClockModel (Canis-Phylogeny.xml:692), StarBeastClock (StarBeastClock.java:9),
+ * or explicit per-node rates from any other BranchRateModel.getRateForBranch */
+enum { SB2_CLOCK_STRICT = 0, SB2_CLOCK_SPECIES_RATES = 1, SB2_CLOCK_EXPLICIT = 2 };
+/* population models: ConstantPopulations.java, LinearWithConstantRoot.java, and analytic integration
+ * (MultispeciesCoalescent.java:200-235 with DummyModel / no populationModel, GeneTree.java:182) */
+enum { SB2_POP_CONSTANT = 0, SB2_POP_LWCR = 1, SB2_POP_ANALYTIC = 2 };
+
+typedef struct {
+    int32_t device;       /* CUDA device ordinal */
+    int32_t exact_order;  /* 1: no FMA in the pruning recursion and strictly sequential pattern / locus sums,
+                                i.e. the reference's (Java) evaluation order; 0: fused multiply-add + fixed-shape
+                                tree reductions (deterministic, bit-stable run to run) */
+    int32_t profile;      /* 1: bracket the pruning kernel with CUDA events (sb2_kernel_time) */
+    int32_t reserved[5];
+} sb2_config;
+
+/* ---- life cycle ------------------------------------------------------------------------------------ */
+
+SB2_API int sb2_create(const sb2_config *cfg, sb2_engine **out);
+SB2_API void sb2_destroy(sb2_engine *e);
+SB2_API const char *sb2_last_error(const sb2_engine *e);
+
+/* Registers one locus = one (GeneTree, TreeLikelihood) pair.  Replaces TreeLikelihood.initAndValidate's
+ * tip-state upload (setStates per leaf) and GeneTree.update's leaf->species map (GeneTree.java:211-226).
+ * tipStates[tip*nPatterns + pattern] in 0..3 (A,C,G,T), >=4 = gap/ambiguous/missing (useAmbiguities=false);
+ * patternWeights = Alignment.getPatternWeight; tipToSpecies[tip] = species-tree LEAF NODE NUMBER
+ * (SpeciesTreeInterface.getTipNumberMap).  Returns the locus index (>=0) or an error (<0). */
+SB2_API int sb2_add_locus(sb2_engine *e, int32_t nTips, int32_t nPatterns, const uint8_t *tipStates,
+                          const int32_t *patternWeights, int32_t nCategories, const int32_t *tipToSpecies,
+                          double ploidy);
+
+/* Shards nothing (one engine = one GPU; the host shards loci over engines), allocates device state. */
+SB2_API int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves);
+
+/* ---- state input (all staged on the host, uploaded by the next sb2_eval_*) --------------------------- */
+
+/* SpeciesTree state node (SpeciesTree.java; read at GeneTree.java:257,337-343).  left/right = -1 for leaves. */
+SB2_API int sb2_set_species_tree(sb2_engine *e, const int32_t *parent, const int32_t *left, const int32_t *right,
+                                 const double *height);
+/* Gene Tree state node of one locus (GeneTree.java:22 `tree`, TreeLikelihood `tree`). */
+SB2_API int sb2_set_gene_tree(sb2_engine *e, int32_t locus, const int32_t *parent, const int32_t *left,
+                              const int32_t *right, const double *height);
+/* Bulk form: nLoci consecutive loci, arrays concatenated in locus order. */
+SB2_API int sb2_set_gene_trees(sb2_engine *e, int32_t firstLocus, int32_t nLoci, const int32_t *parent,
+                               const int32_t *left, const int32_t *right, const double *height);
+/* HKY: params = {kappa, piA, piC, piG, piT}; EIGEN: {eval[4], evec[16], ievc[16], pi[4]} (row-major, the arrays
+ * EigenDecomposition.getEigenValues/getEigenVectors/getInverseEigenVectors return). */
+SB2_API int sb2_set_subst_model(sb2_engine *e, int32_t locus, int32_t kind, const double *params);
+/* SiteModel: catRates[c] = getRateForCategory(c) (already x mutationRate), catProps = getCategoryProportions,
+ * pInv = getProportionInvariant (added on constant patterns at the root, as TreeLikelihood does). */
+SB2_API int sb2_set_site_model(sb2_engine *e, int32_t locus, const double *catRates, const double *catProps,
+                               double pInv);
+/* branchRateModel of the locus.  STRICT: rate = meanRate; SPECIES_RATES: StarBeastClock.update
+ * (StarBeastClock.java:54-75) with meanRate = clock.rate; EXPLICIT: rates[node] given (2*nTips-1 values). */
+SB2_API int sb2_set_clock(sb2_engine *e, int32_t locus, int32_t kind, double meanRate, const double *ratesOrNull);
+/* SpeciesTreeRates.getRatesArray() (SpeciesTreeRates.java:4; UncorrelatedRates.java:173-182), length nSpeciesNodes. */
+SB2_API int sb2_set_species_rates(sb2_engine *e, const double *rates);
+/* CONSTANT: a = populationSizes[nSpeciesNodes] (ConstantPopulations.java:19);
+ * LWCR: a = tipPopulationSizes[nSpeciesLeaves], b = topPopulationSizes[nSpeciesNodes-1] (LinearWithConstantRoot.java:21-22);
+ * ANALYTIC: alpha = populationShape, beta = as MultispeciesCoalescent.checkHyperparameters computes it
+ * (MultispeciesCoalescent.java:134-147, stale-alpha quirk included by the caller). */
+SB2_API int sb2_set_pop_model(sb2_engine *e, int32_t kind, const double *a, const double *b, double alpha, double beta);
+
+/* ---- evaluation ---------------------------------------------------------------------------------------- */
+
+/* MultispeciesCoalescent.calculateLogP (MultispeciesCoalescent.java:150-198): embeds every dirty gene tree
+ * (GeneTree.update, GeneTree.java:202-318), evaluates the per-branch terms.  perLocus[nLoci] = GeneTree.calculateLogP
+ * (-INFINITY when incompatible); perBranch[nSpeciesNodes] = analytic per-branch terms (zeros otherwise);
+ * *total = the distribution's logP.  Output pointers may be NULL. */
+SB2_API int sb2_eval_coalescent(sb2_engine *e, double *perLocus, double *perBranch, double *total);
+/* Sum of TreeLikelihood.calculateLogP over loci (the `likelihood` CompoundDistribution, Canis-Phylogeny.xml:683),
+ * recomputing only dirty branches / nodes.  perLocus[nLoci], *total. */
+SB2_API int sb2_eval_likelihood(sb2_engine *e, double *perLocus, double *total);
+/* Both phases with one device round trip.  total3 = {coalescent, likelihood, coalescent + likelihood}
+ * (likelihood and sum are still produced when the coalescent is -INFINITY; the caller short-circuits). */
+SB2_API int sb2_eval_posterior(sb2_engine *e, double *perLocusCoal, double *perLocusLik, double *perBranch,
+                               double *total3);
+
+/* Split form for multi-GPU hosts: begin() uploads staged state and launches everything up to the rank-local
+ * partial sums, which land in the reduce vector {coalescent, likelihood, nIncompatible, (q,gamma,logR) x nSpeciesNodes}
+ * (MultispeciesCoalescent.java:203-232 needs the per-branch sums over ALL loci before its closed form);
+ * the host all-reduces (sum) that device vector across ranks; end() finishes and downloads. */
+SB2_API int sb2_eval_begin(sb2_engine *e);
+SB2_API int sb2_eval_end(sb2_engine *e, double *perLocusCoal, double *perLocusLik, double *perBranch, double *total3);
+/* Device address and length (in doubles) of the reduce vector; bind an external device buffer (e.g. a
+ * torch tensor handed to torch.distributed.all_reduce) with sb2_bind_reduce_vector before the first eval. */
+SB2_API int sb2_reduce_vector(sb2_engine *e, void **devPtr, int32_t *nDoubles);
+SB2_API int sb2_bind_reduce_vector(sb2_engine *e, void *devPtr);
+/* Run on this CUDA stream (cudaStream_t) instead of the engine's own. */
+SB2_API int sb2_set_stream(sb2_engine *e, void *cudaStream);
+
+/* CalculationNode.store / restore / accept (GeneTree.java:79-123, MultispeciesCoalescent.java:50-88,
+ * StarBeastClock.java:41-52; BeerLikelihoodCore store/restore): double-buffered device state, index flip, no copies
+ * of partials. */
+SB2_API int sb2_store(sb2_engine *e);
+SB2_API int sb2_restore(sb2_engine *e);
+SB2_API int sb2_accept(sb2_engine *e);
+/* Marks every locus and model dirty so that the next eval recomputes everything from the device-resident state
+ * (what BEAST's periodic from-scratch consistency check does; also the bench's "all nodes dirty" regime). */
+SB2_API int sb2_mark_all_dirty(sb2_engine *e);
+
+/* ---- read-back for the plugin classes' getters and for parity tests --------------------------------------- */
+
+/* GeneTree.getSpeciesOccupancy-derived StarBeastClock.getRateForBranch values, [2*nTips-1]. */
+SB2_API int sb2_get_branch_rates(sb2_engine *e, int32_t locus, double *rates);
+/* GeneTree.coalescentLineageCounts / coalescentCounts [nSpeciesNodes], geneNodeSpeciesAssignment [2*nTips-1],
+ * and per-branch GeneTree perBranchLogP [nSpeciesNodes]; any pointer may be NULL. */
+SB2_API int sb2_get_embedding(sb2_engine *e, int32_t locus, int32_t *lineageCounts, int32_t *coalCounts,
+                              int32_t *assignment, double *perBranchLogP);
+/* Current partials of an internal node, [nCategories][nPatterns][4], scaled by 2^-exponent[pattern]
+ * (exponents[nPatterns], cumulative over the subtree). */
+SB2_API int sb2_get_partials(sb2_engine *e, int32_t locus, int32_t node, double *partials, int32_t *exponents);
+/* Current transition matrices of the branch above `node`, [nCategories][16]. */
+SB2_API int sb2_get_matrices(sb2_engine *e, int32_t locus, int32_t node, double *matrices);
+/* patternLogLikelihoods of the last evaluation of this locus, [nPatterns]. */
+SB2_API int sb2_get_pattern_logl(sb2_engine *e, int32_t locus, double *patternLogL);
+
+/* ---- introspection ------------------------------------------------------------------------------------------ */
+
+SB2_API int32_t sb2_num_loci(const sb2_engine *e);
+/* kernels launched by this engine since creation */
+SB2_API int64_t sb2_launch_count(const sb2_engine *e);
+/* number of (node) pruning operations scheduled by the last evaluation, summed over loci */
+SB2_API int64_t sb2_last_node_updates(sb2_engine *e);
+/* profile=1: accumulated device time (ms) and launch count of the pruning kernel since the last call */
+SB2_API int sb2_kernel_time(sb2_engine *e, double *ms, int64_t *launches);
+/* device bytes held by the engine */
+SB2_API int64_t sb2_device_bytes(const sb2_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SB2GPU_H */

@@ -1,0 +1,923 @@
+// Host side of libsb2gpu.so: the engine object behind include/sb2gpu.h.
+//
+// The engine is thin on purpose: the host stages changed inputs in pinned memory and marks loci dirty; every
+// decision that depends on tree state (what is dirty, in which order to prune) is taken on the device by
+// k_prepare, so one evaluation is  H2D(staged ranges) -> k_prepare -> k_treewalk -> k_reduce_local -> [all-reduce]
+// -> k_finish -> D2H(one small vector).  store/restore/accept are a D2D copy / pointer swap of the small state block.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/sb2gpu.h"
+#include "sb2_device.cuh"
+
+using namespace sb2;
+
+namespace {
+
+struct HostLocus {
+    LocusDesc d;
+    std::vector<uint8_t> states;
+    std::vector<int32_t> weights;
+    std::vector<int32_t> tipSpecies;
+    std::vector<uint8_t> constMask;
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+};
+
+}  // namespace
+
+struct sb2_engine {
+    sb2_config cfg{};
+    std::string err;
+    bool finalized = false;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    std::vector<HostLocus> loci;
+    int S = 0, nSpeciesLeaves = 0, L = 0;
+    int64_t totalNodes = 0, totalTips = 0, totalPat = 0, totalCat = 0, totalInt = 0, totalTiles = 0;
+    int maxNodes = 0, nCat = 0, chunksPerTile = 1, stackDepth = 1;
+    int64_t devBytes = 0;
+    int64_t launches = 0;
+    std::vector<void *> devAllocs;
+
+    // static device data
+    LocusDesc *dLoci = nullptr;
+    uint8_t *dStates = nullptr, *dConstMask = nullptr;
+    int32_t *dWeights = nullptr, *dTipSpecies = nullptr, *dTileLocus = nullptr;
+    // big dynamic device data
+    double *dPartials = nullptr, *dMats = nullptr, *dPatLogL = nullptr, *dTileSum = nullptr;
+    int16_t *dCumExp = nullptr;
+    Op *dOps = nullptr;
+    int32_t *dNOps = nullptr;
+    // staged inputs: pinned host mirror + device copy
+    LocusParams *hParams = nullptr, *dParams = nullptr;
+    double *hCat = nullptr, *dCat = nullptr;          // [2][totalCat]: rates then props
+    double *hExplicit = nullptr, *dExplicit = nullptr;  // by node (allocated lazily on first EXPLICIT clock)
+    uint8_t *hInTree = nullptr, *dInTree = nullptr;
+    int64_t inTreeBytes = 0;
+    uint8_t *hFlags = nullptr, *dFlags = nullptr;
+    // species + shared parameters, staged as one contiguous byte block that mirrors the StateBlock's species region
+    uint8_t *hSpecies = nullptr;
+    size_t speciesBytes = 0, speciesOffInBlock = 0;
+    // state blocks
+    uint8_t *blockMem[2] = {nullptr, nullptr};
+    size_t blockBytes = 0;
+    StateBlock blk[2];
+    int curIdx = 0;
+    // outputs
+    double *dRed = nullptr, *dRedOwn = nullptr, *dOut = nullptr, *hOut = nullptr;
+    int nRed = 0, nOut = 0;
+    int popKind = SB2_POP_CONSTANT;
+    // dirtiness
+    std::vector<uint8_t> treeDirty, modelDirty, clockDirty;
+    bool speciesDirty = true, catDirty = true, paramsDirty = true, explicitDirty = false, forceAll = true;
+    bool needPrepare = true, walkPending = false, tilesValid = false, reduced = false;
+    // host mirrors of the stored state (restore() must bring the staging copies back too)
+    LocusParams *hParamsStored = nullptr;
+    double *hCatStored = nullptr, *hExplicitStored = nullptr;
+    uint8_t *hSpeciesStored = nullptr;
+    int popKindStored = SB2_POP_CONSTANT;
+    std::vector<int32_t> touched;        // loci whose parameters changed since the last store()
+    std::vector<uint8_t> touchedFlag;
+    int reuploadFirst = 0x7fffffff, reuploadLast = -1;   // parameter range to re-upload after a restore()
+    // profiling
+    cudaEvent_t evA = nullptr, evB = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evPool;
+    size_t evUsed = 0;
+    double profMs = 0.0;
+    int64_t profLaunches = 0;
+
+    int fail(int code, const char *fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define CUDA_TRY(e, call)                                                                        \
+    do {                                                                                         \
+        cudaError_t _st = (call);                                                                \
+        if (_st != cudaSuccess) return (e)->fail(SB2_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_st)); \
+    } while (0)
+
+namespace {
+
+template <typename T>
+int dev_alloc(sb2_engine *e, T **p, size_t n)
+{
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    cudaError_t st = cudaMalloc((void **)p, bytes);
+    if (st != cudaSuccess) return e->fail(SB2_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(st));
+    e->devAllocs.push_back(*p);
+    e->devBytes += (int64_t)bytes;
+    return SB2_OK;
+}
+
+template <typename T>
+int pin_alloc(sb2_engine *e, T **p, size_t n)
+{
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    cudaError_t st = cudaHostAlloc((void **)p, bytes, cudaHostAllocDefault);
+    if (st != cudaSuccess) return e->fail(SB2_ERR_NOMEM, "cudaHostAlloc(%zu bytes): %s", bytes, cudaGetErrorString(st));
+    memset(*p, 0, bytes);
+    return SB2_OK;
+}
+
+// carve a StateBlock out of one allocation; returns bytes needed.  Species region is contiguous.
+size_t carve_block(StateBlock *b, uint8_t *base, int64_t N, int64_t L, int S, int nLeaves, size_t *speciesOff, size_t *speciesBytes)
+{
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~size_t(15); return r; };
+    const size_t LS = (size_t)L * S;
+    size_t gHeight = take(8 * N), bRate = take(8 * N), bTime = take(8 * N);
+    size_t logL = take(8 * L), coal = take(8 * L);
+    size_t brLogP = take(8 * LS), anG = take(8 * LS), anR = take(8 * LS);
+    size_t gParent = take(4 * N), gLeft = take(4 * N), gRight = take(4 * N), assign = take(4 * N);
+    size_t brN = take(4 * LS), brK = take(4 * LS);
+    size_t curP = take(N), curM = take(N);
+    // species region (kept contiguous: one H2D copy)
+    const size_t sp0 = o;
+    size_t sHeight = take(8 * S), sRates = take(8 * S), popA = take(8 * S), popB = take(8 * S), hyper = take(16);
+    size_t sParent = take(4 * S), sLeft = take(4 * S), sRight = take(4 * S);
+    const size_t sp1 = o;
+    (void)nLeaves;
+    if (speciesOff) *speciesOff = sp0;
+    if (speciesBytes) *speciesBytes = sp1 - sp0;
+    if (b) {
+        b->gHeight = (double *)(base + gHeight); b->bRate = (double *)(base + bRate); b->bTime = (double *)(base + bTime);
+        b->logL = (double *)(base + logL); b->coal = (double *)(base + coal);
+        b->brLogP = (double *)(base + brLogP); b->anG = (double *)(base + anG); b->anR = (double *)(base + anR);
+        b->gParent = (int32_t *)(base + gParent); b->gLeft = (int32_t *)(base + gLeft); b->gRight = (int32_t *)(base + gRight);
+        b->assign = (int32_t *)(base + assign); b->brN = (int32_t *)(base + brN); b->brK = (int32_t *)(base + brK);
+        b->curP = base + curP; b->curM = base + curM;
+        b->sHeight = (double *)(base + sHeight); b->sRates = (double *)(base + sRates);
+        b->popA = (double *)(base + popA); b->popB = (double *)(base + popB); b->hyper = (double *)(base + hyper);
+        b->sParent = (int32_t *)(base + sParent); b->sLeft = (int32_t *)(base + sLeft); b->sRight = (int32_t *)(base + sRight);
+    }
+    return o;
+}
+
+int floor_log2(int x)
+{
+    int r = 0;
+    while ((1 << (r + 1)) <= x) r++;
+    return r;
+}
+
+// host view of the pinned species staging block (same carve as the device block's species region)
+struct SpeciesView {
+    double *sHeight, *sRates, *popA, *popB, *hyper;
+    int32_t *sParent, *sLeft, *sRight;
+};
+SpeciesView species_view(sb2_engine *e)
+{
+    StateBlock tmp;
+    uint8_t *base = reinterpret_cast<uint8_t *>(reinterpret_cast<uintptr_t>(e->hSpecies) - e->speciesOffInBlock);
+    carve_block(&tmp, base, e->totalNodes, e->L, e->S, e->nSpeciesLeaves, nullptr, nullptr);
+    SpeciesView v;
+    v.sHeight = tmp.sHeight; v.sRates = tmp.sRates; v.popA = tmp.popA; v.popB = tmp.popB; v.hyper = tmp.hyper;
+    v.sParent = tmp.sParent; v.sLeft = tmp.sLeft; v.sRight = tmp.sRight;
+    return v;
+}
+
+int check_locus(sb2_engine *e, int32_t locus)
+{
+    if (!e->finalized) return e->fail(SB2_ERR_STATE, "engine not finalized");
+    if (locus < 0 || locus >= e->L) return e->fail(SB2_ERR_ARG, "locus %d out of range [0,%d)", locus, e->L);
+    return SB2_OK;
+}
+
+void touch(sb2_engine *e, int32_t locus)
+{
+    if (!e->touchedFlag[locus]) { e->touchedFlag[locus] = 1; e->touched.push_back(locus); }
+}
+
+StateBlock &cur(sb2_engine *e) { return e->blk[e->curIdx]; }
+StateBlock &stored(sb2_engine *e) { return e->blk[1 - e->curIdx]; }
+
+ReduceArgs reduce_args(sb2_engine *e, bool coalOnly = false)
+{
+    ReduceArgs r;
+    r.useTiles = (!coalOnly && e->tilesValid) ? 1 : 0;
+    r.loci = e->dLoci; r.nOps = e->dNOps; r.tileSum = e->dTileSum; r.patLogL = e->dPatLogL; r.weights = e->dWeights;
+    r.cur = cur(e); r.red = e->dRed; r.out = e->dOut;
+    r.nLoci = e->L; r.S = e->S; r.popKind = e->popKind; r.exact = e->cfg.exact_order;
+    return r;
+}
+
+// upload staged inputs and run k_prepare
+int do_prepare(sb2_engine *e)
+{
+    if (!e->needPrepare) return SB2_OK;
+    cudaStream_t st = e->stream;
+    const int L = e->L;
+    int firstTree = L, lastTree = -1, firstPar = L, lastPar = -1;
+    bool any = false;
+    for (int l = 0; l < L; l++) {
+        uint8_t f = 0;
+        if (e->forceAll) f |= LF_RUN | LF_FORCE_ALL;
+        if (e->speciesDirty) f |= LF_RUN;
+        if (e->treeDirty[l]) { f |= LF_RUN | LF_TREE_IN; firstTree = std::min(firstTree, l); lastTree = l; }
+        if (e->modelDirty[l]) { f |= LF_RUN | LF_FORCE_MATS; firstPar = std::min(firstPar, l); lastPar = l; }
+        if (e->clockDirty[l]) { f |= LF_RUN; firstPar = std::min(firstPar, l); lastPar = l; }
+        e->hFlags[l] = f;
+        any |= f != 0;
+    }
+    CUDA_TRY(e, cudaMemcpyAsync(e->dFlags, e->hFlags, L, cudaMemcpyHostToDevice, st));
+    if (e->speciesDirty)
+        CUDA_TRY(e, cudaMemcpyAsync(e->blockMem[e->curIdx] + e->speciesOffInBlock, e->hSpecies, e->speciesBytes, cudaMemcpyHostToDevice, st));
+    if (e->reuploadLast >= 0) { firstPar = std::min(firstPar, e->reuploadFirst); lastPar = std::max(lastPar, e->reuploadLast); }
+    e->reuploadFirst = 0x7fffffff; e->reuploadLast = -1;
+    if (lastPar >= 0 || e->paramsDirty) {
+        if (e->paramsDirty) { firstPar = 0; lastPar = L - 1; }
+        CUDA_TRY(e, cudaMemcpyAsync(e->dParams + firstPar, e->hParams + firstPar, sizeof(LocusParams) * (size_t)(lastPar - firstPar + 1), cudaMemcpyHostToDevice, st));
+    }
+    if (e->catDirty) CUDA_TRY(e, cudaMemcpyAsync(e->dCat, e->hCat, sizeof(double) * 2 * (size_t)e->totalCat, cudaMemcpyHostToDevice, st));
+    if (e->explicitDirty && e->hExplicit)
+        CUDA_TRY(e, cudaMemcpyAsync(e->dExplicit, e->hExplicit, sizeof(double) * (size_t)e->totalNodes, cudaMemcpyHostToDevice, st));
+    if (lastTree >= 0) {
+        const int64_t b0 = e->loci[firstTree].d.treeOff;
+        const int64_t b1 = e->loci[lastTree].d.treeOff + 20ll * e->loci[lastTree].d.nNodes;
+        CUDA_TRY(e, cudaMemcpyAsync(e->dInTree + b0, e->hInTree + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+    }
+    PrepareArgs a;
+    a.loci = e->dLoci; a.params = e->dParams; a.flags = e->dFlags; a.inTree = e->dInTree; a.tipSpecies = e->dTipSpecies;
+    a.catRates = e->dCat; a.explicitRates = e->dExplicit ? e->dExplicit : e->dCat;
+    a.cur = cur(e); a.stored = stored(e); a.ops = e->dOps; a.nOps = e->dNOps; a.mats = e->dMats;
+    a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L;
+    launch_prepare(a, e->maxNodes, st);
+    e->launches++;
+    CUDA_TRY(e, cudaGetLastError());
+    std::fill(e->treeDirty.begin(), e->treeDirty.end(), 0);
+    std::fill(e->modelDirty.begin(), e->modelDirty.end(), 0);
+    std::fill(e->clockDirty.begin(), e->clockDirty.end(), 0);
+    e->speciesDirty = e->catDirty = e->paramsDirty = e->explicitDirty = e->forceAll = false;
+    e->needPrepare = false;
+    e->walkPending = true;
+    e->tilesValid = false;
+    (void)any;
+    return SB2_OK;
+}
+
+int do_walk(sb2_engine *e)
+{
+    if (!e->walkPending) return SB2_OK;
+    WalkArgs a;
+    a.loci = e->dLoci; a.params = e->dParams; a.tileLocus = e->dTileLocus; a.ops = e->dOps; a.nOps = e->dNOps;
+    a.tipStates = e->dStates; a.weights = e->dWeights; a.constMask = e->dConstMask; a.catProps = e->dCat + e->totalCat;
+    a.mats = e->dMats; a.partials = e->dPartials; a.cumExp = e->dCumExp; a.patLogL = e->dPatLogL; a.tileSum = e->dTileSum;
+    a.nCat = e->nCat; a.chunksPerTile = e->chunksPerTile; a.stackDepth = e->stackDepth;
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    if (e->cfg.profile) {
+        if (e->evUsed == e->evPool.size()) {
+            cudaEvent_t x, y;
+            CUDA_TRY(e, cudaEventCreate(&x));
+            CUDA_TRY(e, cudaEventCreate(&y));
+            e->evPool.push_back({x, y});
+        }
+        ev = e->evPool[e->evUsed++];
+        CUDA_TRY(e, cudaEventRecord(ev.first, e->stream));
+    }
+    launch_treewalk(a, (int)e->totalTiles, e->cfg.exact_order != 0, e->stream);
+    e->launches++;
+    if (e->cfg.profile) CUDA_TRY(e, cudaEventRecord(ev.second, e->stream));
+    CUDA_TRY(e, cudaGetLastError());
+    e->walkPending = false;
+    e->tilesValid = true;
+    return SB2_OK;
+}
+
+int download(sb2_engine *e)
+{
+    CUDA_TRY(e, cudaMemcpyAsync(e->hOut, e->dOut, sizeof(double) * (size_t)e->nOut, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return SB2_OK;
+}
+
+void copy_out(sb2_engine *e, double *perLocusCoal, double *perLocusLik, double *perBranch, double *total3)
+{
+    const int L = e->L;
+    if (total3) memcpy(total3, e->hOut, 3 * sizeof(double));
+    if (perLocusCoal) memcpy(perLocusCoal, e->hOut + 3, sizeof(double) * L);
+    if (perLocusLik) memcpy(perLocusLik, e->hOut + 3 + L, sizeof(double) * L);
+    if (perBranch) memcpy(perBranch, e->hOut + 3 + 2 * L, sizeof(double) * e->S);
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb2_create(const sb2_config *cfg, sb2_engine **out)
+{
+    if (!out) return SB2_ERR_ARG;
+    *out = nullptr;
+    sb2_engine *e = new sb2_engine();
+    if (cfg) e->cfg = *cfg;
+    *out = e;   // handed back even on failure so that sb2_last_error works
+    int nDev = 0;
+    cudaError_t st = cudaGetDeviceCount(&nDev);
+    if (st != cudaSuccess || nDev == 0)
+        return e->fail(SB2_ERR_CUDA, "no CUDA device (%s); libsb2gpu has no CPU fallback", st != cudaSuccess ? cudaGetErrorString(st) : "device count 0");
+    if (e->cfg.device < 0 || e->cfg.device >= nDev) return e->fail(SB2_ERR_ARG, "device %d out of range [0,%d)", e->cfg.device, nDev);
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    cudaDeviceProp prop;
+    CUDA_TRY(e, cudaGetDeviceProperties(&prop, e->cfg.device));
+    if (prop.major != 10) return e->fail(SB2_ERR_CUDA, "device %d is sm_%d%d; libsb2gpu is built for sm_100a only", e->cfg.device, prop.major, prop.minor);
+    CUDA_TRY(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->ownStream = true;
+    return SB2_OK;
+}
+
+void sb2_destroy(sb2_engine *e)
+{
+    if (!e) return;
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void *p : e->devAllocs) cudaFree(p);
+    for (void *p : {(void *)e->hParams, (void *)e->hCat, (void *)e->hExplicit, (void *)e->hInTree, (void *)e->hFlags, (void *)e->hSpecies, (void *)e->hOut,
+                    (void *)e->hParamsStored, (void *)e->hCatStored, (void *)e->hExplicitStored, (void *)e->hSpeciesStored})
+        if (p) cudaFreeHost(p);
+    for (auto &ev : e->evPool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+const char *sb2_last_error(const sb2_engine *e) { return e ? e->err.c_str() : "null engine"; }
+
+int sb2_add_locus(sb2_engine *e, int32_t nTips, int32_t nPatterns, const uint8_t *tipStates, const int32_t *patternWeights,
+                  int32_t nCategories, const int32_t *tipToSpecies, double ploidy)
+{
+    if (!e) return SB2_ERR_ARG;
+    if (e->finalized) return e->fail(SB2_ERR_STATE, "sb2_add_locus after sb2_finalize");
+    if (nTips < 2 || nPatterns < 1 || nCategories < 1 || nCategories > 32 || !tipStates || !patternWeights || !tipToSpecies)
+        return e->fail(SB2_ERR_ARG, "bad locus shape: tips %d patterns %d categories %d (1..32)", nTips, nPatterns, nCategories);
+    if (nTips > 8192) return e->fail(SB2_ERR_ARG, "nTips %d > 8192: cumulative int16 exponents could overflow", nTips);
+    if (!e->loci.empty() && e->loci[0].d.nCat != nCategories)
+        return e->fail(SB2_ERR_ARG, "all loci of one engine must share the category count (%d vs %d)", e->loci[0].d.nCat, nCategories);
+    HostLocus hl;
+    memset(&hl.d, 0, sizeof hl.d);
+    hl.d.nTips = nTips; hl.d.nNodes = 2 * nTips - 1; hl.d.nInt = nTips - 1; hl.d.nPat = nPatterns; hl.d.nCat = nCategories;
+    hl.d.ploidy = ploidy;
+    hl.states.assign(tipStates, tipStates + (size_t)nTips * nPatterns);
+    hl.weights.assign(patternWeights, patternWeights + nPatterns);
+    hl.tipSpecies.assign(tipToSpecies, tipToSpecies + nTips);
+    // TreeLikelihood.calcConstantPatternIndices (useAmbiguities=false): states shared by every unambiguous tip
+    hl.constMask.assign(nPatterns, 0xF);
+    for (int t = 0; t < nTips; t++)
+        for (int p = 0; p < nPatterns; p++) {
+            const uint8_t s = tipStates[(size_t)t * nPatterns + p];
+            if (s < 4) hl.constMask[p] &= (uint8_t)(1u << s);
+        }
+    e->loci.push_back(std::move(hl));
+    return (int)e->loci.size() - 1;
+}
+
+int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
+{
+    if (!e) return SB2_ERR_ARG;
+    if (e->finalized) return e->fail(SB2_ERR_STATE, "already finalized");
+    if (e->loci.empty()) return e->fail(SB2_ERR_STATE, "no loci");
+    if (nSpeciesNodes < 1 || nSpeciesLeaves < 1 || nSpeciesLeaves > nSpeciesNodes) return e->fail(SB2_ERR_ARG, "bad species tree size");
+    e->S = nSpeciesNodes; e->nSpeciesLeaves = nSpeciesLeaves; e->L = (int)e->loci.size();
+    const int L = e->L;
+    e->nCat = e->loci[0].d.nCat;
+    e->chunksPerTile = std::max(1, 4 / e->nCat);
+    const int tilePat = 32 * e->chunksPerTile;
+    int64_t nodeBase = 0, tipBase = 0, patBase = 0, catBase = 0, tileBase = 0, opBase = 0, stateBase = 0, partBase = 0, expBase = 0, matBase = 0, treeOff = 0;
+    e->stackDepth = 1;
+    for (auto &hl : e->loci) {
+        LocusDesc &d = hl.d;
+        for (int t = 0; t < d.nTips; t++)
+            if (hl.tipSpecies[t] < 0 || hl.tipSpecies[t] >= nSpeciesNodes) return e->fail(SB2_ERR_ARG, "tipToSpecies out of range");
+        d.nodeBase = (int32_t)nodeBase; d.tipBase = (int32_t)tipBase; d.patBase = (int32_t)patBase; d.catBase = (int32_t)catBase;
+        d.tileBase = (int32_t)tileBase; d.nTiles = (d.nPat + tilePat - 1) / tilePat; d.opBase = (int32_t)opBase;
+        d.stackDepth = floor_log2(d.nInt) + 1;
+        d.stateBase = stateBase; d.partBase = partBase; d.expBase = expBase; d.matBase = matBase; d.treeOff = treeOff;
+        e->stackDepth = std::max(e->stackDepth, d.stackDepth);
+        e->maxNodes = std::max(e->maxNodes, d.nNodes);
+        nodeBase += d.nNodes; tipBase += d.nTips; patBase += d.nPat; catBase += d.nCat; tileBase += d.nTiles; opBase += d.nInt;
+        stateBase += (int64_t)d.nTips * d.nPat;
+        partBase += 2ll * d.nInt * d.nCat * d.nPat * 4;
+        expBase += 2ll * d.nInt * d.nPat;
+        expBase = (expBase + 7) & ~7ll;
+        matBase += 2ll * d.nNodes * d.nCat * 16;
+        treeOff += 20ll * d.nNodes;
+        treeOff = (treeOff + 7) & ~7ll;
+    }
+    if (nodeBase > 0x7fffffff || patBase > 0x7fffffff) return e->fail(SB2_ERR_ARG, "problem too large for 32-bit node/pattern indices");
+    e->totalNodes = nodeBase; e->totalTips = tipBase; e->totalPat = patBase; e->totalCat = catBase; e->totalTiles = tileBase;
+    e->totalInt = opBase; e->inTreeBytes = treeOff;
+    if (prepare_smem_bytes(e->maxNodes, e->S) > 227 * 1024) return e->fail(SB2_ERR_ARG, "gene tree too large for the per-locus shared-memory kernel");
+    if (treewalk_smem_bytes(e->nCat, e->chunksPerTile, e->stackDepth) > 227 * 1024) return e->fail(SB2_ERR_ARG, "pruning stack does not fit shared memory");
+
+    int rc;
+    // static data
+    std::vector<LocusDesc> descs(L);
+    std::vector<uint8_t> states((size_t)stateBase), cmask((size_t)patBase);
+    std::vector<int32_t> weights((size_t)patBase), tipsp((size_t)tipBase), tileLocus((size_t)tileBase);
+    for (int l = 0; l < L; l++) {
+        const HostLocus &hl = e->loci[l];
+        descs[l] = hl.d;
+        memcpy(states.data() + hl.d.stateBase, hl.states.data(), hl.states.size());
+        memcpy(cmask.data() + hl.d.patBase, hl.constMask.data(), hl.constMask.size());
+        memcpy(weights.data() + hl.d.patBase, hl.weights.data(), hl.weights.size() * 4);
+        memcpy(tipsp.data() + hl.d.tipBase, hl.tipSpecies.data(), hl.tipSpecies.size() * 4);
+        for (int t = 0; t < hl.d.nTiles; t++) tileLocus[hl.d.tileBase + t] = l;
+    }
+    if ((rc = dev_alloc(e, &e->dLoci, L))) return rc;
+    if ((rc = dev_alloc(e, &e->dStates, states.size()))) return rc;
+    if ((rc = dev_alloc(e, &e->dConstMask, cmask.size()))) return rc;
+    if ((rc = dev_alloc(e, &e->dWeights, weights.size()))) return rc;
+    if ((rc = dev_alloc(e, &e->dTipSpecies, tipsp.size()))) return rc;
+    if ((rc = dev_alloc(e, &e->dTileLocus, tileLocus.size()))) return rc;
+    CUDA_TRY(e, cudaMemcpy(e->dLoci, descs.data(), sizeof(LocusDesc) * L, cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpy(e->dStates, states.data(), states.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpy(e->dConstMask, cmask.data(), cmask.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpy(e->dWeights, weights.data(), weights.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpy(e->dTipSpecies, tipsp.data(), tipsp.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpy(e->dTileLocus, tileLocus.data(), tileLocus.size() * 4, cudaMemcpyHostToDevice));
+    for (auto &hl : e->loci) { std::vector<uint8_t>().swap(hl.states); }
+
+    // dynamic data
+    if ((rc = dev_alloc(e, &e->dPartials, (size_t)partBase))) return rc;
+    if ((rc = dev_alloc(e, &e->dCumExp, (size_t)expBase))) return rc;
+    if ((rc = dev_alloc(e, &e->dMats, (size_t)matBase))) return rc;
+    if ((rc = dev_alloc(e, &e->dPatLogL, (size_t)patBase))) return rc;
+    if ((rc = dev_alloc(e, &e->dTileSum, (size_t)tileBase))) return rc;
+    if ((rc = dev_alloc(e, &e->dOps, (size_t)opBase))) return rc;
+    if ((rc = dev_alloc(e, &e->dNOps, L))) return rc;
+    CUDA_TRY(e, cudaMemset(e->dNOps, 0, sizeof(int32_t) * L));
+    CUDA_TRY(e, cudaMemset(e->dCumExp, 0, sizeof(int16_t) * (size_t)std::max<int64_t>(expBase, 1)));
+    if ((rc = dev_alloc(e, &e->dParams, L))) return rc;
+    if ((rc = pin_alloc(e, &e->hParams, L))) return rc;
+    if ((rc = pin_alloc(e, &e->hParamsStored, L))) return rc;
+    if ((rc = dev_alloc(e, &e->dCat, 2 * (size_t)catBase))) return rc;
+    if ((rc = pin_alloc(e, &e->hCat, 2 * (size_t)catBase))) return rc;
+    if ((rc = pin_alloc(e, &e->hCatStored, 2 * (size_t)catBase))) return rc;
+    if ((rc = dev_alloc(e, &e->dInTree, (size_t)treeOff))) return rc;
+    if ((rc = pin_alloc(e, &e->hInTree, (size_t)treeOff))) return rc;
+    if ((rc = dev_alloc(e, &e->dFlags, L))) return rc;
+    if ((rc = pin_alloc(e, &e->hFlags, L))) return rc;
+    for (int l = 0; l < L; l++) {   // defaults: HKY kappa 1 (JC69), one category of rate 1, strict clock rate 1
+        LocusParams &p = e->hParams[l];
+        p.subst[0] = 1.0; p.subst[1] = p.subst[2] = p.subst[3] = p.subst[4] = 0.25;
+        p.clockRate = 1.0; p.pInv = 0.0; p.substKind = SB2_SUBST_HKY; p.clockKind = SB2_CLOCK_STRICT;
+    }
+    for (int64_t i = 0; i < catBase; i++) { e->hCat[i] = 1.0; e->hCat[catBase + i] = 1.0 / e->nCat; }
+
+    // state blocks
+    e->blockBytes = carve_block(nullptr, nullptr, nodeBase, L, e->S, nSpeciesLeaves, &e->speciesOffInBlock, &e->speciesBytes);
+    for (int i = 0; i < 2; i++) {
+        if ((rc = dev_alloc(e, &e->blockMem[i], e->blockBytes))) return rc;
+        CUDA_TRY(e, cudaMemset(e->blockMem[i], 0, e->blockBytes));
+        carve_block(&e->blk[i], e->blockMem[i], nodeBase, L, e->S, nSpeciesLeaves, nullptr, nullptr);
+    }
+    if ((rc = pin_alloc(e, &e->hSpecies, e->speciesBytes))) return rc;
+    if ((rc = pin_alloc(e, &e->hSpeciesStored, e->speciesBytes))) return rc;
+    {
+        SpeciesView v = species_view(e);
+        for (int i = 0; i < e->S; i++) { v.sRates[i] = 1.0; v.popA[i] = 1.0; v.popB[i] = 1.0; v.sParent[i] = v.sLeft[i] = v.sRight[i] = -1; }
+    }
+    // outputs
+    e->nRed = 3 + 3 * e->S;
+    e->nOut = 3 + 2 * L + e->S;
+    if ((rc = dev_alloc(e, &e->dRedOwn, e->nRed))) return rc;
+    e->dRed = e->dRedOwn;
+    if ((rc = dev_alloc(e, &e->dOut, e->nOut))) return rc;
+    if ((rc = pin_alloc(e, &e->hOut, e->nOut))) return rc;
+    CUDA_TRY(e, cudaMemset(e->dOut, 0, sizeof(double) * e->nOut));
+
+    e->treeDirty.assign(L, 0); e->modelDirty.assign(L, 0); e->clockDirty.assign(L, 0); e->touchedFlag.assign(L, 0);
+    memcpy(e->hParamsStored, e->hParams, sizeof(LocusParams) * L);
+    memcpy(e->hCatStored, e->hCat, 16 * (size_t)catBase);
+    memcpy(e->hSpeciesStored, e->hSpecies, e->speciesBytes);
+    e->finalized = true;
+    e->forceAll = true;
+    CUDA_TRY(e, cudaDeviceSynchronize());
+    return SB2_OK;
+}
+
+int sb2_set_species_tree(sb2_engine *e, const int32_t *parent, const int32_t *left, const int32_t *right, const double *height)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    if (!parent || !left || !right || !height) return e->fail(SB2_ERR_ARG, "null species tree array");
+    SpeciesView v = species_view(e);
+    int roots = 0;
+    for (int i = 0; i < e->S; i++) {
+        if (parent[i] >= e->S || left[i] >= e->S || right[i] >= e->S) return e->fail(SB2_ERR_ARG, "species node index out of range");
+        roots += parent[i] < 0;
+    }
+    if (roots != 1) return e->fail(SB2_ERR_ARG, "species tree must have exactly one root (found %d)", roots);
+    memcpy(v.sParent, parent, 4 * e->S); memcpy(v.sLeft, left, 4 * e->S); memcpy(v.sRight, right, 4 * e->S);
+    memcpy(v.sHeight, height, 8 * e->S);
+    e->speciesDirty = true; e->needPrepare = true;
+    return SB2_OK;
+}
+
+int sb2_set_gene_trees(sb2_engine *e, int32_t firstLocus, int32_t nLoci, const int32_t *parent, const int32_t *left,
+                       const int32_t *right, const double *height)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    if (firstLocus < 0 || nLoci < 0 || firstLocus + nLoci > e->L) return e->fail(SB2_ERR_ARG, "locus range [%d,%d) out of range", firstLocus, firstLocus + nLoci);
+    if (!parent || !left || !right || !height) return e->fail(SB2_ERR_ARG, "null gene tree array");
+    size_t o = 0;
+    for (int l = firstLocus; l < firstLocus + nLoci; l++) {
+        const LocusDesc &d = e->loci[l].d;
+        const int G = d.nNodes;
+        int roots = 0;
+        for (int i = 0; i < G; i++) {
+            const int p = parent[o + i], L_ = left[o + i], R_ = right[o + i];
+            if (p >= G || L_ >= G || R_ >= G) return e->fail(SB2_ERR_ARG, "locus %d: node index out of range", l);
+            if (i < d.nTips ? (L_ >= 0 || R_ >= 0) : (L_ < 0 || R_ < 0)) return e->fail(SB2_ERR_ARG, "locus %d: nodes 0..tips-1 must be the leaves", l);
+            roots += p < 0;
+        }
+        if (roots != 1) return e->fail(SB2_ERR_ARG, "locus %d: gene tree must have exactly one root (found %d)", l, roots);
+        uint8_t *dst = e->hInTree + d.treeOff;
+        memcpy(dst, height + o, 8 * (size_t)G);
+        memcpy(dst + 8 * (size_t)G, parent + o, 4 * (size_t)G);
+        memcpy(dst + 12 * (size_t)G, left + o, 4 * (size_t)G);
+        memcpy(dst + 16 * (size_t)G, right + o, 4 * (size_t)G);
+        e->treeDirty[l] = 1;
+        o += G;
+    }
+    e->needPrepare = true;
+    return SB2_OK;
+}
+
+int sb2_set_gene_tree(sb2_engine *e, int32_t locus, const int32_t *parent, const int32_t *left, const int32_t *right, const double *height)
+{
+    return sb2_set_gene_trees(e, locus, 1, parent, left, right, height);
+}
+
+int sb2_set_subst_model(sb2_engine *e, int32_t locus, int32_t kind, const double *params)
+{
+    if (!e) return SB2_ERR_ARG;
+    int rc = check_locus(e, locus);
+    if (rc) return rc;
+    if (!params || (kind != SB2_SUBST_HKY && kind != SB2_SUBST_EIGEN)) return e->fail(SB2_ERR_ARG, "bad substitution model");
+    touch(e, locus);
+    LocusParams &p = e->hParams[locus];
+    p.substKind = kind;
+    memcpy(p.subst, params, sizeof(double) * (kind == SB2_SUBST_HKY ? 5 : 40));
+    e->modelDirty[locus] = 1; e->needPrepare = true;
+    return SB2_OK;
+}
+
+int sb2_set_site_model(sb2_engine *e, int32_t locus, const double *catRates, const double *catProps, double pInv)
+{
+    if (!e) return SB2_ERR_ARG;
+    int rc = check_locus(e, locus);
+    if (rc) return rc;
+    if (!catRates || !catProps) return e->fail(SB2_ERR_ARG, "null site model array");
+    touch(e, locus);
+    const LocusDesc &d = e->loci[locus].d;
+    memcpy(e->hCat + d.catBase, catRates, 8 * d.nCat);
+    memcpy(e->hCat + e->totalCat + d.catBase, catProps, 8 * d.nCat);
+    e->hParams[locus].pInv = pInv;
+    e->modelDirty[locus] = 1; e->catDirty = true; e->needPrepare = true;
+    return SB2_OK;
+}
+
+int sb2_set_clock(sb2_engine *e, int32_t locus, int32_t kind, double meanRate, const double *ratesOrNull)
+{
+    if (!e) return SB2_ERR_ARG;
+    int rc = check_locus(e, locus);
+    if (rc) return rc;
+    if (kind < 0 || kind > 2) return e->fail(SB2_ERR_ARG, "bad clock kind %d", kind);
+    if (kind == SB2_CLOCK_EXPLICIT) {
+        if (!ratesOrNull) return e->fail(SB2_ERR_ARG, "explicit clock needs rates");
+        if (!e->hExplicit) {
+            if ((rc = pin_alloc(e, &e->hExplicit, (size_t)e->totalNodes))) return rc;
+            if ((rc = pin_alloc(e, &e->hExplicitStored, (size_t)e->totalNodes))) return rc;
+            if ((rc = dev_alloc(e, &e->dExplicit, (size_t)e->totalNodes))) return rc;
+            for (int64_t i = 0; i < e->totalNodes; i++) e->hExplicit[i] = e->hExplicitStored[i] = 1.0;
+        }
+    }
+    touch(e, locus);
+    if (kind == SB2_CLOCK_EXPLICIT) {
+        const LocusDesc &d = e->loci[locus].d;
+        memcpy(e->hExplicit + d.nodeBase, ratesOrNull, 8 * (size_t)d.nNodes);
+        e->explicitDirty = true;
+    }
+    e->hParams[locus].clockKind = kind;
+    e->hParams[locus].clockRate = meanRate;
+    e->clockDirty[locus] = 1; e->needPrepare = true;
+    return SB2_OK;
+}
+
+int sb2_set_species_rates(sb2_engine *e, const double *rates)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    if (!rates) return e->fail(SB2_ERR_ARG, "null rates");
+    memcpy(species_view(e).sRates, rates, 8 * e->S);
+    e->speciesDirty = true; e->needPrepare = true;
+    return SB2_OK;
+}
+
+int sb2_set_pop_model(sb2_engine *e, int32_t kind, const double *a, const double *b, double alpha, double beta)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    SpeciesView v = species_view(e);
+    if (kind == SB2_POP_CONSTANT) {
+        if (!a) return e->fail(SB2_ERR_ARG, "ConstantPopulations needs populationSizes");
+        memcpy(v.popA, a, 8 * e->S);
+    } else if (kind == SB2_POP_LWCR) {
+        if (!a || !b) return e->fail(SB2_ERR_ARG, "LinearWithConstantRoot needs tip and top population sizes");
+        memcpy(v.popA, a, 8 * e->nSpeciesLeaves);
+        memcpy(v.popB, b, 8 * (e->S - 1));
+    } else if (kind == SB2_POP_ANALYTIC) {
+        v.hyper[0] = alpha; v.hyper[1] = beta;
+    } else {
+        return e->fail(SB2_ERR_ARG, "bad population model kind %d", kind);
+    }
+    e->popKind = kind;
+    e->speciesDirty = true; e->needPrepare = true;
+    return SB2_OK;
+}
+
+int sb2_eval_begin(sb2_engine *e)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    int rc;
+    if ((rc = do_prepare(e))) return rc;
+    if ((rc = do_walk(e))) return rc;
+    launch_reduce_local(reduce_args(e), e->stream, &e->launches);
+    CUDA_TRY(e, cudaGetLastError());
+    e->reduced = true;
+    return SB2_OK;
+}
+
+int sb2_eval_end(sb2_engine *e, double *perLocusCoal, double *perLocusLik, double *perBranch, double *total3)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    if (!e->reduced) return e->fail(SB2_ERR_STATE, "sb2_eval_end without sb2_eval_begin");
+    launch_finish(reduce_args(e), e->stream, &e->launches);
+    CUDA_TRY(e, cudaGetLastError());
+    int rc = download(e);
+    if (rc) return rc;
+    copy_out(e, perLocusCoal, perLocusLik, perBranch, total3);
+    e->reduced = false;
+    return SB2_OK;
+}
+
+int sb2_eval_posterior(sb2_engine *e, double *perLocusCoal, double *perLocusLik, double *perBranch, double *total3)
+{
+    int rc = sb2_eval_begin(e);
+    if (rc) return rc;
+    return sb2_eval_end(e, perLocusCoal, perLocusLik, perBranch, total3);
+}
+
+int sb2_eval_coalescent(sb2_engine *e, double *perLocus, double *perBranch, double *total)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    int rc;
+    if ((rc = do_prepare(e))) return rc;
+    // phase 1 of the reference's posterior: the pruning kernel has not run for the re-scheduled loci yet, so the
+    // likelihood entries of this pass are the cached ones (coalOnly); sb2_eval_likelihood runs the walk.
+    ReduceArgs r = reduce_args(e, /*coalOnly=*/true);
+    launch_reduce_local(r, e->stream, &e->launches);
+    launch_finish(r, e->stream, &e->launches);
+    CUDA_TRY(e, cudaGetLastError());
+    if ((rc = download(e))) return rc;
+    copy_out(e, perLocus, nullptr, perBranch, nullptr);
+    if (total) *total = e->hOut[0];
+    return SB2_OK;
+}
+
+int sb2_eval_likelihood(sb2_engine *e, double *perLocus, double *total)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    int rc;
+    if ((rc = do_prepare(e))) return rc;
+    if ((rc = do_walk(e))) return rc;
+    ReduceArgs r = reduce_args(e);
+    launch_reduce_local(r, e->stream, &e->launches);
+    launch_finish(r, e->stream, &e->launches);
+    CUDA_TRY(e, cudaGetLastError());
+    if ((rc = download(e))) return rc;
+    copy_out(e, nullptr, perLocus, nullptr, nullptr);
+    if (total) *total = e->hOut[1];
+    return SB2_OK;
+}
+
+int sb2_reduce_vector(sb2_engine *e, void **devPtr, int32_t *nDoubles)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    if (devPtr) *devPtr = e->dRed;
+    if (nDoubles) *nDoubles = e->nRed;
+    return SB2_OK;
+}
+
+int sb2_bind_reduce_vector(sb2_engine *e, void *devPtr)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    e->dRed = devPtr ? (double *)devPtr : e->dRedOwn;
+    return SB2_OK;
+}
+
+int sb2_set_stream(sb2_engine *e, void *cudaStream)
+{
+    if (!e) return SB2_ERR_ARG;
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
+    e->stream = (cudaStream_t)cudaStream;
+    e->ownStream = false;
+    return SB2_OK;
+}
+
+static int flush_pending_walk(sb2_engine *e)
+{
+    // k_prepare already flipped buffer indices for the scheduled nodes; make sure their partials exist before the
+    // state is frozen (only reachable when a host evaluates the coalescent but never the likelihood)
+    if (e->walkPending) {
+        int rc = do_walk(e);
+        if (rc) return rc;
+        launch_reduce_local(reduce_args(e), e->stream, &e->launches);
+        CUDA_TRY(e, cudaGetLastError());
+    }
+    return SB2_OK;
+}
+
+int sb2_store(sb2_engine *e)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    int rc = flush_pending_walk(e);
+    if (rc) return rc;
+    CUDA_TRY(e, cudaMemcpyAsync(e->blockMem[1 - e->curIdx], e->blockMem[e->curIdx], e->blockBytes, cudaMemcpyDeviceToDevice, e->stream));
+    // host staging mirrors of what just became the stored state
+    for (int32_t l : e->touched) {
+        const LocusDesc &d = e->loci[l].d;
+        e->hParamsStored[l] = e->hParams[l];
+        memcpy(e->hCatStored + d.catBase, e->hCat + d.catBase, 8 * (size_t)d.nCat);
+        memcpy(e->hCatStored + e->totalCat + d.catBase, e->hCat + e->totalCat + d.catBase, 8 * (size_t)d.nCat);
+        if (e->hExplicit) memcpy(e->hExplicitStored + d.nodeBase, e->hExplicit + d.nodeBase, 8 * (size_t)d.nNodes);
+        e->touchedFlag[l] = 0;
+    }
+    e->touched.clear();
+    memcpy(e->hSpeciesStored, e->hSpecies, e->speciesBytes);
+    e->popKindStored = e->popKind;
+    return SB2_OK;
+}
+
+int sb2_restore(sb2_engine *e)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    e->curIdx = 1 - e->curIdx;   // swap current / stored, like the reference's restore() methods
+    // staged proposal inputs belong to the rejected state: drop them and bring the host mirrors back
+    std::fill(e->treeDirty.begin(), e->treeDirty.end(), 0);
+    std::fill(e->modelDirty.begin(), e->modelDirty.end(), 0);
+    std::fill(e->clockDirty.begin(), e->clockDirty.end(), 0);
+    for (int32_t l : e->touched) {
+        const LocusDesc &d = e->loci[l].d;
+        e->hParams[l] = e->hParamsStored[l];
+        memcpy(e->hCat + d.catBase, e->hCatStored + d.catBase, 8 * (size_t)d.nCat);
+        memcpy(e->hCat + e->totalCat + d.catBase, e->hCatStored + e->totalCat + d.catBase, 8 * (size_t)d.nCat);
+        if (e->hExplicit) { memcpy(e->hExplicit + d.nodeBase, e->hExplicitStored + d.nodeBase, 8 * (size_t)d.nNodes); e->explicitDirty = true; }
+        e->touchedFlag[l] = 0;
+        e->reuploadFirst = std::min(e->reuploadFirst, (int)l);
+        e->reuploadLast = std::max(e->reuploadLast, (int)l);
+        e->catDirty = true;   // device copies of the parameters still hold the rejected values: re-upload, no recompute
+    }
+    e->touched.clear();
+    memcpy(e->hSpecies, e->hSpeciesStored, e->speciesBytes);
+    e->popKind = e->popKindStored;
+    e->speciesDirty = false;
+    e->forceAll = false;
+    e->needPrepare = e->reuploadLast >= 0;
+    e->walkPending = false; e->tilesValid = false; e->reduced = false;
+    return SB2_OK;
+}
+
+int sb2_accept(sb2_engine *e)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    return flush_pending_walk(e);
+}
+
+int sb2_mark_all_dirty(sb2_engine *e)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    e->forceAll = true; e->needPrepare = true;
+    return SB2_OK;
+}
+
+int sb2_get_branch_rates(sb2_engine *e, int32_t locus, double *rates)
+{
+    if (!e) return SB2_ERR_ARG;
+    int rc = check_locus(e, locus);
+    if (rc) return rc;
+    const LocusDesc &d = e->loci[locus].d;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaMemcpy(rates, cur(e).bRate + d.nodeBase, 8 * (size_t)d.nNodes, cudaMemcpyDeviceToHost));
+    return SB2_OK;
+}
+
+int sb2_get_embedding(sb2_engine *e, int32_t locus, int32_t *lineageCounts, int32_t *coalCounts, int32_t *assignment, double *perBranchLogP)
+{
+    if (!e) return SB2_ERR_ARG;
+    int rc = check_locus(e, locus);
+    if (rc) return rc;
+    const LocusDesc &d = e->loci[locus].d;
+    const size_t o = (size_t)locus * e->S;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (lineageCounts) CUDA_TRY(e, cudaMemcpy(lineageCounts, cur(e).brN + o, 4 * (size_t)e->S, cudaMemcpyDeviceToHost));
+    if (coalCounts) CUDA_TRY(e, cudaMemcpy(coalCounts, cur(e).brK + o, 4 * (size_t)e->S, cudaMemcpyDeviceToHost));
+    if (assignment) CUDA_TRY(e, cudaMemcpy(assignment, cur(e).assign + d.nodeBase, 4 * (size_t)d.nNodes, cudaMemcpyDeviceToHost));
+    if (perBranchLogP) CUDA_TRY(e, cudaMemcpy(perBranchLogP, cur(e).brLogP + o, 8 * (size_t)e->S, cudaMemcpyDeviceToHost));
+    return SB2_OK;
+}
+
+int sb2_get_partials(sb2_engine *e, int32_t locus, int32_t node, double *partials, int32_t *exponents)
+{
+    if (!e) return SB2_ERR_ARG;
+    int rc = check_locus(e, locus);
+    if (rc) return rc;
+    const LocusDesc &d = e->loci[locus].d;
+    if (node < d.nTips || node >= d.nNodes) return e->fail(SB2_ERR_ARG, "node %d is not an internal node", node);
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    uint8_t buf;
+    CUDA_TRY(e, cudaMemcpy(&buf, cur(e).curP + d.nodeBase + node, 1, cudaMemcpyDeviceToHost));
+    const size_t idx = (size_t)buf * d.nInt + (node - d.nTips);
+    if (partials)
+        CUDA_TRY(e, cudaMemcpy(partials, e->dPartials + d.partBase + idx * d.nCat * d.nPat * 4, 8 * (size_t)d.nCat * d.nPat * 4, cudaMemcpyDeviceToHost));
+    if (exponents) {
+        std::vector<int16_t> tmp(d.nPat);
+        CUDA_TRY(e, cudaMemcpy(tmp.data(), e->dCumExp + d.expBase + idx * d.nPat, 2 * (size_t)d.nPat, cudaMemcpyDeviceToHost));
+        for (int p = 0; p < d.nPat; p++) exponents[p] = tmp[p];
+    }
+    return SB2_OK;
+}
+
+int sb2_get_matrices(sb2_engine *e, int32_t locus, int32_t node, double *matrices)
+{
+    if (!e) return SB2_ERR_ARG;
+    int rc = check_locus(e, locus);
+    if (rc) return rc;
+    const LocusDesc &d = e->loci[locus].d;
+    if (node < 0 || node >= d.nNodes) return e->fail(SB2_ERR_ARG, "node %d out of range", node);
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    uint8_t buf;
+    CUDA_TRY(e, cudaMemcpy(&buf, cur(e).curM + d.nodeBase + node, 1, cudaMemcpyDeviceToHost));
+    CUDA_TRY(e, cudaMemcpy(matrices, e->dMats + d.matBase + ((size_t)buf * d.nNodes + node) * d.nCat * 16, 8 * (size_t)d.nCat * 16, cudaMemcpyDeviceToHost));
+    return SB2_OK;
+}
+
+int sb2_get_pattern_logl(sb2_engine *e, int32_t locus, double *patternLogL)
+{
+    if (!e) return SB2_ERR_ARG;
+    int rc = check_locus(e, locus);
+    if (rc) return rc;
+    const LocusDesc &d = e->loci[locus].d;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaMemcpy(patternLogL, e->dPatLogL + d.patBase, 8 * (size_t)d.nPat, cudaMemcpyDeviceToHost));
+    return SB2_OK;
+}
+
+int32_t sb2_num_loci(const sb2_engine *e) { return e ? (int32_t)e->loci.size() : 0; }
+int64_t sb2_launch_count(const sb2_engine *e) { return e ? e->launches : 0; }
+
+int64_t sb2_last_node_updates(sb2_engine *e)
+{
+    if (!e || !e->finalized) return -1;
+    std::vector<int32_t> n(e->L);
+    cudaStreamSynchronize(e->stream);
+    if (cudaMemcpy(n.data(), e->dNOps, 4 * (size_t)e->L, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    int64_t t = 0;
+    for (int v : n) t += v;
+    return t;
+}
+
+int sb2_kernel_time(sb2_engine *e, double *ms, int64_t *launches)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    double t = 0.0;
+    for (size_t i = 0; i < e->evUsed; i++) {
+        float f = 0.f;
+        CUDA_TRY(e, cudaEventElapsedTime(&f, e->evPool[i].first, e->evPool[i].second));
+        t += f;
+    }
+    if (ms) *ms = t;
+    if (launches) *launches = (int64_t)e->evUsed;
+    e->evUsed = 0;
+    return SB2_OK;
+}
+
+int64_t sb2_device_bytes(const sb2_engine *e) { return e ? e->devBytes : 0; }
+
+}  // extern "C"

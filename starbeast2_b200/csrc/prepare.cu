@@ -1,0 +1,448 @@
+// k_prepare: one CTA per locus, the whole locus in shared memory.
+//
+// Does, for every locus flagged LF_RUN, everything of the path that is tree-shaped and latency-bound:
+//   1. takes the incoming gene tree (if any), diffs its topology against the device-resident one;
+//   2. embeds the gene tree in the species tree -- GeneTree.update()/collateCoalescenceEvents
+//      (/root/reference/src/starbeast2/GeneTree.java:202-318, 332-379), one thread per gene leaf, lineages
+//      race rootward and claim nodes with atomicCAS (the reference walks them one after another);
+//      while climbing, each gene edge accumulates its StarBeastClock rate (StarBeastClock.java:54-75)
+//      directly from the species path it crosses -- the G x S speciesOccupancy matrix is never materialised;
+//   3. sorts coalescent times per species branch (GeneTree.getCoalescentTimes, GeneTree.java:387-405) and
+//      evaluates the per-branch population-model terms: ConstantPopulations.constantLogP
+//      (ConstantPopulations.java:95-118), LinearWithConstantRoot.branchLogP/linearLogP
+//      (LinearWithConstantRoot.java:50-70, 155-201) or the analytic-integration summands
+//      (MultispeciesCoalescent.java:207-225);
+//   4. decides which branch matrices and node partials are dirty the way TreeLikelihood.traverse does
+//      (length*rate changed / model dirty / child updated), flips the double-buffer indices
+//      (BeerLikelihoodCore.setNodeMatrixForUpdate / setNodePartialsForUpdate) and emits a post-order,
+//      heavy-child-first pruning schedule whose live results fit a stack of floor(log2(nInt))+1 tiles;
+//   5. computes P = exp(Q d) for every dirty branch x category (HKY closed form or eigen system).
+//
+// This translation unit is compiled with -fmad=false: sums and products associate exactly as in the
+// reference's Java (no fused multiply-add), so these terms differ from it only through log/exp.
+#include <math.h>
+
+#include "sb2_device.cuh"
+
+namespace sb2 {
+
+constexpr int PREP_THREADS = 128;
+
+struct PrepSmem {
+    double *gH, *rate, *times, *sH, *sRate;
+    int *gP, *gL, *gR, *assign, *cnt, *sP, *sL, *sR, *n, *k, *kstart, *misc;
+    uint8_t *matDirty, *dirty, *topo;
+};
+
+__host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, int G, int S)
+{
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 7) & ~size_t(7); return r; };
+    size_t gH = take(8ull * G), rate = take(8ull * G), times = take(8ull * G), sH = take(8ull * S), sRate = take(8ull * S);
+    size_t gP = take(4ull * G), gL = take(4ull * G), gR = take(4ull * G), assign = take(4ull * G), cnt = take(4ull * G);
+    size_t sP = take(4ull * S), sL = take(4ull * S), sR = take(4ull * S), n = take(4ull * S), k = take(4ull * S), ks = take(4ull * (S + 1));
+    size_t misc = take(4ull * 8);
+    size_t md = take(G), di = take(G), to = take(G);
+    if (s) {
+        s->gH = (double *)(base + gH); s->rate = (double *)(base + rate); s->times = (double *)(base + times);
+        s->sH = (double *)(base + sH); s->sRate = (double *)(base + sRate);
+        s->gP = (int *)(base + gP); s->gL = (int *)(base + gL); s->gR = (int *)(base + gR);
+        s->assign = (int *)(base + assign); s->cnt = (int *)(base + cnt);
+        s->sP = (int *)(base + sP); s->sL = (int *)(base + sL); s->sR = (int *)(base + sR);
+        s->n = (int *)(base + n); s->k = (int *)(base + k); s->kstart = (int *)(base + ks); s->misc = (int *)(base + misc);
+        s->matDirty = base + md; s->dirty = base + di; s->topo = base + to;
+    }
+    return o;
+}
+
+size_t prepare_smem_bytes(int maxNodes, int S) { return prep_carve(nullptr, nullptr, maxNodes, S); }
+
+// One gene edge: climb from species branch b (edge starts at height lastH) to the branch that holds height hg.
+// Lineage counts: GeneTree.java:346.  Rate: StarBeastClock.java:60-70 sums r_j*occ_j over species node numbers j
+// ascending (zeros are no-ops), occ_j from GeneTree.java:345,354; reproduced by selecting the path's nodes in
+// ascending order.
+__device__ __forceinline__ int climb_edge(int b, double lastH, double hg, const PrepSmem &s, bool wantRate,
+                                          double clock, double *rateOut)
+{
+    const int b0 = b;
+    int end = b, nseg = 1;
+    while (s.sP[end] >= 0 && hg >= s.sH[s.sP[end]]) {   // note >= (GeneTree.java:337)
+        end = s.sP[end];
+        atomicAdd(&s.n[end], 1);
+        nseg++;
+    }
+    if (wantRate) {
+        double wsum = 0.0, len = 0.0;
+        if (nseg == 1) {
+            const double occ = hg - lastH;
+            wsum = wsum + s.sRate[end] * occ;
+            len = len + occ;
+        } else {
+            int prev = -1;
+            for (int it = 0; it < nseg; it++) {
+                int best = 0x7fffffff;
+                double occBest = 0.0;
+                int j = b0;
+                double lo = lastH;
+                for (;;) {
+                    const double hi = (j == end) ? hg : s.sH[s.sP[j]];
+                    if (j > prev && j < best) { best = j; occBest = hi - lo; }
+                    if (j == end) break;
+                    lo = s.sH[s.sP[j]];
+                    j = s.sP[j];
+                }
+                wsum = wsum + s.sRate[best] * occBest;
+                len = len + occBest;
+                prev = best;
+            }
+        }
+        *rateOut = clock * wsum / len;   // StarBeastClock.java:70
+    }
+    return end;
+}
+
+struct HkyTabs {
+    double fA, fC, fG, fT, tab1A, tab2A, tab3A, tab1C, tab2C, tab3C, tab1G, tab2G, tab3G, tab1T, tab2T, tab3T, beta, A_R, A_Y;
+};
+
+// HKY.setupMatrix (BEAST.base; restated from upstream)
+__device__ __forceinline__ void hky_setup(const double *sp, HkyTabs &t)
+{
+    const double kappa = sp[0];
+    t.fA = sp[1]; t.fC = sp[2]; t.fG = sp[3]; t.fT = sp[4];
+    const double freqR = t.fA + t.fG, freqY = t.fC + t.fT;
+    const double r1 = (1 / freqR) - 1;
+    t.tab1A = t.fA * r1; t.tab3A = t.fA / freqR; t.tab2A = 1 - t.tab3A;
+    const double r2 = 1 / r1;
+    t.tab1C = t.fC * r2; t.tab3C = t.fC / freqY; t.tab2C = 1 - t.tab3C;
+    t.tab1G = t.fG * r1; t.tab3G = t.tab2A; t.tab2G = t.tab3A;
+    t.tab1T = t.fT * r2; t.tab3T = t.tab2C; t.tab2T = t.tab3C;
+    t.beta = -1.0 / (2.0 * (freqR * freqY + kappa * (t.fA * t.fG + t.fC * t.fT)));
+    t.A_R = 1.0 + freqR * (kappa - 1);
+    t.A_Y = 1.0 + freqY * (kappa - 1);
+}
+
+// HKY.getTransitionProbabilities
+__device__ __forceinline__ void hky_matrix(const HkyTabs &t, double distance, double *m)
+{
+    const double xx = t.beta * distance;
+    const double bbR = exp(xx * t.A_R), bbY = exp(xx * t.A_Y), aa = exp(xx);
+    const double oneminusa = 1 - aa;
+    const double t1Aaa = t.tab1A * aa, t1Gaa = t.tab1G * aa, t1Caa = t.tab1C * aa, t1Taa = t.tab1T * aa;
+    m[0] = t.fA + t1Aaa + (t.tab2A * bbR);
+    m[1] = t.fC * oneminusa;
+    m[2] = t.fG + t1Gaa - (t.tab3G * bbR);
+    m[3] = t.fT * oneminusa;
+    m[4] = t.fA * oneminusa;
+    m[5] = t.fC + t1Caa + (t.tab2C * bbY);
+    m[6] = t.fG * oneminusa;
+    m[7] = t.fT + t1Taa - (t.tab3T * bbY);
+    m[8] = t.fA + t1Aaa - (t.tab3A * bbR);
+    m[9] = m[1];
+    m[10] = t.fG + t1Gaa + (t.tab2G * bbR);
+    m[11] = m[3];
+    m[12] = m[4];
+    m[13] = t.fC + t1Caa - (t.tab3C * bbY);
+    m[14] = m[6];
+    m[15] = t.fT + t1Taa + (t.tab2T * bbY);
+}
+
+// GeneralSubstitutionModel.getTransitionProbabilities: |V exp(d L) V^-1|
+__device__ __forceinline__ void eigen_matrix(const double *sp, double distance, double *m)
+{
+    const double *Eval = sp, *Evec = sp + 4, *Ievc = sp + 20;
+    double iexp[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double temp = exp(distance * Eval[i]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) iexp[i * 4 + j] = Ievc[i * 4 + j] * temp;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double temp = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) temp += Evec[i * 4 + k] * iexp[k * 4 + j];
+            m[i * 4 + j] = fabs(temp);
+        }
+}
+
+__global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int maxNodes)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int l = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const uint8_t fl = A.flags[l];
+    if (!(fl & LF_RUN)) {
+        if (tid == 0) A.nOps[l] = 0;
+        return;
+    }
+    const LocusDesc d = A.loci[l];
+    const LocusParams *prm = &A.params[l];
+    const int G = d.nNodes, nT = d.nTips, nI = d.nInt, S = A.S, nb = d.nodeBase, C = d.nCat;
+    PrepSmem s;
+    prep_carve(&s, smem_raw, maxNodes, S);
+    const bool forceAll = fl & LF_FORCE_ALL;
+    const bool forceMats = forceAll || (fl & LF_FORCE_MATS);
+
+    // ---- 1. load species tree and gene tree ------------------------------------------------------------
+    for (int i = tid; i < S; i += nt) {
+        s.sP[i] = A.cur.sParent[i]; s.sL[i] = A.cur.sLeft[i]; s.sR[i] = A.cur.sRight[i];
+        s.sH[i] = A.cur.sHeight[i]; s.sRate[i] = A.cur.sRates[i];
+        s.n[i] = 0; s.k[i] = 0;
+    }
+    if (tid == 0) { s.misc[0] = 1; /* compatible */ s.misc[1] = G - 1; /* root */ }
+    if (fl & LF_TREE_IN) {
+        const double *inH = reinterpret_cast<const double *>(A.inTree + d.treeOff);
+        const int *inP = reinterpret_cast<const int *>(inH + G), *inL = inP + G, *inR = inL + G;
+        for (int i = tid; i < G; i += nt) {
+            const double h = inH[i];
+            const int p = inP[i], L = inL[i], R = inR[i];
+            s.topo[i] = (L != A.cur.gLeft[nb + i]) || (R != A.cur.gRight[nb + i]);
+            A.cur.gHeight[nb + i] = h; A.cur.gParent[nb + i] = p; A.cur.gLeft[nb + i] = L; A.cur.gRight[nb + i] = R;
+            s.gH[i] = h; s.gP[i] = p; s.gL[i] = L; s.gR[i] = R;
+        }
+    } else {
+        for (int i = tid; i < G; i += nt) {
+            s.gH[i] = A.cur.gHeight[nb + i]; s.gP[i] = A.cur.gParent[nb + i];
+            s.gL[i] = A.cur.gLeft[nb + i]; s.gR[i] = A.cur.gRight[nb + i];
+            s.topo[i] = 0;
+        }
+    }
+    for (int i = tid; i < G; i += nt) {
+        s.assign[i] = (i < nT) ? A.tipSpecies[d.tipBase + i] : -1;   // GeneTree.java:243,247
+        s.cnt[i] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < G; i += nt) if (s.gP[i] < 0) s.misc[1] = i;
+    for (int i = tid; i < nT; i += nt) atomicAdd(&s.n[s.assign[i]], 1);   // leafCoalescentLineageCounts, GeneTree.java:222
+    __syncthreads();
+    const int root = s.misc[1];
+
+    // ---- 2. embedding walks (one lineage per thread) ---------------------------------------------------
+    const int clockKind = prm->clockKind;
+    const double clockRate = prm->clockRate;
+    const bool wantRate = clockKind == 1;
+    for (int leaf = tid; leaf < nT; leaf += nt) {
+        int last = leaf, g = s.gP[leaf], b = s.assign[leaf];
+        double lastH = 0.0;   // GeneTree.java:260 (gene tips are taken to sit at height 0, quirk Q6)
+        while (g >= 0) {
+            const double hg = s.gH[g];
+            double r;
+            b = climb_edge(b, lastH, hg, s, wantRate, clockRate, &r);
+            if (wantRate) s.rate[last] = r;
+            const int old = atomicCAS(&s.assign[g], -1, b);   // first lineage to arrive claims the node (:356-359)
+            if (old == -1) {
+                atomicAdd(&s.k[b], 1);
+                last = g; lastH = hg; g = s.gP[g];
+            } else {
+                if (old != b) s.misc[0] = 0;                 // GeneTree.java:375-377 incompatible
+                break;
+            }
+        }
+    }
+    if (!wantRate) {
+        for (int i = tid; i < G; i += nt)
+            s.rate[i] = (clockKind == 2) ? A.explicitRates[nb + i] : clockRate;   // StrictClockModel / explicit
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (wantRate) s.rate[root] = clockRate;   // StarBeastClock.java:72
+        int acc = 0;
+        for (int b = 0; b < S; b++) { s.kstart[b] = acc; acc += s.k[b]; }
+        s.kstart[S] = acc;
+    }
+    const bool compat = s.misc[0] != 0;
+    __syncthreads();
+
+    // ---- 3. per-branch sorted times + population-model terms ------------------------------------------------
+    // rank sort of the internal nodes by (species branch, height): branch b's times are contiguous and ascending
+    for (int i = nT + tid; i < G; i += nt) {
+        const int bi = s.assign[i];
+        const double hi = s.gH[i];
+        int rank = 0;
+        for (int j = nT; j < G; j++) {
+            const int bj = s.assign[j];
+            const double hj = s.gH[j];
+            rank += (bj < bi) || (bj == bi && (hj < hi || (hj == hi && j < i)));
+        }
+        s.times[rank] = hi;
+    }
+    __syncthreads();
+    const double ploidy = d.ploidy;
+    const double logPloidy = log(ploidy);
+    for (int b = tid; b < S; b += nt) {
+        const int n = s.n[b], k = s.k[b];
+        const double *ts = s.times + s.kstart[b];
+        const double t0 = s.sH[b];
+        const double tEnd = (s.sP[b] < 0) ? INFINITY : s.sH[s.sP[b]];   // GeneTree.java:394
+        auto T = [&](int i) { return i == 0 ? t0 : (i <= k ? ts[i - 1] : tEnd); };
+        double term = 0.0, g = 0.0;
+        if (compat) {
+            const bool isRoot = s.sP[b] < 0;
+            bool linear = false;
+            double tipSize = 0.0, topSize = 0.0;
+            if (A.popKind == 1) {   // LinearWithConstantRoot.branchLogP, :50-70
+                tipSize = (s.sL[b] < 0) ? A.cur.popA[b] : (A.cur.popB[s.sL[b]] + A.cur.popB[s.sR[b]]);
+                if (!isRoot) { linear = true; topSize = A.cur.popB[b]; }
+            }
+            if (!linear) {
+                // shared gamma loop: ConstantPopulations.java:96-103 == MultispeciesCoalescent.java:215-222
+                for (int i = 0; i < k; i++) g += (T(i + 1) - T(i)) * (n - i) * (n - (i + 1.0)) / 2.0;
+                if (n - k > 1) g += (T(k + 1) - T(k)) * (n - k) * (n - (k + 1.0)) / 2.0;
+                if (A.popKind == 2) {
+                    term = 0.0;   // analytic: summands only (GeneTree.java:182)
+                } else {
+                    const double popSize = (A.popKind == 0) ? A.cur.popA[b] : tipSize;
+                    const double branchGamma = g / ploidy;
+                    const double branchLogR = -k * logPloidy;
+                    term = branchLogR - (k * log(popSize)) - (branchGamma / popSize);   // ConstantPopulations.java:107
+                }
+            } else {   // LinearWithConstantRoot.linearLogP, :155-201
+                const double fPopSizeTop = topSize * ploidy, fPopSizeBottom = tipSize * ploidy;
+                const double d5 = fPopSizeTop - fPopSizeBottom;
+                const double fTime0 = T(0);
+                const double a = d5 / (T(k + 1) - fTime0);
+                const double bb = fPopSizeBottom;
+                double logP = 0.0;
+                if (fabs(d5) < 1e-10) {
+                    for (int i = 0; i <= k; i++) {
+                        const double fTimeip1 = T(i + 1);
+                        const double fPopSize = a * (fTimeip1 - fTime0) + bb;
+                        if (i < k) logP += -log(fPopSize);
+                        const int i1 = n - i;
+                        logP -= (i1 * (i1 - 1.0) / 2.0) * (fTimeip1 - T(i)) / fPopSize;
+                    }
+                } else {
+                    const double vv = bb - a * fTime0;
+                    for (int i = 0; i <= k; i++) {
+                        const double fPopSize = a * T(i + 1) + vv;
+                        if (i < k) logP += -log(fPopSize);
+                        const double f = fPopSize / (a * T(i) + vv);
+                        const int i1 = n - i;
+                        logP += -(i1 * (i1 - 1.0) / 2.0) * log(f) / a;
+                    }
+                }
+                term = logP;
+            }
+        }
+        const size_t o = (size_t)l * S + b;
+        A.cur.brLogP[o] = term;
+        A.cur.brN[o] = n;
+        A.cur.brK[o] = k;
+        A.cur.anG[o] = g / ploidy;          // MultispeciesCoalescent.java:224
+        A.cur.anR[o] = k * logPloidy;       // :211 (negated when pooled)
+        s.sRate[b] = term;                  // species rates are no longer needed: reuse as the term buffer
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double logP = 0.0;
+        if (!compat) logP = -INFINITY;                       // GeneTree.java:175-178
+        else for (int b = 0; b < S; b++) logP += s.sRate[b];  // GeneTree.java:185-196, node-number order
+        A.cur.coal[l] = logP;
+    }
+
+    // ---- 4. dirtiness (TreeLikelihood.traverse) and the pruning schedule ----------------------------------------
+    for (int i = tid; i < G; i += nt) {
+        uint8_t md = 0;
+        if (s.gP[i] >= 0) {
+            const double bt = (s.gH[s.gP[i]] - s.gH[i]) * s.rate[i];   // node.getLength() * branchRate
+            md = forceMats || !(bt == A.cur.bTime[nb + i]);
+            if (md) {
+                A.cur.bTime[nb + i] = bt;
+                A.cur.curM[nb + i] = 1 - A.stored.curM[nb + i];      // setNodeMatrixForUpdate
+            }
+        }
+        s.matDirty[i] = md;
+        s.dirty[i] = 0;
+        A.cur.bRate[nb + i] = s.rate[i];
+        A.cur.assign[nb + i] = s.assign[i];
+    }
+    __syncthreads();
+    for (int i = nT + tid; i < G; i += nt)
+        if (forceAll || s.topo[i] || s.matDirty[s.gL[i]] || s.matDirty[s.gR[i]]) s.dirty[i] = 1;
+    __syncthreads();
+    // a node is recomputed when anything below it was: mark ancestors (dirty set is upward closed)
+    for (int i = nT + tid; i < G; i += nt)
+        if (s.dirty[i] == 1) {
+            int a = s.gP[i];
+            while (a >= 0 && s.dirty[a] == 0) { s.dirty[a] = 2; a = s.gP[a]; }
+        }
+    __syncthreads();
+    // cnt[i] = number of dirty internal nodes in the subtree of i
+    for (int i = nT + tid; i < G; i += nt)
+        if (s.dirty[i]) {
+            int a = i;
+            while (a >= 0) { atomicAdd(&s.cnt[a], 1); a = s.gP[a]; }
+        }
+    __syncthreads();
+    if (tid == 0) A.nOps[l] = s.dirty[root] ? s.cnt[root] : 0;
+    for (int i = nT + tid; i < G; i += nt) {
+        if (!s.dirty[i]) continue;
+        // position in the post-order and stack slot: walk to the root; at every ancestor whose two children are both
+        // dirty the heavier child (more dirty nodes, ties -> left) is evaluated first and parks its result one slot below
+        int start = 0, base = 0, a = i;
+        while (s.gP[a] >= 0) {
+            const int p = s.gP[a], Lc = s.gL[p], Rc = s.gR[p];
+            const bool dl = Lc >= nT && s.dirty[Lc], dr = Rc >= nT && s.dirty[Rc];
+            if (dl && dr) {
+                const int first = (s.cnt[Rc] > s.cnt[Lc]) ? Rc : Lc;
+                if (a != first) { start += s.cnt[first]; base += 1; }
+            }
+            a = p;
+        }
+        const int pos = start + s.cnt[i] - 1;
+        const int newP = 1 - A.stored.curP[nb + i];                      // setNodePartialsForUpdate
+        A.cur.curP[nb + i] = (uint8_t)newP;
+        const int Lc = s.gL[i], Rc = s.gR[i];
+        const bool dl = Lc >= nT && s.dirty[Lc], dr = Rc >= nT && s.dirty[Rc];
+        const int first = (dl && dr) ? ((s.cnt[Rc] > s.cnt[Lc]) ? Rc : Lc) : (dl ? Lc : Rc);
+        Op o;
+        o.outOff = newP * nI + (i - nT);
+        o.outSlot = (uint8_t)base;
+        o.node = i;
+        o.pad[0] = o.pad[1] = o.pad[2] = 0;
+        auto operand = [&](int c, bool cd, int32_t &off, uint8_t &kind, uint8_t &slot) {
+            slot = 0;
+            if (c < nT) { kind = OPK_TIP; off = c; }
+            else if (cd) { kind = OPK_STACK; off = 0; slot = (uint8_t)((c == first) ? base : base + 1); }
+            else { kind = OPK_GLOBAL; off = A.cur.curP[nb + c] * nI + (c - nT); }
+        };
+        operand(Lc, dl, o.aOff, o.aKind, o.aSlot);
+        operand(Rc, dr, o.bOff, o.bKind, o.bSlot);
+        o.mA = A.cur.curM[nb + Lc] * G + Lc;
+        o.mB = A.cur.curM[nb + Rc] * G + Rc;
+        A.ops[d.opBase + pos] = o;
+    }
+
+    // ---- 5. transition matrices of the dirty branches -----------------------------------------------------------------
+    HkyTabs tabs;
+    const int substKind = prm->substKind;
+    if (substKind == 0) hky_setup(prm->subst, tabs);
+    for (int idx = tid; idx < G * C; idx += nt) {
+        const int i = idx / C, c = idx - i * C;
+        if (!s.matDirty[i]) continue;
+        const double jointBranchRate = A.catRates[d.catBase + c] * s.rate[i];   // siteModel.getRateForCategory * branchRate
+        const double distance = (s.gH[s.gP[i]] - s.gH[i]) * jointBranchRate;
+        double m[16];
+        if (substKind == 0) hky_matrix(tabs, distance, m);
+        else eigen_matrix(prm->subst, distance, m);
+        double *dst = A.mats + d.matBase + ((size_t)(A.cur.curM[nb + i] * G + i) * C + c) * 16;
+#pragma unroll
+        for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(dst + q) = make_double2(m[q], m[q + 1]);
+    }
+}
+
+void launch_prepare(const PrepareArgs &a, int maxNodes, cudaStream_t st)
+{
+    const size_t smem = prepare_smem_bytes(maxNodes, a.S);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    k_prepare<<<a.nLoci, PREP_THREADS, smem, st>>>(a, maxNodes);
+}
+
+}  // namespace sb2

@@ -1,0 +1,151 @@
+// Shared device-side types of libsb2gpu (B200 / sm_100a).
+//
+// HBM layout (one engine = one GPU = one shard of loci), all arrays locus-major:
+//   tipStates   u8  [locus][tip][pattern]                      static
+//   partials    f64 [locus][buf 0/1][internal node][cat][pattern][4]   (BEAST layout per node, two buffers
+//                                                               per node for store/restore, index flip only)
+//   cumExp      i16 [locus][buf][internal node][pattern]       power-of-two scale exponent, cumulative over subtree
+//   mats        f64 [locus][buf][node][cat][16]                P = exp(Q d) per branch x category
+//   StateBlock (x2: current / stored)  small per-node and per-locus state, see below
+//   ops         Op  [locus][internal node]                      post-order pruning schedule built on device
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb2 {
+
+constexpr int SUBST_STRIDE = 40;
+
+struct LocusDesc {
+    int32_t nTips, nNodes, nInt, nPat, nCat;
+    int32_t nodeBase;   // into per-node arrays
+    int32_t tipBase;    // into tipSpecies
+    int32_t patBase;    // into weights / patternLogL / constMask
+    int32_t catBase;    // into catRates / catProps
+    int32_t tileBase;   // first pattern tile
+    int32_t nTiles;
+    int32_t opBase;     // into ops (sum of nInt)
+    int32_t stackDepth; // floor(log2(nInt)) + 1
+    int32_t pad0;
+    int64_t stateBase;  // into tipStates (bytes)
+    int64_t partBase;   // into partials (doubles)
+    int64_t expBase;    // into cumExp (int16)
+    int64_t matBase;    // into mats (doubles)
+    int64_t treeOff;    // into the incoming tree staging buffer (bytes)
+    double ploidy;
+};
+
+// per-locus model parameters (staged on host, uploaded when dirty)
+struct LocusParams {
+    double subst[SUBST_STRIDE];
+    double clockRate;
+    double pInv;
+    int32_t substKind;
+    int32_t clockKind;
+};
+
+// per-eval per-locus flags
+enum : uint8_t {
+    LF_RUN = 1,        // something relevant changed: rebuild embedding, rates and schedule
+    LF_TREE_IN = 2,    // a new gene tree sits in the incoming buffer
+    LF_FORCE_MATS = 4, // substitution / site model changed: every branch matrix is dirty
+    LF_FORCE_ALL = 8,  // first evaluation / mark_all_dirty: everything dirty
+};
+
+// operand kinds of a pruning op
+enum : uint8_t { OPK_TIP = 0, OPK_STACK = 1, OPK_GLOBAL = 2 };
+
+struct __align__(16) Op {
+    int32_t outOff;   // buf*nInt + internal index          -> partials / cumExp of the output
+    int32_t aOff;     // TIP: tip index; GLOBAL: buf*nInt + internal index
+    int32_t bOff;
+    int32_t mA;       // buf*nNodes + node                   -> mats of the branch above operand a
+    int32_t mB;
+    uint8_t aKind, bKind, outSlot, aSlot;
+    uint8_t bSlot, pad[3];
+    int32_t node;     // node number (debug / root test)
+};
+static_assert(sizeof(Op) == 32, "Op must stay 32 bytes");
+
+// Double-buffered small state (current / stored).  restore() swaps the two blocks, store() copies cur->stored.
+struct StateBlock {
+    // by node (sum over loci of nNodes)
+    int32_t *gParent, *gLeft, *gRight;
+    double *gHeight;
+    double *bRate;      // branch rate per node (branchRateModel.getRateForBranch)
+    double *bTime;      // length*rate the current matrices were computed for (TreeLikelihood.m_branchLengths)
+    uint8_t *curP;      // which of the two partials buffers is current, per node
+    uint8_t *curM;      // which of the two matrix buffers is current, per node
+    // by locus
+    double *logL;       // TreeLikelihood logP
+    double *coal;       // GeneTree logP
+    // by (locus, species node)
+    double *brLogP;     // GeneTree.perBranchLogP
+    double *anG;        // analytic: gamma_j / ploidy_j
+    double *anR;        // analytic: k_j * log(ploidy_j)
+    int32_t *brN, *brK; // coalescentLineageCounts / coalescentCounts
+    // by node
+    int32_t *assign;    // geneNodeSpeciesAssignment
+    // species tree + shared parameters
+    int32_t *sParent, *sLeft, *sRight;
+    double *sHeight, *sRates, *popA, *popB;
+    double *hyper;      // {alpha, beta}
+};
+
+struct PrepareArgs {
+    const LocusDesc *loci;
+    const LocusParams *params;
+    const uint8_t *flags;        // [nLoci]
+    const uint8_t *inTree;       // incoming gene trees: per locus {height f64[G], parent, left, right i32[G]}
+    const int32_t *tipSpecies;
+    const double *catRates;
+    const double *explicitRates; // by node
+    StateBlock cur;
+    StateBlock stored;
+    Op *ops;
+    int32_t *nOps;               // [nLoci]
+    double *mats;
+    int32_t S, nSpeciesLeaves, popKind, nLoci;
+};
+
+struct WalkArgs {
+    const LocusDesc *loci;
+    const LocusParams *params;
+    const int32_t *tileLocus;    // [nTiles]
+    const Op *ops;
+    const int32_t *nOps;
+    const uint8_t *tipStates;
+    const int32_t *weights;
+    const uint8_t *constMask;
+    const double *catProps;
+    const double *mats;
+    double *partials;
+    int16_t *cumExp;
+    double *patLogL;             // by pattern
+    double *tileSum;             // [nTiles]
+    int32_t nCat;                // categories of every locus in this launch
+    int32_t chunksPerTile;       // 32-pattern chunks per tile (block = 32 * nCat * chunksPerTile threads)
+    int32_t stackDepth;
+};
+
+struct ReduceArgs {
+    const LocusDesc *loci;
+    const int32_t *nOps;
+    const double *tileSum;
+    const double *patLogL;
+    const int32_t *weights;
+    StateBlock cur;
+    double *red;        // reduce vector {coal, lik, nIncompat, (q, gamma, logR) x S}
+    double *out;        // {total3, perLocusCoal[L], perLocusLik[L], perBranch[S]}
+    int32_t nLoci, S, popKind, exact;
+    int32_t useTiles;   // 0: pruning results are stale or pending -> use the cached per-locus logL
+};
+
+void launch_prepare(const PrepareArgs &a, int maxNodes, cudaStream_t st);
+void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st);
+void launch_reduce_local(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
+void launch_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
+size_t prepare_smem_bytes(int maxNodes, int S);
+size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int stackDepth);
+
+}  // namespace sb2
