@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200.
+
+A "step" is one full posterior evaluation with every node dirty (SURVEY.md 8d regime A): multispecies-coalescent
+embedding + per-branch terms + species-clock rates + transition matrices + Felsenstein pruning of every gene tree
++ root integration, for all loci of the workload.  N=1 workload: BASELINE.json configs[1] ("C2": 50 loci x
+1,000 bp x 30 individuals / 10 species, HKY, ConstantPopulations).  N>1: weak scaling, every rank holds its own
+50-locus shard of one 50*N-locus posterior and each step all-reduces the reduce vector over NCCL.
+
+  value : pattern x node x category partials per second, whole job, inputs resident in HBM (device-timed)
+  e2e   : the same metric through the C ABI with HOST buffers: species tree, all gene trees and parameters are
+          re-sent every step (H2D inside the timed region) and the logP vector is read back (D2H)
+  roofline : the pruning kernel (k_treewalk) alone, timed live with CUDA events on its stream
+  cpu_baseline : the C restatement of the reference's Java path (oracle/), 1 thread, same workload, rank 0 only
+
+`--impl reference` times that CPU restatement on all host threads instead (no JVM exists in this image, so the
+reference's own code cannot run).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pattern·node·cat partials/sec (full multi-locus posterior evaluation, all nodes dirty)"
+UNIT = "partials/s"
+WORKLOAD = "C2"
+L2_FLUSH_BYTES = 512 << 20
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def design_bytes(pb) -> float:
+    """Compulsory HBM bytes of one full evaluation in THIS design (children are consumed from shared memory, so
+    partials are written once and never re-read): 32 B partials + 2/C B exponent per unit, tip states once,
+    pattern log-likelihoods once.  DESIGN.md derives it."""
+    b = 0.0
+    for l in pb.loci:
+        n_int = l.n_tips - 1
+        b += 32.0 * l.n_pat * l.n_cat * n_int + 2.0 * l.n_pat * n_int + l.n_pat * l.n_tips + 8.0 * l.n_pat
+    return b
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the GPU is under the bench load."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+        self.marks = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_problem(rank: int, world: int, loci_per_rank: int, workload: str):
+    from starbeast2_b200 import synth
+    total = loci_per_rank * world
+    return synth.make_problem(workload, n_loci=total, locus_range=(rank * loci_per_rank, (rank + 1) * loci_per_rank))
+
+
+def cpu_baseline(pb, n_threads: int, budget_s: float):
+    import oracle
+    fp = oracle.FlatProblem(pb)
+    oracle.posterior(pb, n_threads=n_threads, flat=fp)   # warm-up (thread pool, page faults)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        r = oracle.posterior(pb, n_threads=n_threads, flat=fp)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or n >= 100000:
+            break
+    return n, dt, r
+
+
+def run_reference(args):
+    """`--impl reference`: the CPU restatement of the reference path (oracle/, kind "port"), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    pb = build_problem(0, 1, args.loci, args.workload)
+    threads = oracle.max_threads()
+    fp = oracle.FlatProblem(pb)
+    for _ in range(max(args.warmup, 1)):
+        oracle.posterior(pb, n_threads=threads, flat=fp)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.posterior(pb, n_threads=threads, flat=fp)
+    dt = time.perf_counter() - t0
+    units = pb.units
+    v = units * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "loci": args.loci, "units_per_step": units,
+                   "note": "C restatement of the reference's Java path (no JVM in this image); one step = one full "
+                           "posterior evaluation of the N=1 workload on the host cores (rank 0 only)"},
+        "posterior_evals_per_sec": args.steps / dt,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} full evaluations of {args.workload} ({args.loci} loci), OpenMP over loci"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--loci", type=int, default=0, help="loci per GPU (default: the workload's own count)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exact", action="store_true")
+    args = ap.parse_args()
+    from starbeast2_b200 import synth
+    if args.loci <= 0:
+        args.loci = synth.CONFIGS[args.workload]["n_loci"]
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from starbeast2_b200 import build as sbuild
+    from starbeast2_b200.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libsb2gpu has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sbuild.build()
+
+    pb = build_problem(rank, world, args.loci, args.workload)
+    eng = Engine.from_problem(pb, device=local, exact_order=args.exact, profile=True)
+    red = eng.bind_torch()
+    units_local = pb.units
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    tot = np.zeros(3)
+
+    def step_device():
+        eng.mark_all_dirty()
+        eng.eval_begin()
+        if world > 1:
+            dist.all_reduce(red)
+        eng.eval_end_total(tot)
+
+    # flat host copies of everything a step of the reference-facing API re-sends
+    trees = [l.tree for l in pb.loci]
+    hp = np.ascontiguousarray(np.concatenate([t.parent for t in trees]), np.int32)
+    hl = np.ascontiguousarray(np.concatenate([t.left for t in trees]), np.int32)
+    hr = np.ascontiguousarray(np.concatenate([t.right for t in trees]), np.int32)
+    hh = np.ascontiguousarray(np.concatenate([t.height for t in trees]), np.float64)
+    n_nodes = int(hp.shape[0])
+    S = pb.species.n_nodes
+    h2d = 20 * n_nodes + 20 * S + 8 * S * 3 + 16 + pb.n_loci          # trees + species block + flags
+    d2h = 8 * (3 + 2 * pb.n_loci + S)
+    coal_buf, lik_buf, br_buf = np.zeros(pb.n_loci), np.zeros(pb.n_loci), np.zeros(S)
+
+    def step_e2e():
+        eng.set_species_tree(pb.species)
+        eng.set_species_rates(pb.species_rates)
+        eng.set_pop_model(pb.pop_kind, pb.pop_a, pb.pop_b, pb.alpha, pb.beta)
+        eng.set_gene_trees_flat(0, pb.n_loci, hp, hl, hr, hh)
+        eng.mark_all_dirty()
+        eng.eval_begin()
+        if world > 1:
+            dist.all_reduce(red)
+        eng._ck(eng._L.sb2_eval_end(eng._h, coal_buf.ctypes.data, lik_buf.ctypes.data, br_buf.ctypes.data, tot.ctypes.data))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, flush_l2=True):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            if flush_l2:
+                flush.fill_(1)          # evict the (L2-resident) working set; outside the timed events
+            a.record(stream)
+            fn()
+            b.record(stream)
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in ev)   # ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        step_device()
+    eng.kernel_time()
+    barrier()
+    l0 = eng.launch_count()
+    t_wall0 = time.time()
+    ms = timed(step_device, args.steps)
+    launches = eng.launch_count() - l0
+    k_ms, k_n = eng.kernel_time()
+    total_ref = float(tot[2])
+    barrier()
+    # e2e
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+    # keep the load up long enough for nvidia-smi to see it (100 ms sampling), same step, untimed
+    t_probe = time.time()
+    while time.time() - t_probe < 1.2:
+        step_device()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    t = torch.tensor([ms, ms_e2e, float(units_local), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, ms_e2e = float(tmax[0]), float(tmax[1])
+        units_total, launches_total = float(tsum[2]), int(tsum[3])
+    else:
+        units_total, launches_total = float(units_local), launches
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_gbs, peak_src = load_peaks()
+    k_us = 1e3 * k_ms / max(k_n, 1)
+    dbytes = design_bytes(pb)
+    sbytes = pb.algorithmic_bytes_survey()
+    achieved = dbytes / (k_us * 1e-6) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload)
+        except Exception:
+            traffic = None
+    value = units_total * args.steps / (ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "loci_per_gpu": args.loci, "loci_total": args.loci * world,
+                   "units_per_step": units_total, "mean_patterns_per_locus": float(np.mean([l.n_pat for l in pb.loci])),
+                   "regime": "A (every node of every locus dirty)", "exact_order": bool(args.exact),
+                   "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write; working set is L2-resident)",
+                   "parallelism": f"loci sharded over {world} GPU(s), 1 all-reduce of {eng.reduce_vector_len()} doubles per step" if world > 1 else "1 GPU"},
+        "posterior_evals_per_sec": args.steps / (ms * 1e-3),
+        "log_posterior": total_ref,
+        "e2e": {"value": units_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps, "posterior_evals_per_sec": args.steps / (ms_e2e * 1e-3)},
+        "gpu_launches": launches_total,
+        "roofline": {"bound": "hbm", "kernel": "k_treewalk", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
+                     "traffic": traffic, "peak_source": peak_src, "us_per_launch": k_us, "launches_timed": k_n,
+                     "algorithmic_bytes_per_launch": dbytes, "bytes_per_unit": dbytes / pb.units,
+                     "survey_formula_bytes_per_launch": sbytes, "survey_formula_GBps": sbytes / (k_us * 1e-6) / 1e9,
+                     "survey_formula_frac": sbytes / (k_us * 1e-6) / 1e9 / hbm_gbs,
+                     "kernel_partials_per_sec": pb.units / (k_us * 1e-6)},
+        "clocks": clocks,
+    }
+    if not args.no_cpu and world == 1:
+        import oracle
+        oracle.build()
+        n, dt, r = cpu_baseline(pb, 1, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": pb.units * n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{n} full evaluations of {args.workload} ({args.loci} loci) in {dt:.1f} s, single thread "
+                                          "(the reference runs threads: 1); C restatement of the Java path, gcc -O2 -ffp-contract=off",
+                                "posterior_evals_per_sec": n / dt,
+                                "log_posterior_rel_diff": abs(r.total - total_ref) / abs(r.total)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

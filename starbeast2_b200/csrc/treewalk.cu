@@ -43,6 +43,8 @@ __device__ __forceinline__ double dot4(const double *m, double a0, double a1, do
     return fma(m[3], a3, fma(m[2], a2, fma(m[1], a1, m[0] * a0)));
 }
 
+constexpr int OPS_BATCH = 64;   // ops staged in shared memory per batch (two halves)
+
 size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int stackDepth)
 {
     const size_t warps = (size_t)nCat * chunksPerTile;
@@ -51,11 +53,54 @@ size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int stackDepth)
     b += 2ull * 2 * nCat * 16 * 8;                        // matrices, double buffered
     b += 2ull * warps * 32 * 4;                           // exponent exchange, double buffered
     b += warps * 8 + 64;
+    b = (b + 15) & ~size_t(15);
+    b += 2ull * OPS_BATCH * sizeof(Op);                   // op schedule, two half batches
     return b;
 }
 
+// raw operand data of one op for this thread's (pattern, category), loaded one op ahead of its use
+struct Operand {
+    double x0, x1, x2, x3;
+    int aux;   // TIP: state; GLOBAL: cumulative exponent
+};
+
+__device__ __forceinline__ void fetch_operand(Operand &r, uint8_t kind, int off, const uint8_t *states, const double *partials,
+                                              const int16_t *cumExp, size_t nodeStride, int nPat, int c, int p)
+{
+    if (kind == OPK_TIP) {
+        r.aux = states[(size_t)off * nPat + p];
+    } else if (kind == OPK_GLOBAL) {
+        ld256_nc(partials + (size_t)off * nodeStride + ((size_t)c * nPat + p) * 4, r.x0, r.x1, r.x2, r.x3);
+        r.aux = cumExp[(size_t)off * nPat + p];
+    }
+}
+
 template <bool EXACT>
-__global__ void __launch_bounds__(1024) k_treewalk(WalkArgs A)
+__device__ __forceinline__ void apply_operand(const Operand &r, uint8_t kind, int slot, const double *M, const double *stack,
+                                              const int *sexp, int warps, int myStack, double &s0, double &s1, double &s2,
+                                              double &s3, int &cum)
+{
+    if (kind == OPK_TIP) {
+        const int s = r.aux;
+        if (s < 4) { s0 = M[s]; s1 = M[4 + s]; s2 = M[8 + s]; s3 = M[12 + s]; }
+        else { s0 = s1 = s2 = s3 = 1.0; }
+        return;
+    }
+    double a0, a1, a2, a3;
+    if (kind == OPK_STACK) {
+        const double4 v = *reinterpret_cast<const double4 *>(stack + ((size_t)slot * warps * 32 + myStack) * 4);
+        a0 = v.x; a1 = v.y; a2 = v.z; a3 = v.w;
+        cum += sexp[slot * warps * 32 + myStack];
+    } else {
+        a0 = r.x0; a1 = r.x1; a2 = r.x2; a3 = r.x3;
+        cum += r.aux;
+    }
+    s0 = dot4<EXACT>(M, a0, a1, a2, a3); s1 = dot4<EXACT>(M + 4, a0, a1, a2, a3);
+    s2 = dot4<EXACT>(M + 8, a0, a1, a2, a3); s3 = dot4<EXACT>(M + 12, a0, a1, a2, a3);
+}
+
+template <bool EXACT, int MAXT>
+__global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 3 : 1)) k_treewalk(WalkArgs A)
 {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int tile = blockIdx.x;
@@ -67,7 +112,7 @@ __global__ void __launch_bounds__(1024) k_treewalk(WalkArgs A)
     const int warps = C * chunks;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int c = w % C, chunk = w / C;
-    const int nPat = d.nPat, nI = d.nInt;
+    const int nPat = d.nPat;
     const int p = (tile - d.tileBase) * (chunks * 32) + chunk * 32 + lane;
     const bool valid = p < nPat;
 
@@ -76,6 +121,7 @@ __global__ void __launch_bounds__(1024) k_treewalk(WalkArgs A)
     double *smat = reinterpret_cast<double *>(sexp + (size_t)depth * warps * 32);  // [2][2][C][16]
     int *smax = reinterpret_cast<int *>(smat + 2 * 2 * C * 16);                    // [2][warps][32]
     double *sred = reinterpret_cast<double *>(smax + 2 * warps * 32);              // [warps]
+    Op *sops = reinterpret_cast<Op *>((reinterpret_cast<uintptr_t>(sred + warps) + 8 + 15) & ~uintptr_t(15));   // [2][OPS_BATCH]
 
     const Op *ops = A.ops + d.opBase;
     const double *mats = A.mats + d.matBase;
@@ -84,63 +130,54 @@ __global__ void __launch_bounds__(1024) k_treewalk(WalkArgs A)
     double *partials = A.partials + d.partBase;
     int16_t *cumExp = A.cumExp + d.expBase;
     const int myStack = (w * 32 + lane);
-    const int nMatThreads = 32 * C;   // 2 matrices x C x 16 doubles
+    const int nMat = 32 * C;   // 2 matrices x C x 16 doubles, one per staging thread
+    const bool stager = tid < nMat;
+    const int mWhich = tid >= 16 * C, mR = tid - mWhich * 16 * C;
 
+    auto load_batch = [&](int b) {
+        const int first = b * OPS_BATCH, cnt = min(OPS_BATCH, nOps - first);
+        const int4 *src = reinterpret_cast<const int4 *>(ops + first);
+        int4 *dst = reinterpret_cast<int4 *>(sops + (b & 1) * OPS_BATCH);
+        for (int t = tid; t < cnt * 2; t += blockDim.x) dst[t] = src[t];
+    };
+    load_batch(0);
+    __syncthreads();
+
+    // software pipeline: while op k is computed, op k+1's matrices, tip states and clean-child partials are in flight
+    Op o = sops[0];
+    double mreg = 0.0;
+    Operand pa, pb;
+    pa.x0 = pa.x1 = pa.x2 = pa.x3 = 0.0; pa.aux = 0; pb = pa;
+    if (stager) mreg = mats[(size_t)(mWhich ? o.mB : o.mA) * C * 16 + mR];
+    if (valid) {
+        fetch_operand(pa, o.aKind, o.aOff, states, partials, cumExp, nodeStride, nPat, c, p);
+        fetch_operand(pb, o.bKind, o.bOff, states, partials, cumExp, nodeStride, nPat, c, p);
+    }
     for (int k = 0; k < nOps; k++) {
-        const Op o = ops[k];
         const int par = k & 1;
-        // stage the op's two branch matrices
         double *sm = smat + par * (2 * C * 16);
-        for (int t = tid; t < nMatThreads; t += blockDim.x) {
-            const int which = t >= 16 * C;
-            const int r = t - which * 16 * C;
-            sm[t] = mats[(size_t)(which ? o.mB : o.mA) * C * 16 + r];
-        }
+        if (stager) sm[tid] = mreg;
+        if (k + 1 < nOps && (k + 1) % OPS_BATCH == 0) load_batch((k + 1) / OPS_BATCH);   // other half: its ops are all consumed
         __syncthreads();
+
+        Op on = o;
+        Operand na = pa, nb = pb;
+        if (k + 1 < nOps) {
+            on = sops[(((k + 1) / OPS_BATCH) & 1) * OPS_BATCH + (k + 1) % OPS_BATCH];
+            if (stager) mreg = mats[(size_t)(mWhich ? on.mB : on.mA) * C * 16 + mR];
+            if (valid) {
+                fetch_operand(na, on.aKind, on.aOff, states, partials, cumExp, nodeStride, nPat, c, p);
+                fetch_operand(nb, on.bKind, on.bOff, states, partials, cumExp, nodeStride, nPat, c, p);
+            }
+        }
 
         double out0 = 0, out1 = 0, out2 = 0, out3 = 0;
         int cum = 0;
         if (valid) {
             const double *M1 = sm + c * 16, *M2 = sm + (C + c) * 16;
             double sa0, sa1, sa2, sa3, sb0, sb1, sb2_, sb3;
-            // operand a
-            if (o.aKind == OPK_TIP) {
-                const int s = states[(size_t)o.aOff * nPat + p];
-                if (s < 4) { sa0 = M1[s]; sa1 = M1[4 + s]; sa2 = M1[8 + s]; sa3 = M1[12 + s]; }
-                else { sa0 = sa1 = sa2 = sa3 = 1.0; }
-            } else {
-                double a0, a1, a2, a3;
-                if (o.aKind == OPK_STACK) {
-                    const double4 *sp = reinterpret_cast<const double4 *>(stack + ((size_t)o.aSlot * warps * 32 + myStack) * 4);
-                    const double4 v = *sp;
-                    a0 = v.x; a1 = v.y; a2 = v.z; a3 = v.w;
-                    cum += sexp[o.aSlot * warps * 32 + myStack];
-                } else {
-                    ld256_nc(partials + (size_t)o.aOff * nodeStride + ((size_t)c * nPat + p) * 4, a0, a1, a2, a3);
-                    cum += cumExp[(size_t)o.aOff * nPat + p];
-                }
-                sa0 = dot4<EXACT>(M1, a0, a1, a2, a3); sa1 = dot4<EXACT>(M1 + 4, a0, a1, a2, a3);
-                sa2 = dot4<EXACT>(M1 + 8, a0, a1, a2, a3); sa3 = dot4<EXACT>(M1 + 12, a0, a1, a2, a3);
-            }
-            // operand b
-            if (o.bKind == OPK_TIP) {
-                const int s = states[(size_t)o.bOff * nPat + p];
-                if (s < 4) { sb0 = M2[s]; sb1 = M2[4 + s]; sb2_ = M2[8 + s]; sb3 = M2[12 + s]; }
-                else { sb0 = sb1 = sb2_ = sb3 = 1.0; }
-            } else {
-                double a0, a1, a2, a3;
-                if (o.bKind == OPK_STACK) {
-                    const double4 *sp = reinterpret_cast<const double4 *>(stack + ((size_t)o.bSlot * warps * 32 + myStack) * 4);
-                    const double4 v = *sp;
-                    a0 = v.x; a1 = v.y; a2 = v.z; a3 = v.w;
-                    cum += sexp[o.bSlot * warps * 32 + myStack];
-                } else {
-                    ld256_nc(partials + (size_t)o.bOff * nodeStride + ((size_t)c * nPat + p) * 4, a0, a1, a2, a3);
-                    cum += cumExp[(size_t)o.bOff * nPat + p];
-                }
-                sb0 = dot4<EXACT>(M2, a0, a1, a2, a3); sb1 = dot4<EXACT>(M2 + 4, a0, a1, a2, a3);
-                sb2_ = dot4<EXACT>(M2 + 8, a0, a1, a2, a3); sb3 = dot4<EXACT>(M2 + 12, a0, a1, a2, a3);
-            }
+            apply_operand<EXACT>(pa, o.aKind, o.aSlot, M1, stack, sexp, warps, myStack, sa0, sa1, sa2, sa3, cum);
+            apply_operand<EXACT>(pb, o.bKind, o.bSlot, M2, stack, sexp, warps, myStack, sb0, sb1, sb2_, sb3, cum);
             out0 = sa0 * sb0; out1 = sa1 * sb1; out2 = sa2 * sb2_; out3 = sa3 * sb3;
         }
         // exponent of the pattern's largest value over categories x states
@@ -165,6 +202,7 @@ __global__ void __launch_bounds__(1024) k_treewalk(WalkArgs A)
             st256(partials + (size_t)o.outOff * nodeStride + ((size_t)c * nPat + p) * 4, out0, out1, out2, out3);
             if (c == 0) cumExp[(size_t)o.outOff * nPat + p] = (int16_t)cum;
         }
+        o = on; pa = na; pb = nb;
     }
     __syncthreads();
 
@@ -223,18 +261,28 @@ __global__ void __launch_bounds__(1024) k_treewalk(WalkArgs A)
     }
 }
 
+template <bool EXACT, int MAXT>
+static void launch_one(const WalkArgs &a, int nTiles, size_t smem, int threads, cudaStream_t st)
+{
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(k_treewalk<EXACT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    k_treewalk<EXACT, MAXT><<<nTiles, threads, smem, st>>>(a);
+}
+
 void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st)
 {
     const size_t smem = treewalk_smem_bytes(a.nCat, a.chunksPerTile, a.stackDepth);
-    static size_t configured[2] = {0, 0};
-    if (smem > 48 * 1024 && smem > configured[exact]) {
-        if (exact) cudaFuncSetAttribute(k_treewalk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        else cudaFuncSetAttribute(k_treewalk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured[exact] = smem;
-    }
     const int threads = 32 * a.nCat * a.chunksPerTile;
-    if (exact) k_treewalk<true><<<nTiles, threads, smem, st>>>(a);
-    else k_treewalk<false><<<nTiles, threads, smem, st>>>(a);
+    if (threads <= 256) {
+        if (exact) launch_one<true, 256>(a, nTiles, smem, threads, st);
+        else launch_one<false, 256>(a, nTiles, smem, threads, st);
+    } else {   // more than 8 rate categories: register-capped variant
+        if (exact) launch_one<true, 1024>(a, nTiles, smem, threads, st);
+        else launch_one<false, 1024>(a, nTiles, smem, threads, st);
+    }
 }
 
 }  // namespace sb2

@@ -207,14 +207,19 @@ CONFIGS = {
 
 
 def make_problem(name: str = "C2", n_loci: Optional[int] = None, n_sites: Optional[int] = None,
-                 seed_offset: int = 0, missing_frac: float = 0.0, **override) -> Problem:
+                 seed_offset: int = 0, missing_frac: float = 0.0, locus_range: Optional[Tuple[int, int]] = None,
+                 **override) -> Problem:
+    """locus_range=(lo, hi): generate only loci lo..hi-1 of the n_loci-locus problem (species tree and shared
+    parameters come from the config seed, each locus from its own (seed, index) stream, so every rank of a
+    multi-GPU run can build just its shard of one consistent global problem)."""
     cfg = dict(CONFIGS[name])
     cfg.update(override)
     if n_loci is not None:
         cfg["n_loci"] = n_loci
     if n_sites is not None:
         cfg["n_sites"] = n_sites
-    rng = np.random.Generator(np.random.PCG64(20260100 + cfg["seed"] + 1000 * seed_offset))
+    base_seed = 20260100 + cfg["seed"] + 1000 * seed_offset
+    rng = np.random.Generator(np.random.PCG64(base_seed))
     n_sp = cfg["n_species"]
     sp = yule_species_tree(rng, n_sp, cfg.get("n_fossils", 0))
     S = sp.n_nodes
@@ -255,7 +260,9 @@ def make_problem(name: str = "C2", n_loci: Optional[int] = None, n_sites: Option
 
     pi_hky = np.array([0.30, 0.20, 0.20, 0.30])
     loci: List[Locus] = []
-    for _ in range(cfg["n_loci"]):
+    lo, hi = locus_range if locus_range is not None else (0, cfg["n_loci"])
+    for li in range(lo, hi):
+        rng = np.random.Generator(np.random.PCG64([base_seed, li]))
         tree, tip_species = simulate_gene_tree(rng, sp, pop_scale, tips_per_leaf)
         n_tips = len(tip_species)
         mu = float(np.exp(rng.normal(0.0, 0.3)))
