@@ -142,8 +142,8 @@ SB2_API int sb2_get_branch_rates(sb2_engine *e, int32_t locus, double *rates);
  * and per-branch GeneTree perBranchLogP [nSpeciesNodes]; any pointer may be NULL. */
 SB2_API int sb2_get_embedding(sb2_engine *e, int32_t locus, int32_t *lineageCounts, int32_t *coalCounts,
                               int32_t *assignment, double *perBranchLogP);
-/* Current partials of an internal node, [nCategories][nPatterns][4], scaled by 2^-exponent[pattern]
- * (exponents[nPatterns], cumulative over the subtree). */
+/* Current partials of an internal node, [nCategories][nPatterns][4], scaled by 2^-exponent
+ * (exponents[nCategories][nPatterns], cumulative over the subtree). */
 SB2_API int sb2_get_partials(sb2_engine *e, int32_t locus, int32_t node, double *partials, int32_t *exponents);
 /* Current transition matrices of the branch above `node`, [nCategories][16]. */
 SB2_API int sb2_get_matrices(sb2_engine *e, int32_t locus, int32_t node, double *matrices);

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -46,7 +47,7 @@ struct sb2_engine {
     std::vector<HostLocus> loci;
     int S = 0, nSpeciesLeaves = 0, L = 0;
     int64_t totalNodes = 0, totalTips = 0, totalPat = 0, totalCat = 0, totalInt = 0, totalTiles = 0;
-    int maxNodes = 0, nCat = 0, chunksPerTile = 1, stackDepth = 1;
+    int maxNodes = 0, nCat = 0, chunksPerTile = 1, patPerThread = 1, stackDepth = 1;
     int64_t devBytes = 0;
     int64_t launches = 0;
     std::vector<void *> devAllocs;
@@ -260,7 +261,7 @@ int do_prepare(sb2_engine *e)
     a.loci = e->dLoci; a.params = e->dParams; a.flags = e->dFlags; a.inTree = e->dInTree; a.tipSpecies = e->dTipSpecies;
     a.catRates = e->dCat; a.explicitRates = e->dExplicit ? e->dExplicit : e->dCat;
     a.cur = cur(e); a.stored = stored(e); a.ops = e->dOps; a.nOps = e->dNOps; a.mats = e->dMats;
-    a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L;
+    a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L; a.stackDepth = e->stackDepth;
     launch_prepare(a, e->maxNodes, st);
     e->launches++;
     CUDA_TRY(e, cudaGetLastError());
@@ -282,7 +283,9 @@ int do_walk(sb2_engine *e)
     a.loci = e->dLoci; a.params = e->dParams; a.tileLocus = e->dTileLocus; a.ops = e->dOps; a.nOps = e->dNOps;
     a.tipStates = e->dStates; a.weights = e->dWeights; a.constMask = e->dConstMask; a.catProps = e->dCat + e->totalCat;
     a.mats = e->dMats; a.partials = e->dPartials; a.cumExp = e->dCumExp; a.patLogL = e->dPatLogL; a.tileSum = e->dTileSum;
-    a.nCat = e->nCat; a.chunksPerTile = e->chunksPerTile; a.stackDepth = e->stackDepth;
+    a.nCat = e->nCat; a.chunksPerTile = e->chunksPerTile; a.patPerThread = e->patPerThread; a.stackDepth = e->stackDepth;
+    a.maxTips = (e->maxNodes + 1) / 2;
+    a.tipsInSmem = treewalk_tips_in_smem(a.maxTips, 32 * e->chunksPerTile * e->patPerThread) ? 1 : 0;
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (e->cfg.profile) {
         if (e->evUsed == e->evPool.size()) {
@@ -396,8 +399,21 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     e->S = nSpeciesNodes; e->nSpeciesLeaves = nSpeciesLeaves; e->L = (int)e->loci.size();
     const int L = e->L;
     e->nCat = e->loci[0].d.nCat;
-    e->chunksPerTile = std::max(1, 4 / e->nCat);
-    const int tilePat = 32 * e->chunksPerTile;
+    // launch geometry of the pruning kernel: a warp = 32*R patterns of one category, a CTA = nCat * chunks warps.
+    // Large problems are instruction-issue bound: R=2 amortises op decode and matrix loads over two patterns;
+    // small ones are latency bound and want as many independent warps as possible (R=1).
+    {
+        int64_t threads1 = 0;
+        for (auto &hl : e->loci) threads1 += (int64_t)hl.d.nPat * hl.d.nCat;
+        e->patPerThread = 1;   // measured on B200: R=1 wins at every shape tried (C2, C3, C5 shard); R=2/4 kept for tuning
+        (void)threads1;
+        e->chunksPerTile = std::max(1, 2 / e->nCat);
+        if (const char *v = getenv("SB2_PATTERNS_PER_THREAD")) e->patPerThread = atoi(v);
+        if (const char *v = getenv("SB2_CHUNKS_PER_TILE")) e->chunksPerTile = atoi(v);
+        if (e->patPerThread != 1 && e->patPerThread != 2 && e->patPerThread != 4) return e->fail(SB2_ERR_ARG, "SB2_PATTERNS_PER_THREAD must be 1, 2 or 4");
+        if (e->chunksPerTile < 1 || 32 * e->nCat * e->chunksPerTile > 256) return e->fail(SB2_ERR_ARG, "nCat * chunks per tile must stay <= 8 warps");
+    }
+    const int tilePat = 32 * e->chunksPerTile * e->patPerThread;
     int64_t nodeBase = 0, tipBase = 0, patBase = 0, catBase = 0, tileBase = 0, opBase = 0, stateBase = 0, partBase = 0, expBase = 0, matBase = 0, treeOff = 0;
     e->stackDepth = 1;
     for (auto &hl : e->loci) {
@@ -413,8 +429,9 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
         nodeBase += d.nNodes; tipBase += d.nTips; patBase += d.nPat; catBase += d.nCat; tileBase += d.nTiles; opBase += d.nInt;
         stateBase += (int64_t)d.nTips * d.nPat;
         partBase += 2ll * d.nInt * d.nCat * d.nPat * 4;
-        expBase += 2ll * d.nInt * d.nPat;
+        expBase += 2ll * d.nInt * d.nCat * d.nPat;
         expBase = (expBase + 7) & ~7ll;
+        if (2ll * d.nInt * d.nCat * d.nPat >= 0x7fffffffll) return e->fail(SB2_ERR_ARG, "locus too large for 32-bit element offsets");
         matBase += 2ll * d.nNodes * d.nCat * 16;
         treeOff += 20ll * d.nNodes;
         treeOff = (treeOff + 7) & ~7ll;
@@ -423,7 +440,10 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     e->totalNodes = nodeBase; e->totalTips = tipBase; e->totalPat = patBase; e->totalCat = catBase; e->totalTiles = tileBase;
     e->totalInt = opBase; e->inTreeBytes = treeOff;
     if (prepare_smem_bytes(e->maxNodes, e->S) > 227 * 1024) return e->fail(SB2_ERR_ARG, "gene tree too large for the per-locus shared-memory kernel");
-    if (treewalk_smem_bytes(e->nCat, e->chunksPerTile, e->stackDepth) > 227 * 1024) return e->fail(SB2_ERR_ARG, "pruning stack does not fit shared memory");
+    e->stackDepth = std::min(e->stackDepth, 4);   // deeper (rare) results are re-read from their global buffer (OPK_SPILL)
+    if (const char *v = getenv("SB2_STACK_DEPTH")) e->stackDepth = std::max(1, atoi(v));
+    if (treewalk_smem_bytes(e->nCat, e->chunksPerTile, e->patPerThread, e->stackDepth, (e->maxNodes + 1) / 2) > 227 * 1024)
+        return e->fail(SB2_ERR_ARG, "pruning stack does not fit shared memory");
 
     int rc;
     // static data
@@ -856,9 +876,10 @@ int sb2_get_partials(sb2_engine *e, int32_t locus, int32_t node, double *partial
     if (partials)
         CUDA_TRY(e, cudaMemcpy(partials, e->dPartials + d.partBase + idx * d.nCat * d.nPat * 4, 8 * (size_t)d.nCat * d.nPat * 4, cudaMemcpyDeviceToHost));
     if (exponents) {
-        std::vector<int16_t> tmp(d.nPat);
-        CUDA_TRY(e, cudaMemcpy(tmp.data(), e->dCumExp + d.expBase + idx * d.nPat, 2 * (size_t)d.nPat, cudaMemcpyDeviceToHost));
-        for (int p = 0; p < d.nPat; p++) exponents[p] = tmp[p];
+        const size_t n = (size_t)d.nCat * d.nPat;
+        std::vector<int16_t> tmp(n);
+        CUDA_TRY(e, cudaMemcpy(tmp.data(), e->dCumExp + d.expBase + idx * n, 2 * n, cudaMemcpyDeviceToHost));
+        for (size_t p = 0; p < n; p++) exponents[p] = tmp[p];
     }
     return SB2_OK;
 }

@@ -399,20 +399,25 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         const bool dl = Lc >= nT && s.dirty[Lc], dr = Rc >= nT && s.dirty[Rc];
         const int first = (dl && dr) ? ((s.cnt[Rc] > s.cnt[Lc]) ? Rc : Lc) : (dl ? Lc : Rc);
         Op o;
-        o.outOff = newP * nI + (i - nT);
-        o.outSlot = (uint8_t)base;
+        const int cp = C * d.nPat;   // (pattern, category) elements per node buffer
+        o.outOff = (newP * nI + (i - nT)) * cp;
+        o.outSlot = (uint8_t)min(base, 255);
         o.node = i;
         o.pad[0] = o.pad[1] = o.pad[2] = 0;
         auto operand = [&](int c, bool cd, int32_t &off, uint8_t &kind, uint8_t &slot) {
             slot = 0;
             if (c < nT) { kind = OPK_TIP; off = c; }
-            else if (cd) { kind = OPK_STACK; off = 0; slot = (uint8_t)((c == first) ? base : base + 1); }
-            else { kind = OPK_GLOBAL; off = A.cur.curP[nb + c] * nI + (c - nT); }
+            else if (cd) {
+                const int sl = (c == first) ? base : base + 1;
+                if (sl < A.stackDepth) { kind = OPK_STACK; off = 0; slot = (uint8_t)sl; }
+                else { kind = OPK_SPILL; off = ((1 - A.stored.curP[nb + c]) * nI + (c - nT)) * cp; }   // the buffer the child is being written to
+            }
+            else { kind = OPK_GLOBAL; off = (A.cur.curP[nb + c] * nI + (c - nT)) * cp; }
         };
         operand(Lc, dl, o.aOff, o.aKind, o.aSlot);
         operand(Rc, dr, o.bOff, o.bKind, o.bSlot);
-        o.mA = A.cur.curM[nb + Lc] * G + Lc;
-        o.mB = A.cur.curM[nb + Rc] * G + Rc;
+        o.mA = (A.cur.curM[nb + Lc] * G + Lc) * C * 16;
+        o.mB = (A.cur.curM[nb + Rc] * G + Rc) * C * 16;
         A.ops[d.opBase + pos] = o;
     }
 

@@ -4,7 +4,7 @@
 //   tipStates   u8  [locus][tip][pattern]                      static
 //   partials    f64 [locus][buf 0/1][internal node][cat][pattern][4]   (BEAST layout per node, two buffers
 //                                                               per node for store/restore, index flip only)
-//   cumExp      i16 [locus][buf][internal node][pattern]       power-of-two scale exponent, cumulative over subtree
+//   cumExp      i16 [locus][buf][internal node][cat][pattern]  power-of-two scale exponent, cumulative over subtree
 //   mats        f64 [locus][buf][node][cat][16]                P = exp(Q d) per branch x category
 //   StateBlock (x2: current / stored)  small per-node and per-locus state, see below
 //   ops         Op  [locus][internal node]                      post-order pruning schedule built on device
@@ -53,13 +53,17 @@ enum : uint8_t {
 };
 
 // operand kinds of a pruning op
-enum : uint8_t { OPK_TIP = 0, OPK_STACK = 1, OPK_GLOBAL = 2 };
+// TIP: tip states; STACK: shared-memory stack slot; GLOBAL: clean node, partials resident in HBM from an earlier
+// evaluation; SPILL: dirty node whose stack slot is deeper than the shared-memory stack -> re-read from the global
+// buffer this launch has just written
+enum : uint8_t { OPK_TIP = 0, OPK_STACK = 1, OPK_GLOBAL = 2, OPK_SPILL = 3 };
 
 struct __align__(16) Op {
-    int32_t outOff;   // buf*nInt + internal index          -> partials / cumExp of the output
-    int32_t aOff;     // TIP: tip index; GLOBAL: buf*nInt + internal index
+    // offsets are pre-multiplied by k_prepare so that the pruning kernel needs one IMAD.WIDE per address:
+    int32_t outOff;   // (buf*nInt + internal index) * nCat*nPat   -> (pattern, category) element of the output
+    int32_t aOff;     // TIP: tip index; GLOBAL / SPILL: (buf*nInt + internal index) * nCat*nPat
     int32_t bOff;
-    int32_t mA;       // buf*nNodes + node                   -> mats of the branch above operand a
+    int32_t mA;       // (buf*nNodes + node) * nCat*16             -> mats of the branch above operand a (doubles)
     int32_t mB;
     uint8_t aKind, bKind, outSlot, aSlot;
     uint8_t bSlot, pad[3];
@@ -106,6 +110,7 @@ struct PrepareArgs {
     int32_t *nOps;               // [nLoci]
     double *mats;
     int32_t S, nSpeciesLeaves, popKind, nLoci;
+    int32_t stackDepth;          // shared-memory stack slots of k_treewalk
 };
 
 struct WalkArgs {
@@ -124,8 +129,11 @@ struct WalkArgs {
     double *patLogL;             // by pattern
     double *tileSum;             // [nTiles]
     int32_t nCat;                // categories of every locus in this launch
-    int32_t chunksPerTile;       // 32-pattern chunks per tile (block = 32 * nCat * chunksPerTile threads)
-    int32_t stackDepth;
+    int32_t chunksPerTile;       // pattern chunks per tile (block = 32 * nCat * chunksPerTile threads)
+    int32_t patPerThread;        // R: patterns per thread (a chunk is 32*R patterns)
+    int32_t stackDepth;          // shared-memory stack slots; deeper results spill to their global buffer
+    int32_t maxTips;             // largest tip count over loci (sizes the shared-memory tip-state tile)
+    int32_t tipsInSmem;          // 1: tip states of the tile are staged in shared memory
 };
 
 struct ReduceArgs {
@@ -146,6 +154,7 @@ void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st)
 void launch_reduce_local(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
 void launch_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
 size_t prepare_smem_bytes(int maxNodes, int S);
-size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int stackDepth);
+size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, int maxTips);
+bool treewalk_tips_in_smem(int maxTips, int tilePat);
 
 }  // namespace sb2

@@ -7,19 +7,22 @@
 //
 // B200-first decomposition: the pruning recursion is independent across site patterns, so the grid is
 // (locus x tile of patterns) and ONE CTA walks the locus's whole dirty subtree for its tile, in the post-order
-// schedule k_prepare emitted.  Results that a later op of the same walk consumes never leave the SM: they sit in a
-// shared-memory stack of floor(log2(nInt))+1 tiles (heavy-child-first order bounds the depth).  Every result is
-// also streamed to HBM once (256-bit stores) because later incremental (dirty-node-only) evaluations read clean
-// siblings from there (256-bit non-allocating loads).  HBM traffic of a full evaluation is therefore the
-// partials written once + tip states + exponents, instead of write + two re-reads per node.
+// schedule k_prepare emitted.  Results that a later op of the same walk consumes stay on the SM: they sit in a
+// small shared-memory stack (heavy-child-first order keeps it shallow; the rare deeper result is re-read from the
+// node's global buffer, which the same thread has just written).  Every result is streamed to HBM exactly once
+// (256-bit stores) because later incremental (dirty-node-only) evaluations read clean siblings from there
+// (256-bit non-allocating loads).  HBM traffic of a full evaluation is therefore partials written once + tip
+// states + exponents, instead of write + two re-reads per node.
 //
-// Thread mapping: one thread per (pattern, rate category); a warp is 32 consecutive patterns of one category, so
-// global and shared accesses are fully coalesced / conflict free.  The two 4x4 matrices of an op are staged in
-// shared memory once per CTA and read as broadcasts.
+// Thread mapping: a warp owns 32*R consecutive patterns of ONE rate category, a thread R of them (stride 32, so
+// every global / shared access is coalesced / conflict free).  Warps never wait for each other inside the walk:
+// each warp streams its own category's transition matrices through a private cp.async ring, the op schedule and
+// the tile's tip states are staged in shared memory once, and rescaling is per (pattern, category).
 //
-// Rescaling: every node, every pattern, by an exact power of two (the exponent of the largest of the pattern's
-// C x 4 values); scaled values keep their mantissas, so rescaling never perturbs a result and evaluation is
-// independent of the update history.  The cumulative exponent of a subtree is stored per (node, pattern) as int16.
+// Rescaling: every node, every (pattern, category), by an exact power of two (the exponent of the largest of
+// the 4 values); scaled values keep their mantissas, so rescaling never perturbs a result and evaluation is
+// independent of the update history.  The cumulative exponent of a subtree is stored as int16 next to the
+// partials; categories are brought to a common exponent only at the root.
 #include <math.h>
 
 #include "sb2_device.cuh"
@@ -35,72 +38,67 @@ __device__ __forceinline__ void st256(double *p, double a, double b, double c, d
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
-template <bool EXACT>
-__device__ __forceinline__ double dot4(const double *m, double a0, double a1, double a2, double a3)
+constexpr int OPS_BATCH = 32;   // ops staged in shared memory per half batch
+constexpr int MAT_RING = 4;     // transition-matrix pairs in flight per warp (cp.async ring)
+constexpr int TIP_SMEM_MAX = 48 * 1024;
+
+__device__ __forceinline__ void ld256_coherent(const double *p, double &a, double &b, double &c, double &d)
 {
-    if (EXACT)   // the reference's order, no fused multiply-add: ((m0 a0 + m1 a1) + m2 a2) + m3 a3
-        return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[0], a0), __dmul_rn(m[1], a1)), __dmul_rn(m[2], a2)), __dmul_rn(m[3], a3));
-    return fma(m[3], a3, fma(m[2], a2, fma(m[1], a1, m[0] * a0)));
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-constexpr int OPS_BATCH = 64;   // ops staged in shared memory per batch (two halves)
+bool treewalk_tips_in_smem(int maxTips, int tilePat) { return (size_t)maxTips * tilePat <= TIP_SMEM_MAX; }
 
-size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int stackDepth)
+size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, int maxTips)
 {
     const size_t warps = (size_t)nCat * chunksPerTile;
-    size_t b = (size_t)stackDepth * warps * 32 * 4 * 8;   // partials stack
-    b += (size_t)stackDepth * warps * 32 * 4;             // exponent stack
-    b += 2ull * 2 * nCat * 16 * 8;                        // matrices, double buffered
-    b += 2ull * warps * 32 * 4;                           // exponent exchange, double buffered
-    b += warps * 8 + 64;
-    b = (b + 15) & ~size_t(15);
-    b += 2ull * OPS_BATCH * sizeof(Op);                   // op schedule, two half batches
-    return b;
+    const size_t tilePat = (size_t)chunksPerTile * 32 * R;
+    size_t b = (size_t)stackDepth * warps * R * 32 * 32;   // partials stack (two double2 planes)
+    b += (size_t)warps * MAT_RING * 2 * 16 * 8;            // per-warp matrix rings
+    b += 2ull * OPS_BATCH * sizeof(Op);                    // op schedule, two half batches
+    b += (size_t)stackDepth * warps * R * 32 * 2;          // exponent stack (int16)
+    b += warps * 8 + 16 * 8 + 16;                          // tile-sum scratch + the ones column
+    if (treewalk_tips_in_smem(maxTips, (int)tilePat)) b += (size_t)maxTips * tilePat;   // tip states of the tile
+    return (b + 15) & ~size_t(15);
 }
 
-// raw operand data of one op for this thread's (pattern, category), loaded one op ahead of its use
-struct Operand {
-    double x0, x1, x2, x3;
-    int aux;   // TIP: state; GLOBAL: cumulative exponent
-};
-
-__device__ __forceinline__ void fetch_operand(Operand &r, uint8_t kind, int off, const uint8_t *states, const double *partials,
-                                              const int16_t *cumExp, size_t nodeStride, int nPat, int c, int p)
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 {
-    if (kind == OPK_TIP) {
-        r.aux = states[(size_t)off * nPat + p];
-    } else if (kind == OPK_GLOBAL) {
-        ld256_nc(partials + (size_t)off * nodeStride + ((size_t)c * nPat + p) * 4, r.x0, r.x1, r.x2, r.x3);
-        r.aux = cumExp[(size_t)off * nPat + p];
-    }
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
 }
 
-template <bool EXACT>
-__device__ __forceinline__ void apply_operand(const Operand &r, uint8_t kind, int slot, const double *M, const double *stack,
-                                              const int *sexp, int warps, int myStack, double &s0, double &s1, double &s2,
-                                              double &s3, int &cum)
+// s[r][i] = sum_j M[i][j] a_r[j] for this thread's R patterns, folded into out (first operand: out = s, second: out *= s)
+template <bool EXACT, int R, bool FIRST>
+__device__ __forceinline__ void rows_times(const double *M, const double (&a)[R][4], double (&out)[R][4])
 {
-    if (kind == OPK_TIP) {
-        const int s = r.aux;
-        if (s < 4) { s0 = M[s]; s1 = M[4 + s]; s2 = M[8 + s]; s3 = M[12 + s]; }
-        else { s0 = s1 = s2 = s3 = 1.0; }
-        return;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double2 m01 = *reinterpret_cast<const double2 *>(M + i * 4);
+        const double2 m23 = *reinterpret_cast<const double2 *>(M + i * 4 + 2);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            double s;
+            if (EXACT)   // the reference's order, no fused multiply-add: ((m0 a0 + m1 a1) + m2 a2) + m3 a3
+                s = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m01.x, a[r][0]), __dmul_rn(m01.y, a[r][1])), __dmul_rn(m23.x, a[r][2])), __dmul_rn(m23.y, a[r][3]));
+            else
+                s = fma(m23.y, a[r][3], fma(m23.x, a[r][2], fma(m01.y, a[r][1], m01.x * a[r][0])));
+            out[r][i] = FIRST ? s : out[r][i] * s;
+        }
     }
-    double a0, a1, a2, a3;
-    if (kind == OPK_STACK) {
-        const double4 v = *reinterpret_cast<const double4 *>(stack + ((size_t)slot * warps * 32 + myStack) * 4);
-        a0 = v.x; a1 = v.y; a2 = v.z; a3 = v.w;
-        cum += sexp[slot * warps * 32 + myStack];
-    } else {
-        a0 = r.x0; a1 = r.x1; a2 = r.x2; a3 = r.x3;
-        cum += r.aux;
-    }
-    s0 = dot4<EXACT>(M, a0, a1, a2, a3); s1 = dot4<EXACT>(M + 4, a0, a1, a2, a3);
-    s2 = dot4<EXACT>(M + 8, a0, a1, a2, a3); s3 = dot4<EXACT>(M + 12, a0, a1, a2, a3);
 }
 
-template <bool EXACT, int MAXT>
-__global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 3 : 1)) k_treewalk(WalkArgs A)
+template <bool EXACT, int R, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
 {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int tile = blockIdx.x;
@@ -113,26 +111,34 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 3 : 1)) k_treewalk(WalkAr
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int c = w % C, chunk = w / C;
     const int nPat = d.nPat;
-    const int p = (tile - d.tileBase) * (chunks * 32) + chunk * 32 + lane;
-    const bool valid = p < nPat;
+    const int tilePat = chunks * 32 * R;
+    const int p0 = (tile - d.tileBase) * tilePat;
+    const int pbase = p0 + chunk * 32 * R + lane;   // pattern r of this thread: pbase + 32 r
+    const bool tipsInSmem = A.tipsInSmem != 0;
+    const bool incremental = nOps < d.nInt;         // only then can operands be clean nodes resident in HBM
 
-    double *stack = reinterpret_cast<double *>(smem_raw);                          // [depth][warps][32][4]
-    int *sexp = reinterpret_cast<int *>(stack + (size_t)depth * warps * 128);      // [depth][warps][32]
-    double *smat = reinterpret_cast<double *>(sexp + (size_t)depth * warps * 32);  // [2][2][C][16]
-    int *smax = reinterpret_cast<int *>(smat + 2 * 2 * C * 16);                    // [2][warps][32]
-    double *sred = reinterpret_cast<double *>(smax + 2 * warps * 32);              // [warps]
-    Op *sops = reinterpret_cast<Op *>((reinterpret_cast<uintptr_t>(sred + warps) + 8 + 15) & ~uintptr_t(15));   // [2][OPS_BATCH]
+    // shared memory carve-up
+    double2 *stLo = reinterpret_cast<double2 *>(smem_raw);                      // [depth][warps][R][32] states 0,1
+    double2 *stHi = stLo + (size_t)depth * warps * R * 32;                      //                       states 2,3
+    double *ring = reinterpret_cast<double *>(stHi + (size_t)depth * warps * R * 32);   // [warps][MAT_RING][2][16]
+    Op *sops = reinterpret_cast<Op *>(ring + (size_t)warps * MAT_RING * 32);    // [2 * OPS_BATCH]
+    int16_t *sexp = reinterpret_cast<int16_t *>(sops + 2 * OPS_BATCH);          // [depth][warps][R][32]
+    double *sred = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(sexp + (size_t)depth * warps * R * 32) + 7) & ~uintptr_t(7));
+    double *sones = sred + warps;                                               // 16 x 1.0: the "column" of a missing tip state
+    uint8_t *sstate = reinterpret_cast<uint8_t *>(sones + 16);                  // [nTips][tilePat]
 
     const Op *ops = A.ops + d.opBase;
-    const double *mats = A.mats + d.matBase;
+    const double *matsL = A.mats + d.matBase + c * 16 + (lane & 15);   // this lane's 8-byte piece of this warp's category
     const uint8_t *states = A.tipStates + d.stateBase;
-    const size_t nodeStride = (size_t)C * nPat * 4;
-    double *partials = A.partials + d.partBase;
-    int16_t *cumExp = A.cumExp + d.expBase;
-    const int myStack = (w * 32 + lane);
-    const int nMat = 32 * C;   // 2 matrices x C x 16 doubles, one per staging thread
-    const bool stager = tid < nMat;
-    const int mWhich = tid >= 16 * C, mR = tid - mWhich * 16 * C;
+    double *partials = A.partials + d.partBase + ((size_t)c * nPat + pbase) * 4;   // + idx*4 (+ r*128)
+    int16_t *cumExp = A.cumExp + d.expBase + (size_t)c * nPat + pbase;              // + idx   (+ r*32)
+    double *myRing = ring + (size_t)w * MAT_RING * 32;
+    const uint8_t *myState = sstate + chunk * 32 * R + lane;
+    const int stackIdx = w * R * 32 + lane;                 // + slot*slotStride + r*32
+    const int slotStride = warps * R * 32;
+    bool valid[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) valid[r] = pbase + 32 * r < nPat;
 
     auto load_batch = [&](int b) {
         const int first = b * OPS_BATCH, cnt = min(OPS_BATCH, nOps - first);
@@ -140,115 +146,172 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 3 : 1)) k_treewalk(WalkAr
         int4 *dst = reinterpret_cast<int4 *>(sops + (b & 1) * OPS_BATCH);
         for (int t = tid; t < cnt * 2; t += blockDim.x) dst[t] = src[t];
     };
+    // this warp's two 4x4 matrices of op k -> ring slot k % MAT_RING, asynchronously (32 lanes x 8 bytes)
+    auto issue_mats = [&](int k) {
+        if (k < nOps) {
+            const Op &q = sops[k & (2 * OPS_BATCH - 1)];
+            cp_async8(myRing + (k & (MAT_RING - 1)) * 32 + lane, matsL + (lane < 16 ? q.mA : q.mB));
+        }
+        cp_async_commit();
+    };
+
     load_batch(0);
-    __syncthreads();
-
-    // software pipeline: while op k is computed, op k+1's matrices, tip states and clean-child partials are in flight
-    Op o = sops[0];
-    double mreg = 0.0;
-    Operand pa, pb;
-    pa.x0 = pa.x1 = pa.x2 = pa.x3 = 0.0; pa.aux = 0; pb = pa;
-    if (stager) mreg = mats[(size_t)(mWhich ? o.mB : o.mA) * C * 16 + mR];
-    if (valid) {
-        fetch_operand(pa, o.aKind, o.aOff, states, partials, cumExp, nodeStride, nPat, c, p);
-        fetch_operand(pb, o.bKind, o.bOff, states, partials, cumExp, nodeStride, nPat, c, p);
+    if (tid < 16) sones[tid] = 1.0;
+    if (tipsInSmem) {   // the tile's tip states, all tips: one burst of independent loads instead of one per op
+        const int total = d.nTips * tilePat;
+        for (int idx = tid; idx < total; idx += blockDim.x) {
+            const int t = idx / tilePat, pp = idx - t * tilePat;
+            sstate[idx] = (p0 + pp < nPat) ? states[(size_t)t * nPat + p0 + pp] : (uint8_t)4;
+        }
     }
-    for (int k = 0; k < nOps; k++) {
-        const int par = k & 1;
-        double *sm = smat + par * (2 * C * 16);
-        if (stager) sm[tid] = mreg;
-        if (k + 1 < nOps && (k + 1) % OPS_BATCH == 0) load_batch((k + 1) / OPS_BATCH);   // other half: its ops are all consumed
-        __syncthreads();
+    __syncthreads();
+    for (int j = 0; j < MAT_RING - 1; j++) issue_mats(j);
 
-        Op on = o;
-        Operand na = pa, nb = pb;
-        if (k + 1 < nOps) {
-            on = sops[(((k + 1) / OPS_BATCH) & 1) * OPS_BATCH + (k + 1) % OPS_BATCH];
-            if (stager) mreg = mats[(size_t)(mWhich ? on.mB : on.mA) * C * 16 + mR];
-            if (valid) {
-                fetch_operand(na, on.aKind, on.aOff, states, partials, cumExp, nodeStride, nPat, c, p);
-                fetch_operand(nb, on.bKind, on.bOff, states, partials, cumExp, nodeStride, nPat, c, p);
+    for (int k = 0; k < nOps; k++) {
+        if ((k & (OPS_BATCH - 1)) == OPS_BATCH / 2 && (k / OPS_BATCH + 1) * OPS_BATCH < nOps) {
+            __syncthreads();                       // every warp has left the previous batch's half
+            load_batch(k / OPS_BATCH + 1);
+            __syncthreads();
+        }
+        cp_async_wait<MAT_RING - 2>();             // this lane's pieces of op k's matrices have landed
+        __syncwarp();                              // ... and the other lanes'; the warp is also done with op k-1
+        issue_mats(k + MAT_RING - 1);              // reuses the ring slot of op k-1
+        if (incremental && k + 2 < nOps) {         // clean children live in HBM: pull their sectors towards L2 two ops ahead
+            const Op &q = sops[(k + 2) & (2 * OPS_BATCH - 1)];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (q.aKind == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.aOff * 4 + r * 128);
+                if (q.bKind == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.bOff * 4 + r * 128);
             }
         }
 
-        double out0 = 0, out1 = 0, out2 = 0, out3 = 0;
-        int cum = 0;
-        if (valid) {
-            const double *M1 = sm + c * 16, *M2 = sm + (C + c) * 16;
-            double sa0, sa1, sa2, sa3, sb0, sb1, sb2_, sb3;
-            apply_operand<EXACT>(pa, o.aKind, o.aSlot, M1, stack, sexp, warps, myStack, sa0, sa1, sa2, sa3, cum);
-            apply_operand<EXACT>(pb, o.bKind, o.bSlot, M2, stack, sexp, warps, myStack, sb0, sb1, sb2_, sb3, cum);
-            out0 = sa0 * sb0; out1 = sa1 * sb1; out2 = sa2 * sb2_; out3 = sa3 * sb3;
+        const Op o = sops[k & (2 * OPS_BATCH - 1)];
+        const double *M1 = myRing + (k & (MAT_RING - 1)) * 32;
+        double out[R][4];
+        int cum[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) cum[r] = 0;
+
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const int kind = side ? o.bKind : o.aKind;
+            const int off = side ? o.bOff : o.aOff;
+            const double *M = M1 + side * 16;
+            if (kind == OPK_TIP) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int st = tipsInSmem ? myState[off * tilePat + 32 * r]
+                                              : (valid[r] ? states[(size_t)off * nPat + pbase + 32 * r] : 4);
+                    const double *col = (st < 4) ? (M + st) : sones;   // missing / ambiguous: factor 1
+                    if (side == 0) { out[r][0] = col[0]; out[r][1] = col[4]; out[r][2] = col[8]; out[r][3] = col[12]; }
+                    else { out[r][0] *= col[0]; out[r][1] *= col[4]; out[r][2] *= col[8]; out[r][3] *= col[12]; }
+                }
+            } else {
+                double a[R][4];
+                if (kind == OPK_STACK) {
+                    const int si0 = (side ? o.bSlot : o.aSlot) * slotStride + stackIdx;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const double2 lo = stLo[si0 + 32 * r], hi = stHi[si0 + 32 * r];
+                        a[r][0] = lo.x; a[r][1] = lo.y; a[r][2] = hi.x; a[r][3] = hi.y;
+                        cum[r] += sexp[si0 + 32 * r];
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0.0;
+                        if (valid[r]) {
+                            const double *src = partials + (size_t)off * 4 + r * 128;
+                            if (kind == OPK_GLOBAL) ld256_nc(src, a[r][0], a[r][1], a[r][2], a[r][3]);
+                            else ld256_coherent(src, a[r][0], a[r][1], a[r][2], a[r][3]);   // OPK_SPILL: written by this thread in this launch
+                            cum[r] += cumExp[(size_t)off + 32 * r];
+                        }
+                    }
+                }
+                if (side == 0) rows_times<EXACT, R, true>(M, a, out);
+                else rows_times<EXACT, R, false>(M, a, out);
+            }
         }
-        // exponent of the pattern's largest value over categories x states
-        const double m = fmax(fmax(out0, out1), fmax(out2, out3));
-        int field = (m > 0.0) ? ((__double2hiint(m) >> 20) & 0x7ff) : 1023;
-        if (C > 1) {
-            int *sx = smax + par * warps * 32;
-            sx[w * 32 + lane] = (m > 0.0) ? field : 0;
-            __syncthreads();
-            int best = 0;
-            for (int cc = 0; cc < C; cc++) best = max(best, sx[(chunk * C + cc) * 32 + lane]);
-            field = best > 0 ? best : 1023;
+
+        // ---- exact power-of-two rescale, store ----
+        double *dst = partials + (size_t)o.outOff * 4;
+        int16_t *dstE = cumExp + (size_t)o.outOff;
+        const bool toStack = o.outSlot < depth;
+        const int so0 = o.outSlot * slotStride + stackIdx;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            // partials are non-negative: the largest value has the largest high word; its exponent field is the scale
+            const int hmax = max(max(__double2hiint(out[r][0]), __double2hiint(out[r][1])), max(__double2hiint(out[r][2]), __double2hiint(out[r][3])));
+            int field = hmax >> 20;                                             // 0 for zero / denormal, >= 0x7ff for inf / nan
+            if (field <= 0 || field > 1023) field = 1023;                       // no scaling: nothing to scale / never scale down
+            const double scale = __hiloint2double((2046 - field) << 20, 0);     // 2^-(field-1023), exact
+            const double o0 = out[r][0] * scale, o1 = out[r][1] * scale, o2 = out[r][2] * scale, o3 = out[r][3] * scale;
+            const int ce = cum[r] + field - 1023;
+            if (toStack) {
+                stLo[so0 + 32 * r] = make_double2(o0, o1);
+                stHi[so0 + 32 * r] = make_double2(o2, o3);
+                sexp[so0 + 32 * r] = (int16_t)ce;
+            }
+            if (valid[r]) {
+                st256(dst + r * 128, o0, o1, o2, o3);
+                dstE[32 * r] = (int16_t)ce;
+            }
         }
-        if (field > 1023) field = 1023;   // never scale down (inf/nan guard)
-        const int e = field - 1023;       // <= 0
-        const double scale = __hiloint2double((1023 - e) << 20, 0);   // 2^-e, exact
-        out0 *= scale; out1 *= scale; out2 *= scale; out3 *= scale;
-        cum += e;
-        if (valid) {
-            *reinterpret_cast<double4 *>(stack + ((size_t)o.outSlot * warps * 32 + myStack) * 4) = make_double4(out0, out1, out2, out3);
-            sexp[o.outSlot * warps * 32 + myStack] = cum;
-            st256(partials + (size_t)o.outOff * nodeStride + ((size_t)c * nPat + p) * 4, out0, out1, out2, out3);
-            if (c == 0) cumExp[(size_t)o.outOff * nPat + p] = (int16_t)cum;
-        }
-        o = on; pa = na; pb = nb;
     }
+    cp_async_wait<0>();
     __syncthreads();
 
     // root: integratePartials over categories, (+pInv on constant patterns), frequencies, log, pattern weight
     double contrib = 0.0;
-    if (c == 0 && valid) {
+    if (c == 0) {
         const LocusParams *prm = &A.params[l];
         const double *freqs = (prm->substKind == 0) ? prm->subst + 1 : prm->subst + 36;
         const double *props = A.catProps + d.catBase;
-        const int cum = sexp[chunk * C * 32 + lane];   // slot 0
-        double acc[4];
-        {
-            const double4 v = *reinterpret_cast<const double4 *>(stack + ((size_t)(chunk * C) * 32 + lane) * 4);
-            const double pr = props[0];
-            acc[0] = v.x * pr; acc[1] = v.y * pr; acc[2] = v.z * pr; acc[3] = v.w * pr;
-        }
-        for (int cc = 1; cc < C; cc++) {
-            const double4 v = *reinterpret_cast<const double4 *>(stack + ((size_t)(chunk * C + cc) * 32 + lane) * 4);
-            const double pr = props[cc];
-            if (EXACT) {
-                acc[0] = __dadd_rn(acc[0], __dmul_rn(v.x, pr)); acc[1] = __dadd_rn(acc[1], __dmul_rn(v.y, pr));
-                acc[2] = __dadd_rn(acc[2], __dmul_rn(v.z, pr)); acc[3] = __dadd_rn(acc[3], __dmul_rn(v.w, pr));
-            } else {
-                acc[0] = fma(v.x, pr, acc[0]); acc[1] = fma(v.y, pr, acc[1]); acc[2] = fma(v.z, pr, acc[2]); acc[3] = fma(v.w, pr, acc[3]);
-            }
-        }
         const double pInv = prm->pInv;
-        const int mask = (pInv > 0.0) ? A.constMask[d.patBase + p] : 0;
-        double lk;
-        if (mask) {
-            // unscale first (underflow here is harmless: pInv dominates), then add pInv on the constant states
-            double sum = 0.0;
-            for (int s = 0; s < 4; s++) {
-                double v = ldexp(acc[s], cum);
-                if (mask & (1 << s)) v = __dadd_rn(v, pInv);
-                sum = __dadd_rn(sum, __dmul_rn(freqs[s], v));
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (!valid[r]) continue;
+            const int p = pbase + 32 * r;
+            // categories carry their own exponents: bring them to the largest one (exact)
+            int E = -32768;
+            for (int cc = 0; cc < C; cc++) E = max(E, (int)sexp[(chunk * C + cc) * R * 32 + 32 * r + lane]);
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int cc = 0; cc < C; cc++) {
+                const int si = (chunk * C + cc) * R * 32 + 32 * r + lane;   // slot 0 holds the root
+                const double2 lo = stLo[si], hi = stHi[si];
+                const int diff = (int)sexp[si] - E;                          // <= 0
+                const double f = (diff < -1022) ? 0.0 : __hiloint2double((1023 + diff) << 20, 0);
+                const double pr = props[cc];
+                const double v0 = lo.x * f, v1 = lo.y * f, v2 = hi.x * f, v3 = hi.y * f;
+                if (cc == 0) {
+                    acc[0] = v0 * pr; acc[1] = v1 * pr; acc[2] = v2 * pr; acc[3] = v3 * pr;
+                } else if (EXACT) {
+                    acc[0] = __dadd_rn(acc[0], __dmul_rn(v0, pr)); acc[1] = __dadd_rn(acc[1], __dmul_rn(v1, pr));
+                    acc[2] = __dadd_rn(acc[2], __dmul_rn(v2, pr)); acc[3] = __dadd_rn(acc[3], __dmul_rn(v3, pr));
+                } else {
+                    acc[0] = fma(v0, pr, acc[0]); acc[1] = fma(v1, pr, acc[1]); acc[2] = fma(v2, pr, acc[2]); acc[3] = fma(v3, pr, acc[3]);
+                }
             }
-            lk = log(sum);
-        } else {
-            double sum = 0.0;
-            for (int s = 0; s < 4; s++) sum = __dadd_rn(sum, __dmul_rn(freqs[s], acc[s]));
-            // 2^cum is exact, so when the unscaled value is representable this is the reference's log(sum) bit for bit
-            lk = (cum > -1000) ? log(ldexp(sum, cum)) : (log(sum) + cum * 0.6931471805599453);
+            const int mask = (pInv > 0.0) ? A.constMask[d.patBase + p] : 0;
+            double lk;
+            if (mask) {
+                // unscale first (underflow here is harmless: pInv dominates), then add pInv on the constant states
+                double sum = 0.0;
+                for (int s = 0; s < 4; s++) {
+                    double v = ldexp(acc[s], E);
+                    if (mask & (1 << s)) v = __dadd_rn(v, pInv);
+                    sum = __dadd_rn(sum, __dmul_rn(freqs[s], v));
+                }
+                lk = log(sum);
+            } else {
+                double sum = 0.0;
+                for (int s = 0; s < 4; s++) sum = __dadd_rn(sum, __dmul_rn(freqs[s], acc[s]));
+                // 2^E is exact, so when the unscaled value is representable this is the reference's log(sum) bit for bit
+                lk = (E > -1000) ? log(ldexp(sum, E)) : (log(sum) + E * 0.6931471805599453);
+            }
+            A.patLogL[d.patBase + p] = lk;
+            contrib += __dmul_rn(lk, (double)A.weights[d.patBase + p]);
         }
-        A.patLogL[d.patBase + p] = lk;
-        contrib = __dmul_rn(lk, (double)A.weights[d.patBase + p]);
     }
     // fixed-shape tile reduction (deterministic)
     for (int off = 16; off > 0; off >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, off);
@@ -261,27 +324,30 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 3 : 1)) k_treewalk(WalkAr
     }
 }
 
-template <bool EXACT, int MAXT>
+template <bool EXACT, int R, int MINB>
 static void launch_one(const WalkArgs &a, int nTiles, size_t smem, int threads, cudaStream_t st)
 {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(k_treewalk<EXACT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_treewalk<EXACT, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    k_treewalk<EXACT, MAXT><<<nTiles, threads, smem, st>>>(a);
+    k_treewalk<EXACT, R, MINB><<<nTiles, threads, smem, st>>>(a);
 }
 
 void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st)
 {
-    const size_t smem = treewalk_smem_bytes(a.nCat, a.chunksPerTile, a.stackDepth);
+    const size_t smem = treewalk_smem_bytes(a.nCat, a.chunksPerTile, a.patPerThread, a.stackDepth, a.maxTips);
     const int threads = 32 * a.nCat * a.chunksPerTile;
-    if (threads <= 256) {
-        if (exact) launch_one<true, 256>(a, nTiles, smem, threads, st);
-        else launch_one<false, 256>(a, nTiles, smem, threads, st);
-    } else {   // more than 8 rate categories: register-capped variant
-        if (exact) launch_one<true, 1024>(a, nTiles, smem, threads, st);
-        else launch_one<false, 1024>(a, nTiles, smem, threads, st);
+    if (a.patPerThread == 1) {
+        if (exact) launch_one<true, 1, 4>(a, nTiles, smem, threads, st);
+        else launch_one<false, 1, 4>(a, nTiles, smem, threads, st);
+    } else if (a.patPerThread == 2) {
+        if (exact) launch_one<true, 2, 2>(a, nTiles, smem, threads, st);
+        else launch_one<false, 2, 2>(a, nTiles, smem, threads, st);
+    } else {
+        if (exact) launch_one<true, 4, 1>(a, nTiles, smem, threads, st);
+        else launch_one<false, 4, 1>(a, nTiles, smem, threads, st);
     }
 }
 

@@ -253,7 +253,7 @@ class Engine:
     def partials(self, locus: int, node: int):
         nt, npat, nc = self._loci_shape[locus]
         p = np.zeros((nc, npat, 4))
-        ex = np.zeros(npat, np.int32)
+        ex = np.zeros((nc, npat), np.int32)
         self._ck(self._L.sb2_get_partials(self._h, locus, node, p.ctypes.data, ex.ctypes.data))
         return p, ex
 

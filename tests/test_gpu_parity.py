@@ -172,7 +172,7 @@ def test_exact_mode_partials_bit_identical(name, kw):
                     out = out * acc
             parts[node] = out
             p, ex = e.partials(l, node)
-            np.testing.assert_array_equal(np.ldexp(p, ex[None, :, None]), out)
+            np.testing.assert_array_equal(np.ldexp(p, ex[:, :, None]), out)
 
 
 def test_deep_tree_rescaling():
@@ -233,3 +233,39 @@ def test_ragged_loci_and_tiny_shapes():
     got = Engine.from_problem(pb).eval_posterior()
     assert rel_close(got.per_locus_lik, want.per_locus_lik) and rel_close(got.per_locus_coal, want.per_locus_coal)
     assert rel_close(got.total, want.total)
+
+
+@pytest.mark.parametrize("env", [
+    {"SB2_STACK_DEPTH": "1"},                                   # every second operand spills to its global buffer
+    {"SB2_PATTERNS_PER_THREAD": "2"},
+    {"SB2_PATTERNS_PER_THREAD": "4", "SB2_STACK_DEPTH": "2"},
+    {"SB2_PATTERNS_PER_THREAD": "2", "SB2_CHUNKS_PER_TILE": "2"},
+    {"SB2_PATTERNS_PER_THREAD": "1", "SB2_CHUNKS_PER_TILE": "1"},
+])
+@pytest.mark.parametrize("name,kw", [("C2", dict(n_loci=4, n_sites=333)), ("C5", dict(n_loci=3, n_sites=150))])
+def test_kernel_geometries_agree_bitwise(env, name, kw, monkeypatch):
+    """Launch geometry (patterns per thread, chunks per CTA, shared-memory stack depth / spills) never changes a bit."""
+    pb = synth.make_problem(name, missing_frac=0.03, **kw)
+    e0 = Engine.from_problem(pb)
+    base = e0.eval_posterior()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    e = Engine.from_problem(pb)
+    got = e.eval_posterior()
+    for l in range(pb.n_loci):   # per-pattern values are bit-identical; only the tile-sum grouping follows the tiling
+        assert np.array_equal(e.pattern_logl(l), e0.pattern_logl(l))
+    assert rel_close(got.per_locus_lik, base.per_locus_lik, rel=1e-13)
+    want = oracle.posterior(pb)
+    assert rel_close(got.per_locus_lik, want.per_locus_lik)
+    # incremental path with spills / multi-pattern threads
+    rng = np.random.default_rng(4)
+    for _ in range(4):
+        l = int(rng.integers(0, pb.n_loci))
+        e.store()
+        pb.loci[l].tree, _ = synth.perturb_gene_tree(rng, pb.loci[l].tree, pb.loci[l].n_tips)
+        e.set_gene_tree(l, pb.loci[l].tree)
+        got = e.eval_posterior()
+        want = oracle.posterior(pb)
+        ok = np.isfinite(want.per_locus_coal)
+        assert rel_close(got.per_locus_lik[ok], want.per_locus_lik[ok])
+        e.accept()
