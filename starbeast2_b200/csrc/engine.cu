@@ -57,7 +57,7 @@ struct sb2_engine {
     uint8_t *dStates = nullptr, *dConstMask = nullptr;
     int32_t *dWeights = nullptr, *dTipSpecies = nullptr, *dTileLocus = nullptr;
     // big dynamic device data
-    double *dPartials = nullptr, *dMats = nullptr, *dPatLogL = nullptr, *dTileSum = nullptr;
+    double *dPartials = nullptr, *dMats = nullptr, *dOpMats = nullptr, *dPatLogL = nullptr, *dTileSum = nullptr;
     int16_t *dCumExp = nullptr;
     Op *dOps = nullptr;
     int32_t *dNOps = nullptr;
@@ -260,7 +260,7 @@ int do_prepare(sb2_engine *e)
     PrepareArgs a;
     a.loci = e->dLoci; a.params = e->dParams; a.flags = e->dFlags; a.inTree = e->dInTree; a.tipSpecies = e->dTipSpecies;
     a.catRates = e->dCat; a.explicitRates = e->dExplicit ? e->dExplicit : e->dCat;
-    a.cur = cur(e); a.stored = stored(e); a.ops = e->dOps; a.nOps = e->dNOps; a.mats = e->dMats;
+    a.cur = cur(e); a.stored = stored(e); a.ops = e->dOps; a.nOps = e->dNOps; a.mats = e->dMats; a.opMats = e->dOpMats;
     a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L; a.stackDepth = e->stackDepth;
     launch_prepare(a, e->maxNodes, st);
     e->launches++;
@@ -282,7 +282,7 @@ int do_walk(sb2_engine *e)
     WalkArgs a;
     a.loci = e->dLoci; a.params = e->dParams; a.tileLocus = e->dTileLocus; a.ops = e->dOps; a.nOps = e->dNOps;
     a.tipStates = e->dStates; a.weights = e->dWeights; a.constMask = e->dConstMask; a.catProps = e->dCat + e->totalCat;
-    a.mats = e->dMats; a.partials = e->dPartials; a.cumExp = e->dCumExp; a.patLogL = e->dPatLogL; a.tileSum = e->dTileSum;
+    a.opMats = e->dOpMats; a.partials = e->dPartials; a.cumExp = e->dCumExp; a.patLogL = e->dPatLogL; a.tileSum = e->dTileSum;
     a.nCat = e->nCat; a.chunksPerTile = e->chunksPerTile; a.patPerThread = e->patPerThread; a.stackDepth = e->stackDepth;
     a.maxTips = (e->maxNodes + 1) / 2;
     a.tipsInSmem = treewalk_tips_in_smem(a.maxTips, 32 * e->chunksPerTile * e->patPerThread) ? 1 : 0;
@@ -441,7 +441,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     e->totalInt = opBase; e->inTreeBytes = treeOff;
     if (prepare_smem_bytes(e->maxNodes, e->S) > 227 * 1024) return e->fail(SB2_ERR_ARG, "gene tree too large for the per-locus shared-memory kernel");
     e->stackDepth = std::min(e->stackDepth, 4);   // deeper (rare) results are re-read from their global buffer (OPK_SPILL)
-    if (const char *v = getenv("SB2_STACK_DEPTH")) e->stackDepth = std::max(1, atoi(v));
+    if (const char *v = getenv("SB2_STACK_DEPTH")) e->stackDepth = std::min(15, std::max(1, atoi(v)));
     if (treewalk_smem_bytes(e->nCat, e->chunksPerTile, e->patPerThread, e->stackDepth, (e->maxNodes + 1) / 2) > 227 * 1024)
         return e->fail(SB2_ERR_ARG, "pruning stack does not fit shared memory");
 
@@ -480,6 +480,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if ((rc = dev_alloc(e, &e->dPatLogL, (size_t)patBase))) return rc;
     if ((rc = dev_alloc(e, &e->dTileSum, (size_t)tileBase))) return rc;
     if ((rc = dev_alloc(e, &e->dOps, (size_t)opBase))) return rc;
+    if ((rc = dev_alloc(e, &e->dOpMats, (size_t)opBase * e->nCat * 32))) return rc;
     if ((rc = dev_alloc(e, &e->dNOps, L))) return rc;
     CUDA_TRY(e, cudaMemset(e->dNOps, 0, sizeof(int32_t) * L));
     CUDA_TRY(e, cudaMemset(e->dCumExp, 0, sizeof(int16_t) * (size_t)std::max<int64_t>(expBase, 1)));

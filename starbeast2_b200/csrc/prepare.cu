@@ -393,49 +393,75 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
             a = p;
         }
         const int pos = start + s.cnt[i] - 1;
+        s.assign[i] = pos;   // geneNodeSpeciesAssignment is already written back: reuse as the node's schedule position
         const int newP = 1 - A.stored.curP[nb + i];                      // setNodePartialsForUpdate
         A.cur.curP[nb + i] = (uint8_t)newP;
         const int Lc = s.gL[i], Rc = s.gR[i];
         const bool dl = Lc >= nT && s.dirty[Lc], dr = Rc >= nT && s.dirty[Rc];
         const int first = (dl && dr) ? ((s.cnt[Rc] > s.cnt[Lc]) ? Rc : Lc) : (dl ? Lc : Rc);
-        Op o;
-        const int cp = C * d.nPat;   // (pattern, category) elements per node buffer
-        o.outOff = (newP * nI + (i - nT)) * cp;
-        o.outSlot = (uint8_t)min(base, 255);
-        o.node = i;
-        o.pad[0] = o.pad[1] = o.pad[2] = 0;
-        auto operand = [&](int c, bool cd, int32_t &off, uint8_t &kind, uint8_t &slot) {
-            slot = 0;
+        const unsigned cp = (unsigned)C * d.nPat;   // (pattern, category) elements per node buffer
+        // the child evaluated last (the second of two dirty children, or the only dirty one) is consumed straight from
+        // registers; only a first-evaluated child is parked: in stack slot `base`, or, beyond the shared-memory stack, in
+        // its own global buffer
+        auto operand = [&](int c, bool cd, uint32_t &off, unsigned &kind, unsigned &slot) {
+            slot = 0; off = 0;
             if (c < nT) { kind = OPK_TIP; off = c; }
             else if (cd) {
-                const int sl = (c == first) ? base : base + 1;
-                if (sl < A.stackDepth) { kind = OPK_STACK; off = 0; slot = (uint8_t)sl; }
+                if (!(dl && dr && c == first)) { kind = OPK_PREV; }
+                else if (base < A.stackDepth) { kind = OPK_STACK; slot = base; }
                 else { kind = OPK_SPILL; off = ((1 - A.stored.curP[nb + c]) * nI + (c - nT)) * cp; }   // the buffer the child is being written to
             }
             else { kind = OPK_GLOBAL; off = (A.cur.curP[nb + c] * nI + (c - nT)) * cp; }
         };
-        operand(Lc, dl, o.aOff, o.aKind, o.aSlot);
-        operand(Rc, dr, o.bOff, o.bKind, o.bSlot);
-        o.mA = (A.cur.curM[nb + Lc] * G + Lc) * C * 16;
-        o.mB = (A.cur.curM[nb + Rc] * G + Rc) * C * 16;
+        Op o;
+        unsigned aKind, bKind, aSlot, bSlot;
+        o.outOff = (newP * nI + (i - nT)) * cp;
+        operand(Lc, dl, o.aOff, aKind, aSlot);
+        operand(Rc, dr, o.bOff, bKind, bSlot);
+        // is this node itself parked?  yes iff it is the first-evaluated child of a parent with two dirty children
+        // (then its slot is the parent's base == its own base); the root parks in slot 0 for the category combine
+        unsigned outSlot = OP_NO_SLOT;
+        const int par = s.gP[i];
+        if (par < 0) outSlot = 0;
+        else {
+            const int pl = s.gL[par], pr = s.gR[par];
+            const bool pdl = pl >= nT && s.dirty[pl], pdr = pr >= nT && s.dirty[pr];
+            if (pdl && pdr && i == ((s.cnt[pr] > s.cnt[pl]) ? pr : pl) && base < A.stackDepth) outSlot = base;
+        }
+        o.ctl = op_ctl(aKind, bKind, aSlot, bSlot, outSlot);
         A.ops[d.opBase + pos] = o;
     }
+    __syncthreads();
 
-    // ---- 5. transition matrices of the dirty branches -----------------------------------------------------------------
+    // ---- 5. transition matrices: recompute the dirty branches; stream every scheduled op's pair in op order ----------------
     HkyTabs tabs;
     const int substKind = prm->substKind;
     if (substKind == 0) hky_setup(prm->subst, tabs);
     for (int idx = tid; idx < G * C; idx += nt) {
         const int i = idx / C, c = idx - i * C;
-        if (!s.matDirty[i]) continue;
-        const double jointBranchRate = A.catRates[d.catBase + c] * s.rate[i];   // siteModel.getRateForCategory * branchRate
-        const double distance = (s.gH[s.gP[i]] - s.gH[i]) * jointBranchRate;
+        const int par = s.gP[i];
+        if (par < 0) continue;
+        const bool md = s.matDirty[i], used = s.dirty[par];   // used: the parent's op reads this matrix
+        if (!md && !used) continue;
+        double *store = A.mats + d.matBase + ((size_t)(A.cur.curM[nb + i] * G + i) * C + c) * 16;
         double m[16];
-        if (substKind == 0) hky_matrix(tabs, distance, m);
-        else eigen_matrix(prm->subst, distance, m);
-        double *dst = A.mats + d.matBase + ((size_t)(A.cur.curM[nb + i] * G + i) * C + c) * 16;
+        if (md) {
+            const double jointBranchRate = A.catRates[d.catBase + c] * s.rate[i];   // siteModel.getRateForCategory * branchRate
+            const double distance = (s.gH[par] - s.gH[i]) * jointBranchRate;
+            if (substKind == 0) hky_matrix(tabs, distance, m);
+            else eigen_matrix(prm->subst, distance, m);
 #pragma unroll
-        for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(dst + q) = make_double2(m[q], m[q + 1]);
+            for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(store + q) = make_double2(m[q], m[q + 1]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 16; q += 2) { const double2 v = *reinterpret_cast<const double2 *>(store + q); m[q] = v.x; m[q + 1] = v.y; }
+        }
+        if (used) {   // [op][category][side][16]: the pruning kernel's warp (one category) reads 256 contiguous bytes per op
+            const int side = (s.gR[par] == i) ? 1 : 0;
+            double *dst = A.opMats + (((size_t)(d.opBase + s.assign[par]) * C + c) * 2 + side) * 16;
+#pragma unroll
+            for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(dst + q) = make_double2(m[q], m[q + 1]);
+        }
     }
 }
 

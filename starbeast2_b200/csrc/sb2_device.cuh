@@ -8,6 +8,7 @@
 //   mats        f64 [locus][buf][node][cat][16]                P = exp(Q d) per branch x category
 //   StateBlock (x2: current / stored)  small per-node and per-locus state, see below
 //   ops         Op  [locus][internal node]                      post-order pruning schedule built on device
+//   opMats      f64 [locus][op][cat][side][16]                  the scheduled ops' matrix pairs, in schedule order
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -53,23 +54,26 @@ enum : uint8_t {
 };
 
 // operand kinds of a pruning op
-// TIP: tip states; STACK: shared-memory stack slot; GLOBAL: clean node, partials resident in HBM from an earlier
-// evaluation; SPILL: dirty node whose stack slot is deeper than the shared-memory stack -> re-read from the global
-// buffer this launch has just written
-enum : uint8_t { OPK_TIP = 0, OPK_STACK = 1, OPK_GLOBAL = 2, OPK_SPILL = 3 };
+// TIP: tip states; PREV: the result of the previous op of the walk, still in registers (every result is consumed
+// exactly once, by its parent, and in post-order the parent follows its last-evaluated child immediately);
+// STACK: a result parked in the shared-memory stack (the first-evaluated child of a node with two dirty children);
+// GLOBAL: clean node, partials resident in HBM from an earlier evaluation; SPILL: parked result whose slot is deeper
+// than the shared-memory stack -> re-read from the global buffer this launch has just written
+enum : uint8_t { OPK_TIP = 0, OPK_STACK = 1, OPK_GLOBAL = 2, OPK_SPILL = 3, OPK_PREV = 4 };
+constexpr unsigned OP_NO_SLOT = 255;   // outSlot: result is not parked (forwarded in registers, or spilled)
 
 struct __align__(16) Op {
     // offsets are pre-multiplied by k_prepare so that the pruning kernel needs one IMAD.WIDE per address:
-    int32_t outOff;   // (buf*nInt + internal index) * nCat*nPat   -> (pattern, category) element of the output
-    int32_t aOff;     // TIP: tip index; GLOBAL / SPILL: (buf*nInt + internal index) * nCat*nPat
-    int32_t bOff;
-    int32_t mA;       // (buf*nNodes + node) * nCat*16             -> mats of the branch above operand a (doubles)
-    int32_t mB;
-    uint8_t aKind, bKind, outSlot, aSlot;
-    uint8_t bSlot, pad[3];
-    int32_t node;     // node number (debug / root test)
+    uint32_t outOff;  // (buf*nInt + internal index) * nCat*nPat   -> (pattern, category) element of the output
+    uint32_t aOff;    // TIP: tip index; GLOBAL / SPILL: (buf*nInt + internal index) * nCat*nPat
+    uint32_t bOff;
+    uint32_t ctl;     // bits 0-2 aKind, 3-5 bKind, 6-9 aSlot, 10-13 bSlot, 14-21 outSlot (>= stack depth: not parked)
 };
-static_assert(sizeof(Op) == 32, "Op must stay 32 bytes");
+static_assert(sizeof(Op) == 16, "Op must stay 16 bytes (one LDS.128)");
+__host__ __device__ inline uint32_t op_ctl(unsigned aKind, unsigned bKind, unsigned aSlot, unsigned bSlot, unsigned outSlot)
+{
+    return aKind | (bKind << 3) | (aSlot << 6) | (bSlot << 10) | (outSlot << 14);
+}
 
 // Double-buffered small state (current / stored).  restore() swaps the two blocks, store() copies cur->stored.
 struct StateBlock {
@@ -109,6 +113,7 @@ struct PrepareArgs {
     Op *ops;
     int32_t *nOps;               // [nLoci]
     double *mats;
+    double *opMats;              // [op][category][side][16]: each scheduled op's two matrices, in schedule order
     int32_t S, nSpeciesLeaves, popKind, nLoci;
     int32_t stackDepth;          // shared-memory stack slots of k_treewalk
 };
@@ -123,7 +128,7 @@ struct WalkArgs {
     const int32_t *weights;
     const uint8_t *constMask;
     const double *catProps;
-    const double *mats;
+    const double *opMats;
     double *partials;
     int16_t *cumExp;
     double *patLogL;             // by pattern

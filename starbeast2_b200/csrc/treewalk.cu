@@ -14,6 +14,10 @@
 // (256-bit non-allocating loads).  HBM traffic of a full evaluation is therefore partials written once + tip
 // states + exponents, instead of write + two re-reads per node.
 //
+// Forwarding: every result is consumed exactly once, by its parent; in post-order the parent follows its
+// last-evaluated child immediately, so that operand is taken from registers (OPK_PREV) and only the first-evaluated
+// child of a node with two dirty children is parked in the shared-memory stack.
+//
 // Thread mapping: a warp owns 32*R consecutive patterns of ONE rate category, a thread R of them (stride 32, so
 // every global / shared access is coalesced / conflict free).  Warps never wait for each other inside the walk:
 // each warp streams its own category's transition matrices through a private cp.async ring, the op schedule and
@@ -24,6 +28,7 @@
 // independent of the update history.  The cumulative exponent of a subtree is stored as int16 next to the
 // partials; categories are brought to a common exponent only at the root.
 #include <math.h>
+#include <stdlib.h>
 
 #include "sb2_device.cuh"
 
@@ -38,7 +43,7 @@ __device__ __forceinline__ void st256(double *p, double a, double b, double c, d
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
-constexpr int OPS_BATCH = 32;   // ops staged in shared memory per half batch
+constexpr int OPS_BATCH = 64;   // ops staged in shared memory per half batch
 constexpr int MAT_RING = 4;     // transition-matrix pairs in flight per warp (cp.async ring)
 constexpr int TIP_SMEM_MAX = 48 * 1024;
 
@@ -66,7 +71,7 @@ size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, i
     b += (size_t)warps * MAT_RING * 2 * 16 * 8;            // per-warp matrix rings
     b += 2ull * OPS_BATCH * sizeof(Op);                    // op schedule, two half batches
     b += (size_t)stackDepth * warps * R * 32 * 2;          // exponent stack (int16)
-    b += warps * 8 + 16 * 8 + 16;                          // tile-sum scratch + the ones column
+    b += ((warps + 1) & ~size_t(1)) * 8 + 16 * 8;          // tile-sum scratch + the ones column
     if (treewalk_tips_in_smem(maxTips, (int)tilePat)) b += (size_t)maxTips * tilePat;   // tip states of the tile
     return (b + 15) & ~size_t(15);
 }
@@ -117,25 +122,26 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     const bool tipsInSmem = A.tipsInSmem != 0;
     const bool incremental = nOps < d.nInt;         // only then can operands be clean nodes resident in HBM
 
-    // shared memory carve-up
-    double2 *stLo = reinterpret_cast<double2 *>(smem_raw);                      // [depth][warps][R][32] states 0,1
-    double2 *stHi = stLo + (size_t)depth * warps * R * 32;                      //                       states 2,3
-    double *ring = reinterpret_cast<double *>(stHi + (size_t)depth * warps * R * 32);   // [warps][MAT_RING][2][16]
-    Op *sops = reinterpret_cast<Op *>(ring + (size_t)warps * MAT_RING * 32);    // [2 * OPS_BATCH]
+    // shared memory carve-up; everything is addressed as an index off one of these bases so that the compiler keeps
+    // the accesses in the shared window (LDS/STS), never generic
+    double2 *st2 = reinterpret_cast<double2 *>(smem_raw);                       // stack: [2 planes][depth][warps][R][32] double2
+    const int planeStride = depth * warps * R * 32;                             //        plane 0 = states 0,1; plane 1 = states 2,3
+    double *smd = reinterpret_cast<double *>(st2 + 2 * planeStride);            // ring [warps][MAT_RING][32] | ones[16] | sred[warps]
+    const int onesIdx = warps * MAT_RING * 32, sredIdx = onesIdx + 16;
+    Op *sops = reinterpret_cast<Op *>(smd + sredIdx + ((warps + 1) & ~1));      // [2 * OPS_BATCH]
     int16_t *sexp = reinterpret_cast<int16_t *>(sops + 2 * OPS_BATCH);          // [depth][warps][R][32]
-    double *sred = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(sexp + (size_t)depth * warps * R * 32) + 7) & ~uintptr_t(7));
-    double *sones = sred + warps;                                               // 16 x 1.0: the "column" of a missing tip state
-    uint8_t *sstate = reinterpret_cast<uint8_t *>(sones + 16);                  // [nTips][tilePat]
+    uint8_t *sstate = reinterpret_cast<uint8_t *>(sexp + planeStride);          // [nTips][tilePat]
 
     const Op *ops = A.ops + d.opBase;
-    const double *matsL = A.mats + d.matBase + c * 16 + (lane & 15);   // this lane's 8-byte piece of this warp's category
+    const double *matStream = A.opMats + ((size_t)d.opBase * C + c) * 32 + lane;   // + k * C*32: this lane's 8 bytes of op k's pair
     const uint8_t *states = A.tipStates + d.stateBase;
     double *partials = A.partials + d.partBase + ((size_t)c * nPat + pbase) * 4;   // + idx*4 (+ r*128)
     int16_t *cumExp = A.cumExp + d.expBase + (size_t)c * nPat + pbase;              // + idx   (+ r*32)
-    double *myRing = ring + (size_t)w * MAT_RING * 32;
-    const uint8_t *myState = sstate + chunk * 32 * R + lane;
+    const int ringIdx = w * MAT_RING * 32;
+    const int stateIdx = chunk * 32 * R + lane;
     const int stackIdx = w * R * 32 + lane;                 // + slot*slotStride + r*32
     const int slotStride = warps * R * 32;
+    const int matStride = C * 32;
     bool valid[R];
 #pragma unroll
     for (int r = 0; r < R; r++) valid[r] = pbase + 32 * r < nPat;
@@ -144,19 +150,21 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
         const int first = b * OPS_BATCH, cnt = min(OPS_BATCH, nOps - first);
         const int4 *src = reinterpret_cast<const int4 *>(ops + first);
         int4 *dst = reinterpret_cast<int4 *>(sops + (b & 1) * OPS_BATCH);
-        for (int t = tid; t < cnt * 2; t += blockDim.x) dst[t] = src[t];
+        for (int t = tid; t < cnt; t += blockDim.x) dst[t] = src[t];
     };
-    // this warp's two 4x4 matrices of op k -> ring slot k % MAT_RING, asynchronously (32 lanes x 8 bytes)
+    // this warp's matrix pair of op k (256 contiguous bytes of the op-ordered stream) -> ring slot k % MAT_RING
     auto issue_mats = [&](int k) {
-        if (k < nOps) {
-            const Op &q = sops[k & (2 * OPS_BATCH - 1)];
-            cp_async8(myRing + (k & (MAT_RING - 1)) * 32 + lane, matsL + (lane < 16 ? q.mA : q.mB));
-        }
+        if (k < nOps) cp_async8(smd + ringIdx + (k & (MAT_RING - 1)) * 32 + lane, matStream + (size_t)k * matStride);
         cp_async_commit();
     };
 
+    double prev[R][4];   // result of the previous op (scaled) and its cumulative exponent
+    int prevCum[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { prev[r][0] = prev[r][1] = prev[r][2] = prev[r][3] = 0.0; prevCum[r] = 0; }
+
     load_batch(0);
-    if (tid < 16) sones[tid] = 1.0;
+    if (tid < 16) smd[onesIdx + tid] = 1.0;
     if (tipsInSmem) {   // the tile's tip states, all tips: one burst of independent loads instead of one per op
         const int total = d.nTips * tilePat;
         for (int idx = tid; idx < total; idx += blockDim.x) {
@@ -164,8 +172,8 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
             sstate[idx] = (p0 + pp < nPat) ? states[(size_t)t * nPat + p0 + pp] : (uint8_t)4;
         }
     }
-    __syncthreads();
     for (int j = 0; j < MAT_RING - 1; j++) issue_mats(j);
+    __syncthreads();
 
     for (int k = 0; k < nOps; k++) {
         if ((k & (OPS_BATCH - 1)) == OPS_BATCH / 2 && (k / OPS_BATCH + 1) * OPS_BATCH < nOps) {
@@ -177,42 +185,50 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
         __syncwarp();                              // ... and the other lanes'; the warp is also done with op k-1
         issue_mats(k + MAT_RING - 1);              // reuses the ring slot of op k-1
         if (incremental && k + 2 < nOps) {         // clean children live in HBM: pull their sectors towards L2 two ops ahead
-            const Op &q = sops[(k + 2) & (2 * OPS_BATCH - 1)];
+            const Op q = sops[(k + 2) & (2 * OPS_BATCH - 1)];
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                if (q.aKind == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.aOff * 4 + r * 128);
-                if (q.bKind == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.bOff * 4 + r * 128);
+                if ((q.ctl & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.aOff * 4 + r * 128);
+                if (((q.ctl >> 3) & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.bOff * 4 + r * 128);
             }
         }
 
         const Op o = sops[k & (2 * OPS_BATCH - 1)];
-        const double *M1 = myRing + (k & (MAT_RING - 1)) * 32;
+        const int mIdx = ringIdx + (k & (MAT_RING - 1)) * 32;
         double out[R][4];
         int cum[R];
 #pragma unroll
         for (int r = 0; r < R; r++) cum[r] = 0;
+        bool usedPrev = false;
 
 #pragma unroll
         for (int side = 0; side < 2; side++) {
-            const int kind = side ? o.bKind : o.aKind;
-            const int off = side ? o.bOff : o.aOff;
-            const double *M = M1 + side * 16;
+            const unsigned kind = (o.ctl >> (3 * side)) & 7;
+            const unsigned off = side ? o.bOff : o.aOff;
+            const int m = mIdx + side * 16;
             if (kind == OPK_TIP) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const int st = tipsInSmem ? myState[off * tilePat + 32 * r]
+                    const int st = tipsInSmem ? sstate[off * tilePat + stateIdx + 32 * r]
                                               : (valid[r] ? states[(size_t)off * nPat + pbase + 32 * r] : 4);
-                    const double *col = (st < 4) ? (M + st) : sones;   // missing / ambiguous: factor 1
-                    if (side == 0) { out[r][0] = col[0]; out[r][1] = col[4]; out[r][2] = col[8]; out[r][3] = col[12]; }
-                    else { out[r][0] *= col[0]; out[r][1] *= col[4]; out[r][2] *= col[8]; out[r][3] *= col[12]; }
+                    const int col = (st < 4) ? (m + st) : onesIdx;   // missing / ambiguous: factor 1
+                    if (side == 0) { out[r][0] = smd[col]; out[r][1] = smd[col + 4]; out[r][2] = smd[col + 8]; out[r][3] = smd[col + 12]; }
+                    else { out[r][0] *= smd[col]; out[r][1] *= smd[col + 4]; out[r][2] *= smd[col + 8]; out[r][3] *= smd[col + 12]; }
                 }
             } else {
                 double a[R][4];
-                if (kind == OPK_STACK) {
-                    const int si0 = (side ? o.bSlot : o.aSlot) * slotStride + stackIdx;
+                if (kind == OPK_PREV) {   // the previous op's result, forwarded in registers
 #pragma unroll
                     for (int r = 0; r < R; r++) {
-                        const double2 lo = stLo[si0 + 32 * r], hi = stHi[si0 + 32 * r];
+                        a[r][0] = prev[r][0]; a[r][1] = prev[r][1]; a[r][2] = prev[r][2]; a[r][3] = prev[r][3];
+                        cum[r] += prevCum[r];
+                    }
+                    usedPrev = true;
+                } else if (kind == OPK_STACK) {
+                    const int si0 = ((o.ctl >> (6 + 4 * side)) & 15) * slotStride + stackIdx;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const double2 lo = st2[si0 + 32 * r], hi = st2[planeStride + si0 + 32 * r];
                         a[r][0] = lo.x; a[r][1] = lo.y; a[r][2] = hi.x; a[r][3] = hi.y;
                         cum[r] += sexp[si0 + 32 * r];
                     }
@@ -228,16 +244,17 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
                         }
                     }
                 }
-                if (side == 0) rows_times<EXACT, R, true>(M, a, out);
-                else rows_times<EXACT, R, false>(M, a, out);
+                if (side == 0) rows_times<EXACT, R, true>(smd + m, a, out);
+                else rows_times<EXACT, R, false>(smd + m, a, out);
             }
         }
 
         // ---- exact power-of-two rescale, store ----
         double *dst = partials + (size_t)o.outOff * 4;
         int16_t *dstE = cumExp + (size_t)o.outOff;
-        const bool toStack = o.outSlot < depth;
-        const int so0 = o.outSlot * slotStride + stackIdx;
+        const int outSlot = (o.ctl >> 14) & 255;
+        const bool toStack = outSlot < depth;
+        const int so0 = outSlot * slotStride + stackIdx;
 #pragma unroll
         for (int r = 0; r < R; r++) {
             // partials are non-negative: the largest value has the largest high word; its exponent field is the scale
@@ -248,15 +265,18 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
             const double o0 = out[r][0] * scale, o1 = out[r][1] * scale, o2 = out[r][2] * scale, o3 = out[r][3] * scale;
             const int ce = cum[r] + field - 1023;
             if (toStack) {
-                stLo[so0 + 32 * r] = make_double2(o0, o1);
-                stHi[so0 + 32 * r] = make_double2(o2, o3);
+                st2[so0 + 32 * r] = make_double2(o0, o1);
+                st2[planeStride + so0 + 32 * r] = make_double2(o2, o3);
                 sexp[so0 + 32 * r] = (int16_t)ce;
             }
             if (valid[r]) {
                 st256(dst + r * 128, o0, o1, o2, o3);
                 dstE[32 * r] = (int16_t)ce;
             }
+            prev[r][0] = o0; prev[r][1] = o1; prev[r][2] = o2; prev[r][3] = o3;
+            prevCum[r] = ce;
         }
+        (void)usedPrev;
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -278,7 +298,7 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             for (int cc = 0; cc < C; cc++) {
                 const int si = (chunk * C + cc) * R * 32 + 32 * r + lane;   // slot 0 holds the root
-                const double2 lo = stLo[si], hi = stHi[si];
+                const double2 lo = st2[si], hi = st2[planeStride + si];
                 const int diff = (int)sexp[si] - E;                          // <= 0
                 const double f = (diff < -1022) ? 0.0 : __hiloint2double((1023 + diff) << 20, 0);
                 const double pr = props[cc];
@@ -315,11 +335,11 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     }
     // fixed-shape tile reduction (deterministic)
     for (int off = 16; off > 0; off >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, off);
-    if (lane == 0) sred[w] = contrib;
+    if (lane == 0) smd[sredIdx + w] = contrib;
     __syncthreads();
     if (tid == 0) {
         double t = 0.0;
-        for (int ch = 0; ch < chunks; ch++) t += sred[ch * C];
+        for (int ch = 0; ch < chunks; ch++) t += smd[sredIdx + ch * C];
         A.tileSum[tile] = t;
     }
 }
@@ -339,9 +359,13 @@ void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st)
 {
     const size_t smem = treewalk_smem_bytes(a.nCat, a.chunksPerTile, a.patPerThread, a.stackDepth, a.maxTips);
     const int threads = 32 * a.nCat * a.chunksPerTile;
-    if (a.patPerThread == 1) {
+    static const int minb = getenv("SB2_MINB") ? atoi(getenv("SB2_MINB")) : 4;   // tuning knob: register cap of the R=1 variant
+    if (a.patPerThread == 1 && minb == 4) {
         if (exact) launch_one<true, 1, 4>(a, nTiles, smem, threads, st);
         else launch_one<false, 1, 4>(a, nTiles, smem, threads, st);
+    } else if (a.patPerThread == 1) {
+        if (exact) launch_one<true, 1, 3>(a, nTiles, smem, threads, st);
+        else launch_one<false, 1, 3>(a, nTiles, smem, threads, st);
     } else if (a.patPerThread == 2) {
         if (exact) launch_one<true, 2, 2>(a, nTiles, smem, threads, st);
         else launch_one<false, 2, 2>(a, nTiles, smem, threads, st);
