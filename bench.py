@@ -49,12 +49,12 @@ def load_peaks():
 
 def design_bytes(pb) -> float:
     """Compulsory HBM bytes of one full evaluation in THIS design (children are consumed from shared memory, so
-    partials are written once and never re-read): 32 B partials + 2/C B exponent per unit, tip states once,
+    partials are written once and never re-read): 32 B partials + 2 B exponent per unit, tip states once,
     pattern log-likelihoods once.  DESIGN.md derives it."""
     b = 0.0
     for l in pb.loci:
         n_int = l.n_tips - 1
-        b += 32.0 * l.n_pat * l.n_cat * n_int + 2.0 * l.n_pat * n_int + l.n_pat * l.n_tips + 8.0 * l.n_pat
+        b += 34.0 * l.n_pat * l.n_cat * n_int + l.n_pat * l.n_tips + 8.0 * l.n_pat
     return b
 
 
@@ -131,7 +131,8 @@ def run_reference(args):
     import oracle
     oracle.build()
     pb = build_problem(0, 1, args.loci, args.workload)
-    threads = oracle.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it is allowed to run on
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     fp = oracle.FlatProblem(pb)
     for _ in range(max(args.warmup, 1)):
         oracle.posterior(pb, n_threads=threads, flat=fp)
@@ -201,9 +202,11 @@ def main():
 
     def step_device():
         eng.mark_all_dirty()
+        if world == 1:
+            eng.eval_posterior_total(tot)
+            return
         eng.eval_begin()
-        if world > 1:
-            dist.all_reduce(red)
+        dist.all_reduce(red)
         eng.eval_end_total(tot)
 
     # flat host copies of everything a step of the reference-facing API re-sends
@@ -224,9 +227,11 @@ def main():
         eng.set_pop_model(pb.pop_kind, pb.pop_a, pb.pop_b, pb.alpha, pb.beta)
         eng.set_gene_trees_flat(0, pb.n_loci, hp, hl, hr, hh)
         eng.mark_all_dirty()
+        if world == 1:
+            eng._ck(eng._L.sb2_eval_posterior(eng._h, coal_buf.ctypes.data, lik_buf.ctypes.data, br_buf.ctypes.data, tot.ctypes.data))
+            return
         eng.eval_begin()
-        if world > 1:
-            dist.all_reduce(red)
+        dist.all_reduce(red)
         eng._ck(eng._L.sb2_eval_end(eng._h, coal_buf.ctypes.data, lik_buf.ctypes.data, br_buf.ctypes.data, tot.ctypes.data))
 
     def barrier():

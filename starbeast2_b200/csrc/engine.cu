@@ -698,9 +698,15 @@ int sb2_eval_end(sb2_engine *e, double *perLocusCoal, double *perLocusLik, doubl
 
 int sb2_eval_posterior(sb2_engine *e, double *perLocusCoal, double *perLocusLik, double *perBranch, double *total3)
 {
-    int rc = sb2_eval_begin(e);
-    if (rc) return rc;
-    return sb2_eval_end(e, perLocusCoal, perLocusLik, perBranch, total3);
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    int rc;
+    if ((rc = do_prepare(e))) return rc;
+    if ((rc = do_walk(e))) return rc;
+    launch_reduce_finish(reduce_args(e), e->stream, &e->launches);   // single GPU: no all-reduce in between
+    CUDA_TRY(e, cudaGetLastError());
+    if ((rc = download(e))) return rc;
+    copy_out(e, perLocusCoal, perLocusLik, perBranch, total3);
+    return SB2_OK;
 }
 
 int sb2_eval_coalescent(sb2_engine *e, double *perLocus, double *perBranch, double *total)
@@ -711,8 +717,7 @@ int sb2_eval_coalescent(sb2_engine *e, double *perLocus, double *perBranch, doub
     // phase 1 of the reference's posterior: the pruning kernel has not run for the re-scheduled loci yet, so the
     // likelihood entries of this pass are the cached ones (coalOnly); sb2_eval_likelihood runs the walk.
     ReduceArgs r = reduce_args(e, /*coalOnly=*/true);
-    launch_reduce_local(r, e->stream, &e->launches);
-    launch_finish(r, e->stream, &e->launches);
+    launch_reduce_finish(r, e->stream, &e->launches);
     CUDA_TRY(e, cudaGetLastError());
     if ((rc = download(e))) return rc;
     copy_out(e, perLocus, nullptr, perBranch, nullptr);
@@ -727,8 +732,7 @@ int sb2_eval_likelihood(sb2_engine *e, double *perLocus, double *total)
     if ((rc = do_prepare(e))) return rc;
     if ((rc = do_walk(e))) return rc;
     ReduceArgs r = reduce_args(e);
-    launch_reduce_local(r, e->stream, &e->launches);
-    launch_finish(r, e->stream, &e->launches);
+    launch_reduce_finish(r, e->stream, &e->launches);
     CUDA_TRY(e, cudaGetLastError());
     if ((rc = download(e))) return rc;
     copy_out(e, nullptr, perLocus, nullptr, nullptr);

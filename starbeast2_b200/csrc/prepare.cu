@@ -29,9 +29,9 @@ namespace sb2 {
 constexpr int PREP_THREADS = 128;
 
 struct PrepSmem {
-    double *gH, *rate, *times, *sH, *sRate;
+    double *gH, *rate, *times, *sH, *sRate, *btOld, *popA, *popB;
     int *gP, *gL, *gR, *assign, *cnt, *sP, *sL, *sR, *n, *k, *kstart, *misc;
-    uint8_t *matDirty, *dirty, *topo;
+    uint8_t *matDirty, *dirty, *topo, *stM, *stP, *curP, *curM;
 };
 
 __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, int G, int S)
@@ -39,10 +39,11 @@ __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, i
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 7) & ~size_t(7); return r; };
     size_t gH = take(8ull * G), rate = take(8ull * G), times = take(8ull * G), sH = take(8ull * S), sRate = take(8ull * S);
+    size_t btOld = take(8ull * G), popA = take(8ull * S), popB = take(8ull * S);
     size_t gP = take(4ull * G), gL = take(4ull * G), gR = take(4ull * G), assign = take(4ull * G), cnt = take(4ull * G);
     size_t sP = take(4ull * S), sL = take(4ull * S), sR = take(4ull * S), n = take(4ull * S), k = take(4ull * S), ks = take(4ull * (S + 1));
     size_t misc = take(4ull * 8);
-    size_t md = take(G), di = take(G), to = take(G);
+    size_t md = take(G), di = take(G), to = take(G), stM = take(G), stP = take(G), cuP = take(G), cuM = take(G);
     if (s) {
         s->gH = (double *)(base + gH); s->rate = (double *)(base + rate); s->times = (double *)(base + times);
         s->sH = (double *)(base + sH); s->sRate = (double *)(base + sRate);
@@ -51,6 +52,8 @@ __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, i
         s->sP = (int *)(base + sP); s->sL = (int *)(base + sL); s->sR = (int *)(base + sR);
         s->n = (int *)(base + n); s->k = (int *)(base + k); s->kstart = (int *)(base + ks); s->misc = (int *)(base + misc);
         s->matDirty = base + md; s->dirty = base + di; s->topo = base + to;
+        s->stM = base + stM; s->stP = base + stP; s->curP = base + cuP; s->curM = base + cuM;
+        s->btOld = (double *)(base + btOld); s->popA = (double *)(base + popA); s->popB = (double *)(base + popB);
     }
     return o;
 }
@@ -190,6 +193,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
     for (int i = tid; i < S; i += nt) {
         s.sP[i] = A.cur.sParent[i]; s.sL[i] = A.cur.sLeft[i]; s.sR[i] = A.cur.sRight[i];
         s.sH[i] = A.cur.sHeight[i]; s.sRate[i] = A.cur.sRates[i];
+        s.popA[i] = A.cur.popA[i]; s.popB[i] = A.cur.popB[i];
         s.n[i] = 0; s.k[i] = 0;
     }
     if (tid == 0) { s.misc[0] = 1; /* compatible */ s.misc[1] = G - 1; /* root */ }
@@ -210,9 +214,15 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
             s.topo[i] = 0;
         }
     }
+    // everything the later phases need from HBM is fetched now, in one wave of independent loads
     for (int i = tid; i < G; i += nt) {
         s.assign[i] = (i < nT) ? A.tipSpecies[d.tipBase + i] : -1;   // GeneTree.java:243,247
         s.cnt[i] = 0;
+        s.btOld[i] = A.cur.bTime[nb + i];
+        s.stM[i] = A.stored.curM[nb + i];
+        s.stP[i] = A.stored.curP[nb + i];
+        s.curP[i] = A.cur.curP[nb + i];
+        s.curM[i] = A.cur.curM[nb + i];
     }
     __syncthreads();
     for (int i = tid; i < G; i += nt) if (s.gP[i] < 0) s.misc[1] = i;
@@ -284,8 +294,8 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
             bool linear = false;
             double tipSize = 0.0, topSize = 0.0;
             if (A.popKind == 1) {   // LinearWithConstantRoot.branchLogP, :50-70
-                tipSize = (s.sL[b] < 0) ? A.cur.popA[b] : (A.cur.popB[s.sL[b]] + A.cur.popB[s.sR[b]]);
-                if (!isRoot) { linear = true; topSize = A.cur.popB[b]; }
+                tipSize = (s.sL[b] < 0) ? s.popA[b] : (s.popB[s.sL[b]] + s.popB[s.sR[b]]);
+                if (!isRoot) { linear = true; topSize = s.popB[b]; }
             }
             if (!linear) {
                 // shared gamma loop: ConstantPopulations.java:96-103 == MultispeciesCoalescent.java:215-222
@@ -294,7 +304,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
                 if (A.popKind == 2) {
                     term = 0.0;   // analytic: summands only (GeneTree.java:182)
                 } else {
-                    const double popSize = (A.popKind == 0) ? A.cur.popA[b] : tipSize;
+                    const double popSize = (A.popKind == 0) ? s.popA[b] : tipSize;
                     const double branchGamma = g / ploidy;
                     const double branchLogR = -k * logPloidy;
                     term = branchLogR - (k * log(popSize)) - (branchGamma / popSize);   // ConstantPopulations.java:107
@@ -348,10 +358,11 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         uint8_t md = 0;
         if (s.gP[i] >= 0) {
             const double bt = (s.gH[s.gP[i]] - s.gH[i]) * s.rate[i];   // node.getLength() * branchRate
-            md = forceMats || !(bt == A.cur.bTime[nb + i]);
+            md = forceMats || !(bt == s.btOld[i]);
             if (md) {
                 A.cur.bTime[nb + i] = bt;
-                A.cur.curM[nb + i] = 1 - A.stored.curM[nb + i];      // setNodeMatrixForUpdate
+                s.curM[i] = 1 - s.stM[i];                              // setNodeMatrixForUpdate
+                A.cur.curM[nb + i] = s.curM[i];
             }
         }
         s.matDirty[i] = md;
@@ -394,7 +405,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         }
         const int pos = start + s.cnt[i] - 1;
         s.assign[i] = pos;   // geneNodeSpeciesAssignment is already written back: reuse as the node's schedule position
-        const int newP = 1 - A.stored.curP[nb + i];                      // setNodePartialsForUpdate
+        const int newP = 1 - s.stP[i];                                   // setNodePartialsForUpdate
         A.cur.curP[nb + i] = (uint8_t)newP;
         const int Lc = s.gL[i], Rc = s.gR[i];
         const bool dl = Lc >= nT && s.dirty[Lc], dr = Rc >= nT && s.dirty[Rc];
@@ -409,9 +420,9 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
             else if (cd) {
                 if (!(dl && dr && c == first)) { kind = OPK_PREV; }
                 else if (base < A.stackDepth) { kind = OPK_STACK; slot = base; }
-                else { kind = OPK_SPILL; off = ((1 - A.stored.curP[nb + c]) * nI + (c - nT)) * cp; }   // the buffer the child is being written to
+                else { kind = OPK_SPILL; off = ((1 - s.stP[c]) * nI + (c - nT)) * cp; }   // the buffer the child is being written to
             }
-            else { kind = OPK_GLOBAL; off = (A.cur.curP[nb + c] * nI + (c - nT)) * cp; }
+            else { kind = OPK_GLOBAL; off = (s.curP[c] * nI + (c - nT)) * cp; }
         };
         Op o;
         unsigned aKind, bKind, aSlot, bSlot;
@@ -443,7 +454,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         if (par < 0) continue;
         const bool md = s.matDirty[i], used = s.dirty[par];   // used: the parent's op reads this matrix
         if (!md && !used) continue;
-        double *store = A.mats + d.matBase + ((size_t)(A.cur.curM[nb + i] * G + i) * C + c) * 16;
+        double *store = A.mats + d.matBase + ((size_t)(s.curM[i] * G + i) * C + c) * 16;
         double m[16];
         if (md) {
             const double jointBranchRate = A.catRates[d.catBase + c] * s.rate[i];   // siteModel.getRateForCategory * branchRate

@@ -38,7 +38,7 @@ __device__ double block_sum(double v, double *scratch)
     return t;
 }
 
-__global__ void __launch_bounds__(RED_THREADS) k_reduce_local(ReduceArgs A)
+__device__ __forceinline__ void reduce_local_body(const ReduceArgs &A)
 {
     __shared__ double scratch[32];
     const int tid = threadIdx.x, nt = blockDim.x, L = A.nLoci, S = A.S;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_local(ReduceArgs A)
     }
 }
 
-__global__ void __launch_bounds__(RED_THREADS) k_finish(ReduceArgs A)
+__device__ __forceinline__ void finish_body(const ReduceArgs &A)
 {
     __shared__ double scratch[32];
     const int tid = threadIdx.x, nt = blockDim.x, L = A.nLoci, S = A.S;
@@ -138,6 +138,23 @@ __global__ void __launch_bounds__(RED_THREADS) k_finish(ReduceArgs A)
     }
     if (incompatible) coal = -INFINITY;   // MultispeciesCoalescent.java:153
     if (tid == 0) { A.out[0] = coal; A.out[1] = lik; A.out[2] = coal + lik; }
+}
+
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_local(ReduceArgs A) { reduce_local_body(A); }
+__global__ void __launch_bounds__(RED_THREADS) k_finish(ReduceArgs A) { finish_body(A); }
+// single-GPU evaluation: no all-reduce between the local sums and the closed forms -> one launch
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_finish(ReduceArgs A)
+{
+    reduce_local_body(A);
+    __threadfence_block();
+    __syncthreads();
+    finish_body(A);
+}
+
+void launch_reduce_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches)
+{
+    k_reduce_finish<<<1, RED_THREADS, 0, st>>>(a);
+    ++*launches;
 }
 
 void launch_reduce_local(const ReduceArgs &a, cudaStream_t st, int64_t *launches)

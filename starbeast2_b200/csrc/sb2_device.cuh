@@ -158,6 +158,7 @@ void launch_prepare(const PrepareArgs &a, int maxNodes, cudaStream_t st);
 void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st);
 void launch_reduce_local(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
 void launch_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
+void launch_reduce_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
 size_t prepare_smem_bytes(int maxNodes, int S);
 size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, int maxTips);
 bool treewalk_tips_in_smem(int maxTips, int tilePat);

@@ -1,0 +1,134 @@
+"""The N>1 path: loci sharded over ranks, one all-reduce(sum) of the reduce vector
+{coalescent, likelihood, nIncompatible, (q, gamma, logR) x species nodes}, closed forms afterwards
+(MultispeciesCoalescent.java:203-232 needs the per-branch sums over ALL loci before log(beta + gamma)).
+
+CPU test (gloo, world_size 2): the sharding + reduce-vector protocol, with the oracle standing in for the device.
+GPU test (gloo over one GPU, world_size 2): Engine.eval_posterior_distributed end to end."""
+import math
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from starbeast2_b200 import synth
+from starbeast2_b200.engine import shard_loci
+from starbeast2_b200.problem import POP_ANALYTIC, Problem
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _local_reduce_vector(pb_shard: Problem):
+    """What k_reduce_local leaves in the reduce vector, restated with the oracle."""
+    S = pb_shard.species.n_nodes
+    res = oracle.posterior(pb_shard)
+    vec = np.zeros(3 + 3 * S)
+    # per-locus GeneTree logP (0 in analytic mode) and likelihoods
+    vec[0] = float(np.sum(res.per_locus_coal))
+    vec[1] = float(np.nansum(res.per_locus_lik))
+    vec[2] = float(np.sum(~np.isfinite(res.per_locus_coal)))
+    if pb_shard.pop_kind == POP_ANALYTIC:
+        for loc in pb_shard.loci:
+            emb = oracle.gene_tree_update(loc.tree, loc.tip_species, pb_shard.species)
+            for b in range(S):
+                t, n, k = emb.coalescent_times(b), int(emb.n[b]), int(emb.k[b])
+                g = sum((t[i + 1] - t[i]) * (n - i) * (n - (i + 1.0)) / 2.0 for i in range(k))
+                if n - k > 1:
+                    g += (t[k + 1] - t[k]) * (n - k) * (n - (k + 1.0)) / 2.0
+                vec[3 + 3 * b] += k
+                vec[3 + 3 * b + 1] += g / loc.ploidy
+                vec[3 + 3 * b + 2] += k * math.log(loc.ploidy)
+    return vec, res
+
+
+def _finish(vec, pb):
+    """k_finish restated: closed form per branch on the globally reduced sums."""
+    S = pb.species.n_nodes
+    coal = vec[0]
+    if pb.pop_kind == POP_ANALYTIC:
+        for b in range(S):
+            q, g, r = int(round(vec[3 + 3 * b])), vec[3 + 3 * b + 1], vec[3 + 3 * b + 2]
+            lgr = sum(math.log(pb.alpha + i) for i in range(q))
+            coal += -r + pb.alpha * math.log(pb.beta) - (pb.alpha + q) * math.log(pb.beta + g) + lgr
+    if vec[2] > 0:
+        coal = -math.inf
+    return coal, vec[1]
+
+
+def _cpu_worker(rank, world, port, name, n_loci, n_sites, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_loci([1.0] * n_loci, world)[rank]
+    shard = synth.make_problem(name, n_loci=n_loci, n_sites=n_sites, locus_range=(lo, hi))
+    vec, _ = _local_reduce_vector(shard)
+    t = torch.from_numpy(vec)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    coal, lik = _finish(t.numpy(), shard)
+    if rank == 0:
+        out.put((coal, lik))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["C4", "C2"])
+def test_sharded_reduce_vector_protocol_gloo_cpu(name):
+    n_loci, n_sites, world = 6, 60, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cpu_worker, args=(r, world, port, name, n_loci, n_sites, q)) for r in range(world)]
+    [p.start() for p in procs]
+    coal, lik = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    full = oracle.posterior(synth.make_problem(name, n_loci=n_loci, n_sites=n_sites))
+    assert coal == pytest.approx(full.coalescent, rel=1e-12)
+    assert lik == pytest.approx(full.likelihood, rel=1e-12)
+
+
+def _gpu_worker(rank, world, port, name, n_loci, n_sites, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # both ranks share cuda:0, so gloo (NCCL wants 1 GPU per rank)
+    from starbeast2_b200.engine import Engine
+    torch.cuda.set_device(0)
+    lo, hi = shard_loci([1.0] * n_loci, world)[rank]
+    shard = synth.make_problem(name, n_loci=n_loci, n_sites=n_sites, locus_range=(lo, hi))
+    e = Engine.from_problem(shard, device=0)
+    e.bind_torch()
+    r = e.eval_posterior_distributed()
+    out.put((rank, r.coalescent, r.likelihood, r.total, r.per_locus_lik.tolist(), r.per_branch.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["C4", "C3"])
+def test_engine_distributed_two_ranks(name):
+    n_loci, n_sites, world = 6, 80, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, name, n_loci, n_sites, q)) for r in range(world)]
+    [p.start() for p in procs]
+    got = sorted(q.get(timeout=300) for _ in range(world))
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    pb = synth.make_problem(name, n_loci=n_loci, n_sites=n_sites)
+    full = oracle.posterior(pb)
+    for rank, coal, lik, total, per_locus, per_branch in got:
+        assert coal == pytest.approx(full.coalescent, rel=1e-9)      # every rank ends with the global totals
+        assert lik == pytest.approx(full.likelihood, rel=1e-9)
+        assert total == pytest.approx(full.total, rel=1e-9)
+        lo, hi = shard_loci([1.0] * n_loci, world)[rank]
+        np.testing.assert_allclose(per_locus, full.per_locus_lik[lo:hi], rtol=1e-9)
+        if pb.pop_kind == POP_ANALYTIC:
+            np.testing.assert_allclose(per_branch, full.per_branch, rtol=1e-9)

@@ -1,0 +1,267 @@
+"""The reference's own JUnit tests (/root/reference/src/sb2tests/*.java), restated against the drop-in plugin classes:
+same construction by initByName, same inputs, same expected values and the reference's tolerance (10e-6).
+Host-only logic runs on CPU; everything that evaluates a logP goes through libsb2gpu and is marked gpu."""
+import math
+
+import numpy as np
+import pytest
+
+import ref_fixtures as rf
+from starbeast2_b200.plugins import (HKY, Alignment, CompoundDistribution, ConstantPopulations, DummyModel, Frequencies, GeneTree,
+                                     IntegerParameter, LinearWithConstantRoot, MultispeciesCoalescent, PassthroughModel,
+                                     RealParameter, SiteModel, SpeciesTreeParser, StarBeastClock, StrictClockModel, Taxon,
+                                     TaxonSet, TreeLikelihood, TreeParser, UncorrelatedRates)
+
+allowedError = rf.ALLOWED_ERROR
+
+
+def generateSuperset(nSpecies=4, individualsPerSpecies=2, fmt_sp="s%d", fmt_tip="s%d_tip%d", base=0):
+    superSetList = []
+    for i in range(nSpecies):
+        taxonList = [Taxon(fmt_tip % (i + base, j + base)) for j in range(individualsPerSpecies)]
+        superSetList.append(TaxonSet(fmt_sp % (i + base), taxonList))
+    return TaxonSet(superSetList)
+
+
+# ---- host-only (CPU) ------------------------------------------------------------------------------------------------
+
+def test_uncorrelated_rates_host():
+    # UncorrelatedRatesTest.java:27-52
+    testTree = TreeParser()
+    testTree.initByName("newick", rf.GENE_CLOCK, "IsLabelledNewick", True)
+    meanRateParameter, stdevParameter, branchRatesParameter = RealParameter(), RealParameter(), IntegerParameter()
+    meanRateParameter.initByName("value", "1.5")
+    stdevParameter.initByName("value", "1.0")
+    branchRatesParameter.initByName("value", "1")
+    clockModel = UncorrelatedRates()
+    clockModel.initByName("tree", testTree, "rates", branchRatesParameter, "stdev", stdevParameter, "estimateRoot", False,
+                          "clock.rate", meanRateParameter)
+    assert branchRatesParameter.getDimension() == 10 and branchRatesParameter.getUpper() == 9
+    for leaves, b in rf.UCLN_BINS.items():
+        branchRatesParameter.setValue(testTree.findNode(leaves), b)
+    for leaves, want in rf.UCLN_EXPECTED.items():
+        assert clockModel.getRateForBranch(testTree.findNode(leaves)) == pytest.approx(want, abs=allowedError)
+
+
+def test_input_validation_matches_reference_errors():
+    speciesTree = SpeciesTreeParser()
+    speciesTree.initByName("newick", rf.SPECIES_4, "IsLabelledNewick", True, "taxonset", generateSuperset())
+    with pytest.raises(ValueError):   # Validate.REQUIRED
+        GeneTree().initByName("speciesTree", speciesTree)
+    with pytest.raises(ValueError):   # unknown input name
+        ConstantPopulations().initByName("speciesTree", speciesTree, "popSizes", RealParameter(value="1.0"))
+    alpha = RealParameter(value="1.5")
+    with pytest.raises(ValueError):   # MultispeciesCoalescent.java:93-96: shape without mean
+        MultispeciesCoalescent().initByName("populationShape", alpha, "distribution", [])
+    with pytest.raises(ValueError):   # MultispeciesCoalescent.java:116-118: children must be GeneTrees
+        MultispeciesCoalescent().initByName("distribution", [CompoundDistribution()])
+
+
+def test_pop_model_dimensions_and_init():
+    speciesTree = SpeciesTreeParser()
+    speciesTree.initByName("newick", rf.SPECIES_4, "IsLabelledNewick", True, "taxonset", generateSuperset())
+    tip, top = RealParameter(), RealParameter()
+    tip.initByName("dimension", "4", "value", 1.0)
+    top.initByName("dimension", "6", "value", 1.0)
+    pm = LinearWithConstantRoot()
+    pm.initByName("tipPopulationSizes", tip, "topPopulationSizes", top, "speciesTree", speciesTree)
+    pm.initPopSizes(0.3)   # LinearWithConstantRoot.java:73-94
+    assert np.all(tip.values == 0.3) and np.all(top.values == 0.15) and top.getDimension() == 6
+    ps = RealParameter(value="0.3")
+    cp = ConstantPopulations()
+    cp.initByName("populationSizes", ps, "speciesTree", speciesTree)
+    assert ps.getDimension() == 7   # ConstantPopulations.java:37
+    assert PassthroughModel(childModel=cp).getBaseModel() is cp
+
+
+def test_stale_alpha_quirk_q1():
+    """checkHyperparameters uses the previous alpha for beta (MultispeciesCoalescent.java:137-138)."""
+    alpha, mean = RealParameter(value="1.5"), RealParameter(value="5.0")
+    msc = MultispeciesCoalescent.__new__(MultispeciesCoalescent)
+    MultispeciesCoalescent.__init__(msc)
+    msc._inputs.update(populationShape=alpha, populationMean=mean)
+    msc.alpha = msc.beta = 0.0
+    msc._check_hyperparameters(True)
+    assert (msc.alpha, msc.beta) == (1.5, -5.0)            # force at init: beta = mean * (0 - 1)
+    msc._check_hyperparameters(False)
+    assert (msc.alpha, msc.beta) == (1.5, 2.5)             # first calculateLogP fixes it
+    alpha.setValue(2.0)
+    msc._check_hyperparameters(False)
+    assert (msc.alpha, msc.beta) == (2.0, 2.5)             # beta lags alpha by one evaluation
+    msc._check_hyperparameters(False)
+    assert (msc.alpha, msc.beta) == (2.0, 5.0)
+
+
+# ---- through the GPU ------------------------------------------------------------------------------------------------
+
+def _gene_trees(speciesTree, newicks, popModel=None, ploidy=2.0):
+    out = []
+    for nw in newicks:
+        geneTree = TreeParser()
+        geneTree.initByName("newick", nw, "IsLabelledNewick", True)
+        w = GeneTree()
+        args = ["tree", geneTree, "ploidy", ploidy, "speciesTree", speciesTree]
+        if popModel is not None:
+            args += ["populationModel", popModel]
+        w.initByName(*args)
+        out.append(w)
+    return out
+
+
+@pytest.mark.gpu
+def test_ConstantPopulationTest():
+    speciesTree = SpeciesTreeParser()
+    speciesTree.initByName("newick", rf.SPECIES_4, "IsLabelledNewick", True, "taxonset", generateSuperset())
+    popsizeParameter = RealParameter()
+    popsizeParameter.initByName("value", "0.3", "dimension", "7")
+    popModel = ConstantPopulations()
+    popModel.initByName("populationSizes", popsizeParameter, "speciesTree", speciesTree)
+    calculatedLogP = 0.0
+    for w in _gene_trees(speciesTree, rf.GENES_4, popModel):
+        calculatedLogP += w.calculateLogP()
+    assert calculatedLogP == pytest.approx(rf.EXPECTED["constant"], abs=allowedError)
+
+
+@pytest.mark.gpu
+def test_LinearWithConstantRootTest():
+    speciesTree = SpeciesTreeParser()
+    speciesTree.initByName("newick", rf.SPECIES_4, "IsLabelledNewick", True, "taxonset", generateSuperset())
+    tip, top = RealParameter(), RealParameter()
+    tip.initByName("dimension", "4", "value", 1.0)
+    top.initByName("dimension", "6", "value", 1.0)
+    popModel = LinearWithConstantRoot()
+    popModel.initByName("tipPopulationSizes", tip, "topPopulationSizes", top, "speciesTree", speciesTree)
+    popModel.initPopSizes(0.3)
+    calculatedLogP = sum(w.calculateLogP() for w in _gene_trees(speciesTree, rf.GENES_4, popModel))
+    assert calculatedLogP == pytest.approx(rf.EXPECTED["lwcr"], abs=allowedError)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("genes,key", [(rf.GENES_4, "analytic"), (rf.GENES_4_MISSING, "analytic_missing")])
+def test_ConstantIOTest(genes, key):
+    alpha, beta = 1.5, 2.5
+    alphaParameter, meanParameter = RealParameter(), RealParameter()
+    alphaParameter.initByName("value", str(alpha))
+    meanParameter.initByName("value", str(beta / (alpha - 1.0)))
+    speciesTree = SpeciesTreeParser()
+    speciesTree.initByName("newick", rf.SPECIES_4, "IsLabelledNewick", True, "taxonset", generateSuperset())
+    wrappers = _gene_trees(speciesTree, genes)
+    msc = MultispeciesCoalescent()
+    msc.initByName("populationShape", alphaParameter, "populationMean", meanParameter, "distribution", wrappers)
+    for gt in wrappers:
+        assert gt.calculateLogP() == 0.0     # MissingDataConstantIOTest.java:97
+    assert msc.calculateLogP() == pytest.approx(rf.EXPECTED[key], abs=allowedError)
+
+
+@pytest.mark.gpu
+def test_IncompatibleTreeTest():
+    speciesTree = SpeciesTreeParser()
+    speciesTree.initByName("newick", rf.SPECIES_8, "IsLabelledNewick", True, "taxonset",
+                           generateSuperset(8, 2, "T%d", "T%d_%d", base=1))
+    popsizeParameter = RealParameter()
+    popsizeParameter.initByName("value", "0.3", "dimension", "15")
+    popModel = ConstantPopulations()
+    popModel.initByName("populationSizes", popsizeParameter, "speciesTree", speciesTree)
+    calculatedLogP = sum(w.calculateLogP() for w in _gene_trees(speciesTree, rf.GENES_8, popModel))
+    assert calculatedLogP == -math.inf
+
+
+@pytest.mark.gpu
+def test_StarbeastClockTest():
+    superset = TaxonSet([TaxonSet(s, [Taxon(f"{s}{j + 1}") for j in range(2)]) for s in "abc"])
+    speciesTree = SpeciesTreeParser()
+    speciesTree.initByName("newick", rf.SPECIES_3, "IsLabelledNewick", True, "taxonset", superset)
+    geneTree = TreeParser()
+    geneTree.initByName("newick", rf.GENE_CLOCK, "IsLabelledNewick", True)
+    geneTreeWrapper = GeneTree()
+    geneTreeWrapper.initByName("tree", geneTree, "ploidy", 2.0, "speciesTree", speciesTree)
+    meanRateParameter, stdevParameter, branchRatesParameter = RealParameter(), RealParameter(), IntegerParameter()
+    meanRateParameter.initByName("value", "1.5")
+    stdevParameter.initByName("value", "1.0")
+    branchRatesParameter.initByName("value", "1")
+    speciesTreeClock = UncorrelatedRates()
+    speciesTreeClock.initByName("tree", speciesTree, "rates", branchRatesParameter, "stdev", stdevParameter, "estimateRoot", True)
+    for leaves, b in rf.CLOCK_SPECIES_BINS.items():
+        branchRatesParameter.setValue(speciesTree.findNode(leaves), b)
+    geneTreeClock = StarBeastClock()
+    geneTreeClock.initByName("geneTree", geneTreeWrapper, "speciesTreeRates", speciesTreeClock, "clock.rate", meanRateParameter)
+    for leaves, want in rf.CLOCK_EXPECTED.items():
+        assert geneTreeClock.getRateForBranch(geneTree.findNode(leaves)) == pytest.approx(want, abs=allowedError)
+
+
+@pytest.mark.gpu
+def test_posterior_protocol_with_tree_likelihoods():
+    """A StarBEAST2-style posterior wired like tutorial/CanisPhylogeny/Canis-Phylogeny.xml:551-700: speciescoalescent first,
+    then likelihood; store / propose / evaluate / restore; the short-circuit on an incompatible proposal."""
+    import oracle
+    from starbeast2_b200 import synth
+    pb = synth.make_problem("C2", n_loci=3, n_sites=120)
+    n_sp = pb.species.n_leaves
+    sp_names = [f"sp{i}" for i in range(n_sp)]
+    superset = TaxonSet([TaxonSet(sp_names[i], [Taxon(f"sp{i}_{j}") for j in range(3)]) for i in range(n_sp)])
+    speciesTree = SpeciesTreeParser()
+    speciesTree.initByName("arrays", pb.species, "labels", sp_names, "taxonset", superset)
+    popSizes = RealParameter()
+    popSizes.initByName("value", " ".join(repr(float(x)) for x in pb.pop_a), "dimension", str(len(pb.pop_a)))
+    popModel = PassthroughModel()
+    popModel.initByName("childModel", ConstantPopulations(populationSizes=popSizes, speciesTree=speciesTree))
+    geneTrees, likelihoods, trees = [], [], []
+    for l, loc in enumerate(pb.loci):
+        labels = [f"sp{loc.tip_species[t]}_{t % 3}" for t in range(loc.n_tips)]
+        tree = TreeParser()
+        tree.initByName("arrays", loc.tree, "labels", labels)
+        trees.append(tree)
+        gt = GeneTree()
+        gt.initByName("tree", tree, "ploidy", loc.ploidy, "speciesTree", speciesTree, "populationModel", popModel)
+        geneTrees.append(gt)
+    for l, loc in enumerate(pb.loci):
+        data = Alignment()
+        data.initByName("patterns", loc.tip_states, "weights", loc.weights, "taxa", trees[l].labels)
+        freqs = Frequencies()
+        freqs.initByName("frequencies", RealParameter(value=" ".join(map(str, loc.subst_params[1:5])), dimension=4))
+        site = SiteModel()
+        site.initByName("substModel", HKY(kappa=RealParameter(value=str(loc.subst_params[0])), frequencies=freqs),
+                        "mutationRate", float(loc.cat_rates[0]))
+        clock = StrictClockModel()
+        clock.initByName("clock.rate", RealParameter(value=repr(float(loc.clock_rate))))
+        tl = TreeLikelihood()
+        tl.initByName("data", data, "tree", trees[l], "siteModel", site, "branchRateModel", clock)
+        likelihoods.append(tl)
+    speciescoalescent = MultispeciesCoalescent()
+    speciescoalescent.initByName("distribution", geneTrees)
+    likelihood = CompoundDistribution()
+    likelihood.initByName("distribution", likelihoods)
+    posterior = CompoundDistribution()
+    posterior.initByName("distribution", [speciescoalescent, likelihood])
+
+    want = oracle.posterior(pb)
+    assert posterior.calculateLogP() == pytest.approx(want.total, rel=1e-9)
+    assert [gt.logP for gt in geneTrees] == pytest.approx(list(want.per_locus_coal), rel=1e-9)
+    assert [tl.logP for tl in likelihoods] == pytest.approx(list(want.per_locus_lik), rel=1e-9)
+
+    # propose: slide a node of locus 1; evaluate; reject; state and value come back
+    rng = np.random.default_rng(3)
+    before = posterior.logP
+    posterior.store()
+    trees[1].store()
+    new_tree, node = synth.perturb_gene_tree(rng, trees[1].arrays, pb.loci[1].n_tips)
+    trees[1].setHeight(node, new_tree.height[node])
+    pb.loci[1].tree = trees[1].arrays
+    proposed = posterior.calculateLogP()
+    w2 = oracle.posterior(pb)
+    assert proposed == pytest.approx(w2.total if math.isfinite(w2.coalescent) else -math.inf, rel=1e-9)
+    trees[1].restore()          # BEAST: state.restore() first ...
+    posterior.restore()         # ... then restoreCalculationNodes()
+    assert posterior.calculateLogP() == before
+
+    # an incompatible proposal: the coalescent is -inf and the likelihood phase is never launched
+    launches_lik = likelihoods[0].session.engine.launch_count()
+    posterior.store(); speciesTree.store()
+    root = speciesTree.getRootNr()
+    child = int(speciesTree.arrays.left[root]) if speciesTree.arrays.left[int(speciesTree.arrays.left[root])] >= 0 else int(speciesTree.arrays.right[root])
+    speciesTree.setHeight(child, speciesTree.arrays.height[root] * 0.9999)
+    assert posterior.calculateLogP() == -math.inf
+    eng = likelihoods[0].session.engine
+    assert eng.launch_count() - launches_lik == 2      # k_prepare + the fused reduction; no pruning kernel
+    speciesTree.restore(); posterior.restore()
+    assert posterior.calculateLogP() == before
