@@ -286,6 +286,7 @@ int do_walk(sb2_engine *e)
     a.nCat = e->nCat; a.chunksPerTile = e->chunksPerTile; a.patPerThread = e->patPerThread; a.stackDepth = e->stackDepth;
     a.maxTips = (e->maxNodes + 1) / 2;
     a.tipsInSmem = treewalk_tips_in_smem(a.maxTips, 32 * e->chunksPerTile * e->patPerThread) ? 1 : 0;
+    if (a.tipsInSmem && getenv("SB2_TIP_STAGE_LEGACY")) a.tipsInSmem = 2;
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (e->cfg.profile) {
         if (e->evUsed == e->evPool.size()) {
@@ -427,7 +428,8 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
         e->stackDepth = std::max(e->stackDepth, d.stackDepth);
         e->maxNodes = std::max(e->maxNodes, d.nNodes);
         nodeBase += d.nNodes; tipBase += d.nTips; patBase += d.nPat; catBase += d.nCat; tileBase += d.nTiles; opBase += d.nInt;
-        stateBase += (int64_t)d.nTips * d.nPat;
+        d.stateStride = (d.nPat + 127) & ~127;
+        stateBase += (int64_t)d.nTips * d.stateStride;
         partBase += 2ll * d.nInt * d.nCat * d.nPat * 4;
         expBase += 2ll * d.nInt * d.nCat * d.nPat;
         expBase = (expBase + 7) & ~7ll;
@@ -448,12 +450,13 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     int rc;
     // static data
     std::vector<LocusDesc> descs(L);
-    std::vector<uint8_t> states((size_t)stateBase), cmask((size_t)patBase);
+    std::vector<uint8_t> states((size_t)stateBase, (uint8_t)4), cmask((size_t)patBase);
     std::vector<int32_t> weights((size_t)patBase), tipsp((size_t)tipBase), tileLocus((size_t)tileBase);
     for (int l = 0; l < L; l++) {
         const HostLocus &hl = e->loci[l];
         descs[l] = hl.d;
-        memcpy(states.data() + hl.d.stateBase, hl.states.data(), hl.states.size());
+        for (int t = 0; t < hl.d.nTips; t++)
+            memcpy(states.data() + hl.d.stateBase + (size_t)t * hl.d.stateStride, hl.states.data() + (size_t)t * hl.d.nPat, hl.d.nPat);
         memcpy(cmask.data() + hl.d.patBase, hl.constMask.data(), hl.constMask.size());
         memcpy(weights.data() + hl.d.patBase, hl.weights.data(), hl.weights.size() * 4);
         memcpy(tipsp.data() + hl.d.tipBase, hl.tipSpecies.data(), hl.tipSpecies.size() * 4);

@@ -182,7 +182,13 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         return;
     }
     const LocusDesc d = A.loci[l];
-    const LocusParams *prm = &A.params[l];
+    __shared__ LocusParams sprm;
+    {   // the locus's parameters, one coalesced read instead of scattered late ones
+        const double *src = reinterpret_cast<const double *>(&A.params[l]);
+        double *dst = reinterpret_cast<double *>(&sprm);
+        for (int i = tid; i < (int)(sizeof(LocusParams) / 8); i += nt) dst[i] = src[i];
+    }
+    const LocusParams *prm = &sprm;
     const int G = d.nNodes, nT = d.nTips, nI = d.nInt, S = A.S, nb = d.nodeBase, C = d.nCat;
     PrepSmem s;
     prep_carve(&s, smem_raw, maxNodes, S);

@@ -1,7 +1,7 @@
 // Shared device-side types of libsb2gpu (B200 / sm_100a).
 //
 // HBM layout (one engine = one GPU = one shard of loci), all arrays locus-major:
-//   tipStates   u8  [locus][tip][pattern]                      static
+//   tipStates   u8  [locus][tip][stateStride]                  static; rows padded to 128 B with 'missing'
 //   partials    f64 [locus][buf 0/1][internal node][cat][pattern][4]   (BEAST layout per node, two buffers
 //                                                               per node for store/restore, index flip only)
 //   cumExp      i16 [locus][buf][internal node][cat][pattern]  power-of-two scale exponent, cumulative over subtree
@@ -27,7 +27,7 @@ struct LocusDesc {
     int32_t nTiles;
     int32_t opBase;     // into ops (sum of nInt)
     int32_t stackDepth; // floor(log2(nInt)) + 1
-    int32_t pad0;
+    int32_t stateStride;// bytes per tip row of tipStates: nPat rounded up to 128, padding = 4 (missing)
     int64_t stateBase;  // into tipStates (bytes)
     int64_t partBase;   // into partials (doubles)
     int64_t expBase;    // into cumExp (int16)

@@ -72,7 +72,7 @@ size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, i
     b += 2ull * OPS_BATCH * sizeof(Op);                    // op schedule, two half batches
     b += (size_t)stackDepth * warps * R * 32 * 2;          // exponent stack (int16)
     b += ((warps + 1) & ~size_t(1)) * 8 + 16 * 8;          // tile-sum scratch + the ones column
-    if (treewalk_tips_in_smem(maxTips, (int)tilePat)) b += (size_t)maxTips * tilePat;   // tip states of the tile
+    if (treewalk_tips_in_smem(maxTips, (int)tilePat)) b += (size_t)maxTips * tilePat + 16;   // tip states of the tile
     return (b + 15) & ~size_t(15);
 }
 
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     const int onesIdx = warps * MAT_RING * 32, sredIdx = onesIdx + 16;
     Op *sops = reinterpret_cast<Op *>(smd + sredIdx + ((warps + 1) & ~1));      // [2 * OPS_BATCH]
     int16_t *sexp = reinterpret_cast<int16_t *>(sops + 2 * OPS_BATCH);          // [depth][warps][R][32]
-    uint8_t *sstate = reinterpret_cast<uint8_t *>(sexp + planeStride);          // [nTips][tilePat]
+    uint8_t *sstate = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sexp + planeStride) + 15) & ~uintptr_t(15));   // [nTips][tilePat]
 
     const Op *ops = A.ops + d.opBase;
     const double *matStream = A.opMats + ((size_t)d.opBase * C + c) * 32 + lane;   // + k * C*32: this lane's 8 bytes of op k's pair
@@ -165,15 +165,26 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
 
     load_batch(0);
     if (tid < 16) smd[onesIdx + tid] = 1.0;
-    if (tipsInSmem) {   // the tile's tip states, all tips: one burst of independent loads instead of one per op
-        const int total = d.nTips * tilePat;
-        for (int idx = tid; idx < total; idx += blockDim.x) {
-            const int t = idx / tilePat, pp = idx - t * tilePat;
-            sstate[idx] = (p0 + pp < nPat) ? states[(size_t)t * nPat + p0 + pp] : (uint8_t)4;
+    if (tipsInSmem) {
+        // the tile's tip states, every tip, as one burst of asynchronous 16-byte copies (rows are padded to 128 bytes with
+        // 'missing', so a tile never leaves its row); they ride in the first cp.async group, which the first op waits for
+        if (A.tipsInSmem == 2) {   // A/B knob: plain byte loads
+            const int total = d.nTips * tilePat;
+            for (int idx = tid; idx < total; idx += blockDim.x) {
+                const int t = idx / tilePat, pp = idx - t * tilePat;
+                sstate[idx] = states[(size_t)t * d.stateStride + p0 + pp];
+            }
+        } else {
+            const int per = tilePat >> 4, total = d.nTips * per;
+            for (int idx = tid; idx < total; idx += blockDim.x) {
+                const int t = idx / per, q = idx - t * per;
+                cp_async16(sstate + t * tilePat + q * 16, states + (size_t)t * d.stateStride + p0 + q * 16);
+            }
         }
     }
     for (int j = 0; j < MAT_RING - 1; j++) issue_mats(j);
-    __syncthreads();
+    cp_async_wait<MAT_RING - 2>();   // group 0 (tip states + op 0's matrices) has landed for this thread ...
+    __syncthreads();                 // ... and for everybody else; the op schedule is visible too
 
     for (int k = 0; k < nOps; k++) {
         if ((k & (OPS_BATCH - 1)) == OPS_BATCH / 2 && (k / OPS_BATCH + 1) * OPS_BATCH < nOps) {
@@ -210,7 +221,7 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     const int st = tipsInSmem ? sstate[off * tilePat + stateIdx + 32 * r]
-                                              : (valid[r] ? states[(size_t)off * nPat + pbase + 32 * r] : 4);
+                                              : states[(size_t)off * d.stateStride + pbase + 32 * r];
                     const int col = (st < 4) ? (m + st) : onesIdx;   // missing / ambiguous: factor 1
                     if (side == 0) { out[r][0] = smd[col]; out[r][1] = smd[col + 4]; out[r][2] = smd[col + 8]; out[r][3] = smd[col + 12]; }
                     else { out[r][0] *= smd[col]; out[r][1] *= smd[col + 4]; out[r][2] *= smd[col + 8]; out[r][3] *= smd[col + 12]; }
