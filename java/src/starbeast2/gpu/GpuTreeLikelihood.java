@@ -1,0 +1,43 @@
+package starbeast2.gpu;
+
+import java.util.List;
+import java.util.Random;
+
+import beast.base.core.Description;
+import beast.base.evolution.likelihood.GenericTreeLikelihood;
+import beast.base.inference.State;
+import starbeast2.SpeciesTreeInterface;
+import starbeast2.StarBeastClock;
+
+/**
+ * Drop-in for beast.base.evolution.likelihood.TreeLikelihood as StarBEAST2 wires it
+ * (fxtemplates/StarBeast2.xml:158-163: data, tree, siteModel, branchRateModel -- all inherited from
+ * GenericTreeLikelihood).  The locus is found through the GpuGeneTree that embeds the same Tree.
+ * UNCOMPILED in the build image (no JDK); the tested twin is starbeast2_b200/plugins.py:TreeLikelihood.
+ */
+@Description("GPU (libsb2gpu) drop-in for TreeLikelihood inside a StarBEAST2 analysis")
+public class GpuTreeLikelihood extends GenericTreeLikelihood {
+    private GpuSession session;
+    private int locus = -1;
+
+    @Override
+    public void initAndValidate() {
+        if (branchRateModelInput.get() instanceof StarBeastClock) {
+            final StarBeastClock clk = (StarBeastClock) branchRateModelInput.get();
+            session = GpuSession.of(clk.geneTreeInput.get().speciesTreeInput.get());
+        }
+        if (session == null) throw new IllegalArgumentException("GpuTreeLikelihood: declare the starbeast2.GpuGeneTree of this tree first, "
+                + "or use a StarBeastClock (the locus is found through its geneTree input)");
+        locus = session.locusOf(treeInput.get());
+        if (locus < 0) throw new IllegalArgumentException("GpuTreeLikelihood: tree " + treeInput.get().getID() + " is not embedded by any GpuGeneTree");
+        session.register(locus, this);
+    }
+    /** Strict-clock analyses (tutorial/CanisPhylogeny): the session is attached by the species tree instead. */
+    public void attach(SpeciesTreeInterface speciesTree) { session = GpuSession.of(speciesTree); }
+
+    @Override public double calculateLogP() { logP = session.likelihood(locus); return logP; }
+    @Override protected boolean requiresRecalculation() { return true; }   // the engine decides on the device what is dirty
+    @Override public List<String> getArguments() { return null; }
+    @Override public List<String> getConditions() { return null; }
+    @Override public void sample(State state, Random random) {}
+}
