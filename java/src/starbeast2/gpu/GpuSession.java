@@ -43,6 +43,12 @@ public final class GpuSession {
         return SESSIONS.computeIfAbsent(speciesTree, GpuSession::new);
     }
 
+    /** The session whose GpuGeneTree embeds this gene tree (strict-clock likelihoods have no other link to it). */
+    public static synchronized GpuSession ofGeneTree(TreeInterface tree) {
+        for (GpuSession s : SESSIONS.values()) if (s.locusOf(tree) >= 0) return s;
+        return null;
+    }
+
     private final SpeciesTreeInterface speciesTree;
     private final List<GpuGeneTree> geneTrees = new ArrayList<>();
     private final Map<Integer, GpuTreeLikelihood> likelihoods = new java.util.HashMap<>();

@@ -6,7 +6,6 @@ import java.util.Random;
 import beast.base.core.Description;
 import beast.base.evolution.likelihood.GenericTreeLikelihood;
 import beast.base.inference.State;
-import starbeast2.SpeciesTreeInterface;
 import starbeast2.StarBeastClock;
 
 /**
@@ -26,15 +25,13 @@ public class GpuTreeLikelihood extends GenericTreeLikelihood {
             final StarBeastClock clk = (StarBeastClock) branchRateModelInput.get();
             session = GpuSession.of(clk.geneTreeInput.get().speciesTreeInput.get());
         }
-        if (session == null) throw new IllegalArgumentException("GpuTreeLikelihood: declare the starbeast2.GpuGeneTree of this tree first, "
-                + "or use a StarBeastClock (the locus is found through its geneTree input)");
+        if (session == null) session = GpuSession.ofGeneTree(treeInput.get());   // strict clock: found through the embedding GpuGeneTree
+        if (session == null) throw new IllegalArgumentException("GpuTreeLikelihood: declare the starbeast2.GpuGeneTree of this tree first "
+                + "(XML order: speciescoalescent before likelihood, as in tutorial/CanisPhylogeny/Canis-Phylogeny.xml:551-684)");
         locus = session.locusOf(treeInput.get());
         if (locus < 0) throw new IllegalArgumentException("GpuTreeLikelihood: tree " + treeInput.get().getID() + " is not embedded by any GpuGeneTree");
         session.register(locus, this);
     }
-    /** Strict-clock analyses (tutorial/CanisPhylogeny): the session is attached by the species tree instead. */
-    public void attach(SpeciesTreeInterface speciesTree) { session = GpuSession.of(speciesTree); }
-
     @Override public double calculateLogP() { logP = session.likelihood(locus); return logP; }
     @Override protected boolean requiresRecalculation() { return true; }   // the engine decides on the device what is dirty
     @Override public List<String> getArguments() { return null; }
