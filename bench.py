@@ -123,6 +123,41 @@ def cpu_baseline(pb, n_threads: int, budget_s: float):
     return n, dt, r
 
 
+def bench_incremental(eng, pb, synth, n_steps=400):
+    """Regime B of SURVEY.md 3.3: one MCMC step = store, move one node of one gene tree (BEAST's Uniform operator),
+    evaluate the posterior through the reference's two-phase protocol (coalescent first, likelihood only if finite),
+    then reject (restore) or accept.  Host-timed, host buffers: this is latency, not throughput."""
+    import math
+    rng = np.random.default_rng(12345)
+    moves = []
+    for _ in range(64):
+        l = int(rng.integers(0, pb.n_loci))
+        t, node = synth.perturb_gene_tree(rng, pb.loci[l].tree, pb.loci[l].n_tips)
+        moves.append((l, t))
+    eng.eval_posterior()
+    updates = []
+
+    def one(i, count=False):
+        l, t = moves[i % len(moves)]
+        eng.store()
+        eng.set_gene_tree(l, t)
+        c, _, _ = eng.eval_coalescent()
+        if math.isfinite(c):
+            eng.eval_likelihood()
+        if count:
+            updates.append(eng.last_node_updates())
+        eng.restore()
+
+    for i in range(20):
+        one(i, count=True)
+    t0 = time.perf_counter()
+    for i in range(n_steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    return {"steps_per_sec": n_steps / dt, "us_per_step": 1e6 * dt / n_steps, "mean_node_updates": float(np.mean(updates)),
+            "protocol": "store, set_gene_tree(1 locus), eval_coalescent, eval_likelihood, restore; host-timed"}
+
+
 def run_reference(args):
     """`--impl reference`: the CPU restatement of the reference path (oracle/, kind "port"), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -258,13 +293,19 @@ def main():
         flush.fill_(1)
         step_device()
     eng.kernel_time()
+    eng.set_profile(False)        # no events between our launches in the timed region (they defeat dependent launch)
     barrier()
     l0 = eng.launch_count()
     t_wall0 = time.time()
     ms = timed(step_device, args.steps)
     launches = eng.launch_count() - l0
-    k_ms, k_n = eng.kernel_time()
     total_ref = float(tot[2])
+    barrier()
+    # roofline pass: the same steps with the pruning kernel bracketed by CUDA events on its own stream
+    eng.set_profile(True)
+    timed(step_device, min(args.steps, 100))
+    k_ms, k_n = eng.kernel_time()
+    eng.set_profile(False)
     barrier()
     # e2e
     for _ in range(3):
@@ -329,6 +370,8 @@ def main():
                      "kernel_partials_per_sec": pb.units / (k_us * 1e-6)},
         "clocks": clocks,
     }
+    if world == 1:
+        line["incremental"] = bench_incremental(eng, pb, synth)
     if not args.no_cpu and world == 1:
         import oracle
         oracle.build()

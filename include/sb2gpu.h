@@ -159,6 +159,9 @@ SB2_API int64_t sb2_launch_count(const sb2_engine *e);
 SB2_API int64_t sb2_last_node_updates(sb2_engine *e);
 /* profile=1: accumulated device time (ms) and launch count of the pruning kernel since the last call */
 SB2_API int sb2_kernel_time(sb2_engine *e, double *ms, int64_t *launches);
+/* switch the CUDA-event bracketing of the pruning kernel on/off (events between launches defeat programmatic
+ * dependent launch, so latency measurements run with profiling off) */
+SB2_API int sb2_set_profile(sb2_engine *e, int32_t on);
 /* device bytes held by the engine */
 SB2_API int64_t sb2_device_bytes(const sb2_engine *e);
 

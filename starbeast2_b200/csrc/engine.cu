@@ -77,7 +77,8 @@ struct sb2_engine {
     StateBlock blk[2];
     int curIdx = 0;
     // outputs
-    double *dRed = nullptr, *dRedOwn = nullptr, *dOut = nullptr, *hOut = nullptr;
+    double *dRed = nullptr, *dRedOwn = nullptr, *dOut = nullptr, *hOut = nullptr, *hOutDev = nullptr;
+    uint32_t *dDone = nullptr, *dLocusDone = nullptr;
     int nRed = 0, nOut = 0;
     int popKind = SB2_POP_CONSTANT;
     // dirtiness
@@ -219,6 +220,7 @@ ReduceArgs reduce_args(sb2_engine *e, bool coalOnly = false)
     r.loci = e->dLoci; r.nOps = e->dNOps; r.tileSum = e->dTileSum; r.patLogL = e->dPatLogL; r.weights = e->dWeights;
     r.cur = cur(e); r.red = e->dRed; r.out = e->dOut;
     r.nLoci = e->L; r.S = e->S; r.popKind = e->popKind; r.exact = e->cfg.exact_order;
+    r.hostOut = e->hOutDev;
     return r;
 }
 
@@ -240,7 +242,9 @@ int do_prepare(sb2_engine *e)
         e->hFlags[l] = f;
         any |= f != 0;
     }
-    CUDA_TRY(e, cudaMemcpyAsync(e->dFlags, e->hFlags, L, cudaMemcpyHostToDevice, st));
+    int uniformFlags = e->hFlags[0];
+    for (int l = 1; l < L; l++) if (e->hFlags[l] != e->hFlags[0]) { uniformFlags = -1; break; }
+    if (uniformFlags < 0) CUDA_TRY(e, cudaMemcpyAsync(e->dFlags, e->hFlags, L, cudaMemcpyHostToDevice, st));
     if (e->speciesDirty)
         CUDA_TRY(e, cudaMemcpyAsync(e->blockMem[e->curIdx] + e->speciesOffInBlock, e->hSpecies, e->speciesBytes, cudaMemcpyHostToDevice, st));
     if (e->reuploadLast >= 0) { firstPar = std::min(firstPar, e->reuploadFirst); lastPar = std::max(lastPar, e->reuploadLast); }
@@ -261,7 +265,7 @@ int do_prepare(sb2_engine *e)
     a.loci = e->dLoci; a.params = e->dParams; a.flags = e->dFlags; a.inTree = e->dInTree; a.tipSpecies = e->dTipSpecies;
     a.catRates = e->dCat; a.explicitRates = e->dExplicit ? e->dExplicit : e->dCat;
     a.cur = cur(e); a.stored = stored(e); a.ops = e->dOps; a.nOps = e->dNOps; a.mats = e->dMats; a.opMats = e->dOpMats;
-    a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L; a.stackDepth = e->stackDepth;
+    a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L; a.stackDepth = e->stackDepth; a.uniformFlags = uniformFlags;
     launch_prepare(a, e->maxNodes, st);
     e->launches++;
     CUDA_TRY(e, cudaGetLastError());
@@ -276,8 +280,11 @@ int do_prepare(sb2_engine *e)
     return SB2_OK;
 }
 
-int do_walk(sb2_engine *e)
+// fuse: 0 = plain; 1 = last CTA also runs k_reduce_local's body; 2 = ... and k_finish's + publish.  *fused tells the
+// caller whether the launch happened (nothing is launched when no walk is pending).
+int do_walk(sb2_engine *e, int fuse = 0, bool *fused = nullptr)
 {
+    if (fused) *fused = false;
     if (!e->walkPending) return SB2_OK;
     WalkArgs a;
     a.loci = e->dLoci; a.params = e->dParams; a.tileLocus = e->dTileLocus; a.ops = e->dOps; a.nOps = e->dNOps;
@@ -285,6 +292,14 @@ int do_walk(sb2_engine *e)
     a.opMats = e->dOpMats; a.partials = e->dPartials; a.cumExp = e->dCumExp; a.patLogL = e->dPatLogL; a.tileSum = e->dTileSum;
     a.nCat = e->nCat; a.chunksPerTile = e->chunksPerTile; a.patPerThread = e->patPerThread; a.stackDepth = e->stackDepth;
     a.maxTips = (e->maxNodes + 1) / 2;
+    // Folding the reductions into the walk's last CTA measured no faster end to end on B200 (69.5 vs 70.5 us at C2) and
+    // lengthens the roofline kernel, so it is opt-in (SB2_FUSE=1); never in exact mode (sequential pattern sums).
+    static const bool wantFuse = getenv("SB2_FUSE") != nullptr;
+    if (e->cfg.exact_order || !wantFuse) fuse = 0;
+    a.fuseReduce = fuse; a.doneCounter = e->dDone; a.locusDone = e->dLocusDone;
+    e->walkPending = false; e->tilesValid = true;
+    a.red = reduce_args(e);
+    a.red.useTiles = 0;                 // fused path: the last tile-CTA of each locus has already summed its tiles
     a.tipsInSmem = treewalk_tips_in_smem(a.maxTips, 32 * e->chunksPerTile * e->patPerThread) ? 1 : 0;
     if (a.tipsInSmem && getenv("SB2_TIP_STAGE_LEGACY")) a.tipsInSmem = 2;
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
@@ -302,15 +317,13 @@ int do_walk(sb2_engine *e)
     e->launches++;
     if (e->cfg.profile) CUDA_TRY(e, cudaEventRecord(ev.second, e->stream));
     CUDA_TRY(e, cudaGetLastError());
-    e->walkPending = false;
-    e->tilesValid = true;
+    if (fused) *fused = fuse != 0;
     return SB2_OK;
 }
 
 int download(sb2_engine *e)
 {
-    CUDA_TRY(e, cudaMemcpyAsync(e->hOut, e->dOut, sizeof(double) * (size_t)e->nOut, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));   // k_finish already published the result vector into host memory
     return SB2_OK;
 }
 
@@ -523,7 +536,16 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if ((rc = dev_alloc(e, &e->dRedOwn, e->nRed))) return rc;
     e->dRed = e->dRedOwn;
     if ((rc = dev_alloc(e, &e->dOut, e->nOut))) return rc;
-    if ((rc = pin_alloc(e, &e->hOut, e->nOut))) return rc;
+    {   // result vector: host memory the kernels write directly (zero-copy), so a download is just a stream sync
+        cudaError_t st = cudaHostAlloc((void **)&e->hOut, sizeof(double) * e->nOut, cudaHostAllocMapped);
+        if (st != cudaSuccess) return e->fail(SB2_ERR_NOMEM, "cudaHostAlloc(mapped): %s", cudaGetErrorString(st));
+        memset(e->hOut, 0, sizeof(double) * e->nOut);
+        CUDA_TRY(e, cudaHostGetDevicePointer((void **)&e->hOutDev, e->hOut, 0));
+    }
+    if ((rc = dev_alloc(e, &e->dDone, 1))) return rc;
+    CUDA_TRY(e, cudaMemset(e->dDone, 0, sizeof(uint32_t)));
+    if ((rc = dev_alloc(e, &e->dLocusDone, L))) return rc;
+    CUDA_TRY(e, cudaMemset(e->dLocusDone, 0, sizeof(uint32_t) * L));
     CUDA_TRY(e, cudaMemset(e->dOut, 0, sizeof(double) * e->nOut));
 
     e->treeDirty.assign(L, 0); e->modelDirty.assign(L, 0); e->clockDirty.assign(L, 0); e->touchedFlag.assign(L, 0);
@@ -678,9 +700,10 @@ int sb2_eval_begin(sb2_engine *e)
 {
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     int rc;
+    bool fused;
     if ((rc = do_prepare(e))) return rc;
-    if ((rc = do_walk(e))) return rc;
-    launch_reduce_local(reduce_args(e), e->stream, &e->launches);
+    if ((rc = do_walk(e, 1, &fused))) return rc;
+    if (!fused) launch_reduce_local(reduce_args(e), e->stream, &e->launches);
     CUDA_TRY(e, cudaGetLastError());
     e->reduced = true;
     return SB2_OK;
@@ -703,9 +726,10 @@ int sb2_eval_posterior(sb2_engine *e, double *perLocusCoal, double *perLocusLik,
 {
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     int rc;
+    bool fused;
     if ((rc = do_prepare(e))) return rc;
-    if ((rc = do_walk(e))) return rc;
-    launch_reduce_finish(reduce_args(e), e->stream, &e->launches);   // single GPU: no all-reduce in between
+    if ((rc = do_walk(e, 2, &fused))) return rc;                                     // single GPU: no all-reduce in between
+    if (!fused) launch_reduce_finish(reduce_args(e), e->stream, &e->launches);
     CUDA_TRY(e, cudaGetLastError());
     if ((rc = download(e))) return rc;
     copy_out(e, perLocusCoal, perLocusLik, perBranch, total3);
@@ -732,10 +756,10 @@ int sb2_eval_likelihood(sb2_engine *e, double *perLocus, double *total)
 {
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     int rc;
+    bool fused;
     if ((rc = do_prepare(e))) return rc;
-    if ((rc = do_walk(e))) return rc;
-    ReduceArgs r = reduce_args(e);
-    launch_reduce_finish(r, e->stream, &e->launches);
+    if ((rc = do_walk(e, 2, &fused))) return rc;
+    if (!fused) launch_reduce_finish(reduce_args(e), e->stream, &e->launches);
     CUDA_TRY(e, cudaGetLastError());
     if ((rc = download(e))) return rc;
     copy_out(e, nullptr, perLocus, nullptr, nullptr);
@@ -773,10 +797,8 @@ static int flush_pending_walk(sb2_engine *e)
     // k_prepare already flipped buffer indices for the scheduled nodes; make sure their partials exist before the
     // state is frozen (only reachable when a host evaluates the coalescent but never the likelihood)
     if (e->walkPending) {
-        int rc = do_walk(e);
+        int rc = do_walk(e, 1);
         if (rc) return rc;
-        launch_reduce_local(reduce_args(e), e->stream, &e->launches);
-        CUDA_TRY(e, cudaGetLastError());
     }
     return SB2_OK;
 }
@@ -944,6 +966,13 @@ int sb2_kernel_time(sb2_engine *e, double *ms, int64_t *launches)
     if (ms) *ms = t;
     if (launches) *launches = (int64_t)e->evUsed;
     e->evUsed = 0;
+    return SB2_OK;
+}
+
+int sb2_set_profile(sb2_engine *e, int32_t on)
+{
+    if (!e) return SB2_ERR_ARG;
+    e->cfg.profile = on ? 1 : 0;
     return SB2_OK;
 }
 

@@ -1,0 +1,148 @@
+// Device bodies of the reductions (see reduce.cu for the description); shared by the stand-alone reduction kernels
+// and by k_treewalk, whose last-finishing CTA runs them in place (one launch fewer on the latency path).
+// Must be compiled with -fmad=false semantics where it matters: all sums here are plain adds.
+#pragma once
+#include <math.h>
+
+#include "sb2_device.cuh"
+
+namespace sb2 {
+
+// deterministic block sum: fixed assignment of elements to threads, fixed-shape tree over threads
+__device__ __forceinline__ double block_sum(double v, double *scratch)
+{
+    const int tid = threadIdx.x;
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((tid & 31) == 0) scratch[tid >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (tid < 32) {
+        t = (tid < (blockDim.x >> 5)) ? scratch[tid] : 0.0;
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    }
+    __syncthreads();
+    if (tid == 0) scratch[0] = t;
+    __syncthreads();
+    t = scratch[0];
+    __syncthreads();
+    return t;
+}
+
+__device__ __forceinline__ void reduce_local_body(const ReduceArgs &A)
+{
+    __shared__ double scratch[32];
+    const int tid = threadIdx.x, nt = blockDim.x, L = A.nLoci, S = A.S;
+    double *perLocusCoal = A.out + 3, *perLocusLik = A.out + 3 + L;
+    double likPart = 0.0, coalPart = 0.0, incPart = 0.0;
+    for (int l = tid; l < L; l += nt) {
+        double lik;
+        if (A.useTiles && A.nOps[l] > 0) {
+            const LocusDesc &d = A.loci[l];
+            lik = 0.0;
+            if (A.exact) {
+                for (int p = 0; p < d.nPat; p++) lik = __dadd_rn(lik, __dmul_rn(__ldcg(A.patLogL + d.patBase + p), (double)A.weights[d.patBase + p]));   // calcLogP order
+            } else {
+                for (int t = 0; t < d.nTiles; t++) lik += __ldcg(A.tileSum + d.tileBase + t);
+            }
+            A.cur.logL[l] = lik;
+        } else {
+            lik = A.cur.logL[l];   // clean locus: cached value (CompoundDistribution uses getCurrentLogP)
+        }
+        const double coal = A.cur.coal[l];
+        perLocusLik[l] = lik;
+        perLocusCoal[l] = coal;
+        likPart += lik;
+        coalPart += coal;
+        incPart += (coal == -INFINITY) ? 1.0 : 0.0;
+    }
+    double likSum, coalSum;
+    if (A.exact) {
+        __syncthreads();
+        likSum = 0.0; coalSum = 0.0;
+        if (tid == 0) {
+            for (int l = 0; l < L; l++) { likSum += perLocusLik[l]; coalSum += perLocusCoal[l]; }
+            scratch[0] = likSum; scratch[1] = coalSum;
+        }
+        __syncthreads();
+        likSum = scratch[0]; coalSum = scratch[1];
+        __syncthreads();
+    } else {
+        likSum = block_sum(likPart, scratch);
+        coalSum = block_sum(coalPart, scratch);
+    }
+    const double inc = block_sum(incPart, scratch);
+    if (tid == 0) { A.red[0] = coalSum; A.red[1] = likSum; A.red[2] = inc; }
+
+    // analytic integration: per-branch sums over this rank's loci
+    if (A.popKind == 2) {
+        const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+        for (int b = warp; b < S; b += nw) {
+            double q = 0.0, g = 0.0, r = 0.0;
+            if (A.exact) {
+                if (lane == 0)
+                    for (int l = 0; l < L; l++) {
+                        const size_t o = (size_t)l * S + b;
+                        q += A.cur.brK[o]; g += A.cur.anG[o]; r += A.cur.anR[o];
+                    }
+            } else {
+                for (int l = lane; l < L; l += 32) {
+                    const size_t o = (size_t)l * S + b;
+                    q += A.cur.brK[o]; g += A.cur.anG[o]; r += A.cur.anR[o];
+                }
+                for (int off = 16; off > 0; off >>= 1) {
+                    q += __shfl_xor_sync(0xffffffffu, q, off);
+                    g += __shfl_xor_sync(0xffffffffu, g, off);
+                    r += __shfl_xor_sync(0xffffffffu, r, off);
+                }
+            }
+            if (lane == 0) { A.red[3 + 3 * b] = q; A.red[3 + 3 * b + 1] = g; A.red[3 + 3 * b + 2] = r; }
+        }
+    } else {
+        for (int i = tid; i < 3 * S; i += nt) A.red[3 + i] = 0.0;
+    }
+}
+
+__device__ __forceinline__ void finish_body(const ReduceArgs &A)
+{
+    __shared__ double scratch[32];
+    const int tid = threadIdx.x, nt = blockDim.x, L = A.nLoci, S = A.S;
+    double *perBranch = A.out + 3 + 2 * L;
+    double coal = A.red[0];
+    const double lik = A.red[1];
+    const bool incompatible = A.red[2] > 0.0;
+    if (A.popKind == 2) {
+        const double alpha = A.cur.hyper[0], beta = A.cur.hyper[1];
+        for (int b = 0; b < S; b++) {
+            const long long q = (long long)(A.red[3 + 3 * b] + 0.5);
+            const double g = A.red[3 + 3 * b + 1], r = A.red[3 + 3 * b + 2];
+            double part = 0.0;
+            for (long long i = tid; i < q; i += nt) part += log(alpha + (double)i);   // logGammaRatio, :227-230
+            const double lgr = block_sum(part, scratch);
+            const double branchLogR = -r;
+            // explicit roundings: this body is also inlined into k_treewalk, whose translation unit allows FMA contraction
+            const double logP = __dadd_rn(__dsub_rn(__dadd_rn(branchLogR, __dmul_rn(alpha, log(beta))),
+                                                    __dmul_rn(__dadd_rn(alpha, (double)q), log(__dadd_rn(beta, g)))), lgr);   // :232
+            if (tid == 0) perBranch[b] = logP;
+            coal += logP;   // MultispeciesCoalescent.java:194: added one by one in node-number order
+        }
+    } else {
+        for (int b = tid; b < S; b += nt) perBranch[b] = 0.0;
+    }
+    if (incompatible) coal = -INFINITY;   // MultispeciesCoalescent.java:153
+    if (tid == 0) { A.out[0] = coal; A.out[1] = lik; A.out[2] = coal + lik; }
+}
+
+
+// copies the result vector to the host-mapped (zero-copy) buffer: the host only has to synchronise the stream
+__device__ __forceinline__ void publish_body(const ReduceArgs &A)
+{
+    __threadfence_block();
+    __syncthreads();
+    if (A.hostOut) {
+        const int n = 3 + 2 * A.nLoci + A.S;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) A.hostOut[i] = A.out[i];   // visible to the host once the kernel completes
+    }
+}
+
+}  // namespace sb2

@@ -116,6 +116,21 @@ struct PrepareArgs {
     double *opMats;              // [op][category][side][16]: each scheduled op's two matrices, in schedule order
     int32_t S, nSpeciesLeaves, popKind, nLoci;
     int32_t stackDepth;          // shared-memory stack slots of k_treewalk
+    int32_t uniformFlags;        // >= 0: every locus uses these flags (no per-step flags upload); < 0: read `flags`
+};
+
+struct ReduceArgs {
+    const LocusDesc *loci;
+    const int32_t *nOps;
+    const double *tileSum;
+    const double *patLogL;
+    const int32_t *weights;
+    StateBlock cur;
+    double *red;        // reduce vector {coal, lik, nIncompat, (q, gamma, logR) x S}
+    double *out;        // {total3, perLocusCoal[L], perLocusLik[L], perBranch[S]}
+    int32_t nLoci, S, popKind, exact;
+    int32_t useTiles;   // 0: pruning results are stale or pending -> use the cached per-locus logL
+    double *hostOut;    // host-mapped copy of `out` (zero-copy download), or nullptr
 };
 
 struct WalkArgs {
@@ -139,20 +154,12 @@ struct WalkArgs {
     int32_t stackDepth;          // shared-memory stack slots; deeper results spill to their global buffer
     int32_t maxTips;             // largest tip count over loci (sizes the shared-memory tip-state tile)
     int32_t tipsInSmem;          // 1: tip states of the tile are staged in shared memory
+    int32_t fuseReduce;          // 0: none; 1: last CTA runs the local reduction; 2: ... and the closed forms + publish
+    uint32_t *doneCounter;       // CTAs finished so far (self-resetting)
+    uint32_t *locusDone;         // [nLoci] tile-CTAs finished per locus (self-resetting)
+    ReduceArgs red;
 };
 
-struct ReduceArgs {
-    const LocusDesc *loci;
-    const int32_t *nOps;
-    const double *tileSum;
-    const double *patLogL;
-    const int32_t *weights;
-    StateBlock cur;
-    double *red;        // reduce vector {coal, lik, nIncompat, (q, gamma, logR) x S}
-    double *out;        // {total3, perLocusCoal[L], perLocusLik[L], perBranch[S]}
-    int32_t nLoci, S, popKind, exact;
-    int32_t useTiles;   // 0: pruning results are stale or pending -> use the cached per-locus logL
-};
 
 void launch_prepare(const PrepareArgs &a, int maxNodes, cudaStream_t st);
 void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st);

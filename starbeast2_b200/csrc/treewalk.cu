@@ -30,7 +30,7 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include "sb2_device.cuh"
+#include "reduce_body.cuh"
 
 namespace sb2 {
 
@@ -43,7 +43,7 @@ __device__ __forceinline__ void st256(double *p, double a, double b, double c, d
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
-constexpr int OPS_BATCH = 64;   // ops staged in shared memory per half batch
+constexpr int OPS_BATCH = 32;   // ops staged in shared memory per half batch
 constexpr int MAT_RING = 4;     // transition-matrix pairs in flight per warp (cp.async ring)
 constexpr int TIP_SMEM_MAX = 48 * 1024;
 
@@ -102,14 +102,69 @@ __device__ __forceinline__ void rows_times(const double *M, const double (&a)[R]
     }
 }
 
+// Reductions folded into the walk (one launch and its ramp fewer per evaluation), hierarchically:
+//   * the last tile-CTA of a locus sums that locus's tile sums in fixed tile order (parallel over loci, hidden in the tail);
+//   * the CTA that finishes last overall sums the per-locus values and, single-GPU, applies the closed forms and
+//     publishes the result vector.  Counters reset themselves.  Not used in exact_order mode (sequential pattern sums).
+__device__ __forceinline__ void walk_epilogue(const WalkArgs &A, int l, int tileBase, int nTiles, bool worked)
+{
+    if (!A.fuseReduce) return;
+    __shared__ unsigned s_last, s_lastOfLocus;
+    __threadfence();            // this CTA's tile sum is visible device-wide
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_lastOfLocus = 0;
+        if (worked) {
+            const unsigned t = atomicAdd(A.locusDone + l, 1u);
+            if (t == (unsigned)nTiles - 1) { A.locusDone[l] = 0; s_lastOfLocus = 1; }
+        }
+    }
+    __syncthreads();
+    if (s_lastOfLocus && threadIdx.x < 32) {
+        // the locus's tiles, loaded in parallel, summed in tile order (fixed order => deterministic)
+        __threadfence();
+        double lik = 0.0;
+        for (int base = 0; base < nTiles; base += 32) {
+            const int i = base + (int)threadIdx.x;
+            const double v = (i < nTiles) ? __ldcg(A.tileSum + tileBase + i) : 0.0;
+            const int cnt = min(32, nTiles - base);
+            for (int j = 0; j < cnt; j++) lik += __shfl_sync(0xffffffffu, v, j);
+        }
+        if (threadIdx.x == 0) { A.red.cur.logL[l] = lik; __threadfence(); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(A.doneCounter, 1u);
+        s_last = (ticket == gridDim.x - 1);
+        if (s_last) *A.doneCounter = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    reduce_local_body(A.red);   // red.useTiles == 0: per-locus values are already summed
+    if (A.fuseReduce == 2) {
+        __threadfence_block();
+        __syncthreads();
+        finish_body(A.red);
+        publish_body(A.red);
+    }
+}
+
 template <bool EXACT, int R, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
 {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int tile = blockIdx.x;
     const int l = A.tileLocus[tile];
+    // Programmatic dependent launch: everything above this line (and the static lookups) overlaps k_prepare's tail;
+    // nOps / ops / opMats are k_prepare's outputs and must not be touched before it has completed.
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();   // the (single-CTA) reduction kernel may queue up behind us already
     const int nOps = A.nOps[l];
-    if (nOps == 0) return;   // locus clean: cached logL stands
+    if (nOps == 0) {         // locus clean: cached logL stands
+        walk_epilogue(A, l, 0, 0, false);
+        return;
+    }
     const LocusDesc d = A.loci[l];
     const int C = A.nCat, chunks = A.chunksPerTile, depth = A.stackDepth;
     const int warps = C * chunks;
@@ -353,6 +408,7 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
         for (int ch = 0; ch < chunks; ch++) t += smd[sredIdx + ch * C];
         A.tileSum[tile] = t;
     }
+    walk_epilogue(A, l, d.tileBase, d.nTiles, true);
 }
 
 template <bool EXACT, int R, int MINB>
@@ -363,7 +419,13 @@ static void launch_one(const WalkArgs &a, int nTiles, size_t smem, int threads, 
         cudaFuncSetAttribute(k_treewalk<EXACT, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    k_treewalk<EXACT, R, MINB><<<nTiles, threads, smem, st>>>(a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nTiles); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_treewalk<EXACT, R, MINB>, a);
 }
 
 void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st)

@@ -280,5 +280,8 @@ class Engine:
         self._ck(self._L.sb2_kernel_time(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def set_profile(self, on: bool):
+        self._ck(self._L.sb2_set_profile(self._h, int(on)))
+
     def device_bytes(self) -> int:
         return int(self._L.sb2_device_bytes(self._h))
