@@ -43,7 +43,13 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A)
             if (A.exact) {
                 for (int p = 0; p < d.nPat; p++) lik = __dadd_rn(lik, __dmul_rn(__ldcg(A.patLogL + d.patBase + p), (double)A.weights[d.patBase + p]));   // calcLogP order
             } else {
-                for (int t = 0; t < d.nTiles; t++) lik += __ldcg(A.tileSum + d.tileBase + t);
+                for (int t0 = 0; t0 < d.nTiles; t0 += 8) {   // loads in flight together, adds in tile order
+                    double v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = (t0 + j < d.nTiles) ? __ldcg(A.tileSum + d.tileBase + t0 + j) : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if (t0 + j < d.nTiles) lik += v[j];
+                }
             }
             A.cur.logL[l] = lik;
         } else {

@@ -150,7 +150,9 @@ __device__ __forceinline__ void walk_epilogue(const WalkArgs &A, int l, int tile
     }
 }
 
-template <bool EXACT, int R, int MINB>
+// NC > 0: the launch geometry (categories, chunks per tile, stack depth, tips staged in shared memory) is a compile-time
+// constant, so every shared-memory offset and stride folds into an immediate; NC == 0 is the generic run-time path.
+template <bool EXACT, int R, int MINB, int NC, int CH, int DEPTH>
 __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
 {
     extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
         return;
     }
     const LocusDesc d = A.loci[l];
-    const int C = A.nCat, chunks = A.chunksPerTile, depth = A.stackDepth;
+    const int C = NC ? NC : A.nCat, chunks = NC ? CH : A.chunksPerTile, depth = NC ? DEPTH : A.stackDepth;
     const int warps = C * chunks;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int c = w % C, chunk = w / C;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     const int tilePat = chunks * 32 * R;
     const int p0 = (tile - d.tileBase) * tilePat;
     const int pbase = p0 + chunk * 32 * R + lane;   // pattern r of this thread: pbase + 32 r
-    const bool tipsInSmem = A.tipsInSmem != 0;
+    const bool tipsInSmem = NC ? true : (A.tipsInSmem != 0);
     const bool incremental = nOps < d.nInt;         // only then can operands be clean nodes resident in HBM
 
     // shared memory carve-up; everything is addressed as an index off one of these bases so that the compiler keeps
@@ -265,7 +267,6 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
         int cum[R];
 #pragma unroll
         for (int r = 0; r < R; r++) cum[r] = 0;
-        bool usedPrev = false;
 
 #pragma unroll
         for (int side = 0; side < 2; side++) {
@@ -282,15 +283,15 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
                     else { out[r][0] *= smd[col]; out[r][1] *= smd[col + 4]; out[r][2] *= smd[col + 8]; out[r][3] *= smd[col + 12]; }
                 }
             } else {
-                double a[R][4];
                 if (kind == OPK_PREV) {   // the previous op's result, forwarded in registers
 #pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        a[r][0] = prev[r][0]; a[r][1] = prev[r][1]; a[r][2] = prev[r][2]; a[r][3] = prev[r][3];
-                        cum[r] += prevCum[r];
-                    }
-                    usedPrev = true;
-                } else if (kind == OPK_STACK) {
+                    for (int r = 0; r < R; r++) cum[r] += prevCum[r];
+                    if (side == 0) rows_times<EXACT, R, true>(smd + m, prev, out);
+                    else rows_times<EXACT, R, false>(smd + m, prev, out);
+                    continue;
+                }
+                double a[R][4];
+                if (kind == OPK_STACK) {
                     const int si0 = ((o.ctl >> (6 + 4 * side)) & 15) * slotStride + stackIdx;
 #pragma unroll
                     for (int r = 0; r < R; r++) {
@@ -342,7 +343,6 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
             prev[r][0] = o0; prev[r][1] = o1; prev[r][2] = o2; prev[r][3] = o3;
             prevCum[r] = ce;
         }
-        (void)usedPrev;
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -411,12 +411,12 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     walk_epilogue(A, l, d.tileBase, d.nTiles, true);
 }
 
-template <bool EXACT, int R, int MINB>
+template <bool EXACT, int R, int MINB, int NC, int CH, int DEPTH>
 static void launch_one(const WalkArgs &a, int nTiles, size_t smem, int threads, cudaStream_t st)
 {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(k_treewalk<EXACT, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_treewalk<EXACT, R, MINB, NC, CH, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     cudaLaunchConfig_t cfg{};
@@ -425,27 +425,31 @@ static void launch_one(const WalkArgs &a, int nTiles, size_t smem, int threads, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_treewalk<EXACT, R, MINB>, a);
+    cudaLaunchKernelEx(&cfg, k_treewalk<EXACT, R, MINB, NC, CH, DEPTH>, a);
+}
+
+template <bool EXACT>
+static void launch_exact(const WalkArgs &a, int nTiles, size_t smem, int threads, cudaStream_t st)
+{
+    static const bool forceGeneric = getenv("SB2_GENERIC") != nullptr;   // A/B knob
+    const bool std4 = a.stackDepth == 4 && a.tipsInSmem == 1 && !forceGeneric;
+    if (a.patPerThread == 1) {
+        if (std4 && a.nCat == 4 && a.chunksPerTile == 1) launch_one<EXACT, 1, 4, 4, 1, 4>(a, nTiles, smem, threads, st);        // GTR+G4 shapes
+        else if (std4 && a.nCat == 1 && a.chunksPerTile == 2) launch_one<EXACT, 1, 4, 1, 2, 4>(a, nTiles, smem, threads, st);   // no rate heterogeneity
+        else launch_one<EXACT, 1, 4, 0, 0, 0>(a, nTiles, smem, threads, st);
+    } else if (a.patPerThread == 2) {
+        launch_one<EXACT, 2, 2, 0, 0, 0>(a, nTiles, smem, threads, st);
+    } else {
+        launch_one<EXACT, 4, 1, 0, 0, 0>(a, nTiles, smem, threads, st);
+    }
 }
 
 void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st)
 {
     const size_t smem = treewalk_smem_bytes(a.nCat, a.chunksPerTile, a.patPerThread, a.stackDepth, a.maxTips);
     const int threads = 32 * a.nCat * a.chunksPerTile;
-    static const int minb = getenv("SB2_MINB") ? atoi(getenv("SB2_MINB")) : 4;   // tuning knob: register cap of the R=1 variant
-    if (a.patPerThread == 1 && minb == 4) {
-        if (exact) launch_one<true, 1, 4>(a, nTiles, smem, threads, st);
-        else launch_one<false, 1, 4>(a, nTiles, smem, threads, st);
-    } else if (a.patPerThread == 1) {
-        if (exact) launch_one<true, 1, 3>(a, nTiles, smem, threads, st);
-        else launch_one<false, 1, 3>(a, nTiles, smem, threads, st);
-    } else if (a.patPerThread == 2) {
-        if (exact) launch_one<true, 2, 2>(a, nTiles, smem, threads, st);
-        else launch_one<false, 2, 2>(a, nTiles, smem, threads, st);
-    } else {
-        if (exact) launch_one<true, 4, 1>(a, nTiles, smem, threads, st);
-        else launch_one<false, 4, 1>(a, nTiles, smem, threads, st);
-    }
+    if (exact) launch_exact<true>(a, nTiles, smem, threads, st);
+    else launch_exact<false>(a, nTiles, smem, threads, st);
 }
 
 }  // namespace sb2
