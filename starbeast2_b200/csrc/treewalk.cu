@@ -187,13 +187,18 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     const int onesIdx = warps * MAT_RING * 32, sredIdx = onesIdx + 16;
     Op *sops = reinterpret_cast<Op *>(smd + sredIdx + ((warps + 1) & ~1));      // [2 * OPS_BATCH]
     int16_t *sexp = reinterpret_cast<int16_t *>(sops + 2 * OPS_BATCH);          // [depth][warps][R][32]
-    uint8_t *sstate = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sexp + planeStride) + 15) & ~uintptr_t(15));   // [nTips][tilePat]
+    uint8_t *sstate = reinterpret_cast<uint8_t *>(sexp + planeStride);          // [nTips][tilePat]; 16-byte aligned by construction
 
     const Op *ops = A.ops + d.opBase;
     const double *matStream = A.opMats + ((size_t)d.opBase * C + c) * 32 + lane;   // + k * C*32: this lane's 8 bytes of op k's pair
     const uint8_t *states = A.tipStates + d.stateBase;
     double *partials = A.partials + d.partBase + ((size_t)c * nPat + pbase) * 4;   // + idx*4 (+ r*128)
     int16_t *cumExp = A.cumExp + d.expBase + (size_t)c * nPat + pbase;              // + idx   (+ r*32)
+    // keep the three per-thread base pointers in registers: under the 64-register cap ptxas otherwise re-derives them
+    // (64-bit multiplies) inside every iteration of the walk
+    asm volatile("" : "+l"(partials));
+    asm volatile("" : "+l"(cumExp));
+    asm volatile("" : "+l"(matStream));
     const int ringIdx = w * MAT_RING * 32;
     const int stateIdx = chunk * 32 * R + lane;
     const int stackIdx = w * R * 32 + lane;                 // + slot*slotStride + r*32
