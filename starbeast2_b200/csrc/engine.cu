@@ -419,8 +419,9 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     {
         int64_t threads1 = 0;
         for (auto &hl : e->loci) threads1 += (int64_t)hl.d.nPat * hl.d.nCat;
-        e->patPerThread = 1;   // measured on B200: R=1 wins at every shape tried (C2, C3, C5 shard); R=2/4 kept for tuning
-        (void)threads1;
+        // measured on B200 (same box A/B): R=2 is 1-6 % faster once the GPU is saturated (C3, C5 shard); small problems
+        // (C2) are latency bound and want as many independent warps as possible
+        e->patPerThread = threads1 > 150000 ? 2 : 1;
         e->chunksPerTile = std::max(1, 2 / e->nCat);
         if (const char *v = getenv("SB2_PATTERNS_PER_THREAD")) e->patPerThread = atoi(v);
         if (const char *v = getenv("SB2_CHUNKS_PER_TILE")) e->chunksPerTile = atoi(v);

@@ -443,7 +443,9 @@ static void launch_exact(const WalkArgs &a, int nTiles, size_t smem, int threads
         else if (std4 && a.nCat == 1 && a.chunksPerTile == 2) launch_one<EXACT, 1, 4, 1, 2, 4>(a, nTiles, smem, threads, st);   // no rate heterogeneity
         else launch_one<EXACT, 1, 4, 0, 0, 0>(a, nTiles, smem, threads, st);
     } else if (a.patPerThread == 2) {
-        launch_one<EXACT, 2, 2, 0, 0, 0>(a, nTiles, smem, threads, st);
+        if (std4 && a.nCat == 4 && a.chunksPerTile == 1) launch_one<EXACT, 2, 2, 4, 1, 4>(a, nTiles, smem, threads, st);
+        else if (std4 && a.nCat == 1 && a.chunksPerTile == 2) launch_one<EXACT, 2, 2, 1, 2, 4>(a, nTiles, smem, threads, st);
+        else launch_one<EXACT, 2, 2, 0, 0, 0>(a, nTiles, smem, threads, st);
     } else {
         launch_one<EXACT, 4, 1, 0, 0, 0>(a, nTiles, smem, threads, st);
     }
