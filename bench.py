@@ -211,6 +211,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
     import torch
     from starbeast2_b200 import build as sbuild
     from starbeast2_b200.engine import Engine
@@ -230,6 +232,12 @@ def main():
     pb = build_problem(rank, world, args.loci, args.workload)
     eng = Engine.from_problem(pb, device=local, exact_order=args.exact, profile=True)
     red = eng.bind_torch()
+    comm = "none"
+    if world > 1:
+        comm = "nccl"
+        if os.environ.get("SB2_COMM", "peer") == "peer" and eng.connect_peers():
+            comm = "peer-memory all-reduce inside the reduction kernel (NVLink stores + flags)"
+    peers = world > 1 and comm != "nccl"
     units_local = pb.units
     stream = torch.cuda.current_stream()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
@@ -237,7 +245,7 @@ def main():
 
     def step_device():
         eng.mark_all_dirty()
-        if world == 1:
+        if world == 1 or peers:
             eng.eval_posterior_total(tot)
             return
         eng.eval_begin()
@@ -262,7 +270,7 @@ def main():
         eng.set_pop_model(pb.pop_kind, pb.pop_a, pb.pop_b, pb.alpha, pb.beta)
         eng.set_gene_trees_flat(0, pb.n_loci, hp, hl, hr, hh)
         eng.mark_all_dirty()
-        if world == 1:
+        if world == 1 or peers:
             eng._ck(eng._L.sb2_eval_posterior(eng._h, coal_buf.ctypes.data, lik_buf.ctypes.data, br_buf.ctypes.data, tot.ctypes.data))
             return
         eng.eval_begin()
@@ -356,7 +364,7 @@ def main():
                    "units_per_step": units_total, "mean_patterns_per_locus": float(np.mean([l.n_pat for l in pb.loci])),
                    "regime": "A (every node of every locus dirty)", "exact_order": bool(args.exact),
                    "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write; working set is L2-resident)",
-                   "parallelism": f"loci sharded over {world} GPU(s), 1 all-reduce of {eng.reduce_vector_len()} doubles per step" if world > 1 else "1 GPU"},
+                   "parallelism": f"loci sharded over {world} GPU(s), 1 all-reduce of {eng.reduce_vector_len()} doubles per step ({comm})" if world > 1 else "1 GPU"},
         "posterior_evals_per_sec": args.steps / (ms * 1e-3),
         "log_posterior": total_ref,
         "e2e": {"value": units_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

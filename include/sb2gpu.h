@@ -121,6 +121,15 @@ SB2_API int sb2_eval_end(sb2_engine *e, double *perLocusCoal, double *perLocusLi
  * torch tensor handed to torch.distributed.all_reduce) with sb2_bind_reduce_vector before the first eval. */
 SB2_API int sb2_reduce_vector(sb2_engine *e, void **devPtr, int32_t *nDoubles);
 SB2_API int sb2_bind_reduce_vector(sb2_engine *e, void *devPtr);
+/* Peer-memory all-reduce for one-process-per-GPU hosts on an NVLink / NVSwitch box: after sb2_comm_connect the
+ * single-call evaluations (sb2_eval_posterior / _coalescent / _likelihood) exchange the reduce vector inside the
+ * reduction kernel (stores into every peer's buffer + sequence flags, summed in rank order: all ranks get
+ * bit-identical totals) instead of needing a host-driven all-reduce between begin() and end().
+ * sb2_comm_handle writes the 64-byte CUDA IPC handle of this engine's communication buffer; the host all-gathers the
+ * handles and passes them, ordered by rank, to sb2_comm_connect on every rank (collective: all ranks must call it,
+ * and afterwards every rank must take part in every evaluation). */
+SB2_API int sb2_comm_handle(sb2_engine *e, void *handle64);
+SB2_API int sb2_comm_connect(sb2_engine *e, int32_t rank, int32_t nRanks, const void *handles);
 /* Run on this CUDA stream (cudaStream_t) instead of the engine's own. */
 SB2_API int sb2_set_stream(sb2_engine *e, void *cudaStream);
 

@@ -79,6 +79,12 @@ struct sb2_engine {
     // outputs
     double *dRed = nullptr, *dRedOwn = nullptr, *dOut = nullptr, *hOut = nullptr, *hOutDev = nullptr;
     uint32_t *dDone = nullptr, *dLocusDone = nullptr;
+    // peer-memory all-reduce
+    void *commBuf = nullptr;
+    size_t commSlotsBytes = 0;
+    std::vector<void *> commOpened;
+    CommArgs comm{};
+    bool commConnected = false;
     int nRed = 0, nOut = 0;
     int popKind = SB2_POP_CONSTANT;
     // dirtiness
@@ -282,6 +288,17 @@ int do_prepare(sb2_engine *e)
 
 // fuse: 0 = plain; 1 = last CTA also runs k_reduce_local's body; 2 = ... and k_finish's + publish.  *fused tells the
 // caller whether the launch happened (nothing is launched when no walk is pending).
+// final reduction of the single-call evaluations: across GPUs over peer memory when connected, else local
+void launch_final(sb2_engine *e, const ReduceArgs &r)
+{
+    if (e->commConnected) {
+        e->comm.seq++;
+        launch_reduce_xgpu(r, e->comm, e->stream, &e->launches);
+    } else {
+        launch_reduce_finish(r, e->stream, &e->launches);
+    }
+}
+
 int do_walk(sb2_engine *e, int fuse = 0, bool *fused = nullptr)
 {
     if (fused) *fused = false;
@@ -295,7 +312,7 @@ int do_walk(sb2_engine *e, int fuse = 0, bool *fused = nullptr)
     // Folding the reductions into the walk's last CTA measured no faster end to end on B200 (69.5 vs 70.5 us at C2) and
     // lengthens the roofline kernel, so it is opt-in (SB2_FUSE=1); never in exact mode (sequential pattern sums).
     static const bool wantFuse = getenv("SB2_FUSE") != nullptr;
-    if (e->cfg.exact_order || !wantFuse) fuse = 0;
+    if (e->cfg.exact_order || !wantFuse || e->commConnected) fuse = 0;
     a.fuseReduce = fuse; a.doneCounter = e->dDone; a.locusDone = e->dLocusDone;
     e->walkPending = false; e->tilesValid = true;
     a.red = reduce_args(e);
@@ -369,6 +386,7 @@ void sb2_destroy(sb2_engine *e)
     for (void *p : {(void *)e->hParams, (void *)e->hCat, (void *)e->hExplicit, (void *)e->hInTree, (void *)e->hFlags, (void *)e->hSpecies, (void *)e->hOut,
                     (void *)e->hParamsStored, (void *)e->hCatStored, (void *)e->hExplicitStored, (void *)e->hSpeciesStored})
         if (p) cudaFreeHost(p);
+    for (void *p : e->commOpened) cudaIpcCloseMemHandle(p);
     for (auto &ev : e->evPool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -545,6 +563,13 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     }
     if ((rc = dev_alloc(e, &e->dDone, 1))) return rc;
     CUDA_TRY(e, cudaMemset(e->dDone, 0, sizeof(uint32_t)));
+    {   // communication buffer: slots [2][COMM_MAX_RANKS][nRed] doubles, then flags [2][COMM_MAX_RANKS] u64 (own cudaMalloc: IPC-exportable)
+        e->commSlotsBytes = sizeof(double) * 2 * COMM_MAX_RANKS * (size_t)e->nRed;
+        unsigned char *cb = nullptr;
+        if ((rc = dev_alloc(e, &cb, e->commSlotsBytes + sizeof(unsigned long long) * 2 * COMM_MAX_RANKS))) return rc;
+        e->commBuf = cb;
+        CUDA_TRY(e, cudaMemset(cb, 0, e->commSlotsBytes + sizeof(unsigned long long) * 2 * COMM_MAX_RANKS));
+    }
     if ((rc = dev_alloc(e, &e->dLocusDone, L))) return rc;
     CUDA_TRY(e, cudaMemset(e->dLocusDone, 0, sizeof(uint32_t) * L));
     CUDA_TRY(e, cudaMemset(e->dOut, 0, sizeof(double) * e->nOut));
@@ -730,7 +755,7 @@ int sb2_eval_posterior(sb2_engine *e, double *perLocusCoal, double *perLocusLik,
     bool fused;
     if ((rc = do_prepare(e))) return rc;
     if ((rc = do_walk(e, 2, &fused))) return rc;                                     // single GPU: no all-reduce in between
-    if (!fused) launch_reduce_finish(reduce_args(e), e->stream, &e->launches);
+    if (!fused) launch_final(e, reduce_args(e));
     CUDA_TRY(e, cudaGetLastError());
     if ((rc = download(e))) return rc;
     copy_out(e, perLocusCoal, perLocusLik, perBranch, total3);
@@ -745,7 +770,7 @@ int sb2_eval_coalescent(sb2_engine *e, double *perLocus, double *perBranch, doub
     // phase 1 of the reference's posterior: the pruning kernel has not run for the re-scheduled loci yet, so the
     // likelihood entries of this pass are the cached ones (coalOnly); sb2_eval_likelihood runs the walk.
     ReduceArgs r = reduce_args(e, /*coalOnly=*/true);
-    launch_reduce_finish(r, e->stream, &e->launches);
+    launch_final(e, r);
     CUDA_TRY(e, cudaGetLastError());
     if ((rc = download(e))) return rc;
     copy_out(e, perLocus, nullptr, perBranch, nullptr);
@@ -760,7 +785,7 @@ int sb2_eval_likelihood(sb2_engine *e, double *perLocus, double *total)
     bool fused;
     if ((rc = do_prepare(e))) return rc;
     if ((rc = do_walk(e, 2, &fused))) return rc;
-    if (!fused) launch_reduce_finish(reduce_args(e), e->stream, &e->launches);
+    if (!fused) launch_final(e, reduce_args(e));
     CUDA_TRY(e, cudaGetLastError());
     if ((rc = download(e))) return rc;
     copy_out(e, nullptr, perLocus, nullptr, nullptr);
@@ -780,6 +805,39 @@ int sb2_bind_reduce_vector(sb2_engine *e, void *devPtr)
 {
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     e->dRed = devPtr ? (double *)devPtr : e->dRedOwn;
+    return SB2_OK;
+}
+
+int sb2_comm_handle(sb2_engine *e, void *handle64)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(e, cudaIpcGetMemHandle(&h, e->commBuf));
+    memcpy(handle64, &h, 64);
+    return SB2_OK;
+}
+
+int sb2_comm_connect(sb2_engine *e, int32_t rank, int32_t nRanks, const void *handles)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    if (nRanks < 1 || nRanks > COMM_MAX_RANKS || rank < 0 || rank >= nRanks || !handles) return e->fail(SB2_ERR_ARG, "bad rank %d / %d (max %d ranks)", rank, nRanks, COMM_MAX_RANKS);
+    for (int r = 0; r < nRanks; r++) {
+        unsigned char *base;
+        if (r == rank) base = (unsigned char *)e->commBuf;
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const unsigned char *)handles + 64 * (size_t)r, 64);
+            void *p = nullptr;
+            CUDA_TRY(e, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            e->commOpened.push_back(p);
+            base = (unsigned char *)p;
+        }
+        e->comm.peerSlots[r] = (double *)base;
+        e->comm.peerFlags[r] = (unsigned long long *)(base + e->commSlotsBytes);
+    }
+    e->comm.rank = rank; e->comm.nRanks = nRanks; e->comm.nRed = e->nRed; e->comm.seq = 0;
+    e->commConnected = nRanks > 1;
     return SB2_OK;
 }
 

@@ -30,6 +30,53 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_finish(ReduceArgs A)
     publish_body(A);
 }
 
+// k_reduce_xgpu: local sums + ALL-REDUCE OVER PEER MEMORY + closed forms, one kernel.
+// Every rank stores its reduce vector straight into slot [parity][rank] of every peer's communication buffer over
+// NVLink, publishes a sequence number per peer (release, system scope), waits until all peers' numbers for this
+// evaluation have arrived in its own buffer, and sums the slots in rank order -- so all ranks obtain bit-identical
+// totals.  Buffer halves alternate with the sequence parity: a rank can be at most one evaluation ahead of a peer
+// (it needs the peer's flag of evaluation s+1 before it can start s+2), so a half is never overwritten while a
+// slow peer still reads it.  A rank that never shows up cannot hang the GPU: the wait gives up after ~2 s and
+// poisons the result with NaN.
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_xgpu(ReduceArgs A, CommArgs Cm)
+{
+    cudaGridDependencySynchronize();
+    reduce_local_body(A);
+    __threadfence_block();
+    __syncthreads();
+    const int tid = threadIdx.x, nt = blockDim.x, nR = Cm.nRanks, n = Cm.nRed;
+    const int half = (int)(Cm.seq & 1ull);
+    for (int idx = tid; idx < nR * n; idx += nt) {
+        const int r = idx / n, i = idx - r * n;
+        Cm.peerSlots[r][((size_t)half * COMM_MAX_RANKS + Cm.rank) * n + i] = A.red[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < nR) {
+        volatile unsigned long long *theirs = Cm.peerFlags[tid] + half * COMM_MAX_RANKS + Cm.rank;
+        *theirs = Cm.seq;
+        volatile unsigned long long *mine = Cm.peerFlags[Cm.rank] + half * COMM_MAX_RANKS + tid;
+        const long long t0 = clock64();
+        while (*mine < Cm.seq) {
+            if (clock64() - t0 > 4000000000ll) { A.red[0] = NAN; break; }   // ~2 s at 2 GHz: a peer is gone
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    const bool poisoned = isnan(A.red[0]);
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        double sum = 0.0;
+        for (int r = 0; r < nR; r++) sum += __ldcv(Cm.peerSlots[Cm.rank] + ((size_t)half * COMM_MAX_RANKS + r) * n + i);
+        A.red[i] = poisoned ? NAN : sum;
+    }
+    __threadfence_block();
+    __syncthreads();
+    finish_body(A);
+    publish_body(A);
+}
+
 template <typename K>
 static void launch_pdl(K kernel, const ReduceArgs &a, cudaStream_t st)
 {
@@ -45,6 +92,18 @@ static void launch_pdl(K kernel, const ReduceArgs &a, cudaStream_t st)
 void launch_reduce_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches)
 {
     launch_pdl(k_reduce_finish, a, st);
+    ++*launches;
+}
+
+void launch_reduce_xgpu(const ReduceArgs &a, const CommArgs &c, cudaStream_t st, int64_t *launches)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(RED_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_reduce_xgpu, a, c);
     ++*launches;
 }
 

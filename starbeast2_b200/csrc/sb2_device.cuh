@@ -161,6 +161,17 @@ struct WalkArgs {
 };
 
 
+// Peer-memory all-reduce of the reduce vector (one process per GPU, NVLink / NVSwitch; see reduce.cu:k_reduce_xgpu)
+constexpr int COMM_MAX_RANKS = 16;
+struct CommArgs {
+    double *peerSlots[COMM_MAX_RANKS];              // every rank's communication buffer: slots [2][COMM_MAX_RANKS][nRed]
+    unsigned long long *peerFlags[COMM_MAX_RANKS];  //                                    flags [2][COMM_MAX_RANKS]
+    int32_t rank, nRanks, nRed;
+    uint32_t pad;
+    unsigned long long seq;                         // evaluation sequence number (parity selects the buffer half)
+};
+void launch_reduce_xgpu(const ReduceArgs &a, const CommArgs &c, cudaStream_t st, int64_t *launches);
+
 void launch_prepare(const PrepareArgs &a, int maxNodes, cudaStream_t st);
 void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st);
 void launch_reduce_local(const ReduceArgs &a, cudaStream_t st, int64_t *launches);

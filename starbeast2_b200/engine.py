@@ -227,9 +227,32 @@ class Engine:
         self._ck(self._L.sb2_set_stream(self._h, st.cuda_stream))
         return self._bound_tensor
 
+    def connect_peers(self, group=None) -> bool:
+        """Collective: exchanges the CUDA-IPC handles of the engines' communication buffers (one all_gather) and switches
+        the single-call evaluations to the in-kernel peer-memory all-reduce.  Returns False (and changes nothing) when
+        there is a single rank."""
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return False
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        buf = (C.c_ubyte * 64)()
+        self._ck(self._L.sb2_comm_handle(self._h, buf))
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(allh, mine, group=group)
+        blob = b"".join(bytes(t.cpu().tolist()) for t in allh)
+        self._ck(self._L.sb2_comm_connect(self._h, rank, world, blob))
+        dist.barrier(group=group)
+        self._peers = True
+        return True
+
     def eval_posterior_distributed(self, group=None) -> EvalResult:
         """begin -> all-reduce(sum) of the reduce vector over ranks -> end.  Totals are global, per-locus arrays local."""
         import torch.distributed as dist
+        if getattr(self, "_peers", False):
+            return self.eval_posterior()      # the all-reduce happens inside the reduction kernel, over peer memory
         self.eval_begin()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             if self._bound_tensor is None:

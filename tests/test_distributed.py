@@ -132,3 +132,74 @@ def test_engine_distributed_two_ranks(name):
         np.testing.assert_allclose(per_locus, full.per_locus_lik[lo:hi], rtol=1e-9)
         if pb.pop_kind == POP_ANALYTIC:
             np.testing.assert_allclose(per_branch, full.per_branch, rtol=1e-9)
+
+
+def _peer_worker(rank, world, port, name, n_loci, n_sites, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from starbeast2_b200.engine import Engine
+    lo, hi = shard_loci([1.0] * n_loci, world)[rank]
+    shard = synth.make_problem(name, n_loci=n_loci, n_sites=n_sites, locus_range=(lo, hi))
+    e = Engine.from_problem(shard, device=rank)
+    e.bind_torch()
+    assert e.connect_peers()
+    totals = []
+    for it in range(5):                       # several evaluations: both buffer halves, sequence numbers
+        e.mark_all_dirty()
+        r = e.eval_posterior_distributed()
+        totals.append((r.coalescent, r.likelihood, r.total))
+    # an incremental step on rank 1's first locus only; every rank still takes part in the evaluation
+    e.store()
+    if rank == 1:
+        rng = np.random.default_rng(5)
+        t, _ = synth.perturb_gene_tree(rng, shard.loci[0].tree, shard.loci[0].n_tips)
+        e.set_gene_tree(0, t)
+        moved = (t.parent.tolist(), t.left.tolist(), t.right.tolist(), t.height.tolist())
+    else:
+        moved = None
+    r2 = e.eval_posterior_distributed()
+    e.restore()
+    r3 = e.eval_posterior_distributed()
+    out.put((rank, totals, (r2.coalescent, r2.likelihood, r2.total), (r3.coalescent, r3.likelihood, r3.total), moved,
+             r.per_branch.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["C4", "C3"])
+def test_peer_memory_allreduce_two_gpus(name):
+    """The in-kernel all-reduce over NVLink peer memory (sb2_comm_connect): needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n_loci, n_sites, world = 6, 80, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, name, n_loci, n_sites, q)) for r in range(world)]
+    [p.start() for p in procs]
+    got = sorted(q.get(timeout=300) for _ in range(world))
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    pb = synth.make_problem(name, n_loci=n_loci, n_sites=n_sites)
+    full = oracle.posterior(pb)
+    for rank, totals, r2, r3, moved, per_branch in got:
+        for coal, lik, total in totals:
+            assert coal == pytest.approx(full.coalescent, rel=1e-9) and lik == pytest.approx(full.likelihood, rel=1e-9)
+            assert total == pytest.approx(full.total, rel=1e-9)
+        assert totals[0] == totals[-1]                    # repeatable bit for bit
+        assert r3 == totals[-1]                           # restore brings the global totals back exactly
+        if pb.pop_kind == POP_ANALYTIC:
+            np.testing.assert_allclose(per_branch, full.per_branch, rtol=1e-9)
+    assert got[0][1] == got[1][1] and got[0][2] == got[1][2]   # summed in rank order: both ranks hold identical bits
+    # the moved state, evaluated by the oracle
+    from starbeast2_b200.problem import TreeArrays
+    m = got[1][4]
+    lo, _ = shard_loci([1.0] * n_loci, world)[1]
+    pb.loci[lo].tree = TreeArrays(*[np.array(x) for x in m])
+    w2 = oracle.posterior(pb)
+    if math.isfinite(w2.coalescent):
+        assert got[0][2][2] == pytest.approx(w2.total, rel=1e-9)
+    else:
+        assert got[0][2][0] == -math.inf
