@@ -30,12 +30,6 @@ struct HostLocus {
     std::vector<uint8_t> constMask;
 };
 
-template <typename T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t n = 0;
-};
-
 }  // namespace
 
 struct sb2_engine {
@@ -100,11 +94,8 @@ struct sb2_engine {
     std::vector<uint8_t> touchedFlag;
     int reuploadFirst = 0x7fffffff, reuploadLast = -1;   // parameter range to re-upload after a restore()
     // profiling
-    cudaEvent_t evA = nullptr, evB = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evPool;
     size_t evUsed = 0;
-    double profMs = 0.0;
-    int64_t profLaunches = 0;
 
     int fail(int code, const char *fmt, ...)
     {

@@ -295,3 +295,14 @@ def test_full_size_configs_match_oracle(name, n_loci):
     e.mark_all_dirty()
     again = e.eval_posterior()
     assert again.total == got.total and np.array_equal(again.per_locus_lik, got.per_locus_lik)
+
+
+def test_committed_golden_cases():
+    """The CUDA path against the committed fixtures (tests/golden/oracle_cases.json)."""
+    import json, os
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_cases.json")))["cases"]
+    for name, c in cases.items():
+        kw = dict(c["make_problem"]); nm = kw.pop("name")
+        got = Engine.from_problem(synth.make_problem(nm, **kw)).eval_posterior()
+        assert rel_close(got.per_locus_lik, c["per_locus_lik"]) and rel_close(got.per_locus_coal, c["per_locus_coal"])
+        assert rel_close(got.total, c["total"])

@@ -104,3 +104,20 @@ def test_starbeast_clock_golden():
     rates = oracle.starbeast_clock(1.5, srates, emb.occupancy)
     for i, s in enumerate(leaf_sets(g, glabels)):
         assert rates[i] == pytest.approx(rf.CLOCK_EXPECTED[tuple(sorted(s))], abs=rf.ALLOWED_ERROR)
+
+
+def test_committed_golden_files_are_current():
+    """tests/golden/*.json (committed) agree with the oracle built here and with the reference's literals."""
+    import json, os
+    from starbeast2_b200 import synth
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    known = json.load(open(os.path.join(here, "reference_known_answers.json")))["cases"]
+    assert known["ConstantPopulationTest"]["expected"] == rf.EXPECTED["constant"]
+    assert abs(known["ConstantIOTest"]["oracle"] - known["ConstantIOTest"]["expected"]) < rf.ALLOWED_ERROR
+    cases = json.load(open(os.path.join(here, "oracle_cases.json")))["cases"]
+    for name, c in cases.items():
+        kw = dict(c["make_problem"]); nm = kw.pop("name")
+        r = oracle.posterior(synth.make_problem(nm, **kw))
+        np.testing.assert_allclose(r.per_locus_lik, c["per_locus_lik"], rtol=1e-13)
+        np.testing.assert_allclose(r.per_locus_coal, c["per_locus_coal"], rtol=1e-13)
+        assert r.total == pytest.approx(c["total"], rel=1e-13)
