@@ -158,15 +158,6 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int tile = blockIdx.x;
     const int l = A.tileLocus[tile];
-    // Programmatic dependent launch: everything above this line (and the static lookups) overlaps k_prepare's tail;
-    // nOps / ops / opMats are k_prepare's outputs and must not be touched before it has completed.
-    cudaGridDependencySynchronize();
-    cudaTriggerProgrammaticLaunchCompletion();   // the (single-CTA) reduction kernel may queue up behind us already
-    const int nOps = A.nOps[l];
-    if (nOps == 0) {         // locus clean: cached logL stands
-        walk_epilogue(A, l, 0, 0, false);
-        return;
-    }
     const LocusDesc d = A.loci[l];
     const int C = NC ? NC : A.nCat, chunks = NC ? CH : A.chunksPerTile, depth = NC ? DEPTH : A.stackDepth;
     const int warps = C * chunks;
@@ -177,7 +168,6 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     const int p0 = (tile - d.tileBase) * tilePat;
     const int pbase = p0 + chunk * 32 * R + lane;   // pattern r of this thread: pbase + 32 r
     const bool tipsInSmem = NC ? true : (A.tipsInSmem != 0);
-    const bool incremental = nOps < d.nInt;         // only then can operands be clean nodes resident in HBM
 
     // shared memory carve-up; everything is addressed as an index off one of these bases so that the compiler keeps
     // the accesses in the shared window (LDS/STS), never generic
@@ -188,10 +178,41 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     Op *sops = reinterpret_cast<Op *>(smd + sredIdx + ((warps + 1) & ~1));      // [2 * OPS_BATCH]
     int16_t *sexp = reinterpret_cast<int16_t *>(sops + 2 * OPS_BATCH);          // [depth][warps][R][32]
     uint8_t *sstate = reinterpret_cast<uint8_t *>(sexp + planeStride);          // [nTips][tilePat]; 16-byte aligned by construction
+    const uint8_t *states = A.tipStates + d.stateBase;
+
+    // ---- static inputs first: under programmatic dependent launch this part overlaps k_prepare's tail ----
+    if (tid < 16) smd[onesIdx + tid] = 1.0;
+    if (tipsInSmem) {
+        // the tile's tip states, every tip, as one burst of asynchronous 16-byte copies (rows are padded to 128 bytes with
+        // 'missing', so a tile never leaves its row); they ride in the first cp.async group, which the first op waits for
+        if (A.tipsInSmem == 2) {   // A/B knob: plain byte loads
+            const int total = d.nTips * tilePat;
+            for (int idx = tid; idx < total; idx += blockDim.x) {
+                const int t = idx / tilePat, pp = idx - t * tilePat;
+                sstate[idx] = states[(size_t)t * d.stateStride + p0 + pp];
+            }
+        } else {
+            const int per = tilePat >> 4, total = d.nTips * per;
+            for (int idx = tid; idx < total; idx += blockDim.x) {
+                const int t = idx / per, q = idx - t * per;
+                cp_async16(sstate + t * tilePat + q * 16, states + (size_t)t * d.stateStride + p0 + q * 16);
+            }
+        }
+    }
+    // nOps / ops / opMats are k_prepare's outputs: they must not be touched before that grid has completed
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();   // the (single-CTA) reduction kernel may queue up behind us already
+    const int nOps = A.nOps[l];
+    if (nOps == 0) {         // locus clean: cached logL stands
+        cp_async_commit();
+        cp_async_wait<0>();
+        walk_epilogue(A, l, 0, 0, false);
+        return;
+    }
+    const bool incremental = nOps < d.nInt;         // only then can operands be clean nodes resident in HBM
 
     const Op *ops = A.ops + d.opBase;
     const double *matStream = A.opMats + ((size_t)d.opBase * C + c) * 32 + lane;   // + k * C*32: this lane's 8 bytes of op k's pair
-    const uint8_t *states = A.tipStates + d.stateBase;
     double *partials = A.partials + d.partBase + ((size_t)c * nPat + pbase) * 4;   // + idx*4 (+ r*128)
     int16_t *cumExp = A.cumExp + d.expBase + (size_t)c * nPat + pbase;              // + idx   (+ r*32)
     // keep the three per-thread base pointers in registers: under the 64-register cap ptxas otherwise re-derives them
@@ -226,24 +247,6 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     for (int r = 0; r < R; r++) { prev[r][0] = prev[r][1] = prev[r][2] = prev[r][3] = 0.0; prevCum[r] = 0; }
 
     load_batch(0);
-    if (tid < 16) smd[onesIdx + tid] = 1.0;
-    if (tipsInSmem) {
-        // the tile's tip states, every tip, as one burst of asynchronous 16-byte copies (rows are padded to 128 bytes with
-        // 'missing', so a tile never leaves its row); they ride in the first cp.async group, which the first op waits for
-        if (A.tipsInSmem == 2) {   // A/B knob: plain byte loads
-            const int total = d.nTips * tilePat;
-            for (int idx = tid; idx < total; idx += blockDim.x) {
-                const int t = idx / tilePat, pp = idx - t * tilePat;
-                sstate[idx] = states[(size_t)t * d.stateStride + p0 + pp];
-            }
-        } else {
-            const int per = tilePat >> 4, total = d.nTips * per;
-            for (int idx = tid; idx < total; idx += blockDim.x) {
-                const int t = idx / per, q = idx - t * per;
-                cp_async16(sstate + t * tilePat + q * 16, states + (size_t)t * d.stateStride + p0 + q * 16);
-            }
-        }
-    }
     for (int j = 0; j < MAT_RING - 1; j++) issue_mats(j);
     cp_async_wait<MAT_RING - 2>();   // group 0 (tip states + op 0's matrices) has landed for this thread ...
     __syncthreads();                 // ... and for everybody else; the op schedule is visible too
