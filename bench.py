@@ -148,14 +148,31 @@ def bench_incremental(eng, pb, synth, n_steps=400):
             updates.append(eng.last_node_updates())
         eng.restore()
 
+    tot = np.zeros(3)
+
+    def one_call(i):
+        l, t = moves[i % len(moves)]
+        eng.store()
+        eng.set_gene_tree(l, t)
+        eng.eval_posterior_total(tot)      # speculative single round trip: coalescent and likelihood together
+        eng.restore()
+
     for i in range(20):
         one(i, count=True)
     t0 = time.perf_counter()
     for i in range(n_steps):
         one(i)
     dt = time.perf_counter() - t0
+    for i in range(20):
+        one_call(i)
+    t0 = time.perf_counter()
+    for i in range(n_steps):
+        one_call(i)
+    dt1 = time.perf_counter() - t0
     return {"steps_per_sec": n_steps / dt, "us_per_step": 1e6 * dt / n_steps, "mean_node_updates": float(np.mean(updates)),
-            "protocol": "store, set_gene_tree(1 locus), eval_coalescent, eval_likelihood, restore; host-timed"}
+            "protocol": "store, set_gene_tree(1 locus), eval_coalescent, eval_likelihood, restore; host-timed",
+            "single_round_trip": {"steps_per_sec": n_steps / dt1, "us_per_step": 1e6 * dt1 / n_steps,
+                                  "protocol": "store, set_gene_tree, eval_posterior, restore"}}
 
 
 def run_reference(args):

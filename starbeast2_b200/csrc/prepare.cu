@@ -265,14 +265,8 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
             s.rate[i] = (clockKind == 2) ? A.explicitRates[nb + i] : clockRate;   // StrictClockModel / explicit
     }
     __syncthreads();
-    if (tid == 0) {
-        if (wantRate) s.rate[root] = clockRate;   // StarBeastClock.java:72
-        int acc = 0;
-        for (int b = 0; b < S; b++) { s.kstart[b] = acc; acc += s.k[b]; }
-        s.kstart[S] = acc;
-    }
+    if (tid == 0 && wantRate) s.rate[root] = clockRate;   // StarBeastClock.java:72 (read again only after the next barrier)
     const bool compat = s.misc[0] != 0;
-    __syncthreads();
 
     // ---- 3. per-branch sorted times + population-model terms ------------------------------------------------
     // rank sort of the internal nodes by (species branch, height): branch b's times are contiguous and ascending
@@ -292,7 +286,9 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
     const double logPloidy = log(ploidy);
     for (int b = tid; b < S; b += nt) {
         const int n = s.n[b], k = s.k[b];
-        const double *ts = s.times + s.kstart[b];
+        int kstart = 0;                       // branch b's block of the rank-sorted times starts after all lower-numbered branches'
+        for (int bb = 0; bb < b; bb++) kstart += s.k[bb];
+        const double *ts = s.times + kstart;
         const double t0 = s.sH[b];
         const double tEnd = (s.sP[b] < 0) ? INFINITY : s.sH[s.sP[b]];   // GeneTree.java:394
         auto T = [&](int i) { return i == 0 ? t0 : (i <= k ? ts[i - 1] : tEnd); };
@@ -379,12 +375,11 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         A.cur.assign[nb + i] = s.assign[i];
     }
     __syncthreads();
+    // a node is recomputed when its own inputs changed or anything below it was recomputed: mark it and its ancestors
+    // (the dirty set is upward closed).  Racing markers are benign: whoever marked a node first keeps climbing.
     for (int i = nT + tid; i < G; i += nt)
-        if (forceAll || s.topo[i] || s.matDirty[s.gL[i]] || s.matDirty[s.gR[i]]) s.dirty[i] = 1;
-    __syncthreads();
-    // a node is recomputed when anything below it was: mark ancestors (dirty set is upward closed)
-    for (int i = nT + tid; i < G; i += nt)
-        if (s.dirty[i] == 1) {
+        if (forceAll || s.topo[i] || s.matDirty[s.gL[i]] || s.matDirty[s.gR[i]]) {
+            s.dirty[i] = 1;
             int a = s.gP[i];
             while (a >= 0 && s.dirty[a] == 0) { s.dirty[a] = 2; a = s.gP[a]; }
         }

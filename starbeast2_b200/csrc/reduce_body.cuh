@@ -29,14 +29,39 @@ __device__ __forceinline__ double block_sum(double v, double *scratch)
     return t;
 }
 
+// three sums in one pass (same fixed shape as block_sum, a third of the barriers)
+__device__ __forceinline__ void block_sum3(double &a, double &b, double &c, double *scratch)
+{
+    const int tid = threadIdx.x, nw = blockDim.x >> 5;
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); c += __shfl_xor_sync(0xffffffffu, c, off);
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { scratch[tid >> 5] = a; scratch[32 + (tid >> 5)] = b; scratch[64 + (tid >> 5)] = c; }
+    __syncthreads();
+    double x = 0.0, y = 0.0, z = 0.0;
+    if (tid < 32) {
+        if (tid < nw) { x = scratch[tid]; y = scratch[32 + tid]; z = scratch[64 + tid]; }
+        for (int off = 16; off > 0; off >>= 1) {
+            x += __shfl_xor_sync(0xffffffffu, x, off); y += __shfl_xor_sync(0xffffffffu, y, off); z += __shfl_xor_sync(0xffffffffu, z, off);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { scratch[0] = x; scratch[1] = y; scratch[2] = z; }
+    __syncthreads();
+    a = scratch[0]; b = scratch[1]; c = scratch[2];
+    __syncthreads();
+}
+
 __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A)
 {
-    __shared__ double scratch[32];
+    __shared__ double scratch[96];
     const int tid = threadIdx.x, nt = blockDim.x, L = A.nLoci, S = A.S;
     double *perLocusCoal = A.out + 3, *perLocusLik = A.out + 3 + L;
     double likPart = 0.0, coalPart = 0.0, incPart = 0.0;
     for (int l = tid; l < L; l += nt) {
         double lik;
+        const double coal = A.cur.coal[l];   // issued before the dependent tile loads
         if (A.useTiles && A.nOps[l] > 0) {
             const LocusDesc &d = A.loci[l];
             lik = 0.0;
@@ -55,7 +80,6 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A)
         } else {
             lik = A.cur.logL[l];   // clean locus: cached value (CompoundDistribution uses getCurrentLogP)
         }
-        const double coal = A.cur.coal[l];
         perLocusLik[l] = lik;
         perLocusCoal[l] = coal;
         likPart += lik;
@@ -73,11 +97,12 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A)
         __syncthreads();
         likSum = scratch[0]; coalSum = scratch[1];
         __syncthreads();
+        incPart = block_sum(incPart, scratch);
     } else {
-        likSum = block_sum(likPart, scratch);
-        coalSum = block_sum(coalPart, scratch);
+        block_sum3(likPart, coalPart, incPart, scratch);
+        likSum = likPart; coalSum = coalPart;
     }
-    const double inc = block_sum(incPart, scratch);
+    const double inc = incPart;
     if (tid == 0) { A.red[0] = coalSum; A.red[1] = likSum; A.red[2] = inc; }
 
     // analytic integration: per-branch sums over this rank's loci
