@@ -281,18 +281,32 @@ def main():
     d2h = 8 * (3 + 2 * pb.n_loci + S)
     coal_buf, lik_buf, br_buf = np.zeros(pb.n_loci), np.zeros(pb.n_loci), np.zeros(S)
 
+    # the reference-facing call sequence of one step, through the C ABI with HOST buffers (addresses resolved once, as a
+    # JNI / FFM caller would): species tree, species rates, population sizes, all gene trees in; per-locus + total logP out
+    from starbeast2_b200 import _lib as sblib
+    raw, h = sblib.load_raw(), eng._h
+    sp = pb.species
+    keep = [np.ascontiguousarray(x) for x in (sp.parent, sp.left, sp.right, sp.height, pb.species_rates,
+                                              pb.pop_a if pb.pop_a is not None else np.zeros(1), pb.pop_b if pb.pop_b is not None else np.zeros(1))]
+    ptr = [a.ctypes.data for a in keep]
+    tp, tl, tr, th = hp.ctypes.data, hl.ctypes.data, hr.ctypes.data, hh.ctypes.data
+    oc, ol, ob, ot = coal_buf.ctypes.data, lik_buf.ctypes.data, br_buf.ctypes.data, tot.ctypes.data
+    n_loci, pop_kind, alpha, beta = pb.n_loci, pb.pop_kind, pb.alpha, pb.beta
+
     def step_e2e():
-        eng.set_species_tree(pb.species)
-        eng.set_species_rates(pb.species_rates)
-        eng.set_pop_model(pb.pop_kind, pb.pop_a, pb.pop_b, pb.alpha, pb.beta)
-        eng.set_gene_trees_flat(0, pb.n_loci, hp, hl, hr, hh)
-        eng.mark_all_dirty()
+        rc = raw.sb2_set_species_tree(h, ptr[0], ptr[1], ptr[2], ptr[3])
+        rc |= raw.sb2_set_species_rates(h, ptr[4])
+        rc |= raw.sb2_set_pop_model(h, pop_kind, ptr[5], ptr[6], alpha, beta)
+        rc |= raw.sb2_set_gene_trees(h, 0, n_loci, tp, tl, tr, th)
+        rc |= raw.sb2_mark_all_dirty(h)
         if world == 1 or peers:
-            eng._ck(eng._L.sb2_eval_posterior(eng._h, coal_buf.ctypes.data, lik_buf.ctypes.data, br_buf.ctypes.data, tot.ctypes.data))
-            return
-        eng.eval_begin()
-        dist.all_reduce(red)
-        eng._ck(eng._L.sb2_eval_end(eng._h, coal_buf.ctypes.data, lik_buf.ctypes.data, br_buf.ctypes.data, tot.ctypes.data))
+            rc |= raw.sb2_eval_posterior(h, oc, ol, ob, ot)
+        else:
+            rc |= raw.sb2_eval_begin(h)
+            dist.all_reduce(red)
+            rc |= raw.sb2_eval_end(h, oc, ol, ob, ot)
+        if rc:
+            eng._ck(-1)
 
     def barrier():
         torch.cuda.synchronize()

@@ -94,3 +94,33 @@ def load() -> C.CDLL:
     L._sb2_signatures = sig
     _lib = L
     return L
+
+
+_raw = None
+
+
+def load_raw() -> C.CDLL:
+    """A second handle on the same library whose hot entry points take raw addresses (c_void_p) instead of checked numpy
+    arrays: what a JNI / FFM caller does -- resolve the buffers once, then just call.  Used by bench.py's e2e loop so that
+    the number reflects the C ABI, not numpy argument validation."""
+    global _raw
+    if _raw is not None:
+        return _raw
+    load()
+    L = C.CDLL(LIB_PATH)
+    E = _vp
+    for name, args in {
+        "sb2_set_species_tree": [E, _vp, _vp, _vp, _vp],
+        "sb2_set_gene_trees": [E, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp],
+        "sb2_set_species_rates": [E, _vp],
+        "sb2_set_pop_model": [E, C.c_int32, _vp, _vp, C.c_double, C.c_double],
+        "sb2_mark_all_dirty": [E],
+        "sb2_eval_posterior": [E, _vp, _vp, _vp, _vp],
+        "sb2_eval_begin": [E],
+        "sb2_eval_end": [E, _vp, _vp, _vp, _vp],
+    }.items():
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
+    _raw = L
+    return L

@@ -265,3 +265,90 @@ def test_posterior_protocol_with_tree_likelihoods():
     assert eng.launch_count() - launches_lik == 2      # k_prepare + the fused reduction; no pruning kernel
     speciesTree.restore(); posterior.restore()
     assert posterior.calculateLogP() == before
+
+
+# ---- BASELINE.json configs[0]: the Canis tutorial data (16 loci x 16 individuals / 8 species, HKY, constant pops) ----------
+
+def _canis():
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "canis_c1.json")))["loci"]
+
+
+def test_canis_fixture_matches_reference_fasta():
+    """Alignment (calcPatterns) on the reference's FASTA files reproduces the committed fixture (runs where the reference is)."""
+    import os
+    from starbeast2_b200.io import read_fasta
+    data = "/root/reference/tutorial/data"
+    if not os.path.isdir(data):
+        pytest.skip("reference tree not present on this machine")
+    for name, fx in _canis().items():
+        a = Alignment()
+        a.initByName("sequences", read_fasta(os.path.join(data, name + ".fasta")))
+        assert a.taxa == fx["taxa"] and a.weights.tolist() == fx["weights"]
+        assert ["".join("ACGT-"[s] for s in row) for row in a.patterns] == fx["patterns"]
+        assert int(a.weights.sum()) == fx["sites"]
+    assert len(_canis()) == 16 and 8 <= min(len(v["weights"]) for v in _canis().values()) and max(len(v["weights"]) for v in _canis().values()) == 41
+
+
+@pytest.mark.gpu
+def test_canis_c1_posterior_through_plugins():
+    """The tutorial's model wiring on the tutorial's alignments (gaps included), random MSC-compatible trees; the CUDA path
+    against the oracle, locus by locus."""
+    import oracle
+    from starbeast2_b200 import synth
+    from starbeast2_b200.problem import POP_CONSTANT, Locus, Problem
+    fx = _canis()
+    species = sorted({t[:-2] for v in fx.values() for t in v["taxa"]})
+    assert len(species) == 8
+    rng = np.random.Generator(np.random.PCG64(20260101))
+    sp_arrays = synth.yule_species_tree(rng, 8)
+    superset = TaxonSet([TaxonSet(s, [Taxon(s + "_a"), Taxon(s + "_b")]) for s in species])
+    speciesTree = SpeciesTreeParser()
+    speciesTree.initByName("arrays", sp_arrays, "labels", species, "taxonset", superset)
+    pop = rng.gamma(2.0, 0.025, size=15)
+    popSizes = RealParameter(value=" ".join(repr(float(x)) for x in pop), dimension=15)
+    popModel = PassthroughModel(childModel=ConstantPopulations(populationSizes=popSizes, speciesTree=speciesTree))
+    clockRate = RealParameter(value="0.05")
+    clock = StrictClockModel()
+    clock.initByName("clock.rate", clockRate)       # one clock shared by all loci (Canis-Phylogeny.xml:692-694)
+    geneTrees, likelihoods, loci = [], [], []
+    code = {c: i for i, c in enumerate("ACGT-")}
+    for name, v in fx.items():
+        arrays, tip_species = synth.simulate_gene_tree(rng, sp_arrays, pop * 2.0, np.array([2] * 8))
+        labels = [species[s] + ("_a" if k % 2 == 0 else "_b") for k, s in enumerate(tip_species)]
+        tree = TreeParser()
+        tree.initByName("arrays", arrays, "labels", labels)
+        gt = GeneTree()
+        gt.initByName("tree", tree, "speciesTree", speciesTree, "populationModel", popModel)   # ploidy defaults to 2.0
+        geneTrees.append(gt)
+        pats = np.array([[code[ch] for ch in row] for row in v["patterns"]], np.uint8)
+        data = Alignment()
+        data.initByName("patterns", pats, "weights", v["weights"], "taxa", v["taxa"])
+        hky = HKY(kappa=RealParameter(value="2.0"), frequencies=Frequencies(data=data))   # empirical frequencies (:689)
+        site = SiteModel()
+        site.initByName("substModel", hky, "mutationRate", RealParameter(value=str(float(rng.lognormal(0, 0.3)))))
+        tl = TreeLikelihood()
+        tl.initByName("data", data, "tree", tree, "siteModel", site, "branchRateModel", clock)
+        likelihoods.append(tl)
+        kind, sparams = hky.engine_params()
+        rates, props = site.category_rates()
+        st, w = data.patterns_for(labels)
+        loci.append(Locus(tree=arrays, tip_states=st, weights=w, tip_species=tip_species, subst_kind=kind, subst_params=sparams,
+                          cat_rates=rates, cat_props=props, clock_rate=0.05))
+    posterior = CompoundDistribution()
+    posterior.initByName("distribution", [MultispeciesCoalescent(distribution=geneTrees), CompoundDistribution(distribution=likelihoods)])
+    got = posterior.calculateLogP()
+    want = oracle.posterior(Problem(species=sp_arrays, loci=loci, pop_kind=POP_CONSTANT, pop_a=pop))
+    assert got == pytest.approx(want.total, rel=1e-9)
+    for tl, w in zip(likelihoods, want.per_locus_lik):
+        assert tl.logP == pytest.approx(w, rel=1e-9)
+    for gt, w in zip(geneTrees, want.per_locus_coal):
+        assert gt.logP == pytest.approx(w, rel=1e-9)
+    # kappa scaler on one locus (Canis-Phylogeny.xml operators): only that locus's likelihood is recomputed
+    eng = likelihoods[0].session.engine
+    posterior.store()
+    likelihoods[3].get("siteModel").get("substModel").get("kappa").setValue(3.3)
+    loci[3].subst_params = likelihoods[3].get("siteModel").get("substModel").engine_params()[1]
+    got2 = posterior.calculateLogP()
+    assert eng.last_node_updates() == 15
+    assert got2 == pytest.approx(oracle.posterior(Problem(species=sp_arrays, loci=loci, pop_kind=POP_CONSTANT, pop_a=pop)).total, rel=1e-9)
