@@ -26,7 +26,7 @@
 
 namespace sb2 {
 
-constexpr int PREP_THREADS = 128;
+constexpr int PREP_THREADS = 256;   // the matrix phase (G x C items, ~400 instructions each) and the rank sort scale with it
 
 struct PrepSmem {
     double *gH, *rate, *times, *sH, *sRate, *btOld, *popA, *popB;
@@ -269,17 +269,30 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
     const bool compat = s.misc[0] != 0;
 
     // ---- 3. per-branch sorted times + population-model terms ------------------------------------------------
-    // rank sort of the internal nodes by (species branch, height): branch b's times are contiguous and ascending
-    for (int i = nT + tid; i < G; i += nt) {
-        const int bi = s.assign[i];
-        const double hi = s.gH[i];
-        int rank = 0;
-        for (int j = nT; j < G; j++) {
-            const int bj = s.assign[j];
-            const double hj = s.gH[j];
-            rank += (bj < bi) || (bj == bi && (hj < hi || (hj == hi && j < i)));
+    // rank sort of the internal nodes by (species branch, height): branch b's times are contiguous and ascending.
+    // O(nInt^2) comparisons, spread over all threads: `split` threads share one node (each scans a strided part of
+    // the list, 4 comparisons in flight) and combine their partial ranks with shuffles.
+    {
+        int split = 1;
+        while (split < 32 && split * 2 * nI <= nt) split *= 2;   // power of two, split * nI <= nt
+        for (int base = 0; base < nI; base += nt / split) {
+            const int ii = base + tid / split, part = tid % split;
+            const bool act = ii < nI;
+            const int i = nT + (act ? ii : 0);
+            const int bi = s.assign[i];
+            const double hi = s.gH[i];
+            int rank = 0;
+            if (act) {
+#pragma unroll 4
+                for (int j = nT + part; j < G; j += split) {
+                    const int bj = s.assign[j];
+                    const double hj = s.gH[j];
+                    rank += (bj < bi) || (bj == bi && (hj < hi || (hj == hi && j < i)));
+                }
+            }
+            for (int off = split >> 1; off > 0; off >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, off);
+            if (act && part == 0) s.times[rank] = hi;
         }
-        s.times[rank] = hi;
     }
     __syncthreads();
     const double ploidy = d.ploidy;
