@@ -32,6 +32,7 @@ struct PrepSmem {
     double *gH, *rate, *times, *sH, *sRate, *btOld, *popA, *popB;
     int *gP, *gL, *gR, *assign, *cnt, *sP, *sL, *sR, *n, *k, *kstart, *misc;
     uint8_t *matDirty, *dirty, *topo, *stM, *stP, *curP, *curM;
+    int *first;   // per internal node with two dirty children: the child evaluated first; else -1
 };
 
 __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, int G, int S)
@@ -42,7 +43,7 @@ __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, i
     size_t btOld = take(8ull * G), popA = take(8ull * S), popB = take(8ull * S);
     size_t gP = take(4ull * G), gL = take(4ull * G), gR = take(4ull * G), assign = take(4ull * G), cnt = take(4ull * G);
     size_t sP = take(4ull * S), sL = take(4ull * S), sR = take(4ull * S), n = take(4ull * S), k = take(4ull * S), ks = take(4ull * (S + 1));
-    size_t misc = take(4ull * 8);
+    size_t misc = take(4ull * 8), first = take(4ull * G);
     size_t md = take(G), di = take(G), to = take(G), stM = take(G), stP = take(G), cuP = take(G), cuM = take(G);
     if (s) {
         s->gH = (double *)(base + gH); s->rate = (double *)(base + rate); s->times = (double *)(base + times);
@@ -51,7 +52,7 @@ __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, i
         s->assign = (int *)(base + assign); s->cnt = (int *)(base + cnt);
         s->sP = (int *)(base + sP); s->sL = (int *)(base + sL); s->sR = (int *)(base + sR);
         s->n = (int *)(base + n); s->k = (int *)(base + k); s->kstart = (int *)(base + ks); s->misc = (int *)(base + misc);
-        s->matDirty = base + md; s->dirty = base + di; s->topo = base + to;
+        s->matDirty = base + md; s->dirty = base + di; s->topo = base + to; s->first = (int *)(base + first);
         s->stM = base + stM; s->stP = base + stP; s->curP = base + cuP; s->curM = base + cuM;
         s->btOld = (double *)(base + btOld); s->popA = (double *)(base + popA); s->popB = (double *)(base + popB);
     }
@@ -245,15 +246,20 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
     for (int leaf = tid; leaf < nT; leaf += nt) {
         int last = leaf, g = s.gP[leaf], b = s.assign[leaf];
         double lastH = 0.0;   // GeneTree.java:260 (gene tips are taken to sit at height 0, quirk Q6)
+        double topH = (s.sP[b] >= 0) ? s.sH[s.sP[b]] : INFINITY;   // height at which the lineage leaves its current species branch
         while (g >= 0) {
             const double hg = s.gH[g];
-            double r;
-            b = climb_edge(b, lastH, hg, s, wantRate, clockRate, &r);
-            if (wantRate) s.rate[last] = r;
+            const int gnext = s.gP[g];   // depends only on g: fetched together with the height
+            if (wantRate || hg >= topH) {   // the lineage climbs, or every edge needs its StarBeastClock rate
+                double r;
+                b = climb_edge(b, lastH, hg, s, wantRate, clockRate, &r);
+                if (wantRate) s.rate[last] = r;
+                topH = (s.sP[b] >= 0) ? s.sH[s.sP[b]] : INFINITY;
+            }
             const int old = atomicCAS(&s.assign[g], -1, b);   // first lineage to arrive claims the node (:356-359)
             if (old == -1) {
                 atomicAdd(&s.k[b], 1);
-                last = g; lastH = hg; g = s.gP[g];
+                last = g; lastH = hg; g = gnext;
             } else {
                 if (old != b) s.misc[0] = 0;                 // GeneTree.java:375-377 incompatible
                 break;
@@ -405,19 +411,22 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         }
     __syncthreads();
     if (tid == 0) A.nOps[l] = s.dirty[root] ? s.cnt[root] : 0;
+    // at a node whose two children are both dirty the heavier child (more dirty nodes, ties -> left) is evaluated first
+    // and parks its result; everywhere else nothing is parked
+    for (int i = nT + tid; i < G; i += nt) {
+        const int Lc = s.gL[i], Rc = s.gR[i];
+        const bool both = Lc >= nT && Rc >= nT && s.dirty[Lc] && s.dirty[Rc];
+        s.first[i] = both ? ((s.cnt[Rc] > s.cnt[Lc]) ? Rc : Lc) : -1;
+    }
+    __syncthreads();
     for (int i = nT + tid; i < G; i += nt) {
         if (!s.dirty[i]) continue;
-        // position in the post-order and stack slot: walk to the root; at every ancestor whose two children are both
-        // dirty the heavier child (more dirty nodes, ties -> left) is evaluated first and parks its result one slot below
+        // position in the post-order and stack slot: walk to the root; every ancestor at which this path comes in through
+        // the second-evaluated child adds the first child's subtree to the position and one parked result to the depth
         int start = 0, base = 0, a = i;
-        while (s.gP[a] >= 0) {
-            const int p = s.gP[a], Lc = s.gL[p], Rc = s.gR[p];
-            const bool dl = Lc >= nT && s.dirty[Lc], dr = Rc >= nT && s.dirty[Rc];
-            if (dl && dr) {
-                const int first = (s.cnt[Rc] > s.cnt[Lc]) ? Rc : Lc;
-                if (a != first) { start += s.cnt[first]; base += 1; }
-            }
-            a = p;
+        for (int p = s.gP[a]; p >= 0; a = p, p = s.gP[p]) {
+            const int f = s.first[p];
+            if (f >= 0 && f != a) { start += s.cnt[f]; base += 1; }
         }
         const int pos = start + s.cnt[i] - 1;
         s.assign[i] = pos;   // geneNodeSpeciesAssignment is already written back: reuse as the node's schedule position
@@ -425,7 +434,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         A.cur.curP[nb + i] = (uint8_t)newP;
         const int Lc = s.gL[i], Rc = s.gR[i];
         const bool dl = Lc >= nT && s.dirty[Lc], dr = Rc >= nT && s.dirty[Rc];
-        const int first = (dl && dr) ? ((s.cnt[Rc] > s.cnt[Lc]) ? Rc : Lc) : (dl ? Lc : Rc);
+        const int first = (dl && dr) ? s.first[i] : (dl ? Lc : Rc);
         const unsigned cp = (unsigned)C * d.nPat;   // (pattern, category) elements per node buffer
         // the child evaluated last (the second of two dirty children, or the only dirty one) is consumed straight from
         // registers; only a first-evaluated child is parked: in stack slot `base`, or, beyond the shared-memory stack, in
@@ -451,9 +460,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         const int par = s.gP[i];
         if (par < 0) outSlot = 0;
         else {
-            const int pl = s.gL[par], pr = s.gR[par];
-            const bool pdl = pl >= nT && s.dirty[pl], pdr = pr >= nT && s.dirty[pr];
-            if (pdl && pdr && i == ((s.cnt[pr] > s.cnt[pl]) ? pr : pl) && base < A.stackDepth) outSlot = base;
+            if (s.first[par] == i && base < A.stackDepth) outSlot = base;
         }
         o.ctl = op_ctl(aKind, bKind, aSlot, bSlot, outSlot);
         A.ops[d.opBase + pos] = o;
