@@ -59,7 +59,7 @@ struct sb2_engine {
     LocusParams *hParams = nullptr, *dParams = nullptr;
     double *hCat = nullptr, *dCat = nullptr;          // [2][totalCat]: rates then props
     double *hExplicit = nullptr, *dExplicit = nullptr;  // by node (allocated lazily on first EXPLICIT clock)
-    uint8_t *hInTree = nullptr, *dInTree = nullptr;
+    uint8_t *hInTree = nullptr, *dInTree = nullptr, *hInTreeDev = nullptr;   // hInTreeDev: device address of the mapped host buffer
     int64_t inTreeBytes = 0;
     uint8_t *hFlags = nullptr, *dFlags = nullptr;
     // species + shared parameters, staged as one contiguous byte block that mirrors the StateBlock's species region
@@ -253,13 +253,20 @@ int do_prepare(sb2_engine *e)
     if (e->catDirty) CUDA_TRY(e, cudaMemcpyAsync(e->dCat, e->hCat, sizeof(double) * 2 * (size_t)e->totalCat, cudaMemcpyHostToDevice, st));
     if (e->explicitDirty && e->hExplicit)
         CUDA_TRY(e, cudaMemcpyAsync(e->dExplicit, e->hExplicit, sizeof(double) * (size_t)e->totalNodes, cudaMemcpyHostToDevice, st));
-    if (lastTree >= 0) {
+    // Uploads of up to 256 KB of trees ride zero-copy (each CTA reads its locus's tree from the mapped host buffer: one
+    // coalesced burst per CTA, measured -10 us end to end at C2); bulk uploads go through the copy engine (zero-copy reads
+    // of 1.2 MB measured +40 us at the C5 shard).  The small species block always goes through the copy engine: having
+    // every CTA fetch it over PCIe measured slower than one 1 KB memcpy.
+    static const bool noZeroCopy = getenv("SB2_NO_ZEROCOPY") != nullptr;
+    const bool zeroCopyTrees = !noZeroCopy && lastTree >= 0 &&
+        (e->loci[lastTree].d.treeOff + 20ll * e->loci[lastTree].d.nNodes - e->loci[firstTree].d.treeOff) <= (256ll << 10);
+    if (lastTree >= 0 && !zeroCopyTrees) {
         const int64_t b0 = e->loci[firstTree].d.treeOff;
         const int64_t b1 = e->loci[lastTree].d.treeOff + 20ll * e->loci[lastTree].d.nNodes;
         CUDA_TRY(e, cudaMemcpyAsync(e->dInTree + b0, e->hInTree + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
     }
     PrepareArgs a;
-    a.loci = e->dLoci; a.params = e->dParams; a.flags = e->dFlags; a.inTree = e->dInTree; a.tipSpecies = e->dTipSpecies;
+    a.loci = e->dLoci; a.params = e->dParams; a.flags = e->dFlags; a.inTree = zeroCopyTrees ? e->hInTreeDev : e->dInTree; a.tipSpecies = e->dTipSpecies;
     a.catRates = e->dCat; a.explicitRates = e->dExplicit ? e->dExplicit : e->dCat;
     a.cur = cur(e); a.stored = stored(e); a.ops = e->dOps; a.nOps = e->dNOps; a.mats = e->dMats; a.opMats = e->dOpMats;
     a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L; a.stackDepth = e->stackDepth; a.uniformFlags = uniformFlags;
@@ -517,7 +524,14 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if ((rc = pin_alloc(e, &e->hCat, 2 * (size_t)catBase))) return rc;
     if ((rc = pin_alloc(e, &e->hCatStored, 2 * (size_t)catBase))) return rc;
     if ((rc = dev_alloc(e, &e->dInTree, (size_t)treeOff))) return rc;
-    if ((rc = pin_alloc(e, &e->hInTree, (size_t)treeOff))) return rc;
+    {   // incoming gene trees: mapped pinned memory, so that k_prepare can read a SMALL proposal's trees straight from the
+        // host (zero-copy) instead of waiting for a separate H2D copy on the latency path
+        const size_t bytes = std::max<size_t>((size_t)treeOff, 16);
+        cudaError_t st = cudaHostAlloc((void **)&e->hInTree, bytes, cudaHostAllocMapped);
+        if (st != cudaSuccess) return e->fail(SB2_ERR_NOMEM, "cudaHostAlloc(mapped trees): %s", cudaGetErrorString(st));
+        memset(e->hInTree, 0, bytes);
+        CUDA_TRY(e, cudaHostGetDevicePointer((void **)&e->hInTreeDev, e->hInTree, 0));
+    }
     if ((rc = dev_alloc(e, &e->dFlags, L))) return rc;
     if ((rc = pin_alloc(e, &e->hFlags, L))) return rc;
     for (int l = 0; l < L; l++) {   // defaults: HKY kappa 1 (JC69), one category of rate 1, strict clock rate 1
