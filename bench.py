@@ -175,6 +175,41 @@ def bench_incremental(eng, pb, synth, n_steps=400):
                                   "protocol": "store, set_gene_tree, eval_posterior, restore"}}
 
 
+def bench_streaming(args, hbm_gbs, peak_src, flush, n_loci=250, steps=30):
+    """The pruning kernel where it actually streams HBM: a C5-shaped shard (GTR+G4, 120 individuals / 40 species, ~450
+    patterns per locus; 250 loci = the per-GPU shard of the 8-GPU config, 1.7 GB of partials per evaluation).  Same accounting as the headline `roofline`.
+    Not a bench line of its own (the C2 workload above is): it documents what bounds the kernel once the GPU is full."""
+    import torch
+    from starbeast2_b200 import synth
+    from starbeast2_b200.engine import Engine
+    pb = synth.make_problem("C5", n_loci=n_loci)
+    eng = Engine.from_problem(pb, device=torch.cuda.current_device(), exact_order=args.exact, profile=True)
+    eng.bind_torch()
+    tot = np.zeros(3)
+    for _ in range(3):
+        eng.mark_all_dirty(); eng.eval_posterior_total(tot)
+    eng.kernel_time()
+    stream = torch.cuda.current_stream()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.fill_(1)
+        a.record(stream)
+        eng.mark_all_dirty(); eng.eval_posterior_total(tot)
+        b.record(stream)
+    torch.cuda.synchronize()
+    step_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    k_ms, k_n = eng.kernel_time()
+    k_us = 1e3 * k_ms / max(k_n, 1)
+    dbytes, sbytes = design_bytes(pb), pb.algorithmic_bytes_survey()
+    achieved = dbytes / (k_us * 1e-6) / 1e9
+    eng.close()
+    return {"workload": f"C5 shard, {n_loci} loci of the 2,000 (GTR+G4, UCLN species clock, 120 tips)", "kernel": "k_treewalk",
+            "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "peak_source": peak_src,
+            "us_per_launch": k_us, "launches_timed": k_n, "algorithmic_bytes_per_launch": dbytes, "bytes_per_unit": dbytes / pb.units,
+            "survey_formula_frac": sbytes / (k_us * 1e-6) / 1e9 / hbm_gbs, "kernel_partials_per_sec": pb.units / (k_us * 1e-6),
+            "step_ms": step_ms, "step_partials_per_sec": pb.units / (step_ms * 1e-3)}
+
+
 def run_reference(args):
     """`--impl reference`: the CPU restatement of the reference path (oracle/, kind "port"), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -220,6 +255,7 @@ def main():
     ap.add_argument("--loci", type=int, default=0, help="loci per GPU (default: the workload's own count)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C5-shard streaming measurement of the pruning kernel")
     ap.add_argument("--exact", action="store_true")
     args = ap.parse_args()
     from starbeast2_b200 import synth
@@ -411,6 +447,9 @@ def main():
     }
     if world == 1:
         line["incremental"] = bench_incremental(eng, pb, synth)
+        if not args.no_extra:
+            eng.close()
+            line["roofline_streaming"] = bench_streaming(args, hbm_gbs, peak_src, flush)
     if not args.no_cpu and world == 1:
         import oracle
         oracle.build()

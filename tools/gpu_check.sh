@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 if [ "$1" == "--notest" ]; then shift; else timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15; fi
 for spec in ${1:-C2:50}; do
   w=${spec%%:*}; n=${spec##*:}
-  timeout 600 python bench.py --workload $w --loci $n --steps ${STEPS:-100} --warmup 5 --no-cpu > gpurun_out/bench_${w}_${n}.json 2> gpurun_out/bench_${w}_${n}.err
+  timeout 600 python bench.py --workload $w --loci $n --steps ${STEPS:-100} --warmup 5 --no-cpu --no-extra > gpurun_out/bench_${w}_${n}.json 2> gpurun_out/bench_${w}_${n}.err
   python - <<PY
 import json
 try:
