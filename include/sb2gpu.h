@@ -159,6 +159,24 @@ SB2_API int sb2_get_matrices(sb2_engine *e, int32_t locus, int32_t node, double 
 /* patternLogLikelihoods of the last evaluation of this locus, [nPatterns]. */
 SB2_API int sb2_get_pattern_logl(sb2_engine *e, int32_t locus, double *patternLogL);
 
+/* ---- operator-side queries over the resident gene trees ---------------------------------- */
+/* Both read the LAST EVALUATED (or restored) state, i.e. the chain's current state when an operator runs;
+ * SB2_ERR_STATE if a gene tree is staged but not yet evaluated.  With loci sharded over several engines the caller
+ * combines the per-engine answers with min().
+ *
+ * CoordinatedUniform.getConnectingNodes + findConnectingNodes (CoordinatedUniform.java:94-177) and the
+ * CoordinatedExponential twins (CoordinatedExponential.java:92-160), for every gene tree at once:
+ *   mask[sum of (2*nTips-1)]  1 where the gene node belongs to a connected component of `speciesNode` (loci concatenated in
+ *                             engine order, node-number order inside a locus), may be NULL;
+ *   freedoms[0] tipwardFreedom, freedoms[1] rootwardFreedom as accumulated by the gene-tree walk (+inf if unconstrained;
+ *   the caller adds the species-branch constraints of :76-81; CoordinatedExponential ignores freedoms[1]);
+ *   count       number of connecting nodes, may be NULL. */
+SB2_API int sb2_connecting_nodes(sb2_engine *e, int32_t speciesNode, uint8_t *mask, double *freedoms, int64_t *count);
+/* NodeReheight2.recalculateMaxHeight (NodeReheight2.java:150-203) without the origin: leafIsRight[species leaf] =
+ * (canonicalMap[leaf] >= centerIndex); *maxHeight = height of the lowest gene node joining a pure-left with a pure-right
+ * subtree over all gene trees (+inf if none). */
+SB2_API int sb2_max_height(sb2_engine *e, const uint8_t *leafIsRight, double *maxHeight);
+
 /* ---- introspection ------------------------------------------------------------------------------------------ */
 
 SB2_API int32_t sb2_num_loci(const sb2_engine *e);

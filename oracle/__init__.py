@@ -85,6 +85,11 @@ def lib():
                                            C.c_int, _f64p, _f64p, _f64p, C.c_double, C.c_void_p, _f64p, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sb2o_posterior.restype = C.c_int
+        L.sb2o_connecting_nodes.restype = C.c_int
+        L.sb2o_connecting_nodes.argtypes = [C.c_int, _i32p, _i32p, C.c_int, C.c_int, _i64p, _i64p, _i32p, _i32p, _i32p, _f64p, _i32p, C.c_int,
+                                            _u8p, _f64p]
+        L.sb2o_max_height.restype = C.c_double
+        L.sb2o_max_height.argtypes = [_i32p, C.c_int, C.c_double, C.c_int, _i64p, _i64p, _i32p, _i32p, _i32p, _f64p, _i32p]
         L.sb2o_posterior.argtypes = [C.POINTER(_Problem), C.c_int, C.c_int, _f64p, _f64p, _f64p, _f64p]
         L.sb2o_max_threads.restype = C.c_int
         _lib = L
@@ -296,6 +301,36 @@ def posterior(pb, n_threads: int = 1, use_scaling: int = 2, flat: Optional[FlatP
     tot = np.zeros(3)
     lib().sb2o_posterior(C.byref(fp.struct), n_threads, use_scaling, coal, lik, br, tot)
     return PosteriorResult(coal, lik, br, tot)
+
+
+def _concat_trees(pb):
+    node_off = np.zeros(len(pb.loci) + 1, np.int64)
+    tip_off = np.zeros(len(pb.loci) + 1, np.int64)
+    for i, loc in enumerate(pb.loci):
+        node_off[i + 1] = node_off[i] + loc.tree.n_nodes
+        tip_off[i + 1] = tip_off[i] + loc.n_tips
+    cat = lambda f, dt: np.ascontiguousarray(np.concatenate([f(loc) for loc in pb.loci]), dt)
+    return (node_off, tip_off, cat(lambda l: l.tree.parent, np.int32), cat(lambda l: l.tree.left, np.int32),
+            cat(lambda l: l.tree.right, np.int32), cat(lambda l: l.tree.height, np.float64), cat(lambda l: l.tip_species, np.int32))
+
+
+def connecting_nodes(pb, species_node: int, exponential: bool = False):
+    """getConnectingNodes of CoordinatedUniform / CoordinatedExponential over all gene trees of `pb`:
+    (mask[sum G] uint8, tipwardFreedom, rootwardFreedom, count)."""
+    node_off, tip_off, gp, gl, gr, gh, ts = _concat_trees(pb)
+    mask = np.zeros(int(node_off[-1]), np.uint8)
+    fr = np.zeros(2)
+    sp = pb.species
+    n = lib().sb2o_connecting_nodes(sp.n_nodes, sp.left, sp.right, int(species_node), len(pb.loci), node_off, tip_off, gp, gl, gr, gh, ts,
+                                    int(exponential), mask, fr)
+    return mask, float(fr[0]), float(fr[1]), n
+
+
+def max_height(pb, canonical_map, center_index: int, origin: float = float("inf")) -> float:
+    """NodeReheight2.recalculateMaxHeight."""
+    node_off, tip_off, gp, gl, gr, gh, ts = _concat_trees(pb)
+    return lib().sb2o_max_height(np.ascontiguousarray(canonical_map, np.int32), int(center_index), float(origin), len(pb.loci),
+                                 node_off, tip_off, gp, gl, gr, gh, ts)
 
 
 def max_threads() -> int:

@@ -569,6 +569,128 @@ SB2O_API double sb2o_tree_likelihood(
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* (1d) operator-side walks over every gene tree -- PARITY UNPINNED: the    */
+/*      reference has no test of CoordinatedUniform / CoordinatedExponential / NodeReheight2,   */
+/*      so these follow the Java recursions literally and are checked by properties only.       */
+/* ------------------------------------------------------------------------------------------ */
+
+enum { DT_LEFT_ONLY = 0, DT_RIGHT_ONLY = 1, DT_BOTH = 2, DT_NEITHER = 3 };
+
+static void min_set(double *stored, double v) { if (v < *stored) *stored = v; }   /* MinimumDouble.java:13-17 */
+
+/* CoordinatedOperator.findDescendants -- CoordinatedOperator.java:27-43, as a membership flag per species leaf */
+static void find_descendants(const int32_t *sLeft, const int32_t *sRight, int node, uint8_t *member)
+{
+    if (sLeft[node] < 0) { member[node] = 1; return; }
+    find_descendants(sLeft, sRight, sLeft[node], member);
+    find_descendants(sLeft, sRight, sRight[node], member);
+}
+
+/* CoordinatedUniform.findConnectingNodes -- CoordinatedUniform.java:118-177 (rootward != NULL) and
+ * CoordinatedExponential.findConnectingNodes -- CoordinatedExponential.java:115-160 (rootward == NULL) */
+static int find_connecting(int node, const int32_t *gLeft, const int32_t *gRight, const double *gHeight, const int32_t *tipSpecies,
+                           const uint8_t *inLeft, const uint8_t *inRight, uint8_t *connecting, double *tipward, double *rootward)
+{
+    if (gLeft[node] < 0) {
+        if (inLeft[tipSpecies[node]]) return DT_LEFT_ONLY;
+        else if (inRight[tipSpecies[node]]) return DT_RIGHT_ONLY;
+        else return DT_NEITHER;
+    }
+    const int l = gLeft[node], r = gRight[node];
+    const int ld = find_connecting(l, gLeft, gRight, gHeight, tipSpecies, inLeft, inRight, connecting, tipward, rootward);
+    const int rd = find_connecting(r, gLeft, gRight, gHeight, tipSpecies, inLeft, inRight, connecting, tipward, rootward);
+    if (ld == rd) {
+        if (ld == DT_BOTH) connecting[node] = 1;
+        return ld;
+    }
+    const double h = gHeight[node];
+    if (ld == DT_BOTH) {
+        if (rd == DT_NEITHER) {
+            if (rootward) min_set(rootward, h - gHeight[l]);
+            return DT_NEITHER;
+        } else {
+            min_set(tipward, h - gHeight[r]);
+            connecting[node] = 1;
+            return DT_BOTH;
+        }
+    } else if (rd == DT_BOTH) {
+        if (ld == DT_NEITHER) {
+            if (rootward) min_set(rootward, h - gHeight[r]);
+            return DT_NEITHER;
+        } else {
+            min_set(tipward, h - gHeight[l]);
+            connecting[node] = 1;
+            return DT_BOTH;
+        }
+    } else if (ld == DT_NEITHER || rd == DT_NEITHER) {
+        return DT_NEITHER;
+    } else {
+        min_set(tipward, h - gHeight[l]);
+        min_set(tipward, h - gHeight[r]);
+        connecting[node] = 1;
+        return DT_BOTH;
+    }
+}
+
+/* getConnectingNodes over all gene trees -- CoordinatedUniform.java:94-116 / CoordinatedExponential.java:92-113.
+ * Trees are concatenated (nodeOff/tipOff prefix sums); connecting[sum G] receives 0/1; freedoms = {tipward, rootward}
+ * start at +inf (MinimumDouble.java:9-11); exponential != 0 leaves rootward untouched.  Returns the number of connecting nodes. */
+SB2O_API int sb2o_connecting_nodes(int S, const int32_t *sLeft, const int32_t *sRight, int speciesNode, int nTrees, const int64_t *nodeOff,
+                          const int64_t *tipOff, const int32_t *gParent, const int32_t *gLeft, const int32_t *gRight, const double *gHeight,
+                          const int32_t *tipSpecies, int exponential, uint8_t *connecting, double *freedoms)
+{
+    uint8_t *inLeft = (uint8_t *)calloc((size_t)S, 1), *inRight = (uint8_t *)calloc((size_t)S, 1);
+    find_descendants(sLeft, sRight, sLeft[speciesNode], inLeft);
+    find_descendants(sLeft, sRight, sRight[speciesNode], inRight);
+    freedoms[0] = INFINITY; freedoms[1] = INFINITY;
+    int count = 0;
+    for (int j = 0; j < nTrees; j++) {
+        const int64_t o = nodeOff[j];
+        const int G = (int)(nodeOff[j + 1] - o);
+        int root = 0;
+        while (gParent[o + root] >= 0) root++;
+        memset(connecting + o, 0, (size_t)G);
+        find_connecting(root, gLeft + o, gRight + o, gHeight + o, tipSpecies + tipOff[j], inLeft, inRight, connecting + o,
+                        &freedoms[0], exponential ? NULL : &freedoms[1]);
+        for (int i = 0; i < G; i++) count += connecting[o + i];
+    }
+    free(inLeft); free(inRight);
+    return count;
+}
+
+enum { RP_LEFT = 0, RP_RIGHT = 1, RP_BOTH = 2 };
+
+/* NodeReheight2.recurseMaxHeight -- NodeReheight2.java:175-203 */
+static int recurse_max_height(int node, const int32_t *gLeft, const int32_t *gRight, const double *gHeight, const uint8_t *leafPositions, double *maxHeight)
+{
+    const int l = gLeft[node], r = gRight[node];
+    const int lp = gLeft[l] < 0 ? leafPositions[l] : recurse_max_height(l, gLeft, gRight, gHeight, leafPositions, maxHeight);
+    const int rp = gLeft[r] < 0 ? leafPositions[r] : recurse_max_height(r, gLeft, gRight, gHeight, leafPositions, maxHeight);
+    if (lp == rp) return lp;
+    if (lp != RP_BOTH && rp != RP_BOTH) *maxHeight = fmin(*maxHeight, gHeight[node]);
+    return RP_BOTH;
+}
+
+/* NodeReheight2.recalculateMaxHeight -- NodeReheight2.java:150-173.  canonicalMap[species node] = index in the canonical
+ * order (:228,:238,:249); a leaf is LEFT when that index < centerIndex.  `origin` = +inf when no origin is specified. */
+SB2O_API double sb2o_max_height(const int32_t *canonicalMap, int centerIndex, double origin, int nTrees, const int64_t *nodeOff, const int64_t *tipOff,
+                       const int32_t *gParent, const int32_t *gLeft, const int32_t *gRight, const double *gHeight, const int32_t *tipSpecies)
+{
+    double maxHeight = origin;
+    for (int i = 0; i < nTrees; i++) {
+        const int64_t o = nodeOff[i];
+        const int nTips = (int)(tipOff[i + 1] - tipOff[i]);
+        uint8_t *leafPositions = (uint8_t *)malloc((size_t)nTips);
+        for (int j = 0; j < nTips; j++) leafPositions[j] = canonicalMap[tipSpecies[tipOff[i] + j]] < centerIndex ? RP_LEFT : RP_RIGHT;
+        int root = 0;
+        while (gParent[o + root] >= 0) root++;
+        recurse_max_height(root, gLeft + o, gRight + o, gHeight + o, leafPositions, &maxHeight);
+        free(leafPositions);
+    }
+    return maxHeight;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* (3) whole-posterior driver: the timed CPU baseline (bench.py cpu_baseline / --impl reference) */
 /* ------------------------------------------------------------------------------------------ */
 

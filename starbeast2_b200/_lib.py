@@ -80,6 +80,8 @@ def load() -> C.CDLL:
         "sb2_get_partials": (C.c_int, [E, C.c_int32, C.c_int32, _vp, _vp]),
         "sb2_get_matrices": (C.c_int, [E, C.c_int32, C.c_int32, _f64p]),
         "sb2_get_pattern_logl": (C.c_int, [E, C.c_int32, _f64p]),
+        "sb2_connecting_nodes": (C.c_int, [E, C.c_int32, _vp, _f64p, C.POINTER(C.c_int64)]),
+        "sb2_max_height": (C.c_int, [E, _u8p, C.POINTER(C.c_double)]),
         "sb2_num_loci": (C.c_int32, [E]),
         "sb2_launch_count": (C.c_int64, [E]),
         "sb2_last_node_updates": (C.c_int64, [E]),

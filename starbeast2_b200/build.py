@@ -22,6 +22,7 @@ SOURCES = {
     "prepare.cu": ["-fmad=false"],
     "reduce.cu": ["-fmad=false"],
     "treewalk.cu": [],
+    "query.cu": ["-fmad=false"],
     "engine.cu": [],
 }
 DEPS = ["sb2_device.cuh", os.path.join("..", "..", "include", "sb2gpu.h")]

@@ -93,6 +93,10 @@ struct sb2_engine {
     std::vector<int32_t> touched;        // loci whose parameters changed since the last store()
     std::vector<uint8_t> touchedFlag;
     int reuploadFirst = 0x7fffffff, reuploadLast = -1;   // parameter range to re-upload after a restore()
+    // operator-side queries (allocated on first use): {result u64[4], leafClass[pad], mask[totalNodes]}
+    uint8_t *dQuery = nullptr, *hQuery = nullptr;
+    size_t queryLeafPad = 0;
+    bool everPrepared = false;
     // profiling
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evPool;
     size_t evUsed = 0;
@@ -278,6 +282,7 @@ int do_prepare(sb2_engine *e)
     std::fill(e->clockDirty.begin(), e->clockDirty.end(), 0);
     e->speciesDirty = e->catDirty = e->paramsDirty = e->explicitDirty = e->forceAll = false;
     e->needPrepare = false;
+    e->everPrepared = true;
     e->walkPending = true;
     e->tilesValid = false;
     (void)any;
@@ -382,7 +387,7 @@ void sb2_destroy(sb2_engine *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void *p : e->devAllocs) cudaFree(p);
     for (void *p : {(void *)e->hParams, (void *)e->hCat, (void *)e->hExplicit, (void *)e->hInTree, (void *)e->hFlags, (void *)e->hSpecies, (void *)e->hOut,
-                    (void *)e->hParamsStored, (void *)e->hCatStored, (void *)e->hExplicitStored, (void *)e->hSpeciesStored})
+                    (void *)e->hParamsStored, (void *)e->hCatStored, (void *)e->hExplicitStored, (void *)e->hSpeciesStored, (void *)e->hQuery})
         if (p) cudaFreeHost(p);
     for (void *p : e->commOpened) cudaIpcCloseMemHandle(p);
     for (auto &ev : e->evPool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -1000,6 +1005,93 @@ int sb2_get_pattern_logl(sb2_engine *e, int32_t locus, double *patternLogL)
     const LocusDesc &d = e->loci[locus].d;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     CUDA_TRY(e, cudaMemcpy(patternLogL, e->dPatLogL + d.patBase, 8 * (size_t)d.nPat, cudaMemcpyDeviceToHost));
+    return SB2_OK;
+}
+
+// ---- operator-side queries over the resident gene trees -----------------------------------------------------------------
+
+static double dec_min(unsigned long long u)
+{
+    const unsigned long long b = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+
+// leafClass: class bits per species leaf.  out3 = {tipward, rootward, maxHeight}; mask may be null.
+static int run_query(sb2_engine *e, int mode, const uint8_t *leafClass, uint8_t *mask, double *out3, int64_t *count)
+{
+    if (!e->everPrepared) return e->fail(SB2_ERR_STATE, "no evaluated state: evaluate the posterior before querying the gene trees");
+    for (int l = 0; l < e->L; l++)
+        if (e->treeDirty[l]) return e->fail(SB2_ERR_STATE, "locus %d has a staged gene tree that was never evaluated: the query reads the last evaluated (or restored) state", l);
+    if (!e->dQuery) {
+        e->queryLeafPad = ((size_t)e->nSpeciesLeaves + 15) & ~(size_t)15;
+        const size_t bytes = 32 + e->queryLeafPad + (size_t)e->totalNodes;
+        int rc;
+        if ((rc = dev_alloc(e, &e->dQuery, bytes))) return rc;
+        if ((rc = pin_alloc(e, &e->hQuery, bytes))) return rc;
+    }
+    unsigned long long *hdr = reinterpret_cast<unsigned long long *>(e->hQuery);
+    hdr[0] = hdr[1] = hdr[2] = 0xFFF0000000000000ull;   // enc(+inf)
+    hdr[3] = 0;
+    memcpy(e->hQuery + 32, leafClass, (size_t)e->nSpeciesLeaves);
+    cudaStream_t st = e->stream;
+    CUDA_TRY(e, cudaMemcpyAsync(e->dQuery, e->hQuery, 32 + e->queryLeafPad, cudaMemcpyHostToDevice, st));
+    QueryArgs a;
+    const StateBlock &c = cur(e);
+    a.loci = e->dLoci; a.tipSpecies = e->dTipSpecies; a.leafClass = e->dQuery + 32;
+    a.gParent = c.gParent; a.gLeft = c.gLeft; a.gRight = c.gRight; a.gHeight = c.gHeight;
+    a.mask = mask ? e->dQuery + 32 + e->queryLeafPad : nullptr;
+    a.result = reinterpret_cast<unsigned long long *>(e->dQuery);
+    a.mode = mode; a.maxNodes = e->maxNodes;
+    if (launch_tip_class_query(a, e->L, st)) return e->fail(SB2_ERR_ARG, "gene trees of %d nodes exceed the query kernel's shared memory", e->maxNodes);
+    e->launches++;
+    CUDA_TRY(e, cudaGetLastError());
+    CUDA_TRY(e, cudaMemcpyAsync(e->hQuery, e->dQuery, mask ? 32 + e->queryLeafPad + (size_t)e->totalNodes : 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(e, cudaStreamSynchronize(st));
+    for (int i = 0; i < 3; i++) out3[i] = dec_min(hdr[i]);
+    if (count) *count = (int64_t)hdr[3];
+    if (mask) memcpy(mask, e->hQuery + 32 + e->queryLeafPad, (size_t)e->totalNodes);
+    return SB2_OK;
+}
+
+int sb2_connecting_nodes(sb2_engine *e, int32_t speciesNode, uint8_t *mask, double *freedoms, int64_t *count)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    if (!freedoms) return e->fail(SB2_ERR_ARG, "null freedoms");
+    SpeciesView v = species_view(e);
+    if (speciesNode < 0 || speciesNode >= e->S || v.sLeft[speciesNode] < 0) return e->fail(SB2_ERR_ARG, "species node %d is not an internal node", speciesNode);
+    // findDescendants (CoordinatedOperator.java:27-43): leaves under the left child -> 1, under the right child -> 2, others -> 4
+    std::vector<uint8_t> cls((size_t)e->nSpeciesLeaves, 4);
+    std::vector<int32_t> stack;
+    for (int side = 0; side < 2; side++) {
+        stack.assign(1, side ? v.sRight[speciesNode] : v.sLeft[speciesNode]);
+        while (!stack.empty()) {
+            const int32_t n = stack.back();
+            stack.pop_back();
+            if (v.sLeft[n] < 0) {
+                if (n >= e->nSpeciesLeaves) return e->fail(SB2_ERR_ARG, "species leaf %d is not numbered below the leaf count", n);
+                cls[n] = (uint8_t)(1 << side);
+            } else { stack.push_back(v.sLeft[n]); stack.push_back(v.sRight[n]); }
+        }
+    }
+    double out3[3];
+    int rc = run_query(e, QUERY_CONNECTING, cls.data(), mask, out3, count);
+    if (rc) return rc;
+    freedoms[0] = out3[0]; freedoms[1] = out3[1];
+    return SB2_OK;
+}
+
+int sb2_max_height(sb2_engine *e, const uint8_t *leafIsRight, double *maxHeight)
+{
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    if (!leafIsRight || !maxHeight) return e->fail(SB2_ERR_ARG, "null argument");
+    std::vector<uint8_t> cls((size_t)e->nSpeciesLeaves);
+    for (int i = 0; i < e->nSpeciesLeaves; i++) cls[i] = leafIsRight[i] ? 2 : 1;
+    double out3[3];
+    int rc = run_query(e, QUERY_MAX_HEIGHT, cls.data(), nullptr, out3, nullptr);
+    if (rc) return rc;
+    *maxHeight = out3[2];
     return SB2_OK;
 }
 

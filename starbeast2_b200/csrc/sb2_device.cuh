@@ -172,6 +172,21 @@ struct CommArgs {
 };
 void launch_reduce_xgpu(const ReduceArgs &a, const CommArgs &c, cudaStream_t st, int64_t *launches);
 
+// Operator-side queries over the resident gene trees (query.cu)
+constexpr int QUERY_THREADS = 128;
+enum : int32_t { QUERY_CONNECTING = 0, QUERY_MAX_HEIGHT = 1 };
+struct QueryArgs {
+    const LocusDesc *loci;
+    const int32_t *tipSpecies;
+    const uint8_t *leafClass;        // [nSpeciesLeaves] class bits of each species leaf: 1, 2 or 4
+    const int32_t *gParent, *gLeft, *gRight;
+    const double *gHeight;
+    uint8_t *mask;                   // [total nodes] connecting-node flags, or nullptr
+    unsigned long long *result;      // {tipward, rootward, maxHeight} order-preserving encodings (pre-set to enc(+inf)), count
+    int32_t mode, maxNodes;
+};
+int launch_tip_class_query(const QueryArgs &a, int nLoci, cudaStream_t st);
+
 void launch_prepare(const PrepareArgs &a, int maxNodes, cudaStream_t st);
 void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st);
 void launch_reduce_local(const ReduceArgs &a, cudaStream_t st, int64_t *launches);

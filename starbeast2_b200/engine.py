@@ -261,6 +261,21 @@ class Engine:
         return self.eval_end()
 
     # -- read-back -------------------------------------------------------------------------------
+    # -- operator-side queries over the resident gene trees (CoordinatedUniform/Exponential, NodeReheight2) ----------
+    def connecting_nodes(self, species_node: int, want_mask: bool = True):
+        """(mask[sum G] uint8 or None, tipwardFreedom, rootwardFreedom, count) of the last evaluated / restored state."""
+        total = sum(2 * sh[0] - 1 for sh in self._loci_shape)
+        mask = np.zeros(total, np.uint8) if want_mask else None
+        fr = np.zeros(2)
+        cnt = C.c_int64(0)
+        self._ck(self._L.sb2_connecting_nodes(self._h, int(species_node), mask.ctypes.data if want_mask else None, fr, C.byref(cnt)))
+        return mask, float(fr[0]), float(fr[1]), int(cnt.value)
+
+    def max_height(self, leaf_is_right) -> float:
+        out = C.c_double(0.0)
+        self._ck(self._L.sb2_max_height(self._h, np.ascontiguousarray(leaf_is_right, np.uint8), C.byref(out)))
+        return float(out.value)
+
     def branch_rates(self, locus: int) -> np.ndarray:
         out = np.zeros(2 * self._loci_shape[locus][0] - 1)
         self._ck(self._L.sb2_get_branch_rates(self._h, locus, out))
