@@ -175,6 +175,45 @@ def bench_incremental(eng, pb, synth, n_steps=400):
                                   "protocol": "store, set_gene_tree, eval_posterior, restore"}}
 
 
+def bench_operator_queries(eng, pb, reps=200):
+    """the all-gene-tree walks of CoordinatedUniform/Exponential and NodeReheight2 as device queries,
+    host-timed per call (host buffers in and out; latency, one proposal = one query)."""
+    sp = pb.species
+    nodes = list(range(sp.n_leaves, sp.n_nodes - 1))
+    side = (np.arange(sp.n_leaves) % 2).astype(np.uint8)
+    eng.eval_posterior()
+    out = {}
+    for name, fn in (("connecting_nodes_with_mask", lambda i: eng.connecting_nodes(nodes[i % len(nodes)])),
+                     ("connecting_nodes_freedoms_only", lambda i: eng.connecting_nodes(nodes[i % len(nodes)], want_mask=False)),
+                     ("max_height", lambda i: eng.max_height(side))):
+        for i in range(10):
+            fn(i)
+        t0 = time.perf_counter()
+        for i in range(reps):
+            fn(i)
+        out[name + "_us"] = 1e6 * (time.perf_counter() - t0) / reps
+    out["gene_nodes_walked_per_query"] = int(sum(l.tree.n_nodes for l in pb.loci))
+    return out
+
+
+def cpu_operator_queries(pb, reps=20):
+    """The same walks by the C restatement of the Java recursions (1 thread; the Java adds HashSet<String> lookups per leaf)."""
+    import oracle
+    sp = pb.species
+    nodes = list(range(sp.n_leaves, sp.n_nodes - 1))
+    cmap = np.arange(sp.n_nodes, dtype=np.int32)
+    oracle.connecting_nodes(pb, nodes[0])
+    t0 = time.perf_counter()
+    for i in range(reps):
+        oracle.connecting_nodes(pb, nodes[i % len(nodes)])
+    t1 = time.perf_counter()
+    for i in range(reps):
+        oracle.max_height(pb, cmap, sp.n_leaves // 2)
+    t2 = time.perf_counter()
+    return {"connecting_nodes_us": 1e6 * (t1 - t0) / reps, "max_height_us": 1e6 * (t2 - t1) / reps,
+            "note": "ctypes call incl. concatenating the trees on the host; C port of the recursion, 1 thread"}
+
+
 def bench_streaming(args, hbm_gbs, peak_src, flush, n_loci=250, steps=30):
     """The pruning kernel where it actually streams HBM: a C5-shaped shard (GTR+G4, 120 individuals / 40 species, ~450
     patterns per locus; 250 loci = the per-GPU shard of the 8-GPU config, 1.7 GB of partials per evaluation).  Same accounting as the headline `roofline`.
@@ -202,8 +241,11 @@ def bench_streaming(args, hbm_gbs, peak_src, flush, n_loci=250, steps=30):
     k_us = 1e3 * k_ms / max(k_n, 1)
     dbytes, sbytes = design_bytes(pb), pb.algorithmic_bytes_survey()
     achieved = dbytes / (k_us * 1e-6) / 1e9
+    queries = bench_operator_queries(eng, pb, reps=100)
+    if not args.no_cpu:
+        queries["cpu_port"] = cpu_operator_queries(pb, reps=5)
     eng.close()
-    return {"workload": f"C5 shard, {n_loci} loci of the 2,000 (GTR+G4, UCLN species clock, 120 tips)", "kernel": "k_treewalk",
+    return {"operator_queries": queries, "workload": f"C5 shard, {n_loci} loci of the 2,000 (GTR+G4, UCLN species clock, 120 tips)", "kernel": "k_treewalk",
             "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "peak_source": peak_src,
             "us_per_launch": k_us, "launches_timed": k_n, "algorithmic_bytes_per_launch": dbytes, "bytes_per_unit": dbytes / pb.units,
             "survey_formula_frac": sbytes / (k_us * 1e-6) / 1e9 / hbm_gbs, "kernel_partials_per_sec": pb.units / (k_us * 1e-6),
@@ -447,6 +489,9 @@ def main():
     }
     if world == 1:
         line["incremental"] = bench_incremental(eng, pb, synth)
+        line["operator_queries"] = bench_operator_queries(eng, pb)
+        if not args.no_cpu:
+            line["operator_queries"]["cpu_port"] = cpu_operator_queries(pb)
         if not args.no_extra:
             eng.close()
             line["roofline_streaming"] = bench_streaming(args, hbm_gbs, peak_src, flush)

@@ -126,3 +126,17 @@ JNIEXPORT jint JNICALL FN(getEmbedding)(JNIEnv *env, jclass c, jlong h, jint loc
     UNPIN(br, pb, 0); UNPIN(assign, pa, 0); UNPIN(k, pk, 0); UNPIN(n, pn, 0);
     return rc;
 }
+JNIEXPORT jint JNICALL FN(connectingNodes)(JNIEnv *env, jclass c, jlong h, jint speciesNode, jbyteArray mask, jdoubleArray freedoms, jlongArray count)
+{
+    void *m = PIN(mask), *f = PIN(freedoms), *n = PIN(count);
+    int rc = sb2_connecting_nodes(E(h), speciesNode, (uint8_t *)m, (double *)f, (int64_t *)n);
+    UNPIN(count, n, 0); UNPIN(freedoms, f, 0); UNPIN(mask, m, 0);
+    return rc;
+}
+JNIEXPORT jint JNICALL FN(maxHeight)(JNIEnv *env, jclass c, jlong h, jbyteArray leafIsRight, jdoubleArray out)
+{
+    void *l = PIN(leafIsRight), *o = PIN(out);
+    int rc = sb2_max_height(E(h), (const uint8_t *)l, (double *)o);
+    UNPIN(out, o, 0); UNPIN(leafIsRight, l, JNI_ABORT);
+    return rc;
+}

@@ -189,6 +189,22 @@ public final class GpuSession {
 
     public double coalescent(int locus) { evalCoalescent(); return perLocusCoal[locus]; }
     public double coalescentTotal() { evalCoalescent(); return coalTotal; }
+
+    // ---- operator-side queries (CoordinatedUniform/Exponential.getConnectingNodes, NodeReheight2.recalculateMaxHeight) ----
+    // Operators run after accept()/restore() of the previous step: evalCoalescent() is a cache hit and the device's
+    // current state is the chain's current state.
+    /** mask[sum of gene node counts] in locus order; freedoms = {tipward, rootward}. */
+    public void connectingNodes(int speciesNodeNr, byte[] mask, double[] freedoms) {
+        evalCoalescent();
+        check(Sb2Gpu.connectingNodes(engine, speciesNodeNr, mask, freedoms, null));
+    }
+    public double maxHeight(byte[] leafIsRight) {
+        evalCoalescent();
+        final double[] out = new double[1];
+        check(Sb2Gpu.maxHeight(engine, leafIsRight, out));
+        return out[0];
+    }
+    public int nodeOffset(int locus) { int o = 0; for (int i = 0; i < locus; i++) o += geneTrees.get(i).getNodeCount(); return o; }
     public double likelihood(int locus) { evalLikelihood(); return perLocusLik[locus]; }
 
     private void evalCoalescent() {

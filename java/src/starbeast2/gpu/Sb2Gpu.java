@@ -35,4 +35,7 @@ public final class Sb2Gpu {
     public static native int markAllDirty(long engine);
     public static native int getBranchRates(long engine, int locus, double[] rates);
     public static native int getEmbedding(long engine, int locus, int[] lineageCounts, int[] coalCounts, int[] assignment, double[] perBranchLogP);
+    // operator-side walks over the resident gene trees (sb2gpu.h: sb2_connecting_nodes, sb2_max_height)
+    public static native int connectingNodes(long engine, int speciesNode, byte[] maskOrNull, double[] freedoms2, long[] count1OrNull);
+    public static native int maxHeight(long engine, byte[] leafIsRight, double[] maxHeight1);
 }
