@@ -41,7 +41,8 @@ struct sb2_engine {
     std::vector<HostLocus> loci;
     int S = 0, nSpeciesLeaves = 0, L = 0;
     int64_t totalNodes = 0, totalTips = 0, totalPat = 0, totalCat = 0, totalInt = 0, totalTiles = 0;
-    int maxNodes = 0, nCat = 0, chunksPerTile = 1, patPerThread = 1, stackDepth = 1;
+    int maxNodes = 0, nCat = 0, chunksPerTile = 1, patPerThread = 1, stackDepth = 1, workers = 1;
+    int32_t *dLaneOps = nullptr;
     int64_t devBytes = 0;
     int64_t launches = 0;
     std::vector<void *> devAllocs;
@@ -274,6 +275,8 @@ int do_prepare(sb2_engine *e)
     a.catRates = e->dCat; a.explicitRates = e->dExplicit ? e->dExplicit : e->dCat;
     a.cur = cur(e); a.stored = stored(e); a.ops = e->dOps; a.nOps = e->dNOps; a.mats = e->dMats; a.opMats = e->dOpMats;
     a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L; a.stackDepth = e->stackDepth; a.uniformFlags = uniformFlags;
+    a.workers = e->workers; a.laneOps = e->dLaneOps;
+    a.pfTipStates = e->dStates; a.pfWeights = e->dWeights; a.pfTileLocus = e->dTileLocus; a.pfConstMask = e->dConstMask; a.pfCatProps = e->dCat + e->totalCat;
     launch_prepare(a, e->maxNodes, st);
     e->launches++;
     CUDA_TRY(e, cudaGetLastError());
@@ -312,6 +315,9 @@ int do_walk(sb2_engine *e, int fuse = 0, bool *fused = nullptr)
     a.opMats = e->dOpMats; a.partials = e->dPartials; a.cumExp = e->dCumExp; a.patLogL = e->dPatLogL; a.tileSum = e->dTileSum;
     a.nCat = e->nCat; a.chunksPerTile = e->chunksPerTile; a.patPerThread = e->patPerThread; a.stackDepth = e->stackDepth;
     a.maxTips = (e->maxNodes + 1) / 2;
+    a.workers = e->workers; a.laneOps = e->dLaneOps;
+    static const int debugMaxOps = getenv("SB2_DEBUG_MAX_OPS") ? atoi(getenv("SB2_DEBUG_MAX_OPS")) : -1;
+    a.debugMaxOps = debugMaxOps;
     // Folding the reductions into the walk's last CTA measured no faster end to end on B200 (69.5 vs 70.5 us at C2) and
     // lengthens the roofline kernel, so it is opt-in (SB2_FUSE=1); never in exact mode (sequential pattern sums).
     static const bool wantFuse = getenv("SB2_FUSE") != nullptr;
@@ -446,6 +452,20 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
         e->chunksPerTile = std::max(1, 2 / e->nCat);
         if (const char *v = getenv("SB2_PATTERNS_PER_THREAD")) e->patPerThread = atoi(v);
         if (const char *v = getenv("SB2_CHUNKS_PER_TILE")) e->chunksPerTile = atoi(v);
+        // Tree-level parallelism (worker warps per chunk, see sb2_device.cuh) is OPT-IN (SB2_WORKERS=2|4): measured on B200 at C2
+        // (same box): the pruning kernel gains ~1 us (18.8 -> 17.7) because half of its time is fixed cost, not the walk, while
+        // k_prepare's worker assignment costs ~4 us -> the step gets slower (50.6 -> 54.9 us).  Kept for very short chains of
+        // large trees; results are bit-identical either way (tests/test_gpu_parity.py).
+        int maxInt = 0;
+        for (auto &hl : e->loci) maxInt = std::max(maxInt, hl.d.nTips - 1);
+        e->workers = 1;
+        if (const char *v = getenv("SB2_WORKERS")) {
+            const int wv = atoi(v);
+            const bool ok = wv == 1 || (maxInt <= WALK_MAX_WORKER_OPS && e->patPerThread == 1 && ((e->nCat == 1 && (wv == 2 || wv == 4)) || (e->nCat == 4 && wv == 2)));
+            if (!ok) return e->fail(SB2_ERR_ARG, "SB2_WORKERS=%d not available for this shape", wv);
+            e->workers = wv;
+        }
+        if (e->workers > 1) e->chunksPerTile = 1;
         if (e->patPerThread != 1 && e->patPerThread != 2 && e->patPerThread != 4) return e->fail(SB2_ERR_ARG, "SB2_PATTERNS_PER_THREAD must be 1, 2 or 4");
         if (e->chunksPerTile < 1 || 32 * e->nCat * e->chunksPerTile > 256) return e->fail(SB2_ERR_ARG, "nCat * chunks per tile must stay <= 8 warps");
     }
@@ -479,7 +499,8 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if (prepare_smem_bytes(e->maxNodes, e->S) > 227 * 1024) return e->fail(SB2_ERR_ARG, "gene tree too large for the per-locus shared-memory kernel");
     e->stackDepth = std::min(e->stackDepth, 4);   // deeper (rare) results are re-read from their global buffer (OPK_SPILL)
     if (const char *v = getenv("SB2_STACK_DEPTH")) e->stackDepth = std::min(15, std::max(1, atoi(v)));
-    if (treewalk_smem_bytes(e->nCat, e->chunksPerTile, e->patPerThread, e->stackDepth, (e->maxNodes + 1) / 2) > 227 * 1024)
+    if (e->workers > 1) e->stackDepth = 3;   // the multi-worker instantiations are compiled for 3 local slots + WALK_MAILBOX
+    if (treewalk_smem_bytes(e->nCat, e->chunksPerTile, e->patPerThread, e->stackDepth, (e->maxNodes + 1) / 2, e->workers) > 227 * 1024)
         return e->fail(SB2_ERR_ARG, "pruning stack does not fit shared memory");
 
     int rc;
@@ -571,6 +592,8 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
         memset(e->hOut, 0, sizeof(double) * e->nOut);
         CUDA_TRY(e, cudaHostGetDevicePointer((void **)&e->hOutDev, e->hOut, 0));
     }
+    if ((rc = dev_alloc(e, &e->dLaneOps, (size_t)L * (WALK_MAX_WORKERS + 1)))) return rc;
+    CUDA_TRY(e, cudaMemset(e->dLaneOps, 0, sizeof(int32_t) * (size_t)L * (WALK_MAX_WORKERS + 1)));
     if ((rc = dev_alloc(e, &e->dDone, 1))) return rc;
     CUDA_TRY(e, cudaMemset(e->dDone, 0, sizeof(uint32_t)));
     {   // communication buffer: slots [2][COMM_MAX_RANKS][nRed] doubles, then flags [2][COMM_MAX_RANKS] u64 (own cudaMalloc: IPC-exportable)

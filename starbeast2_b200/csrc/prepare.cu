@@ -33,6 +33,10 @@ struct PrepSmem {
     int *gP, *gL, *gR, *assign, *cnt, *sP, *sL, *sR, *n, *k, *kstart, *misc;
     uint8_t *matDirty, *dirty, *topo, *stM, *stP, *curP, *curM;
     int *first;   // per internal node with two dirty children: the child evaluated first; else -1
+    // multi-worker walks: per side-subtree root, the helper worker that evaluates it (0 = stays with worker 0), its mailbox
+    // slot and the offset of its ops inside that worker's list; `path` is scratch for the main path
+    uint8_t *wk, *mbx;
+    int *woff, *path;
 };
 
 __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, int G, int S)
@@ -45,7 +49,9 @@ __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, i
     size_t sP = take(4ull * S), sL = take(4ull * S), sR = take(4ull * S), n = take(4ull * S), k = take(4ull * S), ks = take(4ull * (S + 1));
     size_t misc = take(4ull * 8), first = take(4ull * G);
     size_t md = take(G), di = take(G), to = take(G), stM = take(G), stP = take(G), cuP = take(G), cuM = take(G);
+    size_t wk = take(G), mbx = take(G), woff = take(4ull * G), path = take(4ull * G);
     if (s) {
+        s->wk = base + wk; s->mbx = base + mbx; s->woff = (int *)(base + woff); s->path = (int *)(base + path);
         s->gH = (double *)(base + gH); s->rate = (double *)(base + rate); s->times = (double *)(base + times);
         s->sH = (double *)(base + sH); s->sRate = (double *)(base + sRate);
         s->gP = (int *)(base + gP); s->gL = (int *)(base + gL); s->gR = (int *)(base + gR);
@@ -233,6 +239,18 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         s.curP[i] = A.cur.curP[nb + i];
         s.curM[i] = A.cur.curM[nb + i];
     }
+    {   // warm L2 with the pruning kernel's static inputs of this locus (fire and forget)
+        auto warm = [&](const void *p, size_t bytes) {
+            const char *c = reinterpret_cast<const char *>(p);
+            for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)nt * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+        };
+        warm(A.pfTipStates + d.stateBase, (size_t)nT * d.stateStride);
+        warm(A.pfWeights + d.patBase, 4ull * d.nPat);
+        warm(A.pfTileLocus + d.tileBase, 4ull * d.nTiles);
+        warm(A.pfCatProps + d.catBase, 8ull * C);
+        warm(A.pfConstMask + d.patBase, (size_t)d.nPat);
+    }
     __syncthreads();
     for (int i = tid; i < G; i += nt) if (s.gP[i] < 0) s.misc[1] = i;
     for (int i = tid; i < nT; i += nt) atomicAdd(&s.n[s.assign[i]], 1);   // leafCoalescentLineageCounts, GeneTree.java:222
@@ -390,6 +408,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         }
         s.matDirty[i] = md;
         s.dirty[i] = 0;
+        s.wk[i] = 0;
         A.cur.bRate[nb + i] = s.rate[i];
         A.cur.assign[nb + i] = s.assign[i];
     }
@@ -419,16 +438,66 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         s.first[i] = both ? ((s.cnt[Rc] > s.cnt[Lc]) ? Rc : Lc) : -1;
     }
     __syncthreads();
+    // Multi-worker walks (latency-bound shapes): worker 0 keeps the main path -- from the root always into the first-evaluated
+    // (or only) dirty child -- and the small side subtrees; each larger side subtree goes, whole, to the least-loaded helper
+    // that still has a free mailbox.  Helpers meet their subtrees in the order the main path needs them (deepest first).
+    const int W = A.workers;
+    __shared__ int s_lane[WALK_MAX_WORKERS + 1], s_hStart[WALK_MAX_WORKERS * WALK_MAILBOX], s_hCnt[WALK_MAX_WORKERS * WALK_MAILBOX], s_nH;
+    if (W > 1) {
+        if (tid == 0) {
+            int loads[WALK_MAX_WORKERS] = {0, 0, 0, 0}, boxes[WALK_MAX_WORKERS] = {0, 0, 0, 0};
+            int np = 0, nH = 0;
+            for (int p = root; p >= nT && s.dirty[p];) {
+                s.path[np++] = p;
+                const int Lc = s.gL[p], Rc = s.gR[p];
+                const bool dl = Lc >= nT && s.dirty[Lc], dr = Rc >= nT && s.dirty[Rc];
+                p = (dl && dr) ? s.first[p] : (dl ? Lc : (dr ? Rc : -1));
+            }
+            for (int j = np - 1; j >= 0; j--) {
+                const int p = s.path[j], f = s.first[p];
+                if (f < 0) continue;
+                const int c2 = (s.gL[p] == f) ? s.gR[p] : s.gL[p], sz = s.cnt[c2];
+                if (sz < 2) continue;                       // a single op is cheaper done in place than waited for
+                int best = 0;
+                for (int w = 1; w < W; w++)
+                    if (boxes[w] < WALK_MAILBOX && (best == 0 || loads[w] < loads[best])) best = w;
+                if (best == 0) continue;
+                s.wk[c2] = (uint8_t)best; s.mbx[c2] = (uint8_t)boxes[best]++; s.woff[c2] = loads[best];
+                loads[best] += sz;
+                s_hStart[nH] = s.cnt[f]; s_hCnt[nH] = sz; nH++;
+            }
+            s_nH = nH;
+            int helped = 0;
+            for (int w = 1; w < W; w++) helped += loads[w];
+            s_lane[0] = 0; s_lane[1] = (s.dirty[root] ? s.cnt[root] : 0) - helped;
+            for (int w = 1; w < W; w++) s_lane[w + 1] = s_lane[w] + loads[w];
+            for (int w = W; w < WALK_MAX_WORKERS; w++) s_lane[w + 1] = s_lane[W];
+            for (int w = 0; w <= WALK_MAX_WORKERS; w++) A.laneOps[l * (WALK_MAX_WORKERS + 1) + w] = s_lane[w];
+        }
+        __syncthreads();
+    }
     for (int i = nT + tid; i < G; i += nt) {
         if (!s.dirty[i]) continue;
         // position in the post-order and stack slot: walk to the root; every ancestor at which this path comes in through
         // the second-evaluated child adds the first child's subtree to the position and one parked result to the depth
-        int start = 0, base = 0, a = i;
+        int start = 0, base = 0, a = i, sideRoot = -1, sideStart = 0;
         for (int p = s.gP[a]; p >= 0; a = p, p = s.gP[p]) {
             const int f = s.first[p];
-            if (f >= 0 && f != a) { start += s.cnt[f]; base += 1; }
+            if (f >= 0 && f != a) { start += s.cnt[f]; base += 1; sideRoot = a; sideStart = s.cnt[f]; }   // the last one found hangs off the main path
         }
-        const int pos = start + s.cnt[i] - 1;
+        int pos = start + s.cnt[i] - 1;
+
+        if (W > 1) {
+            if (sideRoot >= 0 && s.wk[sideRoot]) {   // inside a helper's subtree: contiguous in the post-order, re-based to the helper's list and stack
+
+                pos = s_lane[s.wk[sideRoot]] + s.woff[sideRoot] + (pos - sideStart);
+                base -= 1;
+            } else {                                 // worker 0: the global order with the helpers' subtrees taken out
+                int sub = 0;
+                for (int h = 0; h < s_nH; h++) if (s_hStart[h] < pos) sub += s_hCnt[h];
+                pos -= sub;
+            }
+        }
         s.assign[i] = pos;   // geneNodeSpeciesAssignment is already written back: reuse as the node's schedule position
         const int newP = 1 - s.stP[i];                                   // setNodePartialsForUpdate
         A.cur.curP[nb + i] = (uint8_t)newP;
@@ -439,11 +508,16 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         // the child evaluated last (the second of two dirty children, or the only dirty one) is consumed straight from
         // registers; only a first-evaluated child is parked: in stack slot `base`, or, beyond the shared-memory stack, in
         // its own global buffer
+        // a second-evaluated child that a helper worker evaluates: it arrives through the helper's mailbox, and the
+        // first-evaluated child is then the op right before this one in worker 0's list (register forwarding)
+        const int second = (dl && dr) ? ((first == Lc) ? Rc : Lc) : -1;
+        const bool remote = W > 1 && second >= 0 && s.wk[second] != 0;
         auto operand = [&](int c, bool cd, uint32_t &off, unsigned &kind, unsigned &slot) {
             slot = 0; off = 0;
             if (c < nT) { kind = OPK_TIP; off = c; }
             else if (cd) {
-                if (!(dl && dr && c == first)) { kind = OPK_PREV; }
+                if (remote && c == second) { kind = OPK_REMOTE; slot = A.stackDepth + s.mbx[c]; off = s.wk[c]; }
+                else if (remote || !(dl && dr && c == first)) { kind = OPK_PREV; }
                 else if (base < A.stackDepth) { kind = OPK_STACK; slot = base; }
                 else { kind = OPK_SPILL; off = ((1 - s.stP[c]) * nI + (c - nT)) * cp; }   // the buffer the child is being written to
             }
@@ -458,11 +532,15 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         // (then its slot is the parent's base == its own base); the root parks in slot 0 for the category combine
         unsigned outSlot = OP_NO_SLOT;
         const int par = s.gP[i];
+        unsigned signal = 0;
         if (par < 0) outSlot = 0;
-        else {
-            if (s.first[par] == i && base < A.stackDepth) outSlot = base;
+        else if (W > 1 && s.wk[i]) { outSlot = A.stackDepth + s.mbx[i]; signal = OP_SIGNAL; }   // a helper's finished subtree
+        else if (s.first[par] == i && base < A.stackDepth) {
+            const int sib = (s.gL[par] == i) ? s.gR[par] : s.gL[par];
+            if (!(W > 1 && s.wk[sib])) outSlot = base;     // sibling evaluated elsewhere: the parent takes this result from registers
         }
-        o.ctl = op_ctl(aKind, bKind, aSlot, bSlot, outSlot);
+        o.ctl = op_ctl(aKind, bKind, aSlot, bSlot, outSlot) | signal;
+
         A.ops[d.opBase + pos] = o;
     }
     __syncthreads();

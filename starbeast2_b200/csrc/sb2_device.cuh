@@ -59,15 +59,25 @@ enum : uint8_t {
 // STACK: a result parked in the shared-memory stack (the first-evaluated child of a node with two dirty children);
 // GLOBAL: clean node, partials resident in HBM from an earlier evaluation; SPILL: parked result whose slot is deeper
 // than the shared-memory stack -> re-read from the global buffer this launch has just written
-enum : uint8_t { OPK_TIP = 0, OPK_STACK = 1, OPK_GLOBAL = 2, OPK_SPILL = 3, OPK_PREV = 4 };
+// REMOTE: (latency-bound shapes only, see WALK_MAX_WORKERS) the result of a side subtree that another worker warp of the
+// same CTA evaluates concurrently; it arrives in that warp's mailbox slot (slot field) and the operand's offset field holds
+// the worker number
+enum : uint8_t { OPK_TIP = 0, OPK_STACK = 1, OPK_GLOBAL = 2, OPK_SPILL = 3, OPK_PREV = 4, OPK_REMOTE = 5 };
 constexpr unsigned OP_NO_SLOT = 255;   // outSlot: result is not parked (forwarded in registers, or spilled)
+constexpr unsigned OP_SIGNAL = 1u << 22;   // ctl: the parked result is awaited by another worker: publish the mailbox flag
+// Tree-level parallelism for latency-bound shapes: the walk of one pattern chunk is split over up to WALK_MAX_WORKERS warps.
+// Worker 0 walks the main (heavy-child) path; side subtrees hanging off it go to the helpers, whose results come back through
+// WALK_MAILBOX dedicated stack slots per helper (slots stackDepth .. stackDepth + WALK_MAILBOX - 1).
+constexpr int WALK_MAX_WORKERS = 4;
+constexpr int WALK_MAILBOX = 2;
+constexpr int WALK_MAX_WORKER_OPS = 64;    // multi-worker walks keep the whole op list in shared memory
 
 struct __align__(16) Op {
     // offsets are pre-multiplied by k_prepare so that the pruning kernel needs one IMAD.WIDE per address:
     uint32_t outOff;  // (buf*nInt + internal index) * nCat*nPat   -> (pattern, category) element of the output
     uint32_t aOff;    // TIP: tip index; GLOBAL / SPILL: (buf*nInt + internal index) * nCat*nPat
     uint32_t bOff;
-    uint32_t ctl;     // bits 0-2 aKind, 3-5 bKind, 6-9 aSlot, 10-13 bSlot, 14-21 outSlot (>= stack depth: not parked)
+    uint32_t ctl;     // bits 0-2 aKind, 3-5 bKind, 6-9 aSlot, 10-13 bSlot, 14-21 outSlot (>= slot count: not parked), 22 OP_SIGNAL
 };
 static_assert(sizeof(Op) == 16, "Op must stay 16 bytes (one LDS.128)");
 __host__ __device__ inline uint32_t op_ctl(unsigned aKind, unsigned bKind, unsigned aSlot, unsigned bSlot, unsigned outSlot)
@@ -117,6 +127,14 @@ struct PrepareArgs {
     int32_t S, nSpeciesLeaves, popKind, nLoci;
     int32_t stackDepth;          // shared-memory stack slots of k_treewalk
     int32_t uniformFlags;        // >= 0: every locus uses these flags (no per-step flags upload); < 0: read `flags`
+    // static inputs of k_treewalk, only prefetched into L2 here (that kernel runs next and would otherwise chase them
+    // through DRAM one dependent miss at a time whenever L2 is cold)
+    const uint8_t *pfTipStates;
+    const int32_t *pfWeights, *pfTileLocus;
+    const uint8_t *pfConstMask;
+    const double *pfCatProps;
+    int32_t workers;             // worker warps per pattern chunk of k_treewalk (1 = single walk)
+    int32_t *laneOps;            // [nLoci][WALK_MAX_WORKERS + 1] first op of each worker's list (workers > 1)
 };
 
 struct ReduceArgs {
@@ -154,6 +172,9 @@ struct WalkArgs {
     int32_t stackDepth;          // shared-memory stack slots; deeper results spill to their global buffer
     int32_t maxTips;             // largest tip count over loci (sizes the shared-memory tip-state tile)
     int32_t tipsInSmem;          // 1: tip states of the tile are staged in shared memory
+    int32_t workers;             // worker warps per pattern chunk (tree-level parallelism), 1 = off
+    int32_t debugMaxOps;         // timing experiments only (SB2_DEBUG_MAX_OPS): walk at most this many ops per worker; < 0 = all
+    const int32_t *laneOps;      // [nLoci][WALK_MAX_WORKERS + 1]
     int32_t fuseReduce;          // 0: none; 1: last CTA runs the local reduction; 2: ... and the closed forms + publish
     uint32_t *doneCounter;       // CTAs finished so far (self-resetting)
     uint32_t *locusDone;         // [nLoci] tile-CTAs finished per locus (self-resetting)
@@ -193,7 +214,7 @@ void launch_reduce_local(const ReduceArgs &a, cudaStream_t st, int64_t *launches
 void launch_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
 void launch_reduce_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
 size_t prepare_smem_bytes(int maxNodes, int S);
-size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, int maxTips);
+size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, int maxTips, int workers);
 bool treewalk_tips_in_smem(int maxTips, int tilePat);
 
 }  // namespace sb2

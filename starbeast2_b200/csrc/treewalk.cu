@@ -60,20 +60,34 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 bool treewalk_tips_in_smem(int maxTips, int tilePat) { return (size_t)maxTips * tilePat <= TIP_SMEM_MAX; }
 
-size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, int maxTips)
+size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, int maxTips, int workers)
 {
-    const size_t warps = (size_t)nCat * chunksPerTile;
+    const size_t warps = (size_t)nCat * chunksPerTile * workers;
     const size_t tilePat = (size_t)chunksPerTile * 32 * R;
-    size_t b = (size_t)stackDepth * warps * R * 32 * 32;   // partials stack (two double2 planes)
+    const size_t slots = (size_t)stackDepth + (workers > 1 ? WALK_MAILBOX : 0);
+    size_t b = slots * warps * R * 32 * 32;                // partials stack (two double2 planes)
     b += (size_t)warps * MAT_RING * 2 * 16 * 8;            // per-warp matrix rings
     b += 2ull * OPS_BATCH * sizeof(Op);                    // op schedule, two half batches
-    b += (size_t)stackDepth * warps * R * 32 * 2;          // exponent stack (int16)
+    b += slots * warps * R * 32 * 2;                       // exponent stack (int16)
     b += ((warps + 1) & ~size_t(1)) * 8 + 16 * 8;          // tile-sum scratch + the ones column
+    if (workers > 1) b += ((slots * warps * 4 + 15) & ~size_t(15));   // mailbox flags
     if (treewalk_tips_in_smem(maxTips, (int)tilePat)) b += (size_t)maxTips * tilePat + 16;   // tip states of the tile
     return (b + 15) & ~size_t(15);
+}
+
+__device__ __forceinline__ unsigned ld_acquire_shared(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_shared(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
@@ -152,7 +166,10 @@ __device__ __forceinline__ void walk_epilogue(const WalkArgs &A, int l, int tile
 
 // NC > 0: the launch geometry (categories, chunks per tile, stack depth, tips staged in shared memory) is a compile-time
 // constant, so every shared-memory offset and stride folds into an immediate; NC == 0 is the generic run-time path.
-template <bool EXACT, int R, int MINB, int NC, int CH, int DEPTH>
+// NW > 1 (tree-level parallelism for latency-bound shapes, see sb2_device.cuh): NW worker warps share one pattern chunk;
+// worker 0 walks the main path, the helpers the side subtrees k_prepare gave them, handing each finished subtree over
+// through a dedicated stack slot (mailbox) guarded by a release / acquire flag in shared memory.
+template <bool EXACT, int R, int MINB, int NC, int CH, int DEPTH, int NW>
 __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
 {
     extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -160,9 +177,12 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     const int l = A.tileLocus[tile];
     const LocusDesc d = A.loci[l];
     const int C = NC ? NC : A.nCat, chunks = NC ? CH : A.chunksPerTile, depth = NC ? DEPTH : A.stackDepth;
-    const int warps = C * chunks;
+    const int inner = C * chunks;                 // warps of one worker
+    const int warps = inner * NW;
+    const int slots = depth + (NW > 1 ? WALK_MAILBOX : 0);
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    const int c = w % C, chunk = w / C;
+    const int worker = NW > 1 ? w / inner : 0, wi = NW > 1 ? w - worker * inner : w;
+    const int c = wi % C, chunk = wi / C;
     const int nPat = d.nPat;
     const int tilePat = chunks * 32 * R;
     const int p0 = (tile - d.tileBase) * tilePat;
@@ -172,16 +192,18 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     // shared memory carve-up; everything is addressed as an index off one of these bases so that the compiler keeps
     // the accesses in the shared window (LDS/STS), never generic
     double2 *st2 = reinterpret_cast<double2 *>(smem_raw);                       // stack: [2 planes][depth][warps][R][32] double2
-    const int planeStride = depth * warps * R * 32;                             //        plane 0 = states 0,1; plane 1 = states 2,3
+    const int planeStride = slots * warps * R * 32;                             //        plane 0 = states 0,1; plane 1 = states 2,3
     double *smd = reinterpret_cast<double *>(st2 + 2 * planeStride);            // ring [warps][MAT_RING][32] | ones[16] | sred[warps]
     const int onesIdx = warps * MAT_RING * 32, sredIdx = onesIdx + 16;
     Op *sops = reinterpret_cast<Op *>(smd + sredIdx + ((warps + 1) & ~1));      // [2 * OPS_BATCH]
-    int16_t *sexp = reinterpret_cast<int16_t *>(sops + 2 * OPS_BATCH);          // [depth][warps][R][32]
-    uint8_t *sstate = reinterpret_cast<uint8_t *>(sexp + planeStride);          // [nTips][tilePat]; 16-byte aligned by construction
+    int16_t *sexp = reinterpret_cast<int16_t *>(sops + 2 * OPS_BATCH);          // [slots][warps][R][32]
+    unsigned *sflag = reinterpret_cast<unsigned *>(sexp + planeStride);         // [slots][warps] mailbox flags (NW > 1 only)
+    uint8_t *sstate = reinterpret_cast<uint8_t *>(sflag + (NW > 1 ? ((slots * warps + 3) & ~3) : 0));   // [nTips][tilePat]; 16-byte aligned by construction
     const uint8_t *states = A.tipStates + d.stateBase;
 
     // ---- static inputs first: under programmatic dependent launch this part overlaps k_prepare's tail ----
     if (tid < 16) smd[onesIdx + tid] = 1.0;
+    if (NW > 1) for (int i = tid; i < slots * warps; i += blockDim.x) sflag[i] = 0u;
     if (tipsInSmem) {
         // the tile's tip states, every tip, as one burst of asynchronous 16-byte copies (rows are padded to 128 bytes with
         // 'missing', so a tile never leaves its row); they ride in the first cp.async group, which the first op waits for
@@ -202,7 +224,26 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     // nOps / ops / opMats are k_prepare's outputs: they must not be touched before that grid has completed
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();   // the (single-CTA) reduction kernel may queue up behind us already
+    const Op *ops = A.ops + d.opBase;
+    const double *matStream = A.opMats + ((size_t)d.opBase * C + c) * 32 + lane;   // + k * C*32: this lane's 8 bytes of op k's pair
+    const int ringIdx = w * MAT_RING * 32;
+    const int matStride = C * 32;
+    // Single-worker walks start at op 0 whatever nOps turns out to be: fetch the first batch of the schedule and the first
+    // matrix pairs in the same wave of loads as nOps itself (bounded by the locus's allocation, so a clean locus merely
+    // reads stale entries) instead of one dependent round trip later.
+    int4 specOp = make_int4(0, 0, 0, 0);
+    if (NW == 1) {
+        if (tid < OPS_BATCH && tid < d.nInt) specOp = reinterpret_cast<const int4 *>(ops)[tid];
+        for (int j = 0; j < MAT_RING - 1; j++) {
+            if (j < d.nInt) cp_async8(smd + ringIdx + j * 32 + lane, matStream + (size_t)j * matStride);
+            cp_async_commit();
+        }
+    }
     const int nOps = A.nOps[l];
+    // this worker's share of the schedule: ops [kBeg, kEnd) of the locus's list
+    const int kBeg = NW > 1 ? A.laneOps[l * (WALK_MAX_WORKERS + 1) + worker] : 0;
+    int kEnd = NW > 1 ? A.laneOps[l * (WALK_MAX_WORKERS + 1) + worker + 1] : nOps;
+    if (A.debugMaxOps >= 0 && NW == 1) kEnd = min(kEnd, kBeg + A.debugMaxOps);   // timing experiments only: results are garbage
     if (nOps == 0) {         // locus clean: cached logL stands
         cp_async_commit();
         cp_async_wait<0>();
@@ -211,8 +252,6 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     }
     const bool incremental = nOps < d.nInt;         // only then can operands be clean nodes resident in HBM
 
-    const Op *ops = A.ops + d.opBase;
-    const double *matStream = A.opMats + ((size_t)d.opBase * C + c) * 32 + lane;   // + k * C*32: this lane's 8 bytes of op k's pair
     double *partials = A.partials + d.partBase + ((size_t)c * nPat + pbase) * 4;   // + idx*4 (+ r*128)
     int16_t *cumExp = A.cumExp + d.expBase + (size_t)c * nPat + pbase;              // + idx   (+ r*32)
     // keep the three per-thread base pointers in registers: under the 64-register cap ptxas otherwise re-derives them
@@ -220,11 +259,9 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     asm volatile("" : "+l"(partials));
     asm volatile("" : "+l"(cumExp));
     asm volatile("" : "+l"(matStream));
-    const int ringIdx = w * MAT_RING * 32;
     const int stateIdx = chunk * 32 * R + lane;
     const int stackIdx = w * R * 32 + lane;                 // + slot*slotStride + r*32
     const int slotStride = warps * R * 32;
-    const int matStride = C * 32;
     bool valid[R];
 #pragma unroll
     for (int r = 0; r < R; r++) valid[r] = pbase + 32 * r < nPat;
@@ -237,7 +274,7 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     };
     // this warp's matrix pair of op k (256 contiguous bytes of the op-ordered stream) -> ring slot k % MAT_RING
     auto issue_mats = [&](int k) {
-        if (k < nOps) cp_async8(smd + ringIdx + (k & (MAT_RING - 1)) * 32 + lane, matStream + (size_t)k * matStride);
+        if (k < kEnd) cp_async8(smd + ringIdx + (k & (MAT_RING - 1)) * 32 + lane, matStream + (size_t)k * matStride);
         cp_async_commit();
     };
 
@@ -246,13 +283,26 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
 #pragma unroll
     for (int r = 0; r < R; r++) { prev[r][0] = prev[r][1] = prev[r][2] = prev[r][3] = 0.0; prevCum[r] = 0; }
 
-    load_batch(0);
-    for (int j = 0; j < MAT_RING - 1; j++) issue_mats(j);
+    if (c == 0 && worker == 0) {   // what the root epilogue will read, pulled into L1 while the walk runs
+        const LocusParams *prm = &A.params[l];
+        prefetch_l1(prm->subst);        // HKY frequencies
+        prefetch_l1(prm->subst + 32);   // eigen-system frequencies, pInv, substKind
+        prefetch_l1(A.catProps + d.catBase);
+#pragma unroll
+        for (int r = 0; r < R; r++) if (valid[r]) prefetch_l1(A.weights + d.patBase + pbase + 32 * r);
+    }
+    if (NW == 1) {
+        if (tid < OPS_BATCH) reinterpret_cast<int4 *>(sops)[tid] = specOp;   // batch 0, fetched above
+    } else {
+        load_batch(0);
+        if (nOps > OPS_BATCH) load_batch(1);   // multi-worker walks are limited to 2 * OPS_BATCH ops: all resident, no reloads
+        for (int j = 0; j < MAT_RING - 1; j++) issue_mats(kBeg + j);
+    }
     cp_async_wait<MAT_RING - 2>();   // group 0 (tip states + op 0's matrices) has landed for this thread ...
     __syncthreads();                 // ... and for everybody else; the op schedule is visible too
 
-    for (int k = 0; k < nOps; k++) {
-        if ((k & (OPS_BATCH - 1)) == OPS_BATCH / 2 && (k / OPS_BATCH + 1) * OPS_BATCH < nOps) {
+    for (int k = kBeg; k < kEnd; k++) {
+        if (NW == 1 && (k & (OPS_BATCH - 1)) == OPS_BATCH / 2 && (k / OPS_BATCH + 1) * OPS_BATCH < nOps) {
             __syncthreads();                       // every warp has left the previous batch's half
             load_batch(k / OPS_BATCH + 1);
             __syncthreads();
@@ -260,7 +310,7 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
         cp_async_wait<MAT_RING - 2>();             // this lane's pieces of op k's matrices have landed
         __syncwarp();                              // ... and the other lanes'; the warp is also done with op k-1
         issue_mats(k + MAT_RING - 1);              // reuses the ring slot of op k-1
-        if (incremental && k + 2 < nOps) {         // clean children live in HBM: pull their sectors towards L2 two ops ahead
+        if (incremental && k + 2 < kEnd) {         // clean children live in HBM: pull their sectors towards L2 two ops ahead
             const Op q = sops[(k + 2) & (2 * OPS_BATCH - 1)];
 #pragma unroll
             for (int r = 0; r < R; r++) {
@@ -299,8 +349,14 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
                     continue;
                 }
                 double a[R][4];
-                if (kind == OPK_STACK) {
-                    const int si0 = ((o.ctl >> (6 + 4 * side)) & 15) * slotStride + stackIdx;
+                if (kind == OPK_STACK || (NW > 1 && kind == OPK_REMOTE)) {
+                    int si0 = ((o.ctl >> (6 + 4 * side)) & 15) * slotStride + stackIdx;
+                    if (NW > 1 && kind == OPK_REMOTE) {   // a helper's finished subtree: wait for its mailbox flag, read its slot
+                        const int src = (int)off * inner + wi;
+                        const unsigned *flag = sflag + ((o.ctl >> (6 + 4 * side)) & 15) * warps + src;
+                        while (ld_acquire_shared(flag) == 0u) { }
+                        si0 += (src - w) * R * 32;
+                    }
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         const double2 lo = st2[si0 + 32 * r], hi = st2[planeStride + si0 + 32 * r];
@@ -328,7 +384,7 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
         double *dst = partials + (size_t)o.outOff * 4;
         int16_t *dstE = cumExp + (size_t)o.outOff;
         const int outSlot = (o.ctl >> 14) & 255;
-        const bool toStack = outSlot < depth;
+        const bool toStack = outSlot < slots;
         const int so0 = outSlot * slotStride + stackIdx;
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -351,13 +407,17 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
             prev[r][0] = o0; prev[r][1] = o1; prev[r][2] = o2; prev[r][3] = o3;
             prevCum[r] = ce;
         }
+        if (NW > 1 && (o.ctl & OP_SIGNAL)) {   // hand the finished subtree to worker 0
+            __syncwarp();
+            if (lane == 0) st_release_shared(sflag + outSlot * warps + w, 1u);
+        }
     }
     cp_async_wait<0>();
     __syncthreads();
 
     // root: integratePartials over categories, (+pInv on constant patterns), frequencies, log, pattern weight
     double contrib = 0.0;
-    if (c == 0) {
+    if (c == 0 && worker == 0) {
         const LocusParams *prm = &A.params[l];
         const double *freqs = (prm->substKind == 0) ? prm->subst + 1 : prm->subst + 36;
         const double *props = A.catProps + d.catBase;
@@ -419,12 +479,12 @@ __global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
     walk_epilogue(A, l, d.tileBase, d.nTiles, true);
 }
 
-template <bool EXACT, int R, int MINB, int NC, int CH, int DEPTH>
+template <bool EXACT, int R, int MINB, int NC, int CH, int DEPTH, int NW = 1>
 static void launch_one(const WalkArgs &a, int nTiles, size_t smem, int threads, cudaStream_t st)
 {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(k_treewalk<EXACT, R, MINB, NC, CH, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_treewalk<EXACT, R, MINB, NC, CH, DEPTH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
     cudaLaunchConfig_t cfg{};
@@ -433,7 +493,7 @@ static void launch_one(const WalkArgs &a, int nTiles, size_t smem, int threads, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_treewalk<EXACT, R, MINB, NC, CH, DEPTH>, a);
+    cudaLaunchKernelEx(&cfg, k_treewalk<EXACT, R, MINB, NC, CH, DEPTH, NW>, a);
 }
 
 template <bool EXACT>
@@ -441,6 +501,13 @@ static void launch_exact(const WalkArgs &a, int nTiles, size_t smem, int threads
 {
     static const bool forceGeneric = getenv("SB2_GENERIC") != nullptr;   // A/B knob
     const bool std4 = a.stackDepth == 4 && a.tipsInSmem == 1 && !forceGeneric;
+    if (a.workers > 1) {   // tree-level parallelism: engine.cu only selects it for these shapes
+        if (a.nCat == 1 && a.workers == 4) launch_one<EXACT, 1, 4, 1, 1, 3, 4>(a, nTiles, smem, threads, st);
+        else if (a.nCat == 1 && a.workers == 2) launch_one<EXACT, 1, 4, 1, 1, 3, 2>(a, nTiles, smem, threads, st);
+        else if (a.nCat == 4 && a.workers == 2) launch_one<EXACT, 1, 4, 4, 1, 3, 2>(a, nTiles, smem, threads, st);
+        else abort();
+        return;
+    }
     if (a.patPerThread == 1) {
         if (std4 && a.nCat == 4 && a.chunksPerTile == 1) launch_one<EXACT, 1, 4, 4, 1, 4>(a, nTiles, smem, threads, st);        // GTR+G4 shapes
         else if (std4 && a.nCat == 1 && a.chunksPerTile == 2) launch_one<EXACT, 1, 4, 1, 2, 4>(a, nTiles, smem, threads, st);   // no rate heterogeneity
@@ -456,8 +523,8 @@ static void launch_exact(const WalkArgs &a, int nTiles, size_t smem, int threads
 
 void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st)
 {
-    const size_t smem = treewalk_smem_bytes(a.nCat, a.chunksPerTile, a.patPerThread, a.stackDepth, a.maxTips);
-    const int threads = 32 * a.nCat * a.chunksPerTile;
+    const size_t smem = treewalk_smem_bytes(a.nCat, a.chunksPerTile, a.patPerThread, a.stackDepth, a.maxTips, a.workers);
+    const int threads = 32 * a.nCat * a.chunksPerTile * a.workers;
     if (exact) launch_exact<true>(a, nTiles, smem, threads, st);
     else launch_exact<false>(a, nTiles, smem, threads, st);
 }

@@ -271,6 +271,56 @@ def test_kernel_geometries_agree_bitwise(env, name, kw, monkeypatch):
         e.accept()
 
 
+@pytest.mark.parametrize("name,kw,workers", [("C2", dict(n_loci=4, n_sites=333), 1), ("C2", dict(n_loci=4, n_sites=333), 2),
+                                             ("C2", dict(n_loci=4, n_sites=333), 4), ("C4", dict(n_loci=6, n_sites=200), 4),
+                                             ("C4", dict(n_loci=6, n_sites=200), 1), ("C3", dict(n_loci=3, n_sites=150), 2),
+                                             ("C3", dict(n_loci=3, n_sites=150), 1)])
+def test_tree_level_parallel_walk_agrees_bitwise(name, kw, workers, monkeypatch):
+    """Splitting a chunk's walk over worker warps (side subtrees evaluated concurrently, handed over through shared-memory
+    mailboxes) changes the order in which nodes are evaluated, never a bit of any partial or pattern likelihood."""
+    pb = synth.make_problem(name, missing_frac=0.03, **kw)
+    monkeypatch.setenv("SB2_WORKERS", "1")
+    e0 = Engine.from_problem(pb, exact_order=True)
+    base = e0.eval_posterior()
+    monkeypatch.setenv("SB2_WORKERS", str(workers))
+    for exact in (True, False):
+        e = Engine.from_problem(pb, exact_order=exact)
+        got = e.eval_posterior()
+        want = oracle.posterior(pb)
+        assert rel_close(got.per_locus_lik, want.per_locus_lik)
+        if exact:
+            for l in range(pb.n_loci):
+                assert np.array_equal(e.pattern_logl(l), e0.pattern_logl(l))
+                for node in range(pb.loci[l].n_tips, pb.loci[l].tree.n_nodes):
+                    p0, x0 = e0.partials(l, node)
+                    p1, x1 = e.partials(l, node)
+                    assert np.array_equal(p0, p1) and np.array_equal(x0, x1)
+            assert np.array_equal(got.per_locus_lik, base.per_locus_lik)
+        # incremental steps (mostly single-path walks: the helpers idle), store / restore and full re-evaluation
+        rng = np.random.default_rng(9)
+        for it in range(6):
+            l = int(rng.integers(0, pb.n_loci))
+            e.store()
+            old = pb.loci[l].tree
+            pb.loci[l].tree, _ = synth.perturb_gene_tree(rng, old, pb.loci[l].n_tips)
+            e.set_gene_tree(l, pb.loci[l].tree)
+            got = e.eval_posterior()
+            want = oracle.posterior(pb)
+            ok = np.isfinite(want.per_locus_coal)
+            assert rel_close(got.per_locus_lik[ok], want.per_locus_lik[ok])
+            if it % 2:
+                e.restore()
+                pb.loci[l].tree = old
+            else:
+                e.accept()
+        e.mark_all_dirty()
+        got = e.eval_posterior()
+        want = oracle.posterior(pb)
+        assert rel_close(got.per_locus_lik, want.per_locus_lik)
+        e.close()
+    e0.close()
+
+
 @pytest.mark.parametrize("name,n_loci", [("C2", 50), ("C3", 200), ("C4", 500), ("C5", 120)])
 def test_full_size_configs_match_oracle(name, n_loci):
     """BASELINE.json configs at their full per-GPU shapes (C5: a 120-locus slice of the 2,000; its per-GPU shard is 250),
