@@ -25,7 +25,7 @@ SOURCES = {
     "query.cu": ["-fmad=false"],
     "engine.cu": [],
 }
-DEPS = ["sb2_device.cuh", os.path.join("..", "..", "include", "sb2gpu.h")]
+DEPS = ["sb2_device.cuh", "reduce_body.cuh", os.path.join("..", "..", "include", "sb2gpu.h")]
 
 
 def _newer(target: str, deps) -> bool:

@@ -192,11 +192,6 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
     }
     const LocusDesc d = A.loci[l];
     __shared__ LocusParams sprm;
-    {   // the locus's parameters, one coalesced read instead of scattered late ones
-        const double *src = reinterpret_cast<const double *>(&A.params[l]);
-        double *dst = reinterpret_cast<double *>(&sprm);
-        for (int i = tid; i < (int)(sizeof(LocusParams) / 8); i += nt) dst[i] = src[i];
-    }
     const LocusParams *prm = &sprm;
     const int G = d.nNodes, nT = d.nTips, nI = d.nInt, S = A.S, nb = d.nodeBase, C = d.nCat;
     PrepSmem s;
@@ -204,40 +199,47 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
     const bool forceAll = fl & LF_FORCE_ALL;
     const bool forceMats = forceAll || (fl & LF_FORCE_MATS);
 
-    // ---- 1. load species tree and gene tree ------------------------------------------------------------
-    for (int i = tid; i < S; i += nt) {
-        s.sP[i] = A.cur.sParent[i]; s.sL[i] = A.cur.sLeft[i]; s.sR[i] = A.cur.sRight[i];
-        s.sH[i] = A.cur.sHeight[i]; s.sRate[i] = A.cur.sRates[i];
-        s.popA[i] = A.cur.popA[i]; s.popB[i] = A.cur.popB[i];
-        s.n[i] = 0; s.k[i] = 0;
-    }
-    if (tid == 0) { s.misc[0] = 1; /* compatible */ s.misc[1] = G - 1; /* root */ }
-    if (fl & LF_TREE_IN) {
+    // ---- 1. everything any phase needs from HBM, fetched in ONE wave of independent loads -------------------------------
+    // (parameters, species tree, gene tree, cached per-node state).  With a cold L2 every dependent round trip costs about a
+    // microsecond on this latency path, so each thread first issues all its loads (indices clamped instead of predicated,
+    // so that nothing stands between them) and only then stores to shared memory.
+    {
+        constexpr int NP = (int)(sizeof(LocusParams) / 8);
+        const double *prmSrc = reinterpret_cast<const double *>(&A.params[l]);
+        double *prmDst = reinterpret_cast<double *>(&sprm);
+        const bool treeIn = fl & LF_TREE_IN;
         const double *inH = reinterpret_cast<const double *>(A.inTree + d.treeOff);
         const int *inP = reinterpret_cast<const int *>(inH + G), *inL = inP + G, *inR = inL + G;
-        for (int i = tid; i < G; i += nt) {
-            const double h = inH[i];
-            const int p = inP[i], L = inL[i], R = inR[i];
-            s.topo[i] = (L != A.cur.gLeft[nb + i]) || (R != A.cur.gRight[nb + i]);
-            A.cur.gHeight[nb + i] = h; A.cur.gParent[nb + i] = p; A.cur.gLeft[nb + i] = L; A.cur.gRight[nb + i] = R;
-            s.gH[i] = h; s.gP[i] = p; s.gL[i] = L; s.gR[i] = R;
+        const int span = max(max(G, S), NP);
+        for (int base = 0; base < span; base += nt) {
+            const int i = base + tid;
+            const int ip = min(i, NP - 1), is = min(i, S - 1), ig = min(i, G - 1), it = min(i, nT - 1);
+            const int sp = A.cur.sParent[is], sl = A.cur.sLeft[is], sr = A.cur.sRight[is];
+            const double sh = A.cur.sHeight[is], srt = A.cur.sRates[is], pa = A.cur.popA[is], pb = A.cur.popB[is];
+            const int curL = A.cur.gLeft[nb + ig], curR = A.cur.gRight[nb + ig];
+            double h;
+            int p, L, R;
+            if (treeIn) { h = inH[ig]; p = inP[ig]; L = inL[ig]; R = inR[ig]; }
+            else { h = A.cur.gHeight[nb + ig]; p = A.cur.gParent[nb + ig]; L = curL; R = curR; }
+            const int tipSp = A.tipSpecies[d.tipBase + it];
+            const double bt = A.cur.bTime[nb + ig];
+            const uint8_t stM = A.stored.curM[nb + ig], stP = A.stored.curP[nb + ig], cuP = A.cur.curP[nb + ig], cuM = A.cur.curM[nb + ig];
+            const double pv = prmSrc[ip];
+            if (i < S) {
+                s.sP[i] = sp; s.sL[i] = sl; s.sR[i] = sr; s.sH[i] = sh; s.sRate[i] = srt; s.popA[i] = pa; s.popB[i] = pb;
+                s.n[i] = 0; s.k[i] = 0;
+            }
+            if (i < G) {
+                s.gH[i] = h; s.gP[i] = p; s.gL[i] = L; s.gR[i] = R;
+                s.topo[i] = treeIn && ((L != curL) || (R != curR));
+                if (treeIn) { A.cur.gHeight[nb + i] = h; A.cur.gParent[nb + i] = p; A.cur.gLeft[nb + i] = L; A.cur.gRight[nb + i] = R; }
+                s.assign[i] = (i < nT) ? tipSp : -1;   // GeneTree.java:243,247
+                s.cnt[i] = 0;
+                s.btOld[i] = bt; s.stM[i] = stM; s.stP[i] = stP; s.curP[i] = cuP; s.curM[i] = cuM;
+            }
+            if (i < NP) prmDst[i] = pv;
         }
-    } else {
-        for (int i = tid; i < G; i += nt) {
-            s.gH[i] = A.cur.gHeight[nb + i]; s.gP[i] = A.cur.gParent[nb + i];
-            s.gL[i] = A.cur.gLeft[nb + i]; s.gR[i] = A.cur.gRight[nb + i];
-            s.topo[i] = 0;
-        }
-    }
-    // everything the later phases need from HBM is fetched now, in one wave of independent loads
-    for (int i = tid; i < G; i += nt) {
-        s.assign[i] = (i < nT) ? A.tipSpecies[d.tipBase + i] : -1;   // GeneTree.java:243,247
-        s.cnt[i] = 0;
-        s.btOld[i] = A.cur.bTime[nb + i];
-        s.stM[i] = A.stored.curM[nb + i];
-        s.stP[i] = A.stored.curP[nb + i];
-        s.curP[i] = A.cur.curP[nb + i];
-        s.curM[i] = A.cur.curM[nb + i];
+        if (tid == 0) { s.misc[0] = 1; /* compatible */ s.misc[1] = G - 1; /* root */ }
     }
     {   // warm L2 with the pruning kernel's static inputs of this locus (fire and forget)
         auto warm = [&](const void *p, size_t bytes) {

@@ -136,27 +136,34 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A)
 
 __device__ __forceinline__ void finish_body(const ReduceArgs &A)
 {
-    __shared__ double scratch[32];
     const int tid = threadIdx.x, nt = blockDim.x, L = A.nLoci, S = A.S;
     double *perBranch = A.out + 3 + 2 * L;
     double coal = A.red[0];
     const double lik = A.red[1];
     const bool incompatible = A.red[2] > 0.0;
     if (A.popKind == 2) {
+        // one warp per species branch (no block barriers on this latency path); the per-branch terms are then added one by
+        // one in node-number order (MultispeciesCoalescent.java:194)
         const double alpha = A.cur.hyper[0], beta = A.cur.hyper[1];
-        for (int b = 0; b < S; b++) {
+        const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+        for (int b = warp; b < S; b += nw) {
             const long long q = (long long)(A.red[3 + 3 * b] + 0.5);
             const double g = A.red[3 + 3 * b + 1], r = A.red[3 + 3 * b + 2];
-            double part = 0.0;
-            for (long long i = tid; i < q; i += nt) part += log(alpha + (double)i);   // logGammaRatio, :227-230
-            const double lgr = block_sum(part, scratch);
+            double lgr = 0.0;   // logGammaRatio, :227-230
+            if (A.exact) {
+                if (lane == 0) for (long long i = 0; i < q; i++) lgr += log(alpha + (double)i);   // the reference's order
+            } else {
+                for (long long i = lane; i < q; i += 32) lgr += log(alpha + (double)i);
+                for (int off = 16; off > 0; off >>= 1) lgr += __shfl_xor_sync(0xffffffffu, lgr, off);
+            }
             const double branchLogR = -r;
             // explicit roundings: this body is also inlined into k_treewalk, whose translation unit allows FMA contraction
             const double logP = __dadd_rn(__dsub_rn(__dadd_rn(branchLogR, __dmul_rn(alpha, log(beta))),
                                                     __dmul_rn(__dadd_rn(alpha, (double)q), log(__dadd_rn(beta, g)))), lgr);   // :232
-            if (tid == 0) perBranch[b] = logP;
-            coal += logP;   // MultispeciesCoalescent.java:194: added one by one in node-number order
+            if (lane == 0) perBranch[b] = logP;
         }
+        __syncthreads();
+        if (tid == 0) for (int b = 0; b < S; b++) coal += perBranch[b];
     } else {
         for (int b = tid; b < S; b += nt) perBranch[b] = 0.0;
     }
