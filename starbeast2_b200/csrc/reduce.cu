@@ -22,8 +22,10 @@ __global__ void __launch_bounds__(RED_THREADS) k_finish(ReduceArgs A) { finish_b
 // single-GPU evaluation: no all-reduce between the local sums and the closed forms -> one launch
 __global__ void __launch_bounds__(RED_THREADS) k_reduce_finish(ReduceArgs A)
 {
+    int tb = -1, ntl = 0;
+    if ((int)threadIdx.x < A.nLoci) { tb = A.loci[threadIdx.x].tileBase; ntl = A.loci[threadIdx.x].nTiles; }   // static: fetched while the pruning kernel still runs
     cudaGridDependencySynchronize();   // launched with programmatic serialization: wait for the pruning kernel's results
-    reduce_local_body(A);
+    reduce_local_body(A, tb, ntl);
     __threadfence_block();
     __syncthreads();
     finish_body(A);

@@ -53,7 +53,9 @@ __device__ __forceinline__ void block_sum3(double &a, double &b, double &c, doub
     __syncthreads();
 }
 
-__device__ __forceinline__ void reduce_local_body(const ReduceArgs &A)
+// preTileBase / preNTiles: tileBase / nTiles of locus threadIdx.x, fetched by the caller before it waited for the pruning
+// kernel (static data: one dependent round trip less on the latency path); preTileBase < 0 = not provided
+__device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preTileBase = -1, int preNTiles = 0)
 {
     __shared__ double scratch[96];
     const int tid = threadIdx.x, nt = blockDim.x, L = A.nLoci, S = A.S;
@@ -68,12 +70,14 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A)
             if (A.exact) {
                 for (int p = 0; p < d.nPat; p++) lik = __dadd_rn(lik, __dmul_rn(__ldcg(A.patLogL + d.patBase + p), (double)A.weights[d.patBase + p]));   // calcLogP order
             } else {
-                for (int t0 = 0; t0 < d.nTiles; t0 += 8) {   // loads in flight together, adds in tile order
+                const bool pre = preTileBase >= 0 && l == tid;
+                const int tileBase = pre ? preTileBase : d.tileBase, nTiles = pre ? preNTiles : d.nTiles;
+                for (int t0 = 0; t0 < nTiles; t0 += 8) {   // loads in flight together, adds in tile order
                     double v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) v[j] = (t0 + j < d.nTiles) ? __ldcg(A.tileSum + d.tileBase + t0 + j) : 0.0;
+                    for (int j = 0; j < 8; j++) v[j] = (t0 + j < nTiles) ? __ldcg(A.tileSum + tileBase + t0 + j) : 0.0;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) if (t0 + j < d.nTiles) lik += v[j];
+                    for (int j = 0; j < 8; j++) if (t0 + j < nTiles) lik += v[j];
                 }
             }
             A.cur.logL[l] = lik;
@@ -82,6 +86,7 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A)
         }
         perLocusLik[l] = lik;
         perLocusCoal[l] = coal;
+        if (A.hostOut) { A.hostOut[3 + L + l] = lik; A.hostOut[3 + l] = coal; }   // zero-copy result vector, written as soon as known
         likPart += lik;
         coalPart += coal;
         incPart += (coal == -INFINITY) ? 1.0 : 0.0;
@@ -160,27 +165,28 @@ __device__ __forceinline__ void finish_body(const ReduceArgs &A)
             // explicit roundings: this body is also inlined into k_treewalk, whose translation unit allows FMA contraction
             const double logP = __dadd_rn(__dsub_rn(__dadd_rn(branchLogR, __dmul_rn(alpha, log(beta))),
                                                     __dmul_rn(__dadd_rn(alpha, (double)q), log(__dadd_rn(beta, g)))), lgr);   // :232
-            if (lane == 0) perBranch[b] = logP;
+            if (lane == 0) { perBranch[b] = logP; if (A.hostOut) A.hostOut[3 + 2 * L + b] = logP; }
         }
         __syncthreads();
         if (tid == 0) for (int b = 0; b < S; b++) coal += perBranch[b];
     } else {
-        for (int b = tid; b < S; b += nt) perBranch[b] = 0.0;
+        for (int b = tid; b < S; b += nt) { perBranch[b] = 0.0; if (A.hostOut) A.hostOut[3 + 2 * L + b] = 0.0; }
     }
     if (incompatible) coal = -INFINITY;   // MultispeciesCoalescent.java:153
-    if (tid == 0) { A.out[0] = coal; A.out[1] = lik; A.out[2] = coal + lik; }
+    if (tid == 0) {
+        A.out[0] = coal; A.out[1] = lik; A.out[2] = coal + lik;
+        if (A.hostOut) { A.hostOut[0] = coal; A.hostOut[1] = lik; A.hostOut[2] = coal + lik; }
+    }
 }
 
 
-// copies the result vector to the host-mapped (zero-copy) buffer: the host only has to synchronise the stream
+// The result vector lives twice: in device memory (`out`) and in host-mapped memory (`hostOut`, zero-copy download: the
+// host only has to synchronise the stream).  Both copies are written where the values are produced, so nothing is left to do
+// here but make sure the block's writes are ordered before the kernel ends.
 __device__ __forceinline__ void publish_body(const ReduceArgs &A)
 {
-    __threadfence_block();
-    __syncthreads();
-    if (A.hostOut) {
-        const int n = 3 + 2 * A.nLoci + A.S;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) A.hostOut[i] = A.out[i];   // visible to the host once the kernel completes
-    }
+    (void)A;
+    __threadfence_system();
 }
 
 }  // namespace sb2
