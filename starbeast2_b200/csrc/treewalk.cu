@@ -170,7 +170,7 @@ __device__ __forceinline__ void walk_epilogue(const WalkArgs &A, int l, int tile
 // worker 0 walks the main path, the helpers the side subtrees k_prepare gave them, handing each finished subtree over
 // through a dedicated stack slot (mailbox) guarded by a release / acquire flag in shared memory.
 template <bool EXACT, int R, int MINB, int NC, int CH, int DEPTH, int NW>
-__global__ void __launch_bounds__(256, MINB) k_treewalk(WalkArgs A)
+__global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk(WalkArgs A)
 {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int tile = blockIdx.x;
@@ -513,7 +513,8 @@ static void launch_exact(const WalkArgs &a, int nTiles, size_t smem, int threads
         else if (std4 && a.nCat == 1 && a.chunksPerTile == 2) launch_one<EXACT, 1, 4, 1, 2, 4>(a, nTiles, smem, threads, st);   // no rate heterogeneity
         else launch_one<EXACT, 1, 4, 0, 0, 0>(a, nTiles, smem, threads, st);
     } else if (a.patPerThread == 2) {
-        if (std4 && a.nCat == 4 && a.chunksPerTile == 1) launch_one<EXACT, 2, 2, 4, 1, 4>(a, nTiles, smem, threads, st);
+        if (a.stackDepth == 3 && a.tipsInSmem == 1 && a.nCat == 4 && a.chunksPerTile == 1) launch_one<EXACT, 2, 5, 4, 1, 3>(a, nTiles, smem, threads, st);   // 5 CTAs / SM
+        else if (std4 && a.nCat == 4 && a.chunksPerTile == 1) launch_one<EXACT, 2, 2, 4, 1, 4>(a, nTiles, smem, threads, st);
         else if (std4 && a.nCat == 1 && a.chunksPerTile == 2) launch_one<EXACT, 2, 2, 1, 2, 4>(a, nTiles, smem, threads, st);
         else launch_one<EXACT, 2, 2, 0, 0, 0>(a, nTiles, smem, threads, st);
     } else {

@@ -238,6 +238,7 @@ def test_ragged_loci_and_tiny_shapes():
 @pytest.mark.parametrize("env", [
     {"SB2_STACK_DEPTH": "1"},                                   # every second operand spills to its global buffer
     {"SB2_PATTERNS_PER_THREAD": "2"},
+    {"SB2_PATTERNS_PER_THREAD": "2", "SB2_STACK_DEPTH": "3"},  # the 5-CTAs-per-SM instantiation
     {"SB2_PATTERNS_PER_THREAD": "4", "SB2_STACK_DEPTH": "2"},
     {"SB2_PATTERNS_PER_THREAD": "2", "SB2_CHUNKS_PER_TILE": "2"},
     {"SB2_PATTERNS_PER_THREAD": "1", "SB2_CHUNKS_PER_TILE": "1"},
