@@ -244,8 +244,9 @@ def bench_streaming(args, hbm_gbs, peak_src, flush, n_loci=250, steps=30):
     queries = bench_operator_queries(eng, pb, reps=100)
     if not args.no_cpu:
         queries["cpu_port"] = cpu_operator_queries(pb, reps=5)
+    dev_bytes = eng.device_bytes()
     eng.close()
-    return {"operator_queries": queries, "workload": f"C5 shard, {n_loci} loci of the 2,000 (GTR+G4, UCLN species clock, 120 tips)", "kernel": "k_treewalk",
+    return {"operator_queries": queries, "device_bytes": dev_bytes, "workload": f"C5 shard, {n_loci} loci of the 2,000 (GTR+G4, UCLN species clock, 120 tips)", "kernel": "k_treewalk",
             "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "peak_source": peak_src,
             "us_per_launch": k_us, "launches_timed": k_n, "algorithmic_bytes_per_launch": dbytes, "bytes_per_unit": dbytes / pb.units,
             "survey_formula_frac": sbytes / (k_us * 1e-6) / 1e9 / hbm_gbs, "kernel_partials_per_sec": pb.units / (k_us * 1e-6),
@@ -471,7 +472,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "loci_per_gpu": args.loci, "loci_total": args.loci * world,
                    "units_per_step": units_total, "mean_patterns_per_locus": float(np.mean([l.n_pat for l in pb.loci])),
-                   "regime": "A (every node of every locus dirty)", "exact_order": bool(args.exact),
+                   "regime": "A (every node of every locus dirty)", "device_bytes": eng.device_bytes(), "exact_order": bool(args.exact),
                    "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write; working set is L2-resident)",
                    "parallelism": f"loci sharded over {world} GPU(s), 1 all-reduce of {eng.reduce_vector_len()} doubles per step ({comm})" if world > 1 else "1 GPU"},
         "posterior_evals_per_sec": args.steps / (ms * 1e-3),
