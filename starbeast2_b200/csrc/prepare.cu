@@ -37,6 +37,7 @@ struct PrepSmem {
     // slot and the offset of its ops inside that worker's list; `path` is scratch for the main path
     uint8_t *wk, *mbx;
     int *woff, *path;
+    int *pos;     // schedule position of each dirty internal node
 };
 
 __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, int G, int S)
@@ -49,8 +50,9 @@ __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, i
     size_t sP = take(4ull * S), sL = take(4ull * S), sR = take(4ull * S), n = take(4ull * S), k = take(4ull * S), ks = take(4ull * (S + 1));
     size_t misc = take(4ull * 8), first = take(4ull * G);
     size_t md = take(G), di = take(G), to = take(G), stM = take(G), stP = take(G), cuP = take(G), cuM = take(G);
-    size_t wk = take(G), mbx = take(G), woff = take(4ull * G), path = take(4ull * G);
+    size_t wk = take(G), mbx = take(G), woff = take(4ull * G), path = take(4ull * G), pos = take(4ull * G);
     if (s) {
+        s->pos = (int *)(base + pos);
         s->wk = base + wk; s->mbx = base + mbx; s->woff = (int *)(base + woff); s->path = (int *)(base + path);
         s->gH = (double *)(base + gH); s->rate = (double *)(base + rate); s->times = (double *)(base + times);
         s->sH = (double *)(base + sH); s->sRate = (double *)(base + sRate);
@@ -259,11 +261,21 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
     __syncthreads();
     const int root = s.misc[1];
 
-    // ---- 2. embedding walks (one lineage per thread) ---------------------------------------------------
+    // ---- warp specialisation -----------------------------------------------------------------------------------------------
+    // The multispecies-coalescent half (2. embedding, 3. sorted times + population terms) and the likelihood half (4. dirty
+    // detection + pruning schedule, 5. transition matrices) only meet in the branch rates, so on this latency path they run
+    // CONCURRENTLY: group A = threads 0..127, group B = threads 128..255, each with its own named barrier.  With a species-tree
+    // clock B waits (barrier 3) until A's embedding walks have produced the rates; with a strict / explicit clock it starts at once.
+    constexpr int gn = PREP_THREADS / 2;
+    const int grpId = tid / gn, gt = tid - grpId * gn;
+    auto gsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grpId), "n"(gn) : "memory"); };
     const int clockKind = prm->clockKind;
     const double clockRate = prm->clockRate;
     const bool wantRate = clockKind == 1;
-    for (int leaf = tid; leaf < nT; leaf += nt) {
+    __shared__ int s_lane[WALK_MAX_WORKERS + 1], s_hStart[WALK_MAX_WORKERS * WALK_MAILBOX], s_hCnt[WALK_MAX_WORKERS * WALK_MAILBOX], s_nH;
+    if (grpId == 0) {
+    // ---- 2. embedding walks (one lineage per thread) ---------------------------------------------------
+    for (int leaf = gt; leaf < nT; leaf += gn) {
         int last = leaf, g = s.gP[leaf], b = s.assign[leaf];
         double lastH = 0.0;   // GeneTree.java:260 (gene tips are taken to sit at height 0, quirk Q6)
         double topH = (s.sP[b] >= 0) ? s.sH[s.sP[b]] : INFINITY;   // height at which the lineage leaves its current species branch
@@ -286,13 +298,14 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
             }
         }
     }
-    if (!wantRate) {
-        for (int i = tid; i < G; i += nt)
-            s.rate[i] = (clockKind == 2) ? A.explicitRates[nb + i] : clockRate;   // StrictClockModel / explicit
+    gsync();
+    if (wantRate) {   // the rates are complete: release group B (it waits on barrier 3 for them)
+        if (gt == 0) s.rate[root] = clockRate;   // StarBeastClock.java:72
+        __threadfence_block();
+        asm volatile("bar.arrive 3, %0;" ::"n"(PREP_THREADS) : "memory");
     }
-    __syncthreads();
-    if (tid == 0 && wantRate) s.rate[root] = clockRate;   // StarBeastClock.java:72 (read again only after the next barrier)
     const bool compat = s.misc[0] != 0;
+    for (int i = gt; i < G; i += gn) A.cur.assign[nb + i] = s.assign[i];
 
     // ---- 3. per-branch sorted times + population-model terms ------------------------------------------------
     // rank sort of the internal nodes by (species branch, height): branch b's times are contiguous and ascending.
@@ -300,9 +313,9 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
     // the list, 4 comparisons in flight) and combine their partial ranks with shuffles.
     {
         int split = 1;
-        while (split < 32 && split * 2 * nI <= nt) split *= 2;   // power of two, split * nI <= nt
-        for (int base = 0; base < nI; base += nt / split) {
-            const int ii = base + tid / split, part = tid % split;
+        while (split < 32 && split * 2 * nI <= gn) split *= 2;   // power of two, split * nI <= gn
+        for (int base = 0; base < nI; base += gn / split) {
+            const int ii = base + gt / split, part = gt % split;
             const bool act = ii < nI;
             const int i = nT + (act ? ii : 0);
             const int bi = s.assign[i];
@@ -320,10 +333,10 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
             if (act && part == 0) s.times[rank] = hi;
         }
     }
-    __syncthreads();
+    gsync();
     const double ploidy = d.ploidy;
     const double logPloidy = log(ploidy);
-    for (int b = tid; b < S; b += nt) {
+    for (int b = gt; b < S; b += gn) {
         const int n = s.n[b], k = s.k[b];
         int kstart = 0;                       // branch b's block of the rank-sorted times starts after all lower-numbered branches'
         for (int bb = 0; bb < b; bb++) kstart += s.k[bb];
@@ -388,16 +401,24 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         A.cur.anR[o] = k * logPloidy;       // :211 (negated when pooled)
         s.sRate[b] = term;                  // species rates are no longer needed: reuse as the term buffer
     }
-    __syncthreads();
-    if (tid == 0) {
+    gsync();
+    if (gt == 0) {
         double logP = 0.0;
         if (!compat) logP = -INFINITY;                       // GeneTree.java:175-178
         else for (int b = 0; b < S; b++) logP += s.sRate[b];  // GeneTree.java:185-196, node-number order
         A.cur.coal[l] = logP;
     }
 
+    } else {
+    if (wantRate) {
+        asm volatile("bar.sync 3, %0;" ::"n"(PREP_THREADS) : "memory");
+    } else {
+        for (int i = gt; i < G; i += gn)
+            s.rate[i] = (clockKind == 2) ? A.explicitRates[nb + i] : clockRate;   // StrictClockModel / explicit
+        gsync();
+    }
     // ---- 4. dirtiness (TreeLikelihood.traverse) and the pruning schedule ----------------------------------------
-    for (int i = tid; i < G; i += nt) {
+    for (int i = gt; i < G; i += gn) {
         uint8_t md = 0;
         if (s.gP[i] >= 0) {
             const double bt = (s.gH[s.gP[i]] - s.gH[i]) * s.rate[i];   // node.getLength() * branchRate
@@ -412,41 +433,39 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         s.dirty[i] = 0;
         s.wk[i] = 0;
         A.cur.bRate[nb + i] = s.rate[i];
-        A.cur.assign[nb + i] = s.assign[i];
     }
-    __syncthreads();
+    gsync();
     // a node is recomputed when its own inputs changed or anything below it was recomputed: mark it and its ancestors
     // (the dirty set is upward closed).  Racing markers are benign: whoever marked a node first keeps climbing.
-    for (int i = nT + tid; i < G; i += nt)
+    for (int i = nT + gt; i < G; i += gn)
         if (forceAll || s.topo[i] || s.matDirty[s.gL[i]] || s.matDirty[s.gR[i]]) {
             s.dirty[i] = 1;
             int a = s.gP[i];
             while (a >= 0 && s.dirty[a] == 0) { s.dirty[a] = 2; a = s.gP[a]; }
         }
-    __syncthreads();
+    gsync();
     // cnt[i] = number of dirty internal nodes in the subtree of i
-    for (int i = nT + tid; i < G; i += nt)
+    for (int i = nT + gt; i < G; i += gn)
         if (s.dirty[i]) {
             int a = i;
             while (a >= 0) { atomicAdd(&s.cnt[a], 1); a = s.gP[a]; }
         }
-    __syncthreads();
-    if (tid == 0) A.nOps[l] = s.dirty[root] ? s.cnt[root] : 0;
+    gsync();
+    if (gt == 0) A.nOps[l] = s.dirty[root] ? s.cnt[root] : 0;
     // at a node whose two children are both dirty the heavier child (more dirty nodes, ties -> left) is evaluated first
     // and parks its result; everywhere else nothing is parked
-    for (int i = nT + tid; i < G; i += nt) {
+    for (int i = nT + gt; i < G; i += gn) {
         const int Lc = s.gL[i], Rc = s.gR[i];
         const bool both = Lc >= nT && Rc >= nT && s.dirty[Lc] && s.dirty[Rc];
         s.first[i] = both ? ((s.cnt[Rc] > s.cnt[Lc]) ? Rc : Lc) : -1;
     }
-    __syncthreads();
+    gsync();
     // Multi-worker walks (latency-bound shapes): worker 0 keeps the main path -- from the root always into the first-evaluated
     // (or only) dirty child -- and the small side subtrees; each larger side subtree goes, whole, to the least-loaded helper
     // that still has a free mailbox.  Helpers meet their subtrees in the order the main path needs them (deepest first).
     const int W = A.workers;
-    __shared__ int s_lane[WALK_MAX_WORKERS + 1], s_hStart[WALK_MAX_WORKERS * WALK_MAILBOX], s_hCnt[WALK_MAX_WORKERS * WALK_MAILBOX], s_nH;
     if (W > 1) {
-        if (tid == 0) {
+        if (gt == 0) {
             int loads[WALK_MAX_WORKERS] = {0, 0, 0, 0}, boxes[WALK_MAX_WORKERS] = {0, 0, 0, 0};
             int np = 0, nH = 0;
             for (int p = root; p >= nT && s.dirty[p];) {
@@ -476,9 +495,9 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
             for (int w = W; w < WALK_MAX_WORKERS; w++) s_lane[w + 1] = s_lane[W];
             for (int w = 0; w <= WALK_MAX_WORKERS; w++) A.laneOps[l * (WALK_MAX_WORKERS + 1) + w] = s_lane[w];
         }
-        __syncthreads();
+        gsync();
     }
-    for (int i = nT + tid; i < G; i += nt) {
+    for (int i = nT + gt; i < G; i += gn) {
         if (!s.dirty[i]) continue;
         // position in the post-order and stack slot: walk to the root; every ancestor at which this path comes in through
         // the second-evaluated child adds the first child's subtree to the position and one parked result to the depth
@@ -500,7 +519,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
                 pos -= sub;
             }
         }
-        s.assign[i] = pos;   // geneNodeSpeciesAssignment is already written back: reuse as the node's schedule position
+        s.pos[i] = pos;
         const int newP = 1 - s.stP[i];                                   // setNodePartialsForUpdate
         A.cur.curP[nb + i] = (uint8_t)newP;
         const int Lc = s.gL[i], Rc = s.gR[i];
@@ -545,13 +564,19 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
 
         A.ops[d.opBase + pos] = o;
     }
-    __syncthreads();
+    gsync();
 
+    }
     // ---- 5. transition matrices: recompute the dirty branches; stream every scheduled op's pair in op order ----------------
+    // few matrices: group B computes them alone, without waiting for group A; many: all threads, after a full barrier
+    const bool matsByB = G * C <= gn;
+    if (matsByB) { if (grpId == 0) return; }
+    else __syncthreads();
+    const int mt = matsByB ? gt : tid, mn = matsByB ? gn : nt;
     HkyTabs tabs;
     const int substKind = prm->substKind;
     if (substKind == 0) hky_setup(prm->subst, tabs);
-    for (int idx = tid; idx < G * C; idx += nt) {
+    for (int idx = mt; idx < G * C; idx += mn) {
         const int i = idx / C, c = idx - i * C;
         const int par = s.gP[i];
         if (par < 0) continue;
@@ -572,7 +597,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         }
         if (used) {   // [op][category][side][16]: the pruning kernel's warp (one category) reads 256 contiguous bytes per op
             const int side = (s.gR[par] == i) ? 1 : 0;
-            double *dst = A.opMats + (((size_t)(d.opBase + s.assign[par]) * C + c) * 2 + side) * 16;
+            double *dst = A.opMats + (((size_t)(d.opBase + s.pos[par]) * C + c) * 2 + side) * 16;
 #pragma unroll
             for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(dst + q) = make_double2(m[q], m[q + 1]);
         }
