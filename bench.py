@@ -241,12 +241,14 @@ def bench_streaming(args, hbm_gbs, peak_src, flush, n_loci=250, steps=30):
     k_us = 1e3 * k_ms / max(k_n, 1)
     dbytes, sbytes = design_bytes(pb), pb.algorithmic_bytes_survey()
     achieved = dbytes / (k_us * 1e-6) / 1e9
+    eng.set_profile(False)
+    incremental = bench_incremental(eng, pb, synth, n_steps=200)
     queries = bench_operator_queries(eng, pb, reps=100)
     if not args.no_cpu:
         queries["cpu_port"] = cpu_operator_queries(pb, reps=5)
     dev_bytes = eng.device_bytes()
     eng.close()
-    return {"operator_queries": queries, "device_bytes": dev_bytes, "workload": f"C5 shard, {n_loci} loci of the 2,000 (GTR+G4, UCLN species clock, 120 tips)", "kernel": "k_treewalk",
+    return {"operator_queries": queries, "incremental": incremental, "device_bytes": dev_bytes, "workload": f"C5 shard, {n_loci} loci of the 2,000 (GTR+G4, UCLN species clock, 120 tips)", "kernel": "k_treewalk",
             "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "peak_source": peak_src,
             "us_per_launch": k_us, "launches_timed": k_n, "algorithmic_bytes_per_launch": dbytes, "bytes_per_unit": dbytes / pb.units,
             "survey_formula_frac": sbytes / (k_us * 1e-6) / 1e9 / hbm_gbs, "kernel_partials_per_sec": pb.units / (k_us * 1e-6),

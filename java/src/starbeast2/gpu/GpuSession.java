@@ -21,6 +21,7 @@ import starbeast2.DummyModel;
 import starbeast2.GpuGeneTree;
 import starbeast2.GpuMultispeciesCoalescent;
 import starbeast2.LinearWithConstantRoot;
+import starbeast2.UniformPopulations;
 import starbeast2.PopulationModel;
 import starbeast2.SpeciesTreeInterface;
 import starbeast2.SpeciesTreeRates;
@@ -135,6 +136,13 @@ public final class GpuSession {
             final RealParameter tip = ((LinearWithConstantRoot) pop).tipPopSizesInput.get(), top = ((LinearWithConstantRoot) pop).topPopSizesInput.get();
             if (firstPush || tip.somethingIsDirty() || top.somethingIsDirty()) {
                 check(Sb2Gpu.setPopModel(engine, Sb2Gpu.POP_LWCR, tip.getDoubleValues(), top.getDoubleValues(), 0, 0)); dirty = true;
+            }
+        } else if (pop instanceof UniformPopulations) {   // one size for every branch: the constant model with the value broadcast
+            final RealParameter u = ((UniformPopulations) pop).universalSizeInput.get();
+            if (firstPush || u.somethingIsDirty()) {
+                final double[] n = new double[speciesTree.getNodeCount()];
+                java.util.Arrays.fill(n, u.getValue());
+                check(Sb2Gpu.setPopModel(engine, Sb2Gpu.POP_CONSTANT, n, null, 0, 0)); dirty = true;
             }
         } else if (pop == null || pop instanceof DummyModel) {
             final double a = msc != null && msc.analytic() ? msc.alpha() : 1.0, b = msc != null && msc.analytic() ? msc.beta() : 1.0;

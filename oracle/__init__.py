@@ -85,6 +85,8 @@ def lib():
                                            C.c_int, _f64p, _f64p, _f64p, C.c_double, C.c_void_p, _f64p, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sb2o_posterior.restype = C.c_int
+        L.sb2o_random_local_rates.restype = None
+        L.sb2o_random_local_rates.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f64p, _u8p, _f64p, C.c_double, _f64p]
         L.sb2o_connecting_nodes.restype = C.c_int
         L.sb2o_connecting_nodes.argtypes = [C.c_int, _i32p, _i32p, C.c_int, C.c_int, _i64p, _i64p, _i32p, _i32p, _i32p, _f64p, _i32p, C.c_int,
                                             _u8p, _f64p]
@@ -301,6 +303,18 @@ def posterior(pb, n_threads: int = 1, use_scaling: int = 2, flat: Optional[FlatP
     tot = np.zeros(3)
     lib().sb2o_posterior(C.byref(fp.struct), n_threads, use_scaling, coal, lik, br, tot)
     return PosteriorResult(coal, lik, br, tot)
+
+
+def random_local_rates(species, indicators, branch_rates, mean: float = 1.0) -> np.ndarray:
+    """RandomLocalRates.update(): rates by species node number (indicators / branch_rates have S-1 entries)."""
+    S = species.n_nodes
+    out = np.zeros(S)
+    ind = np.zeros(S, np.uint8)
+    ind[: S - 1] = np.asarray(indicators, bool)[: S - 1]
+    br = np.zeros(S)
+    br[: S - 1] = np.asarray(branch_rates, float)[: S - 1]
+    lib().sb2o_random_local_rates(S, species.root, species.left, species.right, species.height, ind, br, float(mean), out)
+    return out
 
 
 def _concat_trees(pb):

@@ -291,6 +291,35 @@ SB2O_API void sb2o_uncorrelated_rates(int S, int nEstimated, const int32_t *binI
     (void)S;
 }
 
+/* RandomLocalRates.recurseBranchRates -- RandomLocalRates.java:72-90 */
+static void rlr_recurse(int node, double parentHeight, double rate, int rootNodeNumber, const int32_t *left, const int32_t *right,
+                        const double *height, const uint8_t *indicators, const double *branchRates, double *ratesArray,
+                        double *strictTotal, double *relaxedTotal)
+{
+    const double nodeHeight = height[node];
+    if (node < rootNodeNumber && indicators[node]) rate = branchRates[node];
+    const double branchLength = parentHeight - nodeHeight;
+    *strictTotal += branchLength;
+    *relaxedTotal += branchLength * rate;
+    ratesArray[node] = rate;
+    if (left[node] >= 0) {
+        rlr_recurse(left[node], nodeHeight, rate, rootNodeNumber, left, right, height, indicators, branchRates, ratesArray, strictTotal, relaxedTotal);
+        rlr_recurse(right[node], nodeHeight, rate, rootNodeNumber, left, right, height, indicators, branchRates, ratesArray, strictTotal, relaxedTotal);
+    }
+}
+
+/* RandomLocalRates.update -- RandomLocalRates.java:92-117 (no reference test: PARITY UNPINNED).  root = node S-1 (:54). */
+SB2O_API void sb2o_random_local_rates(int S, int root, const int32_t *left, const int32_t *right, const double *height,
+                                      const uint8_t *indicators, const double *branchRates, double estimatedMean, double *ratesArray)
+{
+    const int rootNodeNumber = S - 1;
+    double strictTotal = 0.0, relaxedTotal = 0.0;
+    ratesArray[rootNodeNumber] = estimatedMean;
+    rlr_recurse(root, height[root], 1.0, rootNodeNumber, left, right, height, indicators, branchRates, ratesArray, &strictTotal, &relaxedTotal);
+    const double scaleFactor = estimatedMean * strictTotal / relaxedTotal;
+    for (int i = 0; i < rootNodeNumber; i++) ratesArray[i] = ratesArray[i] * scaleFactor;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* (2) BEAST.base half -- PARITY UNPINNED (see header)                                         */
 /* ------------------------------------------------------------------------------------------ */

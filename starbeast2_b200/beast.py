@@ -161,6 +161,16 @@ class IntegerParameter(RealParameter):
     DTYPE = np.int64
 
 
+class BooleanParameter(RealParameter):
+    DTYPE = np.bool_
+
+    def initAndValidate(self):
+        v = self.get("value")
+        if isinstance(v, str):
+            self._inputs["value"] = [x.lower() in ("true", "1") for x in v.split()]
+        super().initAndValidate()
+
+
 class Tree(StateNode):
     """beast.base.evolution.tree.Tree as flat arrays by node number (leaves first, root last)."""
     INPUTS = {"newick": None, "IsLabelledNewick": True, "taxonset": None, "adjustTipHeights": True, "arrays": None, "labels": None}

@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from .beast import (BEASTObject, CalculationNode, CompoundDistribution, Distribution, IntegerParameter, RealParameter,
+from .beast import (BEASTObject, BooleanParameter, CalculationNode, CompoundDistribution, Distribution, IntegerParameter, RealParameter,
                     Taxon, TaxonSet, Tree, TreeParser)
 from .engine import Engine
 from .problem import (CLOCK_SPECIES_RATES, CLOCK_STRICT, POP_ANALYTIC, POP_CONSTANT, POP_LWCR, SUBST_EIGEN, SUBST_HKY,
@@ -30,7 +30,7 @@ from .problem import (CLOCK_SPECIES_RATES, CLOCK_STRICT, POP_ANALYTIC, POP_CONST
 
 REQ = BEASTObject.REQUIRED
 __all__ = ["SpeciesTree", "SpeciesTreeParser", "GpuSession", "ConstantPopulations", "LinearWithConstantRoot",
-           "PassthroughModel", "DummyModel", "GeneTree", "MultispeciesCoalescent", "StrictClockModel", "UncorrelatedRates",
+           "UniformPopulations", "RandomLocalRates", "BooleanParameter", "PassthroughModel", "DummyModel", "GeneTree", "MultispeciesCoalescent", "StrictClockModel", "UncorrelatedRates",
            "StarBeastClock", "Alignment", "Frequencies", "HKY", "GTR", "SiteModel", "TreeLikelihood", "RealParameter",
            "IntegerParameter", "Taxon", "TaxonSet", "Tree", "TreeParser", "CompoundDistribution"]
 
@@ -257,6 +257,30 @@ class ConstantPopulations(PopulationModel):
         e.set_pop_model(POP_CONSTANT, self.get("populationSizes").values)
 
 
+class UniformPopulations(PopulationModel):
+    """starbeast2.UniformPopulations (UniformPopulations.java:16-18: inputs speciesTree, universalSize): one population size
+    for every branch.  uniformLogP (:74-99) is the constant-population formula, so the engine runs its constant model with the
+    universal size broadcast over the species nodes."""
+    INPUTS = {"speciesTree": REQ, "universalSize": REQ}
+
+    def initAndValidate(self):
+        self.speciesTree = self.get("speciesTree")
+
+    def initPopSizes(self, popInitial: float):   # :46-55
+        p = self.get("universalSize")
+        if p.get("estimate") and p.getLower() < popInitial < p.getUpper():
+            p.setValue(0, popInitial)
+
+    def _sizes(self) -> np.ndarray:
+        return np.full(self.speciesTree.getNodeCount(), float(self.get("universalSize").getValue()))
+
+    def signature(self):
+        return (POP_CONSTANT, self._sizes().tobytes())
+
+    def push(self, e: Engine):
+        e.set_pop_model(POP_CONSTANT, self._sizes())
+
+
 class LinearWithConstantRoot(PopulationModel):
     """starbeast2.LinearWithConstantRoot (LinearWithConstantRoot.java:19-48)."""
     INPUTS = {"speciesTree": REQ, "tipPopulationSizes": REQ, "topPopulationSizes": REQ}
@@ -460,6 +484,53 @@ class UncorrelatedRates(BranchRateModel):
         out[: self.nEstimatedRates] = self.binRates[idx] * mean
         if not self.estimateRoot:
             out[self.rootNodeNumber] = mean   # :161
+        return out
+
+    def getRateForBranch(self, node: int) -> float:
+        return float(self.getRatesArray()[node])
+
+
+class RandomLocalRates(BranchRateModel):
+    """starbeast2.RandomLocalRates (RandomLocalRates.java:15-19: inputs tree, noCache, rates, indicators, clock.rate):
+    SpeciesTreeRates of a random local clock.  Host work in the reference too; the engine consumes getRatesArray().
+    Quirk kept (Q9): the recursion starts at the root with rate 1.0 and stores it (:84, :110), overwriting the mean rate
+    written just before (:106), and the normalisation loop stops below the root (:114-116) -- so the root branch carries
+    rate 1.0, not clock.rate."""
+    INPUTS = {"tree": REQ, "noCache": False, "rates": REQ, "indicators": REQ}
+
+    def initAndValidate(self):   # :49-70
+        tree = self.get("tree")
+        self.rootNodeNumber = tree.getNodeCount() - 1
+        rates, ind = self.get("rates"), self.get("indicators")
+        rates.setDimension(self.rootNodeNumber)
+        ind.setDimension(self.rootNodeNumber)
+        if rates.get("lower") is None or rates.getLower() < 0.0:
+            rates.setLower(0.0)
+        if rates.get("upper") is None or rates.getUpper() < 0.0:
+            rates.setUpper(float(np.finfo(np.float64).max))
+
+    def getRatesArray(self) -> np.ndarray:   # update(), :92-117
+        t = self.get("tree").arrays
+        ind = np.asarray(self.get("indicators").values, bool)
+        br = np.asarray(self.get("rates").values, float)
+        mean = self.mean_rate()
+        out = np.zeros(t.n_nodes)
+        out[self.rootNodeNumber] = mean
+        strict = relaxed = 0.0
+        stack = [(t.root, float(t.height[t.root]), 1.0)]
+        while stack:   # recurseBranchRates, :72-90, pre-order: node, left subtree, right subtree (the sums depend on this order)
+            node, parent_h, rate = stack.pop()
+            if node < self.rootNodeNumber and ind[node]:
+                rate = float(br[node])
+            length = parent_h - float(t.height[node])
+            strict += length
+            relaxed += length * rate
+            out[node] = rate
+            if t.left[node] >= 0:
+                stack.append((int(t.right[node]), float(t.height[node]), rate))
+                stack.append((int(t.left[node]), float(t.height[node]), rate))
+        scale = mean * strict / relaxed
+        out[: self.rootNodeNumber] = out[: self.rootNodeNumber] * scale
         return out
 
     def getRateForBranch(self, node: int) -> float:

@@ -352,3 +352,102 @@ def test_canis_c1_posterior_through_plugins():
     got2 = posterior.calculateLogP()
     assert eng.last_node_updates() == 15
     assert got2 == pytest.approx(oracle.posterior(Problem(species=sp_arrays, loci=loci, pop_kind=POP_CONSTANT, pop_a=pop)).total, rel=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# UniformPopulations and RandomLocalRates (host-side models that feed the same engine inputs)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_random_local_rates_mirror_matches_oracle_and_hand_worked_case():
+    """No reference test exists for RandomLocalRates (parity unpinned): hand-worked 3-species case + oracle recursion."""
+    from starbeast2_b200 import synth
+    from starbeast2_b200.plugins import BooleanParameter, RandomLocalRates, RealParameter, SpeciesTreeParser
+    from starbeast2_b200.problem import TreeArrays
+    import oracle
+    # ((A:1,B:1)ab:1,C:2)root -- nodes A0 B1 C2 ab3 root4
+    sp = TreeArrays([3, 3, 4, 4, -1], [-1, -1, -1, 0, 3], [-1, -1, -1, 1, 2], [0, 0, 0, 1.0, 2.0])
+    tree = SpeciesTreeParser()
+    tree.initByName("arrays", sp, "labels", ["A", "B", "C"])
+    rates = RealParameter(value="2.0 3.0 4.0 5.0", dimension=4)
+    ind = BooleanParameter(value="false true false true", dimension=4)
+    rlr = RandomLocalRates(tree=tree, rates=rates, indicators=ind)
+    got = rlr.getRatesArray()
+    # unscaled: ab switches to 5 (indicator on), A inherits 5, B switches to 3, C inherits the root's 1; lengths A1 B1 C2 ab1
+    raw = np.array([5.0, 3.0, 1.0, 5.0])
+    scale = 1.0 * (1 + 1 + 2 + 1) / (5 * 1 + 3 * 1 + 1 * 2 + 5 * 1)
+    assert np.allclose(got[:4], raw * scale, rtol=1e-15)
+    assert got[4] == 1.0                                      # quirk Q9: the root keeps the recursion's start rate
+    want = oracle.random_local_rates(sp, ind.values, rates.values, 1.0)
+    assert np.array_equal(got, want)
+    # with a clock.rate the weighted mean of the non-root rates equals it
+    rlr2 = RandomLocalRates(tree=tree, rates=rates, indicators=ind, **{"clock.rate": RealParameter(value="0.01")})
+    r2 = rlr2.getRatesArray()
+    lengths = np.array([1.0, 1.0, 2.0, 1.0])
+    assert np.dot(r2[:4], lengths) / lengths.sum() == pytest.approx(0.01, rel=1e-14)
+    assert np.array_equal(r2, oracle.random_local_rates(sp, ind.values, rates.values, 0.01))
+    rng = np.random.default_rng(3)
+    pb = synth.make_problem("C3", n_loci=1, n_sites=10)
+    S = pb.species.n_nodes
+    t2 = SpeciesTreeParser()
+    t2.initByName("arrays", pb.species, "labels", [f"s{i}" for i in range(pb.species.n_leaves)])
+    for _ in range(5):
+        rr = RealParameter(value=" ".join(repr(float(x)) for x in rng.gamma(2.0, 0.5, S - 1)), dimension=S - 1)
+        ii = BooleanParameter(value=" ".join("true" if x else "false" for x in rng.random(S - 1) < 0.3), dimension=S - 1)
+        m = RandomLocalRates(tree=t2, rates=rr, indicators=ii)
+        assert np.array_equal(m.getRatesArray(), oracle.random_local_rates(pb.species, ii.values, rr.values, 1.0))
+
+
+@pytest.mark.gpu
+def test_uniform_populations_and_random_local_rates_through_the_engine():
+    """UniformPopulations == ConstantPopulations with one size everywhere; RandomLocalRates feeds StarBeastClock."""
+    import oracle
+    from starbeast2_b200 import synth
+    from test_mcmc_trace import build
+    from starbeast2_b200.plugins import (BooleanParameter, GeneTree, MultispeciesCoalescent, RandomLocalRates, RealParameter, StarBeastClock,
+                                         UniformPopulations)
+    pb = synth.make_problem("C3", n_loci=3, n_sites=80)          # species-tree clock, LWCR pops
+    speciesTree, trees, params, posterior = build(pb)
+    # swap the population model for UniformPopulations(0.03) on fresh GeneTrees of a second session-less check via the oracle
+    S = pb.species.n_nodes
+    rng = np.random.default_rng(1)
+    rr = RealParameter(value=" ".join(repr(float(x)) for x in rng.gamma(2.0, 0.5, S - 1)), dimension=S - 1)
+    ii = BooleanParameter(value=" ".join("true" if x else "false" for x in rng.random(S - 1) < 0.3), dimension=S - 1)
+    rlr = RandomLocalRates(tree=speciesTree, rates=rr, indicators=ii)
+    likelihoods = posterior.get("distribution")[1].get("distribution")
+    for tl in likelihoods:
+        tl.get("branchRateModel")._inputs["speciesTreeRates"] = rlr
+    got = posterior.calculateLogP()
+    pb.species_rates = rlr.getRatesArray()
+    want = oracle.posterior(pb)
+    assert got == pytest.approx(want.total, rel=1e-9)
+    # an indicator flip changes the rates of a whole clade: picked up by the session, still equal to the oracle
+    ii.setValue(S - 3, not bool(ii.getValue(S - 3)))
+    got = posterior.calculateLogP()
+    pb.species_rates = rlr.getRatesArray()
+    assert got == pytest.approx(oracle.posterior(pb).total, rel=1e-9)
+
+    pb2 = synth.make_problem("C2", n_loci=3, n_sites=80)
+    from starbeast2_b200.plugins import SpeciesTreeParser, Taxon, TaxonSet, TreeParser
+    n_sp = pb2.species.n_leaves
+    names = [f"sp{i}" for i in range(n_sp)]
+    superset = TaxonSet([TaxonSet(names[i], [Taxon(f"sp{i}_{j}") for j in range(3)]) for i in range(n_sp)])
+    st = SpeciesTreeParser()
+    st.initByName("arrays", pb2.species, "labels", names, "taxonset", superset)
+    uni = UniformPopulations(speciesTree=st, universalSize=RealParameter(value="0.03"))
+    gts = []
+    for loc in pb2.loci:
+        counts, labels = {}, []
+        for sidx in loc.tip_species:
+            labels.append(f"sp{sidx}_{counts.get(int(sidx), 0)}")
+            counts[int(sidx)] = counts.get(int(sidx), 0) + 1
+        t = TreeParser()
+        t.initByName("arrays", loc.tree, "labels", labels)
+        gts.append(GeneTree(tree=t, speciesTree=st, ploidy=loc.ploidy, populationModel=uni))
+    msc = MultispeciesCoalescent(distribution=gts)
+    got = msc.calculateLogP()
+    pb2.pop_a = np.full(pb2.species.n_nodes, 0.03)
+    want = oracle.posterior(pb2)
+    assert got == pytest.approx(float(np.sum(want.per_locus_coal)), rel=1e-12)
+    uni.get("universalSize").setValue(0, 0.05)
+    pb2.pop_a = np.full(pb2.species.n_nodes, 0.05)
+    assert msc.calculateLogP() == pytest.approx(float(np.sum(oracle.posterior(pb2).per_locus_coal)), rel=1e-12)
