@@ -597,7 +597,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if ((rc = dev_alloc(e, &e->dDone, 1))) return rc;
     CUDA_TRY(e, cudaMemset(e->dDone, 0, sizeof(uint32_t)));
     {   // communication buffer: slots [2][COMM_MAX_RANKS][nRed] doubles, then flags [2][COMM_MAX_RANKS] u64 (own cudaMalloc: IPC-exportable)
-        e->commSlotsBytes = sizeof(double) * 2 * COMM_MAX_RANKS * (size_t)e->nRed;
+        e->commSlotsBytes = 2 * sizeof(unsigned long long) * 2 * COMM_MAX_RANKS * (size_t)e->nRed;   // two {32 data bits, 32 flag bits} words per double
         unsigned char *cb = nullptr;
         if ((rc = dev_alloc(e, &cb, e->commSlotsBytes + sizeof(unsigned long long) * 2 * COMM_MAX_RANKS))) return rc;
         e->commBuf = cb;
@@ -866,7 +866,7 @@ int sb2_comm_connect(sb2_engine *e, int32_t rank, int32_t nRanks, const void *ha
             e->commOpened.push_back(p);
             base = (unsigned char *)p;
         }
-        e->comm.peerSlots[r] = (double *)base;
+        e->comm.peerSlots[r] = (unsigned long long *)base;
         e->comm.peerFlags[r] = (unsigned long long *)(base + e->commSlotsBytes);
     }
     e->comm.rank = rank; e->comm.nRanks = nRanks; e->comm.nRed = e->nRed; e->comm.seq = 0;

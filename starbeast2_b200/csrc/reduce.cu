@@ -34,47 +34,55 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_finish(ReduceArgs A)
 
 // k_reduce_xgpu: local sums + ALL-REDUCE OVER PEER MEMORY + closed forms, one kernel.
 // Every rank stores its reduce vector straight into slot [parity][rank] of every peer's communication buffer over
-// NVLink, publishes a sequence number per peer (release, system scope), waits until all peers' numbers for this
-// evaluation have arrived in its own buffer, and sums the slots in rank order -- so all ranks obtain bit-identical
-// totals.  Buffer halves alternate with the sequence parity: a rank can be at most one evaluation ahead of a peer
-// (it needs the peer's flag of evaluation s+1 before it can start s+2), so a half is never overwritten while a
-// slow peer still reads it.  A rank that never shows up cannot hang the GPU: the wait gives up after ~2 s and
-// poisons the result with NaN.
+// NVLink, each double as two 8-byte words that carry the evaluation's sequence tag in their upper half (flag-in-data, the
+// idea of NCCL's LL protocol): the receiver polls the words themselves, so there is no fence and no separate flag on the
+// critical path -- one one-way NVLink trip.  All ranks sum the slots in rank order and obtain bit-identical totals.
+// Buffer halves alternate with the sequence parity: a rank can be at most one evaluation ahead of a peer (it needs the
+// peer's words of evaluation s+1 before it can finish s+1 and start s+2), so a half is never overwritten while a slow peer
+// still reads it.  A rank that never shows up cannot hang the GPU: the wait gives up after ~2 s and poisons the result
+// with NaN.
 __global__ void __launch_bounds__(RED_THREADS) k_reduce_xgpu(ReduceArgs A, CommArgs Cm)
 {
+    int tb = -1, ntl = 0;
+    if ((int)threadIdx.x < A.nLoci) { tb = A.loci[threadIdx.x].tileBase; ntl = A.loci[threadIdx.x].nTiles; }
     cudaGridDependencySynchronize();
-    reduce_local_body(A);
+    reduce_local_body(A, tb, ntl);
     __threadfence_block();
     __syncthreads();
     const int tid = threadIdx.x, nt = blockDim.x, nR = Cm.nRanks, n = Cm.nRed;
     const int half = (int)(Cm.seq & 1ull);
+    // Flag-in-data exchange: every double travels as two 8-byte words {32 data bits | 32-bit sequence tag}.  An 8-byte store
+    // is atomic, so a receiver that sees the tag of this evaluation in a word also sees its data: no fence, no separate flag,
+    // one one-way NVLink trip between "my sums are ready" and "I can add yours".
+    const unsigned long long tag = (0x80000000ull | (Cm.seq & 0x7fffffffull)) << 32;
     for (int idx = tid; idx < nR * n; idx += nt) {
         const int r = idx / n, i = idx - r * n;
-        Cm.peerSlots[r][((size_t)half * COMM_MAX_RANKS + Cm.rank) * n + i] = A.red[i];
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(A.red[i]);
+        volatile unsigned long long *dst = Cm.peerSlots[r] + (((size_t)half * COMM_MAX_RANKS + Cm.rank) * n + i) * 2;
+        dst[0] = tag | (bits & 0xffffffffull);
+        dst[1] = tag | (bits >> 32);
     }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < nR) {
-        volatile unsigned long long *theirs = Cm.peerFlags[tid] + half * COMM_MAX_RANKS + Cm.rank;
-        *theirs = Cm.seq;
-        volatile unsigned long long *mine = Cm.peerFlags[Cm.rank] + half * COMM_MAX_RANKS + tid;
-        const long long t0 = clock64();
-        while (*mine < Cm.seq) {
-            if (clock64() - t0 > 4000000000ll) { A.red[0] = NAN; break; }   // ~2 s at 2 GHz: a peer is gone
-            __nanosleep(100);
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    const bool poisoned = isnan(A.red[0]);
+    __shared__ int s_poison;
+    if (tid == 0) s_poison = 0;
     __syncthreads();
     for (int i = tid; i < n; i += nt) {
         double sum = 0.0;
-        for (int r = 0; r < nR; r++) sum += __ldcv(Cm.peerSlots[Cm.rank] + ((size_t)half * COMM_MAX_RANKS + r) * n + i);
-        A.red[i] = poisoned ? NAN : sum;
+        const long long t0 = clock64();
+        for (int r = 0; r < nR; r++) {   // rank order: every rank adds the same numbers in the same order
+            const volatile unsigned long long *src = Cm.peerSlots[Cm.rank] + (((size_t)half * COMM_MAX_RANKS + r) * n + i) * 2;
+            unsigned long long w0, w1;
+            for (;;) {
+                w0 = src[0]; w1 = src[1];
+                if ((w0 & 0xffffffff00000000ull) == tag && (w1 & 0xffffffff00000000ull) == tag) break;
+                if (clock64() - t0 > 4000000000ll) { s_poison = 1; w0 = w1 = 0; break; }   // ~2 s at 2 GHz: a peer is gone
+            }
+            sum += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+        }
+        A.red[i] = sum;
     }
     __threadfence_block();
     __syncthreads();
+    if (s_poison) { for (int i = tid; i < n; i += nt) A.red[i] = NAN; __threadfence_block(); __syncthreads(); }
     finish_body(A);
     publish_body(A);
 }

@@ -185,8 +185,9 @@ struct WalkArgs {
 // Peer-memory all-reduce of the reduce vector (one process per GPU, NVLink / NVSwitch; see reduce.cu:k_reduce_xgpu)
 constexpr int COMM_MAX_RANKS = 16;
 struct CommArgs {
-    double *peerSlots[COMM_MAX_RANKS];              // every rank's communication buffer: slots [2][COMM_MAX_RANKS][nRed]
-    unsigned long long *peerFlags[COMM_MAX_RANKS];  //                                    flags [2][COMM_MAX_RANKS]
+    unsigned long long *peerSlots[COMM_MAX_RANKS];  // every rank's communication buffer: slots [2][COMM_MAX_RANKS][nRed][2] words,
+                                                    // each word = {32 bits of the double, 32-bit sequence flag} (one 8-byte store)
+    unsigned long long *peerFlags[COMM_MAX_RANKS];  // (unused since the flags travel inside the data words)
     int32_t rank, nRanks, nRed;
     uint32_t pad;
     unsigned long long seq;                         // evaluation sequence number (parity selects the buffer half)
