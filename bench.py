@@ -170,7 +170,8 @@ def bench_incremental(eng, pb, synth, n_steps=400):
         one_call(i)
     dt1 = time.perf_counter() - t0
     return {"steps_per_sec": n_steps / dt, "us_per_step": 1e6 * dt / n_steps, "mean_node_updates": float(np.mean(updates)),
-            "protocol": "store, set_gene_tree(1 locus), eval_coalescent, eval_likelihood, restore; host-timed",
+            "protocol": "store, set_gene_tree(1 locus), eval_coalescent (likelihood evaluated speculatively in the same device pass), "
+                        "eval_likelihood (cached), restore; host-timed",
             "single_round_trip": {"steps_per_sec": n_steps / dt1, "us_per_step": 1e6 * dt1 / n_steps,
                                   "protocol": "store, set_gene_tree, eval_posterior, restore"}}
 

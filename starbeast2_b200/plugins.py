@@ -10,8 +10,10 @@ their state into one process-wide GpuSession, which batches ALL registered loci 
   * the first calculateLogP() of the coalescent phase (MultispeciesCoalescent or any GeneTree) triggers one
     sb2_eval_coalescent for every locus; later calls of the phase return cached per-locus values;
   * the first TreeLikelihood.calculateLogP() triggers one sb2_eval_likelihood for every dirty locus;
-  * an incompatible gene tree makes the coalescent -inf, the posterior CompoundDistribution returns early and the
-    likelihood phase never launches (the reference's short-circuit).
+  * an incompatible gene tree makes the coalescent -inf, the posterior CompoundDistribution returns early and no
+    TreeLikelihood is asked for its value (the reference's short-circuit).  By default the engine has
+    by then evaluated the likelihood speculatively in the same device pass (one host round trip per step); with
+    SB2_NO_SPECULATION=1 the pruning kernel is not even launched.
 
 The Java twins of these classes (java/ in this repo, uncompiled: no JDK in the image) bind the same C ABI through JNI.
 """

@@ -254,17 +254,28 @@ def test_posterior_protocol_with_tree_likelihoods():
     posterior.restore()         # ... then restoreCalculationNodes()
     assert posterior.calculateLogP() == before
 
-    # an incompatible proposal: the coalescent is -inf and the likelihood phase is never launched
-    launches_lik = likelihoods[0].session.engine.launch_count()
-    posterior.store(); speciesTree.store()
-    root = speciesTree.getRootNr()
-    child = int(speciesTree.arrays.left[root]) if speciesTree.arrays.left[int(speciesTree.arrays.left[root])] >= 0 else int(speciesTree.arrays.right[root])
-    speciesTree.setHeight(child, speciesTree.arrays.height[root] * 0.9999)
-    assert posterior.calculateLogP() == -math.inf
-    eng = likelihoods[0].session.engine
-    assert eng.launch_count() - launches_lik == 2      # k_prepare + the fused reduction; no pruning kernel
-    speciesTree.restore(); posterior.restore()
-    assert posterior.calculateLogP() == before
+    # an incompatible proposal: the coalescent is -inf and no TreeLikelihood is asked for its value.  Strict protocol
+    # (SB2_NO_SPECULATION): the pruning kernel is never launched; default: it ran speculatively in the same device pass and
+    # its result is dropped with the restore.
+    import os
+    for strict in (True, False):
+        if strict:
+            os.environ["SB2_NO_SPECULATION"] = "1"
+        else:
+            os.environ.pop("SB2_NO_SPECULATION", None)
+        try:
+            launches_lik = likelihoods[0].session.engine.launch_count()
+            posterior.store(); speciesTree.store()
+            root = speciesTree.getRootNr()
+            child = int(speciesTree.arrays.left[root]) if speciesTree.arrays.left[int(speciesTree.arrays.left[root])] >= 0 else int(speciesTree.arrays.right[root])
+            speciesTree.setHeight(child, speciesTree.arrays.height[root] * 0.9999)
+            assert posterior.calculateLogP() == -math.inf
+            eng = likelihoods[0].session.engine
+            assert eng.launch_count() - launches_lik == (2 if strict else 3)   # k_prepare (+ speculative pruning kernel) + the fused reduction
+            speciesTree.restore(); posterior.restore()
+            assert posterior.calculateLogP() == before
+        finally:
+            os.environ.pop("SB2_NO_SPECULATION", None)
 
 
 # ---- BASELINE.json configs[0]: the Canis tutorial data (16 loci x 16 individuals / 8 species, HKY, constant pops) ----------
