@@ -271,6 +271,31 @@ class Engine:
         self._ck(self._L.sb2_connecting_nodes(self._h, int(species_node), mask.ctypes.data if want_mask else None, fr, C.byref(cnt)))
         return mask, float(fr[0]), float(fr[1]), int(cnt.value)
 
+    def connecting_nodes_distributed(self, species_node: int, group=None):
+        """Loci sharded over ranks: the mask is this rank's, the freedoms are the minima over all ranks (the operator's draw
+        must be the same everywhere), the count is global."""
+        import torch
+        import torch.distributed as dist
+        mask, tip, root, cnt = self.connecting_nodes(species_node)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+            fr = torch.tensor([tip, root], dtype=torch.float64, device=dev)
+            dist.all_reduce(fr, op=dist.ReduceOp.MIN, group=group)
+            c = torch.tensor([cnt], dtype=torch.int64, device=dev)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
+            tip, root, cnt = float(fr[0]), float(fr[1]), int(c[0])
+        return mask, tip, root, cnt
+
+    def max_height_distributed(self, leaf_is_right, group=None) -> float:
+        import torch
+        import torch.distributed as dist
+        h = self.max_height(leaf_is_right)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            t = torch.tensor([h], dtype=torch.float64, device="cuda" if dist.get_backend(group) == "nccl" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            h = float(t[0])
+        return h
+
     def max_height(self, leaf_is_right) -> float:
         out = C.c_double(0.0)
         self._ck(self._L.sb2_max_height(self._h, np.ascontiguousarray(leaf_is_right, np.uint8), C.byref(out)))

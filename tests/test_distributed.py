@@ -105,7 +105,13 @@ def _gpu_worker(rank, world, port, name, n_loci, n_sites, out):
     e = Engine.from_problem(shard, device=0)
     e.bind_torch()
     r = e.eval_posterior_distributed()
-    out.put((rank, r.coalescent, r.likelihood, r.total, r.per_locus_lik.tolist(), r.per_branch.tolist()))
+    # the operators' gene-tree walks over sharded loci: local mask, global freedoms / count / max height
+    sp = shard.species
+    node = sp.n_leaves + 1
+    mask, tip, root, cnt = e.connecting_nodes_distributed(node)
+    side = (np.arange(sp.n_leaves) % 2).astype(np.uint8)
+    mh = e.max_height_distributed(side)
+    out.put((rank, r.coalescent, r.likelihood, r.total, r.per_locus_lik.tolist(), r.per_branch.tolist(), (mask.tolist(), tip, root, cnt, mh)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -124,7 +130,16 @@ def test_engine_distributed_two_ranks(name):
     assert all(p.exitcode == 0 for p in procs)
     pb = synth.make_problem(name, n_loci=n_loci, n_sites=n_sites)
     full = oracle.posterior(pb)
-    for rank, coal, lik, total, per_locus, per_branch in got:
+    sp = pb.species
+    w_mask, w_tip, w_root, w_cnt = oracle.connecting_nodes(pb, sp.n_leaves + 1)
+    cmap = np.zeros(sp.n_nodes, np.int32)
+    cmap[: sp.n_leaves] = np.arange(sp.n_leaves) % 2            # "right" leaves get canonical index 1 >= centre 1
+    w_mh = oracle.max_height(pb, cmap, 1)
+    node_off = np.concatenate([[0], np.cumsum([l.tree.n_nodes for l in pb.loci])])
+    for rank, coal, lik, total, per_locus, per_branch, q in got:
+        lo, hi = shard_loci([1.0] * n_loci, world)[rank]
+        assert q[0] == w_mask[node_off[lo]:node_off[hi]].tolist()
+        assert q[1:] == (w_tip, w_root, w_cnt, w_mh)
         assert coal == pytest.approx(full.coalescent, rel=1e-9)      # every rank ends with the global totals
         assert lik == pytest.approx(full.likelihood, rel=1e-9)
         assert total == pytest.approx(full.total, rel=1e-9)
