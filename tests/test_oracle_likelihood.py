@@ -163,3 +163,98 @@ def test_posterior_driver_consistent_with_pieces():
                    for b in range(pb.species.n_nodes))
         assert coal == pytest.approx(res.per_locus_coal[l], rel=1e-13)
     assert res.total == pytest.approx(res.coalescent + res.likelihood)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Size-independent properties of the pruning algorithm (the BEAST.base half is parity-unpinned: these pin it from the
+# mathematics side at realistic tree sizes, where brute-force enumeration is impossible)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _random_locus(rng, n_tips=24, n_pat=40, kind="gtr", ncat=4, missing=0.05):
+    from starbeast2_b200.problem import TreeArrays
+    # random binary tree by successive joins at increasing heights (node numbers: leaves first, root last)
+    G = 2 * n_tips - 1
+    parent, left, right, height = np.full(G, -1), np.full(G, -1), np.full(G, -1), np.zeros(G)
+    active = list(range(n_tips))
+    h = 0.0
+    for node in range(n_tips, G):
+        i, j = rng.choice(len(active), 2, replace=False)
+        a, b = active[i], active[j]
+        h += rng.exponential(0.03)
+        left[node], right[node], height[node] = a, b, h
+        parent[a] = parent[b] = node
+        active = [x for x in active if x not in (a, b)] + [node]
+    tree = TreeArrays(parent, left, right, height)
+    pats = rng.integers(0, 4, size=(n_tips, n_pat)).astype(np.uint8)
+    pats[rng.random(pats.shape) < missing] = 4
+    w = rng.integers(1, 4, size=n_pat).astype(np.int32)
+    pi = np.array([0.31, 0.19, 0.22, 0.28])
+    if kind == "hky":
+        sk, spar = SUBST_HKY, hky_params(2.7, pi)
+    else:
+        sk, spar = SUBST_EIGEN, gtr_eigen_params((1, 3, 0.8, 1.2, 3.5, 1), pi)
+    rates = synth.discrete_gamma_rates(0.5, ncat) * 0.9
+    return Locus(tree=tree, tip_states=pats, weights=w, tip_species=np.zeros(n_tips, np.int32), subst_kind=sk, subst_params=spar,
+                 cat_rates=rates, cat_props=np.full(ncat, 1.0 / ncat))
+
+
+@pytest.mark.parametrize("kind,ncat", [("hky", 1), ("gtr", 4)])
+def test_pulley_principle_root_position_is_irrelevant_for_reversible_models(kind, ncat):
+    """Felsenstein's pulley principle: for a time-reversible model only the SUM of the two root branch lengths matters.
+    Sliding the root along its branch (explicit per-branch rates stretch one root branch and shrink the other) leaves every
+    pattern likelihood unchanged."""
+    rng = np.random.default_rng(17)
+    loc = _random_locus(rng, kind=kind, ncat=ncat)
+    t = loc.tree
+    br = np.ones(t.n_nodes)
+    base, det = oracle.tree_likelihood(loc, br, want_details=True)
+    a, b = t.left[t.root], t.right[t.root]
+    la, lb = t.height[t.root] - t.height[a], t.height[t.root] - t.height[b]
+    for shift in (0.3, -0.25, 0.9):
+        delta = shift * min(la, lb)
+        br2 = br.copy()
+        br2[a] = (la + delta) / la        # length * rate: the branch above a becomes la + delta
+        br2[b] = (lb - delta) / lb        # ... and the one above b becomes lb - delta
+        got, det2 = oracle.tree_likelihood(loc, br2, want_details=True)
+        assert got == pytest.approx(base, rel=1e-12)
+        np.testing.assert_allclose(det2["pattern_logl"], det["pattern_logl"], rtol=1e-11)
+
+
+def test_all_missing_tip_and_pattern_permutation_do_not_change_the_likelihood():
+    rng = np.random.default_rng(23)
+    loc = _random_locus(rng, n_tips=16, n_pat=30, kind="gtr", ncat=2)
+    br = rng.uniform(0.6, 1.6, loc.tree.n_nodes)
+    base, det = oracle.tree_likelihood(loc, br, want_details=True)
+    # permuting the patterns permutes the pattern likelihoods and leaves the total unchanged up to summation order
+    perm = rng.permutation(loc.n_pat)
+    loc2 = Locus(tree=loc.tree, tip_states=loc.tip_states[:, perm], weights=loc.weights[perm], tip_species=loc.tip_species,
+                 subst_kind=loc.subst_kind, subst_params=loc.subst_params, cat_rates=loc.cat_rates, cat_props=loc.cat_props)
+    got2, det2 = oracle.tree_likelihood(loc2, br, want_details=True)
+    assert np.array_equal(det2["pattern_logl"], det["pattern_logl"][perm])
+    assert got2 == pytest.approx(base, rel=1e-13)
+    # a tip that is missing everywhere contributes a factor 1: same as pruning it (its sibling then hangs on the summed branch)
+    from starbeast2_b200.problem import TreeArrays
+    t = loc.tree
+    tip = 3
+    blank = loc.tip_states.copy()
+    blank[tip, :] = 4
+    loc3 = Locus(tree=t, tip_states=blank, weights=loc.weights, tip_species=loc.tip_species, subst_kind=loc.subst_kind,
+                 subst_params=loc.subst_params, cat_rates=loc.cat_rates, cat_props=loc.cat_props)
+    with_blank = oracle.tree_likelihood(loc3, np.ones(t.n_nodes))
+    # build the pruned tree: remove `tip` and its parent p; the sibling s attaches to p's parent (heights keep branch sums)
+    p = t.parent[tip]
+    s = t.right[p] if t.left[p] == tip else t.left[p]
+    gp = t.parent[p]
+    assert gp >= 0
+    keep = [i for i in range(t.n_nodes) if i not in (tip, p)]
+    renum = {old: new for new, old in enumerate(keep)}
+    par = np.array([-1 if t.parent[i] < 0 else renum[gp if t.parent[i] == p else t.parent[i]] for i in keep])
+    def child(c):
+        return -1 if c < 0 else renum[s if c == p else c]
+    lef = np.array([child(t.left[i]) for i in keep])
+    rig = np.array([child(t.right[i]) for i in keep])
+    pruned = TreeArrays(par, lef, rig, t.height[keep])
+    loc4 = Locus(tree=pruned, tip_states=np.delete(loc.tip_states, tip, axis=0), weights=loc.weights,
+                 tip_species=np.zeros(loc.n_tips - 1, np.int32), subst_kind=loc.subst_kind, subst_params=loc.subst_params,
+                 cat_rates=loc.cat_rates, cat_props=loc.cat_props)
+    assert oracle.tree_likelihood(loc4, np.ones(pruned.n_nodes)) == pytest.approx(with_blank, rel=1e-12)
