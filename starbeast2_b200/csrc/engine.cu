@@ -492,7 +492,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     for (auto &hl : e->loci) {
         LocusDesc &d = hl.d;
         for (int t = 0; t < d.nTips; t++)
-            if (hl.tipSpecies[t] < 0 || hl.tipSpecies[t] >= nSpeciesNodes) return e->fail(SB2_ERR_ARG, "tipToSpecies out of range");
+            if (hl.tipSpecies[t] < 0 || hl.tipSpecies[t] >= nSpeciesLeaves) return e->fail(SB2_ERR_ARG, "tipToSpecies must name a species LEAF (node number below the leaf count)");
         d.nodeBase = (int32_t)nodeBase; d.tipBase = (int32_t)tipBase; d.patBase = (int32_t)patBase; d.catBase = (int32_t)catBase;
         d.tileBase = (int32_t)tileBase; d.nTiles = (d.nPat + tilePat - 1) / tilePat; d.opBase = (int32_t)opBase;
         d.stackDepth = floor_log2(d.nInt) + 1;
