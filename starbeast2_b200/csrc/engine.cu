@@ -299,6 +299,8 @@ int do_prepare(sb2_engine *e)
 // final reduction of the single-call evaluations: across GPUs over peer memory when connected, else local
 void launch_final(sb2_engine *e, const ReduceArgs &r)
 {
+    static const bool skip = getenv("SB2_DEBUG_SKIP_REDUCE") != nullptr;   // timing experiments only: results are stale
+    if (skip) return;
     if (e->commConnected) {
         e->comm.seq++;
         launch_reduce_xgpu(r, e->comm, e->stream, &e->launches);
@@ -341,7 +343,8 @@ int do_walk(sb2_engine *e, int fuse = 0, bool *fused = nullptr)
         ev = e->evPool[e->evUsed++];
         CUDA_TRY(e, cudaEventRecord(ev.first, e->stream));
     }
-    launch_treewalk(a, (int)e->totalTiles, e->cfg.exact_order != 0, e->stream);
+    static const bool skipWalk = getenv("SB2_DEBUG_SKIP_WALK") != nullptr;   // timing experiments only
+    if (!skipWalk) launch_treewalk(a, (int)e->totalTiles, e->cfg.exact_order != 0, e->stream);
     e->launches++;
     if (e->cfg.profile) CUDA_TRY(e, cudaEventRecord(ev.second, e->stream));
     CUDA_TRY(e, cudaGetLastError());
