@@ -121,6 +121,11 @@ SB2_API int sb2_eval_end(sb2_engine *e, double *perLocusCoal, double *perLocusLi
  * torch tensor handed to torch.distributed.all_reduce) with sb2_bind_reduce_vector before the first eval. */
 SB2_API int sb2_reduce_vector(sb2_engine *e, void **devPtr, int32_t *nDoubles);
 SB2_API int sb2_bind_reduce_vector(sb2_engine *e, void *devPtr);
+/* One host thread driving several engines (one per GPU, loci sharded): after sb2_eval_begin on
+ * every engine, read each engine's reduce vector into host memory (synchronises that engine's stream), add them up, write
+ * the sum back into every engine, then sb2_eval_end.  host has sb2_reduce_vector's nDoubles entries. */
+SB2_API int sb2_read_reduce_vector(sb2_engine *e, double *host);
+SB2_API int sb2_write_reduce_vector(sb2_engine *e, const double *host);
 /* Peer-memory all-reduce for one-process-per-GPU hosts on an NVLink / NVSwitch box: after sb2_comm_connect the
  * single-call evaluations (sb2_eval_posterior / _coalescent / _likelihood) exchange the reduce vector inside the
  * reduction kernel (stores into every peer's buffer + sequence flags, summed in rank order: all ranks get

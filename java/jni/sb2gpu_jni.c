@@ -140,3 +140,39 @@ JNIEXPORT jint JNICALL FN(maxHeight)(JNIEnv *env, jclass c, jlong h, jbyteArray 
     UNPIN(out, o, 0); UNPIN(leafIsRight, l, JNI_ABORT);
     return rc;
 }
+JNIEXPORT jint JNICALL FN(evalBegin)(JNIEnv *env, jclass c, jlong h) { return sb2_eval_begin(E(h)); }
+JNIEXPORT jint JNICALL FN(evalEnd)(JNIEnv *env, jclass c, jlong h, jdoubleArray coal, jdoubleArray lik, jdoubleArray br, jdoubleArray tot)
+{
+    void *pc = PIN(coal), *pl = PIN(lik), *pb = PIN(br), *pt = PIN(tot);
+    int rc = sb2_eval_end(E(h), pc, pl, pb, pt);
+    UNPIN(tot, pt, 0); UNPIN(br, pb, 0); UNPIN(lik, pl, 0); UNPIN(coal, pc, 0);
+    return rc;
+}
+JNIEXPORT jint JNICALL FN(reduceVectorLength)(JNIEnv *env, jclass c, jlong h)
+{
+    void *dev = NULL; int32_t n = 0;
+    return sb2_reduce_vector(E(h), &dev, &n) == SB2_OK ? n : -1;
+}
+JNIEXPORT jint JNICALL FN(readReduceVector)(JNIEnv *env, jclass c, jlong h, jdoubleArray host)
+{
+    void *p = PIN(host);
+    int rc = sb2_read_reduce_vector(E(h), p);
+    UNPIN(host, p, 0);
+    return rc;
+}
+JNIEXPORT jint JNICALL FN(writeReduceVector)(JNIEnv *env, jclass c, jlong h, jdoubleArray host)
+{
+    void *p = PIN(host);
+    int rc = sb2_write_reduce_vector(E(h), p);
+    UNPIN(host, p, JNI_ABORT);
+    return rc;
+}
+JNIEXPORT jint JNICALL FN(setGeneTrees)(JNIEnv *env, jclass c, jlong h, jint first, jint n, jintArray par, jintArray left, jintArray right, jdoubleArray height)
+{
+    void *p = PIN(par), *l = PIN(left), *r = PIN(right), *hh = PIN(height);
+    int rc = sb2_set_gene_trees(E(h), first, n, p, l, r, hh);
+    UNPIN(height, hh, JNI_ABORT); UNPIN(right, r, JNI_ABORT); UNPIN(left, l, JNI_ABORT); UNPIN(par, p, JNI_ABORT);
+    return rc;
+}
+JNIEXPORT jint JNICALL FN(numLoci)(JNIEnv *env, jclass c, jlong h) { return sb2_num_loci(E(h)); }
+JNIEXPORT jlong JNICALL FN(launchCount)(JNIEnv *env, jclass c, jlong h) { return sb2_launch_count(E(h)); }

@@ -38,4 +38,13 @@ public final class Sb2Gpu {
     // operator-side walks over the resident gene trees (sb2gpu.h: sb2_connecting_nodes, sb2_max_height)
     public static native int connectingNodes(long engine, int speciesNode, byte[] maskOrNull, double[] freedoms2, long[] count1OrNull);
     public static native int maxHeight(long engine, byte[] leafIsRight, double[] maxHeight1);
+    // several engines (one per GPU) driven by this JVM thread: begin on all, sum the reduce vectors on the host, end on all
+    public static native int evalBegin(long engine);
+    public static native int evalEnd(long engine, double[] perLocusCoal, double[] perLocusLik, double[] perBranch, double[] total3);
+    public static native int reduceVectorLength(long engine);
+    public static native int readReduceVector(long engine, double[] host);
+    public static native int writeReduceVector(long engine, double[] host);
+    public static native int setGeneTrees(long engine, int firstLocus, int nLoci, int[] parent, int[] left, int[] right, double[] height);
+    public static native int numLoci(long engine);
+    public static native long launchCount(long engine);
 }

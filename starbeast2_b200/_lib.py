@@ -68,6 +68,8 @@ def load() -> C.CDLL:
         "sb2_eval_end": (C.c_int, [E, _vp, _vp, _vp, _vp]),
         "sb2_reduce_vector": (C.c_int, [E, C.POINTER(_vp), C.POINTER(C.c_int32)]),
         "sb2_bind_reduce_vector": (C.c_int, [E, _vp]),
+        "sb2_read_reduce_vector": (C.c_int, [E, _f64p]),
+        "sb2_write_reduce_vector": (C.c_int, [E, _f64p]),
         "sb2_comm_handle": (C.c_int, [E, _vp]),
         "sb2_comm_connect": (C.c_int, [E, C.c_int32, C.c_int32, _vp]),
         "sb2_set_stream": (C.c_int, [E, _vp]),

@@ -375,7 +375,9 @@ static int eval_full(sb2_engine *e)
     int rc;
     bool fused;
     if ((rc = do_prepare(e))) return rc;
-    if (e->resultValid && !e->walkPending) return SB2_OK;
+    // cached result: only without peers -- with a connected communicator EVERY evaluation call is one exchange on every
+    // rank, whatever this rank's local state is (a rank whose loci did not change must still contribute)
+    if (e->resultValid && !e->walkPending && !e->commConnected) return SB2_OK;
     if ((rc = do_walk(e, 2, &fused))) return rc;                                     // single GPU: no all-reduce in between
     if (!fused) launch_final(e, reduce_args(e));
     CUDA_TRY(e, cudaGetLastError());
@@ -410,6 +412,7 @@ int sb2_create(const sb2_config *cfg, sb2_engine **out)
 void sb2_destroy(sb2_engine *e)
 {
     if (!e) return;
+    cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void *p : e->devAllocs) cudaFree(p);
     for (void *p : {(void *)e->hParams, (void *)e->hCat, (void *)e->hExplicit, (void *)e->hInTree, (void *)e->hFlags, (void *)e->hSpecies, (void *)e->hOut,
@@ -426,6 +429,7 @@ const char *sb2_last_error(const sb2_engine *e) { return e ? e->err.c_str() : "n
 int sb2_add_locus(sb2_engine *e, int32_t nTips, int32_t nPatterns, const uint8_t *tipStates, const int32_t *patternWeights,
                   int32_t nCategories, const int32_t *tipToSpecies, double ploidy)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     if (e->finalized) return e->fail(SB2_ERR_STATE, "sb2_add_locus after sb2_finalize");
     if (nTips < 2 || nPatterns < 1 || nCategories < 1 || nCategories > 32 || !tipStates || !patternWeights || !tipToSpecies)
@@ -453,6 +457,7 @@ int sb2_add_locus(sb2_engine *e, int32_t nTips, int32_t nPatterns, const uint8_t
 
 int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     if (e->finalized) return e->fail(SB2_ERR_STATE, "already finalized");
     if (e->loci.empty()) return e->fail(SB2_ERR_STATE, "no loci");
@@ -639,6 +644,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
 
 int sb2_set_species_tree(sb2_engine *e, const int32_t *parent, const int32_t *left, const int32_t *right, const double *height)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (!parent || !left || !right || !height) return e->fail(SB2_ERR_ARG, "null species tree array");
     SpeciesView v = species_view(e);
@@ -657,6 +663,7 @@ int sb2_set_species_tree(sb2_engine *e, const int32_t *parent, const int32_t *le
 int sb2_set_gene_trees(sb2_engine *e, int32_t firstLocus, int32_t nLoci, const int32_t *parent, const int32_t *left,
                        const int32_t *right, const double *height)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (firstLocus < 0 || nLoci < 0 || firstLocus + nLoci > e->L) return e->fail(SB2_ERR_ARG, "locus range [%d,%d) out of range", firstLocus, firstLocus + nLoci);
     if (!parent || !left || !right || !height) return e->fail(SB2_ERR_ARG, "null gene tree array");
@@ -686,11 +693,13 @@ int sb2_set_gene_trees(sb2_engine *e, int32_t firstLocus, int32_t nLoci, const i
 
 int sb2_set_gene_tree(sb2_engine *e, int32_t locus, const int32_t *parent, const int32_t *left, const int32_t *right, const double *height)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     return sb2_set_gene_trees(e, locus, 1, parent, left, right, height);
 }
 
 int sb2_set_subst_model(sb2_engine *e, int32_t locus, int32_t kind, const double *params)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     int rc = check_locus(e, locus);
     if (rc) return rc;
@@ -705,6 +714,7 @@ int sb2_set_subst_model(sb2_engine *e, int32_t locus, int32_t kind, const double
 
 int sb2_set_site_model(sb2_engine *e, int32_t locus, const double *catRates, const double *catProps, double pInv)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     int rc = check_locus(e, locus);
     if (rc) return rc;
@@ -720,6 +730,7 @@ int sb2_set_site_model(sb2_engine *e, int32_t locus, const double *catRates, con
 
 int sb2_set_clock(sb2_engine *e, int32_t locus, int32_t kind, double meanRate, const double *ratesOrNull)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     int rc = check_locus(e, locus);
     if (rc) return rc;
@@ -747,6 +758,7 @@ int sb2_set_clock(sb2_engine *e, int32_t locus, int32_t kind, double meanRate, c
 
 int sb2_set_species_rates(sb2_engine *e, const double *rates)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (!rates) return e->fail(SB2_ERR_ARG, "null rates");
     memcpy(species_view(e).sRates, rates, 8 * e->S);
@@ -756,6 +768,7 @@ int sb2_set_species_rates(sb2_engine *e, const double *rates)
 
 int sb2_set_pop_model(sb2_engine *e, int32_t kind, const double *a, const double *b, double alpha, double beta)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     SpeciesView v = species_view(e);
     if (kind == SB2_POP_CONSTANT) {
@@ -777,6 +790,7 @@ int sb2_set_pop_model(sb2_engine *e, int32_t kind, const double *a, const double
 
 int sb2_eval_begin(sb2_engine *e)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     int rc;
     bool fused;
@@ -790,6 +804,7 @@ int sb2_eval_begin(sb2_engine *e)
 
 int sb2_eval_end(sb2_engine *e, double *perLocusCoal, double *perLocusLik, double *perBranch, double *total3)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (!e->reduced) return e->fail(SB2_ERR_STATE, "sb2_eval_end without sb2_eval_begin");
     launch_finish(reduce_args(e), e->stream, &e->launches);
@@ -803,6 +818,7 @@ int sb2_eval_end(sb2_engine *e, double *perLocusCoal, double *perLocusLik, doubl
 
 int sb2_eval_posterior(sb2_engine *e, double *perLocusCoal, double *perLocusLik, double *perBranch, double *total3)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     int rc;
     if ((rc = eval_full(e))) return rc;
@@ -812,6 +828,7 @@ int sb2_eval_posterior(sb2_engine *e, double *perLocusCoal, double *perLocusLik,
 
 int sb2_eval_coalescent(sb2_engine *e, double *perLocus, double *perBranch, double *total)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     int rc;
     // Phase 1 of the reference's posterior.  By default the likelihood phase is evaluated SPECULATIVELY in the same device
@@ -837,6 +854,7 @@ int sb2_eval_coalescent(sb2_engine *e, double *perLocus, double *perBranch, doub
 
 int sb2_eval_likelihood(sb2_engine *e, double *perLocus, double *total)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     int rc;
     if ((rc = eval_full(e))) return rc;
@@ -847,6 +865,7 @@ int sb2_eval_likelihood(sb2_engine *e, double *perLocus, double *total)
 
 int sb2_reduce_vector(sb2_engine *e, void **devPtr, int32_t *nDoubles)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (devPtr) *devPtr = e->dRed;
     if (nDoubles) *nDoubles = e->nRed;
@@ -855,13 +874,35 @@ int sb2_reduce_vector(sb2_engine *e, void **devPtr, int32_t *nDoubles)
 
 int sb2_bind_reduce_vector(sb2_engine *e, void *devPtr)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     e->dRed = devPtr ? (double *)devPtr : e->dRedOwn;
     return SB2_OK;
 }
 
+int sb2_read_reduce_vector(sb2_engine *e, double *host)
+{
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    if (!host) return e->fail(SB2_ERR_ARG, "null host buffer");
+    CUDA_TRY(e, cudaMemcpyAsync(host, e->dRed, sizeof(double) * (size_t)e->nRed, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return SB2_OK;
+}
+
+int sb2_write_reduce_vector(sb2_engine *e, const double *host)
+{
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    if (!host) return e->fail(SB2_ERR_ARG, "null host buffer");
+    CUDA_TRY(e, cudaMemcpyAsync(e->dRed, host, sizeof(double) * (size_t)e->nRed, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));   // `host` may be reused by the caller as soon as this returns
+    return SB2_OK;
+}
+
 int sb2_comm_handle(sb2_engine *e, void *handle64)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
@@ -872,6 +913,7 @@ int sb2_comm_handle(sb2_engine *e, void *handle64)
 
 int sb2_comm_connect(sb2_engine *e, int32_t rank, int32_t nRanks, const void *handles)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (nRanks < 1 || nRanks > COMM_MAX_RANKS || rank < 0 || rank >= nRanks || !handles) return e->fail(SB2_ERR_ARG, "bad rank %d / %d (max %d ranks)", rank, nRanks, COMM_MAX_RANKS);
     for (int r = 0; r < nRanks; r++) {
@@ -895,6 +937,7 @@ int sb2_comm_connect(sb2_engine *e, int32_t rank, int32_t nRanks, const void *ha
 
 int sb2_set_stream(sb2_engine *e, void *cudaStream)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
@@ -916,6 +959,7 @@ static int flush_pending_walk(sb2_engine *e)
 
 int sb2_store(sb2_engine *e)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     int rc = flush_pending_walk(e);
     if (rc) return rc;
@@ -937,6 +981,7 @@ int sb2_store(sb2_engine *e)
 
 int sb2_restore(sb2_engine *e)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     e->curIdx = 1 - e->curIdx;   // swap current / stored, like the reference's restore() methods
     // staged proposal inputs belong to the rejected state: drop them and bring the host mirrors back
@@ -966,12 +1011,14 @@ int sb2_restore(sb2_engine *e)
 
 int sb2_accept(sb2_engine *e)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     return flush_pending_walk(e);
 }
 
 int sb2_mark_all_dirty(sb2_engine *e)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     e->forceAll = true; e->needPrepare = true;
     return SB2_OK;
@@ -979,6 +1026,7 @@ int sb2_mark_all_dirty(sb2_engine *e)
 
 int sb2_get_branch_rates(sb2_engine *e, int32_t locus, double *rates)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     int rc = check_locus(e, locus);
     if (rc) return rc;
@@ -990,6 +1038,7 @@ int sb2_get_branch_rates(sb2_engine *e, int32_t locus, double *rates)
 
 int sb2_get_embedding(sb2_engine *e, int32_t locus, int32_t *lineageCounts, int32_t *coalCounts, int32_t *assignment, double *perBranchLogP)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     int rc = check_locus(e, locus);
     if (rc) return rc;
@@ -1005,6 +1054,7 @@ int sb2_get_embedding(sb2_engine *e, int32_t locus, int32_t *lineageCounts, int3
 
 int sb2_get_partials(sb2_engine *e, int32_t locus, int32_t node, double *partials, int32_t *exponents)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     int rc = check_locus(e, locus);
     if (rc) return rc;
@@ -1027,6 +1077,7 @@ int sb2_get_partials(sb2_engine *e, int32_t locus, int32_t node, double *partial
 
 int sb2_get_matrices(sb2_engine *e, int32_t locus, int32_t node, double *matrices)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     int rc = check_locus(e, locus);
     if (rc) return rc;
@@ -1041,6 +1092,7 @@ int sb2_get_matrices(sb2_engine *e, int32_t locus, int32_t node, double *matrice
 
 int sb2_get_pattern_logl(sb2_engine *e, int32_t locus, double *patternLogL)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     int rc = check_locus(e, locus);
     if (rc) return rc;
@@ -1099,6 +1151,7 @@ static int run_query(sb2_engine *e, int mode, const uint8_t *leafClass, uint8_t 
 
 int sb2_connecting_nodes(sb2_engine *e, int32_t speciesNode, uint8_t *mask, double *freedoms, int64_t *count)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (!freedoms) return e->fail(SB2_ERR_ARG, "null freedoms");
     SpeciesView v = species_view(e);
@@ -1126,6 +1179,7 @@ int sb2_connecting_nodes(sb2_engine *e, int32_t speciesNode, uint8_t *mask, doub
 
 int sb2_max_height(sb2_engine *e, const uint8_t *leafIsRight, double *maxHeight)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (!leafIsRight || !maxHeight) return e->fail(SB2_ERR_ARG, "null argument");
     std::vector<uint8_t> cls((size_t)e->nSpeciesLeaves);
@@ -1142,6 +1196,7 @@ int64_t sb2_launch_count(const sb2_engine *e) { return e ? e->launches : 0; }
 
 int64_t sb2_last_node_updates(sb2_engine *e)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return -1;
     std::vector<int32_t> n(e->L);
     cudaStreamSynchronize(e->stream);
@@ -1153,6 +1208,7 @@ int64_t sb2_last_node_updates(sb2_engine *e)
 
 int sb2_kernel_time(sb2_engine *e, double *ms, int64_t *launches)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     double t = 0.0;
@@ -1169,6 +1225,7 @@ int sb2_kernel_time(sb2_engine *e, double *ms, int64_t *launches)
 
 int sb2_set_profile(sb2_engine *e, int32_t on)
 {
+    if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     e->cfg.profile = on ? 1 : 0;
     return SB2_OK;

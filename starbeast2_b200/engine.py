@@ -248,6 +248,29 @@ class Engine:
         self._peers = True
         return True
 
+    def read_reduce_vector(self) -> np.ndarray:
+        out = np.zeros(self.reduce_vector_len())
+        self._ck(self._L.sb2_read_reduce_vector(self._h, out))
+        return out
+
+    def write_reduce_vector(self, v):
+        self._ck(self._L.sb2_write_reduce_vector(self._h, np.ascontiguousarray(v, np.float64)))
+
+    @staticmethod
+    def eval_posterior_multi(engines: Sequence["Engine"]) -> List[EvalResult]:
+        """One host thread, several engines (one per GPU, loci sharded): the in-process twin of eval_posterior_distributed,
+        what a single JVM does.  All engines run their kernels concurrently; the reduce vectors
+        are summed on the host in engine order, so every engine finishes with the same global totals."""
+        for e in engines:
+            e.eval_begin()
+        total = None
+        for e in engines:
+            v = e.read_reduce_vector()
+            total = v if total is None else total + v
+        for e in engines:
+            e.write_reduce_vector(total)
+        return [e.eval_end() for e in engines]
+
     def eval_posterior_distributed(self, group=None) -> EvalResult:
         """begin -> all-reduce(sum) of the reduce vector over ranks -> end.  Totals are global, per-locus arrays local."""
         import torch.distributed as dist

@@ -63,3 +63,23 @@ def test_shard_loci_partitions():
         assert all(parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
         loads = [w[a:b].sum() for a, b in parts]
         assert max(loads) <= w.sum() / ws + w.max()
+
+
+def test_java_jni_sources_stay_consistent_with_the_header():
+    """java/ cannot be compiled here (no JDK), so at least keep it honest: every `native` method of Sb2Gpu.java has a JNI
+    implementation and vice versa, every sb2_* function the shim calls is declared in include/sb2gpu.h, and every entry point
+    a JVM host needs is bound (the unbound remainder is the process-per-GPU / torch / introspection surface)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    java = open(os.path.join(root, "java", "src", "starbeast2", "gpu", "Sb2Gpu.java")).read()
+    jni = open(os.path.join(root, "java", "jni", "sb2gpu_jni.c")).read()
+    natives = set(re.findall(r"native\s+[\w\[\]]+\s+(\w+)\s*\(", java))
+    impls = set(re.findall(r"JNICALL FN\((\w+)\)", jni))
+    assert natives == impls, (sorted(natives - impls), sorted(impls - natives))
+    called = set(re.findall(r"\b(sb2_\w+)\s*\(", jni))
+    declared = set(_lib.header_symbols())
+    assert called <= declared, sorted(called - declared)
+    not_for_a_jvm = {"sb2_bind_reduce_vector", "sb2_comm_connect", "sb2_comm_handle", "sb2_set_stream",          # torch / one process per GPU
+                     "sb2_device_bytes", "sb2_get_matrices", "sb2_get_partials", "sb2_get_pattern_logl", "sb2_kernel_time",
+                     "sb2_last_node_updates", "sb2_set_profile"}                                                      # introspection for tests / bench
+    assert declared - called == not_for_a_jvm, sorted((declared - called) ^ not_for_a_jvm)

@@ -176,8 +176,18 @@ def _peer_worker(rank, world, port, name, n_loci, n_sites, out):
     r2 = e.eval_posterior_distributed()
     e.restore()
     r3 = e.eval_posterior_distributed()
+    # the reference's two-phase protocol with an asymmetric proposal (only rank 1 stages a tree): every call is one exchange
+    # on every rank, whatever the rank's local state, so the phases must reproduce r2's global totals on both ranks
+    e.store()
+    if rank == 1:
+        e.set_gene_tree(0, t)
+    c_tot, _, _ = e.eval_coalescent()
+    l_tot, _ = e.eval_likelihood()
+    e.restore()
+    r4 = e.eval_posterior_distributed()
+    assert (r4.coalescent, r4.likelihood) == (r3.coalescent, r3.likelihood)
     out.put((rank, totals, (r2.coalescent, r2.likelihood, r2.total), (r3.coalescent, r3.likelihood, r3.total), moved,
-             r.per_branch.tolist()))
+             r.per_branch.tolist(), (c_tot, l_tot)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -199,7 +209,8 @@ def test_peer_memory_allreduce_two_gpus(name):
     assert all(p.exitcode == 0 for p in procs)
     pb = synth.make_problem(name, n_loci=n_loci, n_sites=n_sites)
     full = oracle.posterior(pb)
-    for rank, totals, r2, r3, moved, per_branch in got:
+    for rank, totals, r2, r3, moved, per_branch, two_phase in got:
+        assert two_phase == (r2[0], r2[1])                    # coalescent / likelihood phases == the single-call evaluation
         for coal, lik, total in totals:
             assert coal == pytest.approx(full.coalescent, rel=1e-9) and lik == pytest.approx(full.likelihood, rel=1e-9)
             assert total == pytest.approx(full.total, rel=1e-9)
@@ -218,3 +229,35 @@ def test_peer_memory_allreduce_two_gpus(name):
         assert got[0][2][2] == pytest.approx(w2.total, rel=1e-9)
     else:
         assert got[0][2][0] == -math.inf
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["C4", "C2"])
+def test_one_host_thread_several_engines(name):
+    """one JVM thread drives one engine per GPU.  Here: three engines with the loci sharded over
+    them -- on different GPUs when the box has them, else all on cuda:0 -- evaluated through begin / read / host sum / write /
+    end.  Every engine ends with the global totals; per-locus values are its shard's."""
+    from starbeast2_b200.engine import Engine
+    n_loci, world = 9, 3
+    n_dev = torch.cuda.device_count()
+    pb = synth.make_problem(name, n_loci=n_loci, n_sites=80)
+    full = oracle.posterior(pb)
+    shards = shard_loci([1.0] * n_loci, world)
+    engines = []
+    for r, (lo, hi) in enumerate(shards):
+        shard = synth.make_problem(name, n_loci=n_loci, n_sites=80, locus_range=(lo, hi))
+        engines.append(Engine.from_problem(shard, device=r % n_dev))
+    for rep in range(2):
+        res = Engine.eval_posterior_multi(engines)
+        for (lo, hi), r in zip(shards, res):
+            assert r.coalescent == pytest.approx(full.coalescent, rel=1e-9)
+            assert r.likelihood == pytest.approx(full.likelihood, rel=1e-9)
+            assert r.total == pytest.approx(full.total, rel=1e-9)
+            np.testing.assert_allclose(r.per_locus_lik, full.per_locus_lik[lo:hi], rtol=1e-9)
+            if pb.pop_kind == POP_ANALYTIC:
+                np.testing.assert_allclose(r.per_branch, full.per_branch, rtol=1e-9)
+        assert res[0].total == res[1].total == res[2].total          # same summation order everywhere
+        for e in engines:
+            e.mark_all_dirty()
+    for e in engines:
+        e.close()
