@@ -182,6 +182,16 @@ SB2_API int sb2_connecting_nodes(sb2_engine *e, int32_t speciesNode, uint8_t *ma
  * subtree over all gene trees (+inf if none). */
 SB2_API int sb2_max_height(sb2_engine *e, const uint8_t *leafIsRight, double *maxHeight);
 
+/* ---- alignment -> site patterns (engine-independent) ---------------------------------------- */
+/* BEAST.base Alignment.calcPatterns (the <data> blocks of the reference's XML, e.g. tutorial/CanisPhylogeny/
+ * Canis-Phylogeny.xml:3-23): sequences[tip][site] (0-3, >= 4 missing / ambiguous) -> the unique site columns in
+ * lexicographic order (taxon 0 most significant) as patterns[tip][*nPatterns] (compact rows), their multiplicities
+ * weights[*nPatterns] and, optionally, siteToPattern[nSites].  Buffers must hold nSites entries per row / array.
+ * Feed the result to sb2_add_locus.  At most 16384 sites per call.  Errors: sb2_compress_last_error(). */
+SB2_API int sb2_compress_alignment(int32_t device, int32_t nTips, int32_t nSites, const uint8_t *sequences, uint8_t *patterns,
+                                   int32_t *weights, int32_t *siteToPattern, int32_t *nPatterns);
+SB2_API const char *sb2_compress_last_error(void);
+
 /* ---- introspection ------------------------------------------------------------------------------------------ */
 
 SB2_API int32_t sb2_num_loci(const sb2_engine *e);

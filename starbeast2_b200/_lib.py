@@ -84,6 +84,8 @@ def load() -> C.CDLL:
         "sb2_get_pattern_logl": (C.c_int, [E, C.c_int32, _f64p]),
         "sb2_connecting_nodes": (C.c_int, [E, C.c_int32, _vp, _f64p, C.POINTER(C.c_int64)]),
         "sb2_max_height": (C.c_int, [E, _u8p, C.POINTER(C.c_double)]),
+        "sb2_compress_alignment": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _u8p, _u8p, _i32p, _vp, C.POINTER(C.c_int32)]),
+        "sb2_compress_last_error": (C.c_char_p, []),
         "sb2_num_loci": (C.c_int32, [E]),
         "sb2_launch_count": (C.c_int64, [E]),
         "sb2_last_node_updates": (C.c_int64, [E]),

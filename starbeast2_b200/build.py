@@ -23,6 +23,7 @@ SOURCES = {
     "reduce.cu": ["-fmad=false"],
     "treewalk.cu": [],
     "query.cu": ["-fmad=false"],
+    "compress.cu": [],
     "engine.cu": [],
 }
 DEPS = ["sb2_device.cuh", "reduce_body.cuh", os.path.join("..", "..", "include", "sb2gpu.h")]
