@@ -176,6 +176,34 @@ def bench_incremental(eng, pb, synth, n_steps=400):
                                   "protocol": "store, set_gene_tree, eval_posterior, restore"}}
 
 
+def cpu_incremental(pb, synth, n_steps=300):
+    """Regime B on the host: the C restatement of what the reference evaluates when one gene tree changed (oracle
+    IncrementalBaseline: embedding of EVERY locus -- GeneTree.requiresRecalculation() is always true --, population terms,
+    clock rates and incremental TreeLikelihood of the changed locus), 1 thread like the reference's MCMC."""
+    import oracle
+    if pb.pop_kind not in (0, 1):
+        return None
+    rng = np.random.default_rng(12345)
+    inc = oracle.IncrementalBaseline(pb)
+    moves = []
+    for _ in range(64):
+        l = int(rng.integers(0, pb.n_loci))
+        t, _ = synth.perturb_gene_tree(rng, pb.loci[l].tree, pb.loci[l].n_tips)
+        moves.append((l, t, pb.loci[l].tree))
+    for l, t, t0 in moves[:8]:
+        inc.step(l, t); inc.step(l, t0)
+    t_start = time.perf_counter()
+    for i in range(n_steps):
+        l, t, t0 = moves[i % len(moves)]
+        inc.step(l, t)          # propose + evaluate
+        inc.step(l, t0)         # the move back is an equally small update; both are counted as steps
+    dt = time.perf_counter() - t_start
+    inc.close()
+    return {"steps_per_sec": 2 * n_steps / dt, "us_per_step": 1e6 * dt / (2 * n_steps), "cores": 1, "kind": "port",
+            "note": "C restatement of the reference's per-step work (all-loci embedding + one-locus incremental likelihood), "
+                    "gcc -O2 -ffp-contract=off; not the JVM"}
+
+
 def bench_operator_queries(eng, pb, reps=200):
     """the all-gene-tree walks of CoordinatedUniform/Exponential and NodeReheight2 as device queries,
     host-timed per call (host buffers in and out; latency, one proposal = one query)."""
@@ -247,6 +275,7 @@ def bench_streaming(args, hbm_gbs, peak_src, flush, n_loci=250, steps=30):
     queries = bench_operator_queries(eng, pb, reps=100)
     if not args.no_cpu:
         queries["cpu_port"] = cpu_operator_queries(pb, reps=5)
+        incremental["cpu_port"] = cpu_incremental(pb, synth, n_steps=60)
     dev_bytes = eng.device_bytes()
     eng.close()
     return {"operator_queries": queries, "incremental": incremental, "device_bytes": dev_bytes, "workload": f"C5 shard, {n_loci} loci of the 2,000 (GTR+G4, UCLN species clock, 120 tips)", "kernel": "k_treewalk",
@@ -496,6 +525,7 @@ def main():
         line["operator_queries"] = bench_operator_queries(eng, pb)
         if not args.no_cpu:
             line["operator_queries"]["cpu_port"] = cpu_operator_queries(pb)
+            line["incremental"]["cpu_port"] = cpu_incremental(pb, synth)
         if not args.no_extra:
             eng.close()
             line["roofline_streaming"] = bench_streaming(args, hbm_gbs, peak_src, flush)

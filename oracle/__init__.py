@@ -279,6 +279,8 @@ class FlatProblem:
         cat = lambda f, dt: k(np.concatenate([np.asarray(f(l)).reshape(-1) for l in pb.loci]), dt)
         st.gParent, st.gLeft, st.gRight = cat(lambda l: l.tree.parent, np.int32), cat(lambda l: l.tree.left, np.int32), cat(lambda l: l.tree.right, np.int32)
         st.gHeight = cat(lambda l: l.tree.height, np.float64)
+        self.g_parent, self.g_left, self.g_right, self.g_height = self.keep[-4:]   # writable views for set_gene_tree
+        self.node_off = prefix(G)
         st.tipSpecies = cat(lambda l: l.tip_species, np.int32)
         st.tipStates = cat(lambda l: l.tip_states, np.uint8)
         st.weights = cat(lambda l: l.weights, np.int32)
@@ -303,6 +305,53 @@ def posterior(pb, n_threads: int = 1, use_scaling: int = 2, flat: Optional[FlatP
     tot = np.zeros(3)
     lib().sb2o_posterior(C.byref(fp.struct), n_threads, use_scaling, coal, lik, br, tot)
     return PosteriorResult(coal, lik, br, tot)
+
+
+class IncrementalBaseline:
+    """Regime-B CPU baseline (sb2o_incr_*): one MCMC step the way the reference evaluates it when ONE gene tree changed --
+    embedding of every locus (quirk Q2), population terms + clock rates + incremental TreeLikelihood of the changed locus.
+    Non-analytic population models.  Test / bench infrastructure like everything under oracle/."""
+
+    def __init__(self, pb):
+        L = lib()
+        L.sb2o_incr_create.restype = C.c_void_p
+        L.sb2o_incr_create.argtypes = [C.POINTER(_Problem)]
+        L.sb2o_incr_step.restype = C.c_double
+        L.sb2o_incr_step.argtypes = [C.c_void_p, C.POINTER(_Problem), C.c_int]
+        L.sb2o_incr_destroy.restype = None
+        L.sb2o_incr_destroy.argtypes = [C.c_void_p]
+        self._L = L
+        self.fp = FlatProblem(pb)
+        self._h = L.sb2o_incr_create(C.byref(self.fp.struct))
+        if not self._h:
+            raise ValueError("the incremental baseline supports the constant / linear population models only")
+
+    def set_gene_tree(self, locus: int, tree):
+        o, n = int(self.fp.node_off[locus]), tree.n_nodes
+        self.fp.g_parent[o:o + n] = tree.parent
+        self.fp.g_left[o:o + n] = tree.left
+        self.fp.g_right[o:o + n] = tree.right
+        self.fp.g_height[o:o + n] = tree.height
+
+    def step(self, locus: int, tree=None) -> float:
+        if tree is not None:
+            self.set_gene_tree(locus, tree)
+        return self._L.sb2o_incr_step(self._h, C.byref(self.fp.struct), int(locus))
+
+    def raw_step(self):
+        """(function, handle, struct pointer) for a timing loop without Python argument handling."""
+        return self._L.sb2o_incr_step, self._h, C.byref(self.fp.struct)
+
+    def close(self):
+        if self._h:
+            self._L.sb2o_incr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def random_local_rates(species, indicators, branch_rates, mean: float = 1.0) -> np.ndarray:

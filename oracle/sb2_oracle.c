@@ -719,6 +719,86 @@ SB2O_API double sb2o_max_height(const int32_t *canonicalMap, int centerIndex, do
     return maxHeight;
 }
 
+/*
+ * TreeLikelihood.traverse with BEAST's dirtiness logic, for the regime-B CPU baseline: the matrix of a
+ * branch is recomputed when branchChanged[node] is set (node dirty, or length x rate differs from the cached value), and the
+ * partials of an internal node when either child reported an update.  Unscaled cache (the lazy rule never switched
+ * scaling on); returns the update flag like the Java.
+ */
+static int tl_traverse_update(const tl_ctx *c, int node, const uint8_t *branchChanged)
+{
+    int update = 0;
+    const int par = c->parent[node];
+    if (par >= 0 && branchChanged[node]) {
+        const double branchRate = c->branchRates[node];
+        for (int i = 0; i < c->nCat; i++) {
+            const double distance = (c->height[par] - c->height[node]) * (c->catRates[i] * branchRate);
+            transition_matrix(c->substKind, c->substParams, distance, c->matrices + ((size_t)node * c->nCat + i) * 16);
+        }
+        update = 1;
+    }
+    if (node >= c->nTips) {
+        const int c1 = c->left[node], c2 = c->right[node];
+        const int u1 = tl_traverse_update(c, c1, branchChanged);
+        const int u2 = tl_traverse_update(c, c2, branchChanged);
+        if (u1 || u2) {
+            const size_t psz = (size_t)c->nCat * c->nPat * 4;
+            double *p3 = c->partials + (size_t)(node - c->nTips) * psz;
+            const double *m1 = c->matrices + (size_t)c1 * c->nCat * 16, *m2 = c->matrices + (size_t)c2 * c->nCat * 16;
+            if (c1 < c->nTips) {
+                if (c2 < c->nTips)
+                    states_states(c->tipStates + (size_t)c1 * c->nPat, m1, c->tipStates + (size_t)c2 * c->nPat, m2, p3, c->nPat, c->nCat);
+                else
+                    states_partials(c->tipStates + (size_t)c1 * c->nPat, m1, c->partials + (size_t)(c2 - c->nTips) * psz, m2, p3, c->nPat, c->nCat);
+            } else {
+                if (c2 < c->nTips)
+                    states_partials(c->tipStates + (size_t)c2 * c->nPat, m2, c->partials + (size_t)(c1 - c->nTips) * psz, m1, p3, c->nPat, c->nCat);
+                else
+                    partials_partials(c->partials + (size_t)(c1 - c->nTips) * psz, m1, c->partials + (size_t)(c2 - c->nTips) * psz, m2, p3, c->nPat, c->nCat);
+            }
+            update = 1;
+        }
+    }
+    return update;
+}
+
+/* Incremental TreeLikelihood.calculateLogP on cached (unscaled) partials / matrices from sb2o_tree_likelihood(useScaling=0).
+ * Returns the log-likelihood; *nodesUpdated receives the number of internal nodes whose partials were recomputed. */
+SB2O_API double sb2o_tree_likelihood_update(
+    int G, int nTips, int nPat, int nCat,
+    const int32_t *parent, const int32_t *left, const int32_t *right, const double *height,
+    const uint8_t *tipStates, const int32_t *weights,
+    int substKind, const double *substParams,
+    const double *catRates, const double *catProps, double pInv, const uint8_t *constMask,
+    const double *branchRates, const uint8_t *branchChanged,
+    double *partials, double *matrices, double *rootPartials /* scratch [nPat*4] */)
+{
+    const size_t psz = (size_t)nCat * nPat * 4;
+    int root = G - 1;
+    for (int i = 0; i < G; i++) if (parent[i] < 0) root = i;
+    const double *freqs = subst_freqs(substKind, substParams);
+    tl_ctx c = {G, nTips, nPat, nCat, left, right, parent, height, tipStates, substKind, substParams,
+                catRates, branchRates, partials, matrices, NULL};
+    tl_traverse_update(&c, root, branchChanged);
+    const double *rp = partials + (size_t)(root - nTips) * psz;
+    for (int k = 0; k < nPat; k++)
+        for (int i = 0; i < 4; i++) rootPartials[k * 4 + i] = rp[k * 4 + i] * catProps[0];
+    for (int l = 1; l < nCat; l++)
+        for (int k = 0; k < nPat; k++)
+            for (int i = 0; i < 4; i++) rootPartials[k * 4 + i] += rp[((size_t)l * nPat + k) * 4 + i] * catProps[l];
+    if (pInv > 0.0 && constMask)
+        for (int k = 0; k < nPat; k++)
+            for (int i = 0; i < 4; i++)
+                if (constMask[k] & (1 << i)) rootPartials[k * 4 + i] += pInv;
+    double logP = 0.0;
+    for (int k = 0; k < nPat; k++) {
+        double sum = 0.0;
+        for (int i = 0; i < 4; i++) sum += freqs[i] * rootPartials[k * 4 + i];
+        logP += log(sum) * weights[k];
+    }
+    return logP;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* (3) whole-posterior driver: the timed CPU baseline (bench.py cpu_baseline / --impl reference) */
 /* ------------------------------------------------------------------------------------------ */
@@ -853,3 +933,103 @@ SB2O_API int sb2o_max_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* (4) regime-B CPU baseline: one MCMC step the way the reference evaluates it  */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * What the reference does when ONE gene tree changed (single Java thread):
+ *   - GeneTree.update() of EVERY locus (requiresRecalculation() is unconditionally true, GeneTree.java:73-76, quirk Q2),
+ *     including the G x S occupancy fill;
+ *   - per-branch population terms only where the embedding changed (GeneTree.java:187); here: all branches of the changed
+ *     locus (an upper bound), cached values for the others;
+ *   - StarBeastClock rates + TreeLikelihood.traverse for the changed locus only: matrices of branches whose length x rate
+ *     changed, partials of the nodes above them, root integration over all patterns.
+ * Non-analytic population models only.  The caller owns the problem; the proposed tree of `locus` is already in place.
+ */
+typedef struct {
+    int L, maxG, S;
+    double **partials, **matrices, **branchLen;   /* per locus: unscaled partials, matrices, cached length*rate per node */
+    double *coal, *logL;
+    int32_t *n, *k, *assign; double *times, *occ, *bt, *rates, *rootPartials; uint8_t *changed;
+} sb2o_incr;
+
+static double incr_locus(sb2o_incr *c, const sb2o_problem *pb, int l, int full)
+{
+    const int S = pb->S, nTips = pb->nTips[l], G = 2 * nTips - 1, blk = nTips;
+    const int64_t no = pb->nodeOff[l];
+    const int ok = sb2o_gene_tree_update(G, nTips, pb->gParent + no, pb->gHeight + no, pb->tipSpecies + pb->tipOff[l],
+                                         S, pb->nSpeciesLeaves, pb->sParent, pb->sHeight, blk, c->n, c->k, c->times, c->assign, c->occ);
+    if (!full) return ok ? c->coal[l] : -INFINITY;          /* clean locus: embedding only, cached terms */
+    if (!ok) { c->coal[l] = -INFINITY; return -INFINITY; }
+    double coal = 0.0;
+    for (int b = 0; b < S; b++) {
+        sb2o_coalescent_times(b, pb->sParent, pb->sHeight, c->k, c->times, blk, c->bt);
+        coal += pb->popKind == SB2O_POP_CONSTANT
+                    ? sb2o_constant_logp(pb->popA[b], pb->ploidy[l], c->bt, c->n[b], c->k[b])
+                    : sb2o_lwcr_branch_logp(b, pb->nSpeciesLeaves, pb->sParent, pb->sLeft, pb->sRight, pb->popA, pb->popB, pb->ploidy[l], c->bt, c->n[b], c->k[b]);
+    }
+    c->coal[l] = coal;
+    const double *br;
+    if (pb->clockKind[l] == SB2O_CLOCK_SPECIES_RATES) { sb2o_starbeast_clock(G, S, pb->clockRate[l], pb->speciesRates, c->occ, c->rates); br = c->rates; }
+    else if (pb->clockKind[l] == SB2O_CLOCK_EXPLICIT) br = pb->explicitRates + no;
+    else { for (int i = 0; i < G; i++) c->rates[i] = pb->clockRate[l]; br = c->rates; }
+    for (int i = 0; i < G; i++) {                            /* TreeLikelihood.traverse: branchTime != m_branchLengths[i] */
+        const int par = pb->gParent[no + i];
+        const double len = par >= 0 ? (pb->gHeight[no + par] - pb->gHeight[no + i]) * br[i] : 0.0;
+        c->changed[i] = (uint8_t)(c->branchLen[l][i] != len);
+        c->branchLen[l][i] = len;
+    }
+    c->logL[l] = sb2o_tree_likelihood_update(G, nTips, pb->nPat[l], pb->nCat[l], pb->gParent + no, pb->gLeft + no, pb->gRight + no,
+                                             pb->gHeight + no, pb->tipStates + pb->stateOff[l], pb->weights + pb->patOff[l],
+                                             pb->substKind[l], pb->substParams + (size_t)l * SB2O_SUBST_STRIDE,
+                                             pb->catRates + pb->catOff[l], pb->catProps + pb->catOff[l], pb->pInv[l],
+                                             pb->constMask ? pb->constMask + pb->patOff[l] : NULL, br, c->changed,
+                                             c->partials[l], c->matrices[l], c->rootPartials);
+    return coal;
+}
+
+SB2O_API sb2o_incr *sb2o_incr_create(const sb2o_problem *pb)
+{
+    if (pb->popKind == SB2O_POP_ANALYTIC) return NULL;
+    sb2o_incr *c = (sb2o_incr *)calloc(1, sizeof(sb2o_incr));
+    const int L = pb->nLoci, S = pb->S;
+    int maxG = 0, maxP = 0;
+    for (int l = 0; l < L; l++) { const int G = 2 * pb->nTips[l] - 1; if (G > maxG) maxG = G; if (pb->nPat[l] > maxP) maxP = pb->nPat[l]; }
+    c->L = L; c->maxG = maxG; c->S = S;
+    c->partials = (double **)calloc(L, sizeof(double *)); c->matrices = (double **)calloc(L, sizeof(double *)); c->branchLen = (double **)calloc(L, sizeof(double *));
+    c->coal = (double *)calloc(L, sizeof(double)); c->logL = (double *)calloc(L, sizeof(double));
+    c->n = (int32_t *)malloc(sizeof(int32_t) * S); c->k = (int32_t *)malloc(sizeof(int32_t) * S); c->assign = (int32_t *)malloc(sizeof(int32_t) * maxG);
+    c->times = (double *)malloc(sizeof(double) * (size_t)S * maxG); c->occ = (double *)malloc(sizeof(double) * (size_t)maxG * S);
+    c->bt = (double *)malloc(sizeof(double) * (maxG + 2)); c->rates = (double *)malloc(sizeof(double) * maxG);
+    c->rootPartials = (double *)malloc(sizeof(double) * (size_t)maxP * 4); c->changed = (uint8_t *)malloc(maxG);
+    for (int l = 0; l < L; l++) {
+        const int nTips = pb->nTips[l], G = 2 * nTips - 1;
+        c->partials[l] = (double *)calloc((size_t)(G - nTips) * pb->nCat[l] * pb->nPat[l] * 4, sizeof(double));
+        c->matrices[l] = (double *)calloc((size_t)G * pb->nCat[l] * 16, sizeof(double));
+        c->branchLen[l] = (double *)malloc(sizeof(double) * G);
+        for (int i = 0; i < G; i++) c->branchLen[l][i] = NAN;          /* everything dirty the first time */
+        incr_locus(c, pb, l, 1);
+    }
+    return c;
+}
+
+/* one step: the tree of `locus` changed (already written into pb).  Returns the posterior; -inf if incompatible. */
+SB2O_API double sb2o_incr_step(sb2o_incr *c, const sb2o_problem *pb, int locus)
+{
+    double coal = 0.0, lik = 0.0;
+    for (int l = 0; l < c->L; l++) coal += incr_locus(c, pb, l, l == locus);
+    if (!(coal > -INFINITY)) return -INFINITY;                 /* CompoundDistribution short-circuit */
+    for (int l = 0; l < c->L; l++) lik += c->logL[l];
+    return coal + lik;
+}
+
+SB2O_API void sb2o_incr_destroy(sb2o_incr *c)
+{
+    if (!c) return;
+    for (int l = 0; l < c->L; l++) { free(c->partials[l]); free(c->matrices[l]); free(c->branchLen[l]); }
+    free(c->partials); free(c->matrices); free(c->branchLen); free(c->coal); free(c->logL);
+    free(c->n); free(c->k); free(c->assign); free(c->times); free(c->occ); free(c->bt); free(c->rates); free(c->rootPartials); free(c->changed);
+    free(c);
+}
+

@@ -258,3 +258,24 @@ def test_all_missing_tip_and_pattern_permutation_do_not_change_the_likelihood():
                  tip_species=np.zeros(loc.n_tips - 1, np.int32), subst_kind=loc.subst_kind, subst_params=loc.subst_params,
                  cat_rates=loc.cat_rates, cat_props=loc.cat_props)
     assert oracle.tree_likelihood(loc4, np.ones(pruned.n_nodes)) == pytest.approx(with_blank, rel=1e-12)
+
+
+@pytest.mark.parametrize("name,kw", [("C2", dict(n_loci=5, n_sites=120)), ("C3", dict(n_loci=3, n_sites=90))])
+def test_incremental_baseline_equals_full_evaluation(name, kw):
+    """The regime-B CPU baseline (embedding of every locus + incremental TreeLikelihood of the changed one) returns exactly
+    what a from-scratch evaluation of the proposed state returns, move after move, and -inf for an incompatible tree."""
+    import math
+    pb = synth.make_problem(name, **kw)
+    inc = oracle.IncrementalBaseline(pb)
+    rng = np.random.default_rng(2)
+    for step in range(12):
+        l = int(rng.integers(0, pb.n_loci))
+        t, _ = synth.perturb_gene_tree(rng, pb.loci[l].tree, pb.loci[l].n_tips)
+        pb.loci[l].tree = t
+        got = inc.step(l, t)
+        want = oracle.posterior(pb, use_scaling=0)
+        if math.isfinite(want.coalescent):
+            assert got == pytest.approx(want.total, rel=1e-13)
+        else:
+            assert got == -math.inf
+    inc.close()
