@@ -248,7 +248,12 @@ int do_prepare(sb2_engine *e)
     }
     int uniformFlags = e->hFlags[0];
     for (int l = 1; l < L; l++) if (e->hFlags[l] != e->hFlags[0]) { uniformFlags = -1; break; }
-    if (uniformFlags < 0) CUDA_TRY(e, cudaMemcpyAsync(e->dFlags, e->hFlags, L, cudaMemcpyHostToDevice, st));
+    // the common MCMC step touches one locus: its index and flags ride in the kernel arguments, no flags upload
+    int singleLocus = -1, nFlagged = 0;
+    if (uniformFlags < 0)
+        for (int l = 0; l < L; l++) if (e->hFlags[l]) { nFlagged++; singleLocus = l; }
+    if (nFlagged != 1) singleLocus = -1;
+    if (uniformFlags < 0 && singleLocus < 0) CUDA_TRY(e, cudaMemcpyAsync(e->dFlags, e->hFlags, L, cudaMemcpyHostToDevice, st));
     if (e->speciesDirty)
         CUDA_TRY(e, cudaMemcpyAsync(e->blockMem[e->curIdx] + e->speciesOffInBlock, e->hSpecies, e->speciesBytes, cudaMemcpyHostToDevice, st));
     if (e->reuploadLast >= 0) { firstPar = std::min(firstPar, e->reuploadFirst); lastPar = std::max(lastPar, e->reuploadLast); }
@@ -278,6 +283,7 @@ int do_prepare(sb2_engine *e)
     a.cur = cur(e); a.stored = stored(e); a.ops = e->dOps; a.nOps = e->dNOps; a.mats = e->dMats; a.opMats = e->dOpMats;
     a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L; a.stackDepth = e->stackDepth; a.uniformFlags = uniformFlags;
     a.workers = e->workers; a.laneOps = e->dLaneOps;
+    a.singleLocus = singleLocus; a.singleFlags = singleLocus >= 0 ? e->hFlags[singleLocus] : 0;
     a.pfTipStates = e->dStates; a.pfWeights = e->dWeights; a.pfTileLocus = e->dTileLocus; a.pfConstMask = e->dConstMask; a.pfCatProps = e->dCat + e->totalCat;
     launch_prepare(a, e->maxNodes, st);
     e->launches++;

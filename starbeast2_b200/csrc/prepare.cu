@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
     const int l = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     // let the pruning kernel's CTAs launch now: they stage their static inputs and then wait for this grid to complete
     cudaTriggerProgrammaticLaunchCompletion();
-    const uint8_t fl = A.uniformFlags >= 0 ? (uint8_t)A.uniformFlags : A.flags[l];
+    const uint8_t fl = A.uniformFlags >= 0 ? (uint8_t)A.uniformFlags
+                     : (A.singleLocus >= 0 ? (uint8_t)(l == A.singleLocus ? A.singleFlags : 0) : A.flags[l]);
     if (!(fl & LF_RUN)) {
         if (tid == 0) A.nOps[l] = 0;
         return;

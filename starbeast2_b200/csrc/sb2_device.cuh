@@ -127,6 +127,8 @@ struct PrepareArgs {
     int32_t S, nSpeciesLeaves, popKind, nLoci;
     int32_t stackDepth;          // shared-memory stack slots of k_treewalk
     int32_t uniformFlags;        // >= 0: every locus uses these flags (no per-step flags upload); < 0: read `flags`
+    int32_t singleLocus;         // >= 0 (and uniformFlags < 0): only this locus has non-zero flags, `singleFlags` (the common MCMC step)
+    int32_t singleFlags;
     // static inputs of k_treewalk, only prefetched into L2 here (that kernel runs next and would otherwise chase them
     // through DRAM one dependent miss at a time whenever L2 is cold)
     const uint8_t *pfTipStates;

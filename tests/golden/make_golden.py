@@ -55,6 +55,17 @@ def main():
         cases[name] = {"make_problem": dict(name=name, missing_frac=0.02, **kw), "per_locus_coal": r.per_locus_coal.tolist(),
                        "per_locus_lik": r.per_locus_lik.tolist(), "per_branch": r.per_branch.tolist(), "coalescent": r.coalescent,
                        "likelihood": r.likelihood, "total": r.total}
+        # operator-side walks (sb2_connecting_nodes / sb2_max_height): every internal species node; one canonical order
+        sp = pb.species
+        q = {}
+        for node in range(sp.n_leaves, sp.n_nodes):
+            mask, tip, root, cnt = oracle.connecting_nodes(pb, node)
+            q[str(node)] = {"connecting": np.flatnonzero(mask).tolist(), "tipward": None if np.isinf(tip) else tip,
+                            "rootward": None if np.isinf(root) else root, "count": cnt}
+        cmap = np.zeros(sp.n_nodes, np.int32)
+        cmap[: sp.n_leaves] = np.arange(sp.n_leaves)                  # leaves in number order; centre after the first half
+        mh = oracle.max_height(pb, cmap, sp.n_leaves // 2)
+        cases[name]["operator_queries"] = {"connecting_nodes": q, "max_height_center": sp.n_leaves // 2, "max_height": None if np.isinf(mh) else mh}
     json.dump({"generator": "tests/golden/make_golden.py (oracle/sb2_oracle.c, gcc -O2 -ffp-contract=off)", "cases": cases},
               open(os.path.join(HERE, "oracle_cases.json"), "w"), indent=1)
     print("wrote", os.listdir(HERE))

@@ -354,9 +354,22 @@ def test_committed_golden_cases():
     cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_cases.json")))["cases"]
     for name, c in cases.items():
         kw = dict(c["make_problem"]); nm = kw.pop("name")
-        got = Engine.from_problem(synth.make_problem(nm, **kw)).eval_posterior()
+        pb = synth.make_problem(nm, **kw)
+        e = Engine.from_problem(pb)
+        got = e.eval_posterior()
         assert rel_close(got.per_locus_lik, c["per_locus_lik"]) and rel_close(got.per_locus_coal, c["per_locus_coal"])
         assert rel_close(got.total, c["total"])
+        # the operators' gene-tree walks against the committed answers: bit-exact (integer masks, minima of doubles)
+        inf = float("inf")
+        q = c["operator_queries"]
+        for node, want in q["connecting_nodes"].items():
+            mask, tip, root, cnt = e.connecting_nodes(int(node))
+            assert np.flatnonzero(mask).tolist() == want["connecting"] and cnt == want["count"]
+            assert tip == (inf if want["tipward"] is None else want["tipward"])
+            assert root == (inf if want["rootward"] is None else want["rootward"])
+        side = (np.arange(pb.species.n_leaves) >= q["max_height_center"]).astype(np.uint8)
+        assert e.max_height(side) == (inf if q["max_height"] is None else q["max_height"])
+        e.close()
 
 
 @pytest.mark.parametrize("name,n_loci", [("C2", 50), ("C5", 24)])

@@ -121,3 +121,13 @@ def test_committed_golden_files_are_current():
         np.testing.assert_allclose(r.per_locus_lik, c["per_locus_lik"], rtol=1e-13)
         np.testing.assert_allclose(r.per_locus_coal, c["per_locus_coal"], rtol=1e-13)
         assert r.total == pytest.approx(c["total"], rel=1e-13)
+        pb = synth.make_problem(nm, **kw)
+        inf = float("inf")
+        q = c["operator_queries"]
+        for node, want in q["connecting_nodes"].items():
+            mask, tip, root, cnt = oracle.connecting_nodes(pb, int(node))
+            assert np.flatnonzero(mask).tolist() == want["connecting"] and cnt == want["count"]
+            assert tip == (inf if want["tipward"] is None else want["tipward"]) and root == (inf if want["rootward"] is None else want["rootward"])
+        cmap = np.zeros(pb.species.n_nodes, np.int32)
+        cmap[: pb.species.n_leaves] = np.arange(pb.species.n_leaves)
+        assert oracle.max_height(pb, cmap, q["max_height_center"]) == (inf if q["max_height"] is None else q["max_height"])
