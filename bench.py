@@ -136,26 +136,42 @@ def bench_incremental(eng, pb, synth, n_steps=400):
         moves.append((l, t))
     eng.eval_posterior()
     updates = []
+    # through the C ABI with host buffers, addresses resolved once (what a JNI / FFM caller does; the Python convenience
+    # wrappers add ~15 us of numpy argument handling per step that is not the engine's)
+    from starbeast2_b200 import _lib as sblib
+    raw, h = sblib.load_raw(), eng._h
+    keep = []
+    ptrs = []
+    for l, t in moves:
+        arrs = [np.ascontiguousarray(t.parent, np.int32), np.ascontiguousarray(t.left, np.int32), np.ascontiguousarray(t.right, np.int32),
+                np.ascontiguousarray(t.height, np.float64)]
+        keep.append(arrs)
+        ptrs.append((l, arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data))
+    coal_buf, lik_buf, br_buf = np.zeros(pb.n_loci), np.zeros(pb.n_loci), np.zeros(pb.species.n_nodes)
+    c1, l1, tot = np.zeros(1), np.zeros(1), np.zeros(3)
+    pc, pl, pbr, pc1, pl1, pt = (a.ctypes.data for a in (coal_buf, lik_buf, br_buf, c1, l1, tot))
 
     def one(i, count=False):
-        l, t = moves[i % len(moves)]
-        eng.store()
-        eng.set_gene_tree(l, t)
-        c, _, _ = eng.eval_coalescent()
-        if math.isfinite(c):
-            eng.eval_likelihood()
+        l, a, b, c, d = ptrs[i % len(ptrs)]
+        rc = raw.sb2_store(h)
+        rc |= raw.sb2_set_gene_trees(h, l, 1, a, b, c, d)
+        rc |= raw.sb2_eval_coalescent(h, pc, pbr, pc1)
+        if math.isfinite(c1[0]):
+            rc |= raw.sb2_eval_likelihood(h, pl, pl1)
         if count:
             updates.append(eng.last_node_updates())
-        eng.restore()
-
-    tot = np.zeros(3)
+        rc |= raw.sb2_restore(h)
+        if rc:
+            eng._ck(-1)
 
     def one_call(i):
-        l, t = moves[i % len(moves)]
-        eng.store()
-        eng.set_gene_tree(l, t)
-        eng.eval_posterior_total(tot)      # speculative single round trip: coalescent and likelihood together
-        eng.restore()
+        l, a, b, c, d = ptrs[i % len(ptrs)]
+        rc = raw.sb2_store(h)
+        rc |= raw.sb2_set_gene_trees(h, l, 1, a, b, c, d)
+        rc |= raw.sb2_eval_posterior(h, pc, pl, pbr, pt)      # speculative single round trip: coalescent and likelihood together
+        rc |= raw.sb2_restore(h)
+        if rc:
+            eng._ck(-1)
 
     for i in range(20):
         one(i, count=True)

@@ -124,6 +124,11 @@ def load_raw() -> C.CDLL:
         "sb2_eval_posterior": [E, _vp, _vp, _vp, _vp],
         "sb2_eval_begin": [E],
         "sb2_eval_end": [E, _vp, _vp, _vp, _vp],
+        "sb2_eval_coalescent": [E, _vp, _vp, _vp],
+        "sb2_eval_likelihood": [E, _vp, _vp],
+        "sb2_store": [E],
+        "sb2_restore": [E],
+        "sb2_accept": [E],
     }.items():
         fn = getattr(L, name)
         fn.restype = C.c_int
