@@ -86,6 +86,11 @@ struct sb2_engine {
     std::vector<uint8_t> treeDirty, modelDirty, clockDirty;
     bool speciesDirty = true, catDirty = true, paramsDirty = true, explicitDirty = false, forceAll = true;
     bool needPrepare = true, walkPending = false, tilesValid = false, reduced = false;
+    // lazy store(): the physical copy cur -> stored is owed until the next k_prepare, which does it for the few loci that
+    // differ (`diffLoci`: changed since the blocks were last equal) -- or the host copies the whole block when everything differs
+    bool storePending = false, diffAll = true;
+    std::vector<int32_t> diffLoci;
+    std::vector<uint8_t> diffFlag;
     bool resultValid = false;   // hOut holds a full evaluation (coalescent AND likelihood) of exactly the staged state
     // host mirrors of the stored state (restore() must bring the staging copies back too)
     LocusParams *hParamsStored = nullptr;
@@ -248,6 +253,23 @@ int do_prepare(sb2_engine *e)
     }
     int uniformFlags = e->hFlags[0];
     for (int l = 1; l < L; l++) if (e->hFlags[l] != e->hFlags[0]) { uniformFlags = -1; break; }
+    // (a) the copy owed by store(): bring the stored block up to the current one where they differ, before this evaluation
+    //     changes anything -- a handful of loci: their CTAs do it (kernel arguments); otherwise one whole-block copy
+    int nSync = 0;
+    int32_t syncLoci[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static const bool eagerStore = getenv("SB2_EAGER_STORE") != nullptr;   // A/B knob: whole-block copy every time
+    if (e->storePending) {
+        if (e->diffAll || e->diffLoci.size() > 8 || eagerStore) {
+            CUDA_TRY(e, cudaMemcpyAsync(e->blockMem[1 - e->curIdx], e->blockMem[e->curIdx], e->blockBytes, cudaMemcpyDeviceToDevice, st));
+        } else {
+            for (int32_t l : e->diffLoci) syncLoci[nSync++] = l;
+        }
+        for (int32_t l : e->diffLoci) e->diffFlag[l] = 0;
+        e->diffLoci.clear(); e->diffAll = false; e->storePending = false;
+    }
+    // (b) what this evaluation is about to change
+    if (e->forceAll || e->speciesDirty || e->catDirty || e->paramsDirty || e->explicitDirty || uniformFlags > 0) e->diffAll = true;
+    else for (int l = 0; l < L; l++) if (e->hFlags[l] && !e->diffFlag[l]) { e->diffFlag[l] = 1; e->diffLoci.push_back(l); }
     // the common MCMC step touches one locus: its index and flags ride in the kernel arguments, no flags upload
     int singleLocus = -1, nFlagged = 0;
     if (uniformFlags < 0)
@@ -284,6 +306,8 @@ int do_prepare(sb2_engine *e)
     a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L; a.stackDepth = e->stackDepth; a.uniformFlags = uniformFlags;
     a.workers = e->workers; a.laneOps = e->dLaneOps;
     a.singleLocus = singleLocus; a.singleFlags = singleLocus >= 0 ? e->hFlags[singleLocus] : 0;
+    a.nSync = nSync;
+    for (int j = 0; j < 8; j++) a.syncLoci[j] = syncLoci[j];
     a.pfTipStates = e->dStates; a.pfWeights = e->dWeights; a.pfTileLocus = e->dTileLocus; a.pfConstMask = e->dConstMask; a.pfCatProps = e->dCat + e->totalCat;
     launch_prepare(a, e->maxNodes, st);
     e->launches++;
@@ -639,6 +663,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     CUDA_TRY(e, cudaMemset(e->dOut, 0, sizeof(double) * e->nOut));
 
     e->treeDirty.assign(L, 0); e->modelDirty.assign(L, 0); e->clockDirty.assign(L, 0); e->touchedFlag.assign(L, 0);
+    e->diffFlag.assign(L, 0);
     memcpy(e->hParamsStored, e->hParams, sizeof(LocusParams) * L);
     memcpy(e->hCatStored, e->hCat, 16 * (size_t)catBase);
     memcpy(e->hSpeciesStored, e->hSpecies, e->speciesBytes);
@@ -969,7 +994,7 @@ int sb2_store(sb2_engine *e)
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     int rc = flush_pending_walk(e);
     if (rc) return rc;
-    CUDA_TRY(e, cudaMemcpyAsync(e->blockMem[1 - e->curIdx], e->blockMem[e->curIdx], e->blockBytes, cudaMemcpyDeviceToDevice, e->stream));
+    e->storePending = true;   // the device copy is owed to the next k_prepare (do_prepare), which knows how little differs
     // host staging mirrors of what just became the stored state
     for (int32_t l : e->touched) {
         const LocusDesc &d = e->loci[l].d;
@@ -989,7 +1014,9 @@ int sb2_restore(sb2_engine *e)
 {
     if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
-    e->curIdx = 1 - e->curIdx;   // swap current / stored, like the reference's restore() methods
+    // swap current / stored, like the reference's restore() methods -- unless nothing was evaluated since store(): then the
+    // device state IS the stored state (and the stored block's owed copy has not happened yet)
+    if (!e->storePending) e->curIdx = 1 - e->curIdx;
     // staged proposal inputs belong to the rejected state: drop them and bring the host mirrors back
     std::fill(e->treeDirty.begin(), e->treeDirty.end(), 0);
     std::fill(e->modelDirty.begin(), e->modelDirty.end(), 0);

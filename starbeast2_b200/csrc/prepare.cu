@@ -187,6 +187,31 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
     const int l = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     // let the pruning kernel's CTAs launch now: they stage their static inputs and then wait for this grid to complete
     cudaTriggerProgrammaticLaunchCompletion();
+    if (A.nSync) {   // lazy store(): this locus changed in the previous step -> stored := cur for its slices, before anything moves
+        bool mine = false;
+        for (int j = 0; j < A.nSync; j++) mine |= A.syncLoci[j] == l;
+        if (mine) {
+            const LocusDesc ds = A.loci[l];
+            const int nbs = ds.nodeBase, Gs = ds.nNodes;
+            for (int i = tid; i < Gs; i += nt) {
+                const int k = nbs + i;
+                const double h = A.cur.gHeight[k], br = A.cur.bRate[k], bt = A.cur.bTime[k];
+                const int p = A.cur.gParent[k], L = A.cur.gLeft[k], R = A.cur.gRight[k], as = A.cur.assign[k];
+                const uint8_t cp = A.cur.curP[k], cm = A.cur.curM[k];
+                A.stored.gHeight[k] = h; A.stored.bRate[k] = br; A.stored.bTime[k] = bt;
+                A.stored.gParent[k] = p; A.stored.gLeft[k] = L; A.stored.gRight[k] = R; A.stored.assign[k] = as;
+                A.stored.curP[k] = cp; A.stored.curM[k] = cm;
+            }
+            for (int b = tid; b < A.S; b += nt) {
+                const size_t o = (size_t)l * A.S + b;
+                const double x = A.cur.brLogP[o], g = A.cur.anG[o], r = A.cur.anR[o];
+                const int n = A.cur.brN[o], k = A.cur.brK[o];
+                A.stored.brLogP[o] = x; A.stored.anG[o] = g; A.stored.anR[o] = r; A.stored.brN[o] = n; A.stored.brK[o] = k;
+            }
+            if (tid == 0) { A.stored.logL[l] = A.cur.logL[l]; A.stored.coal[l] = A.cur.coal[l]; }
+            __syncthreads();   // the stored-state reads below (buffer indices) must see these writes
+        }
+    }
     const uint8_t fl = A.uniformFlags >= 0 ? (uint8_t)A.uniformFlags
                      : (A.singleLocus >= 0 ? (uint8_t)(l == A.singleLocus ? A.singleFlags : 0) : A.flags[l]);
     if (!(fl & LF_RUN)) {

@@ -127,6 +127,11 @@ struct PrepareArgs {
     int32_t S, nSpeciesLeaves, popKind, nLoci;
     int32_t stackDepth;          // shared-memory stack slots of k_treewalk
     int32_t uniformFlags;        // >= 0: every locus uses these flags (no per-step flags upload); < 0: read `flags`
+    // lazy store(): loci whose slice of the `stored` block must first be brought up to `cur` (they changed in the previous
+    // step); each such locus's CTA copies its own slices before anything else.  nSync == 0: nothing owed (or the host did a
+    // whole-block copy)
+    int32_t nSync;
+    int32_t syncLoci[8];
     int32_t singleLocus;         // >= 0 (and uniformFlags < 0): only this locus has non-zero flags, `singleFlags` (the common MCMC step)
     int32_t singleFlags;
     // static inputs of k_treewalk, only prefetched into L2 here (that kernel runs next and would otherwise chase them

@@ -262,3 +262,62 @@ def test_topology_change_nni():
     emb = oracle.gene_tree_update(t, loc.tip_species, pb.species)
     if emb.compatible:
         assert rel_close(got.per_locus_lik[1], want.per_locus_lik[1])
+
+
+def test_lazy_store_edge_cases():
+    """store() owes its device copy to the next evaluation (which brings the stored block up to date only where it differs).
+    Sequences that stress that bookkeeping: restore without any evaluation since store, store after accept without
+    evaluation, more than 8 loci touched in one step, parameter changes, and alternating loci."""
+    pb = synth.make_problem("C2", n_loci=12, n_sites=60)
+    e = Engine.from_problem(pb)
+    rng = np.random.default_rng(21)
+    base = e.eval_posterior()
+
+    def same(a, b):
+        return a.total == b.total and np.array_equal(a.per_locus_lik, b.per_locus_lik) and np.array_equal(a.per_locus_coal, b.per_locus_coal)
+
+    def move(l):
+        while True:   # a node slide that keeps the gene tree inside the species tree
+            t, _ = synth.perturb_gene_tree(rng, pb.loci[l].tree, pb.loci[l].n_tips)
+            if oracle.gene_tree_update(t, pb.loci[l].tip_species, pb.species, want_occupancy=False).compatible:
+                break
+        e.set_gene_tree(l, t)
+        return t
+
+    # (1) store, then restore with nothing evaluated in between (an operator that failed outright)
+    e.store(); e.restore()
+    assert same(e.eval_posterior(), base)
+    e.store(); move(3); e.restore()                      # staged but never evaluated: dropped
+    assert same(e.eval_posterior(), base)
+    # (2) accept a move, store, restore without evaluation: the accepted state stands
+    e.store(); pb.loci[2].tree = move(2); acc = e.eval_posterior(); e.accept()
+    e.store(); e.restore()
+    assert same(e.eval_posterior(), acc)
+    want = oracle.posterior(pb)
+    assert rel_close(acc.per_locus_lik, want.per_locus_lik)
+    # (3) alternating loci, rejected every time: always back to `acc`, bit for bit
+    for l in (5, 2, 7, 7, 0, 11):
+        e.store(); move(l); r = e.eval_posterior(); assert not same(r, acc); e.restore()
+        assert same(e.eval_posterior(), acc)
+    # (4) ten loci in one step (more than the in-kernel sync list takes), rejected, then a single-locus step, rejected
+    e.store()
+    for l in range(10):
+        move(l)
+    e.eval_posterior(); e.restore()
+    assert same(e.eval_posterior(), acc)
+    e.store(); move(4); e.eval_posterior(); e.restore()
+    assert same(e.eval_posterior(), acc)
+    # (5) a parameter change (population sizes: every locus's coalescent terms move), rejected; then accepted
+    e.store(); e.set_pop_model(pb.pop_kind, pb.pop_a * 1.1, pb.pop_b); r = e.eval_posterior(); assert r.coalescent != acc.coalescent; e.restore()
+    assert same(e.eval_posterior(), acc)
+    e.store(); e.set_pop_model(pb.pop_kind, pb.pop_a * 1.1, pb.pop_b); r2 = e.eval_posterior(); e.accept()
+    assert r2.total == r.total
+    e.store(); move(6); e.eval_posterior(); e.restore()
+    assert same(e.eval_posterior(), r2)
+    # (6) the whole thing still equals a from-scratch evaluation of the final state
+    e.mark_all_dirty()
+    pb.pop_a = pb.pop_a * 1.1
+    final = e.eval_posterior()
+    assert same(final, r2)
+    assert rel_close(final.per_locus_lik, oracle.posterior(pb).per_locus_lik)
+    e.close()
