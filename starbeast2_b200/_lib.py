@@ -12,7 +12,7 @@ import re
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsb2gpu.so")
+LIB_PATH = os.environ.get("SB2_LIB") or os.path.join(HERE, "lib", "libsb2gpu.so")   # SB2_LIB: A/B against another build
 HEADER = os.path.join(os.path.dirname(HERE), "include", "sb2gpu.h")
 
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C")

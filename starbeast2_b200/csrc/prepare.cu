@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         if (mine) {
             const LocusDesc ds = A.loci[l];
             const int nbs = ds.nodeBase, Gs = ds.nNodes;
+#pragma unroll 1
             for (int i = tid; i < Gs; i += nt) {
                 const int k = nbs + i;
                 const double h = A.cur.gHeight[k], br = A.cur.bRate[k], bt = A.cur.bTime[k];
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
                 A.stored.gParent[k] = p; A.stored.gLeft[k] = L; A.stored.gRight[k] = R; A.stored.assign[k] = as;
                 A.stored.curP[k] = cp; A.stored.curM[k] = cm;
             }
+#pragma unroll 1
             for (int b = tid; b < A.S; b += nt) {
                 const size_t o = (size_t)l * A.S + b;
                 const double x = A.cur.brLogP[o], g = A.cur.anG[o], r = A.cur.anR[o];
