@@ -863,7 +863,7 @@ int sb2_eval_coalescent(sb2_engine *e, double *perLocus, double *perBranch, doub
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     int rc;
     // Phase 1 of the reference's posterior.  By default the likelihood phase is evaluated SPECULATIVELY in the same device
-    // pass (one host round trip per MCMC step instead of two: 60 -> 46 us at C2); its result is only handed out by
+    // pass (one host round trip per MCMC step instead of two: -10 us per step at C2); its result is only handed out by
     // sb2_eval_likelihood, which the reference's CompoundDistribution never calls when this phase returns -infinity.
     // SB2_NO_SPECULATION=1 restores the strict protocol: no pruning kernel is launched before the coalescent is known.
     const bool speculate = getenv("SB2_NO_SPECULATION") == nullptr;   // read per call: tests flip it
