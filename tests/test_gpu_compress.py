@@ -63,3 +63,27 @@ def test_simulated_locus_and_engine_round_trip():
     want = oracle.posterior(pb)
     np.testing.assert_allclose(got.per_locus_lik, want.per_locus_lik, rtol=1e-10)
     e.close()
+
+
+def test_device_compression_equals_the_host_alignment_mirror(tmp_path):
+    """FASTA -> plugins.Alignment (host numpy, what the Java side's BEAST Alignment does) and -> the device path give the
+    same patterns and weights."""
+    from starbeast2_b200.plugins import Alignment
+    rng = np.random.default_rng(5)
+    names = [f"t{i:02d}" for i in range(12)]
+    base = rng.integers(0, 4, size=300)
+    lines = []
+    mats = {}
+    for n in names:
+        s = base.copy()
+        flip = rng.random(300) < 0.04
+        s[flip] = rng.integers(0, 4, size=int(flip.sum()))
+        gaps = rng.random(300) < 0.02
+        mats[n] = np.where(gaps, 4, s)
+        lines.append(f">{n}\n" + "".join("ACGT-"[x] for x in mats[n]) + "\n")
+    fa = tmp_path / "x.fasta"
+    fa.write_text("".join(lines))
+    aln = Alignment(sequences=read_fasta(str(fa)))
+    mat = np.array([mats[n] for n in sorted(names)], np.uint8)
+    pats, w, smap = compress_alignment(mat)
+    assert np.array_equal(pats, aln.patterns) and np.array_equal(w, aln.weights)

@@ -462,3 +462,27 @@ def test_uniform_populations_and_random_local_rates_through_the_engine():
     uni.get("universalSize").setValue(0, 0.05)
     pb2.pop_a = np.full(pb2.species.n_nodes, 0.05)
     assert msc.calculateLogP() == pytest.approx(float(np.sum(oracle.posterior(pb2).per_locus_coal)), rel=1e-12)
+
+
+def test_fasta_to_alignment_patterns_and_frequencies(tmp_path):
+    """Data format on the way into the path: FASTA (the reference ships tutorial/data/*.fasta) ->
+    Alignment -> unique site patterns in lexicographic order, weights, empirical frequencies."""
+    from starbeast2_b200.io import read_fasta
+    fa = tmp_path / "locus.fasta"
+    fa.write_text(">b_2 some description\nACGTAC\nGTNN\n>a_1\nACGTACGT-A\n>c_3\nACGAACGTCA\n")
+    seqs = read_fasta(str(fa))
+    assert seqs == {"b_2": "ACGTACGTNN", "a_1": "ACGTACGT-A", "c_3": "ACGAACGTCA"}
+    aln = Alignment(sequences=seqs)
+    assert aln.taxa == ["a_1", "b_2", "c_3"]                       # taxa sorted by name
+    full = np.array([[0, 1, 2, 3, 0, 1, 2, 3, 4, 0], [0, 1, 2, 3, 0, 1, 2, 3, 4, 4], [0, 1, 2, 0, 0, 1, 2, 3, 1, 0]], np.uint8)
+    assert aln.getPatternCount() == 7 and int(aln.weights.sum()) == 10
+    # every site is represented by its pattern with the right multiplicity
+    for col in full.T:
+        j = [k for k in range(aln.getPatternCount()) if np.array_equal(aln.patterns[:, k], col)]
+        assert len(j) == 1 and aln.weights[j[0]] == int(np.sum(np.all(full.T == col, axis=1)))
+    assert all(tuple(aln.patterns[:, k]) < tuple(aln.patterns[:, k + 1]) for k in range(aln.getPatternCount() - 1))   # lexicographic
+    states, w = aln.patterns_for(["c_3", "a_1", "b_2"])           # rows follow the gene tree's tip order
+    assert np.array_equal(states[1], aln.patterns[0]) and w is aln.weights
+    f = aln.empirical_frequencies()
+    counts = np.array([(full == s).sum() for s in range(4)], float)
+    assert np.allclose(f, counts / counts.sum()) and abs(f.sum() - 1) < 1e-15
