@@ -104,6 +104,8 @@ struct sb2_engine {
     uint8_t *dQuery = nullptr, *hQuery = nullptr;
     size_t queryLeafPad = 0;
     bool everPrepared = false;
+    bool hasStored = false;              // sb2_store has been called at least once (sb2_restore needs a stored state)
+    std::vector<int32_t> scratchStack;   // check_tree
     // profiling
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evPool;
     size_t evUsed = 0;
@@ -232,10 +234,52 @@ ReduceArgs reduce_args(sb2_engine *e, bool coalOnly = false)
     return r;
 }
 
+int do_walk(sb2_engine *e, int fuse = 0, bool *fused = nullptr);
+
+// Structural check of a host-supplied binary tree in BEAST node numbering (leaves first): exactly one root, every
+// internal node has two distinct children that name it as their parent, leaves have none, and a walk from the root
+// reaches all n nodes.  Together these rule out cycles and detached components, on which the device-side rootward
+// walks (k_prepare, k_tip_class_query) and the host-side descents would never terminate.  nLeaves < 0: leaves are
+// recognised by left < 0 (species tree), otherwise nodes 0..nLeaves-1 must be the leaves (gene trees).
+// Returns nullptr when the tree is sound, else what is wrong.  `stack` is scratch.
+const char *check_tree(int n, int nLeaves, const int32_t *parent, const int32_t *left, const int32_t *right, std::vector<int32_t> &stack)
+{
+    int root = -1, roots = 0;
+    for (int i = 0; i < n; i++) {
+        if (parent[i] >= n) return "node index out of range";
+        if (parent[i] < 0) { root = i; roots++; }
+    }
+    if (roots != 1) return "tree must have exactly one root";
+    stack.clear();
+    stack.push_back(root);
+    int seen = 0;
+    while (!stack.empty()) {
+        const int i = stack.back();
+        stack.pop_back();
+        seen++;
+        const int L = left[i], R = right[i];
+        const bool leaf = nLeaves < 0 ? (L < 0) : (i < nLeaves);
+        if (leaf) {
+            if (L >= 0 || R >= 0) return nLeaves < 0 ? "left and right must both be -1 at a leaf" : "nodes 0..tips-1 must be the leaves";
+            continue;
+        }
+        if (L < 0 || R < 0) return nLeaves < 0 ? "left and right must both be -1 at a leaf" : "nodes 0..tips-1 must be the leaves";
+        if (L >= n || R >= n) return "node index out of range";
+        if (L == R || parent[L] != i || parent[R] != i) return "parent / child arrays disagree";
+        stack.push_back(L);
+        stack.push_back(R);
+    }
+    if (seen != n) return "tree is not connected (cycle or detached nodes)";
+    return nullptr;
+}
+
 // upload staged inputs and run k_prepare
 int do_prepare(sb2_engine *e)
 {
     if (!e->needPrepare) return SB2_OK;
+    // A walk scheduled by an earlier k_prepare (strict two-phase protocol: coalescent evaluated, likelihood never asked for)
+    // must run before the next k_prepare re-schedules: that one would treat the already-flipped nodes as clean.
+    if (e->walkPending) { int rc = do_walk(e); if (rc) return rc; }
     e->resultValid = false;
     cudaStream_t st = e->stream;
     const int L = e->L;
@@ -309,9 +353,8 @@ int do_prepare(sb2_engine *e)
     a.nSync = nSync;
     for (int j = 0; j < 8; j++) a.syncLoci[j] = syncLoci[j];
     a.pfTipStates = e->dStates; a.pfWeights = e->dWeights; a.pfTileLocus = e->dTileLocus; a.pfConstMask = e->dConstMask; a.pfCatProps = e->dCat + e->totalCat;
-    launch_prepare(a, e->maxNodes, st);
+    CUDA_TRY(e, launch_prepare(a, e->maxNodes, st));
     e->launches++;
-    CUDA_TRY(e, cudaGetLastError());
     std::fill(e->treeDirty.begin(), e->treeDirty.end(), 0);
     std::fill(e->modelDirty.begin(), e->modelDirty.end(), 0);
     std::fill(e->clockDirty.begin(), e->clockDirty.end(), 0);
@@ -327,19 +370,20 @@ int do_prepare(sb2_engine *e)
 // fuse: 0 = plain; 1 = last CTA also runs k_reduce_local's body; 2 = ... and k_finish's + publish.  *fused tells the
 // caller whether the launch happened (nothing is launched when no walk is pending).
 // final reduction of the single-call evaluations: across GPUs over peer memory when connected, else local
-void launch_final(sb2_engine *e, const ReduceArgs &r)
+int launch_final(sb2_engine *e, const ReduceArgs &r)
 {
     static const bool skip = getenv("SB2_DEBUG_SKIP_REDUCE") != nullptr;   // timing experiments only: results are stale
-    if (skip) return;
+    if (skip) return SB2_OK;
     if (e->commConnected) {
         e->comm.seq++;
-        launch_reduce_xgpu(r, e->comm, e->stream, &e->launches);
+        CUDA_TRY(e, launch_reduce_xgpu(r, e->comm, e->stream, &e->launches));
     } else {
-        launch_reduce_finish(r, e->stream, &e->launches);
+        CUDA_TRY(e, launch_reduce_finish(r, e->stream, &e->launches));
     }
+    return SB2_OK;
 }
 
-int do_walk(sb2_engine *e, int fuse = 0, bool *fused = nullptr)
+int do_walk(sb2_engine *e, int fuse, bool *fused)
 {
     if (fused) *fused = false;
     if (!e->walkPending) return SB2_OK;
@@ -374,7 +418,7 @@ int do_walk(sb2_engine *e, int fuse = 0, bool *fused = nullptr)
         CUDA_TRY(e, cudaEventRecord(ev.first, e->stream));
     }
     static const bool skipWalk = getenv("SB2_DEBUG_SKIP_WALK") != nullptr;   // timing experiments only
-    if (!skipWalk) launch_treewalk(a, (int)e->totalTiles, e->cfg.exact_order != 0, e->stream);
+    if (!skipWalk) CUDA_TRY(e, launch_treewalk(a, (int)e->totalTiles, e->cfg.exact_order != 0, e->stream));
     e->launches++;
     if (e->cfg.profile) CUDA_TRY(e, cudaEventRecord(ev.second, e->stream));
     CUDA_TRY(e, cudaGetLastError());
@@ -409,8 +453,7 @@ static int eval_full(sb2_engine *e)
     // rank, whatever this rank's local state is (a rank whose loci did not change must still contribute)
     if (e->resultValid && !e->walkPending && !e->commConnected) return SB2_OK;
     if ((rc = do_walk(e, 2, &fused))) return rc;                                     // single GPU: no all-reduce in between
-    if (!fused) launch_final(e, reduce_args(e));
-    CUDA_TRY(e, cudaGetLastError());
+    if (!fused && (rc = launch_final(e, reduce_args(e)))) return rc;
     if ((rc = download(e))) return rc;
     e->resultValid = true;
     return SB2_OK;
@@ -679,12 +722,7 @@ int sb2_set_species_tree(sb2_engine *e, const int32_t *parent, const int32_t *le
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (!parent || !left || !right || !height) return e->fail(SB2_ERR_ARG, "null species tree array");
     SpeciesView v = species_view(e);
-    int roots = 0;
-    for (int i = 0; i < e->S; i++) {
-        if (parent[i] >= e->S || left[i] >= e->S || right[i] >= e->S) return e->fail(SB2_ERR_ARG, "species node index out of range");
-        roots += parent[i] < 0;
-    }
-    if (roots != 1) return e->fail(SB2_ERR_ARG, "species tree must have exactly one root (found %d)", roots);
+    if (const char *why = check_tree(e->S, -1, parent, left, right, e->scratchStack)) return e->fail(SB2_ERR_ARG, "species tree: %s", why);
     memcpy(v.sParent, parent, 4 * e->S); memcpy(v.sLeft, left, 4 * e->S); memcpy(v.sRight, right, 4 * e->S);
     memcpy(v.sHeight, height, 8 * e->S);
     e->speciesDirty = true; e->needPrepare = true;
@@ -702,14 +740,7 @@ int sb2_set_gene_trees(sb2_engine *e, int32_t firstLocus, int32_t nLoci, const i
     for (int l = firstLocus; l < firstLocus + nLoci; l++) {
         const LocusDesc &d = e->loci[l].d;
         const int G = d.nNodes;
-        int roots = 0;
-        for (int i = 0; i < G; i++) {
-            const int p = parent[o + i], L_ = left[o + i], R_ = right[o + i];
-            if (p >= G || L_ >= G || R_ >= G) return e->fail(SB2_ERR_ARG, "locus %d: node index out of range", l);
-            if (i < d.nTips ? (L_ >= 0 || R_ >= 0) : (L_ < 0 || R_ < 0)) return e->fail(SB2_ERR_ARG, "locus %d: nodes 0..tips-1 must be the leaves", l);
-            roots += p < 0;
-        }
-        if (roots != 1) return e->fail(SB2_ERR_ARG, "locus %d: gene tree must have exactly one root (found %d)", l, roots);
+        if (const char *why = check_tree(G, d.nTips, parent + o, left + o, right + o, e->scratchStack)) return e->fail(SB2_ERR_ARG, "locus %d: gene %s", l, why);
         uint8_t *dst = e->hInTree + d.treeOff;
         memcpy(dst, height + o, 8 * (size_t)G);
         memcpy(dst + 8 * (size_t)G, parent + o, 4 * (size_t)G);
@@ -827,8 +858,7 @@ int sb2_eval_begin(sb2_engine *e)
     bool fused;
     if ((rc = do_prepare(e))) return rc;
     if ((rc = do_walk(e, 1, &fused))) return rc;
-    if (!fused) launch_reduce_local(reduce_args(e), e->stream, &e->launches);
-    CUDA_TRY(e, cudaGetLastError());
+    if (!fused) CUDA_TRY(e, launch_reduce_local(reduce_args(e), e->stream, &e->launches));
     e->reduced = true;
     return SB2_OK;
 }
@@ -838,8 +868,7 @@ int sb2_eval_end(sb2_engine *e, double *perLocusCoal, double *perLocusLik, doubl
     if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (!e->reduced) return e->fail(SB2_ERR_STATE, "sb2_eval_end without sb2_eval_begin");
-    launch_finish(reduce_args(e), e->stream, &e->launches);
-    CUDA_TRY(e, cudaGetLastError());
+    CUDA_TRY(e, launch_finish(reduce_args(e), e->stream, &e->launches));
     int rc = download(e);
     if (rc) return rc;
     copy_out(e, perLocusCoal, perLocusLik, perBranch, total3);
@@ -874,8 +903,7 @@ int sb2_eval_coalescent(sb2_engine *e, double *perLocus, double *perBranch, doub
         // the pruning kernel has not run for the re-scheduled loci yet, so the likelihood entries of this pass are the
         // cached ones (coalOnly); sb2_eval_likelihood runs the walk
         ReduceArgs r = reduce_args(e, /*coalOnly=*/true);
-        launch_final(e, r);
-        CUDA_TRY(e, cudaGetLastError());
+        if ((rc = launch_final(e, r))) return rc;
         if ((rc = download(e))) return rc;
     }
     copy_out(e, perLocus, nullptr, perBranch, nullptr);
@@ -992,8 +1020,12 @@ int sb2_store(sb2_engine *e)
 {
     if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
-    int rc = flush_pending_walk(e);
-    if (rc) return rc;
+    // Inputs staged since the last evaluation belong to the state that is being stored (the host mirrors below include
+    // them): bring the device state up to them first, or a later restore() would drop them without ever uploading them.
+    int rc = SB2_OK;
+    if (e->needPrepare && (rc = do_prepare(e))) return rc;
+    if ((rc = flush_pending_walk(e))) return rc;
+    e->hasStored = true;
     e->storePending = true;   // the device copy is owed to the next k_prepare (do_prepare), which knows how little differs
     // host staging mirrors of what just became the stored state
     for (int32_t l : e->touched) {
@@ -1014,6 +1046,7 @@ int sb2_restore(sb2_engine *e)
 {
     if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    if (!e->hasStored) return e->fail(SB2_ERR_STATE, "sb2_restore without a prior sb2_store");
     // swap current / stored, like the reference's restore() methods -- unless nothing was evaluated since store(): then the
     // device state IS the stored state (and the stored block's owed copy has not happened yet)
     if (!e->storePending) e->curIdx = 1 - e->curIdx;
@@ -1171,9 +1204,9 @@ static int run_query(sb2_engine *e, int mode, const uint8_t *leafClass, uint8_t 
     a.mask = mask ? e->dQuery + 32 + e->queryLeafPad : nullptr;
     a.result = reinterpret_cast<unsigned long long *>(e->dQuery);
     a.mode = mode; a.maxNodes = e->maxNodes;
-    if (launch_tip_class_query(a, e->L, st)) return e->fail(SB2_ERR_ARG, "gene trees of %d nodes exceed the query kernel's shared memory", e->maxNodes);
+    if (8 * (size_t)e->maxNodes > 227 * 1024) return e->fail(SB2_ERR_ARG, "gene trees of %d nodes exceed the query kernel's shared memory", e->maxNodes);
+    CUDA_TRY(e, launch_tip_class_query(a, e->L, st));
     e->launches++;
-    CUDA_TRY(e, cudaGetLastError());
     CUDA_TRY(e, cudaMemcpyAsync(e->hQuery, e->dQuery, mask ? 32 + e->queryLeafPad + (size_t)e->totalNodes : 32, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(e, cudaStreamSynchronize(st));
     for (int i = 0; i < 3; i++) out3[i] = dec_min(hdr[i]);

@@ -79,15 +79,15 @@ __global__ void __launch_bounds__(QUERY_THREADS) k_tip_class_query(QueryArgs A)
     }
 }
 
-int launch_tip_class_query(const QueryArgs &a, int nLoci, cudaStream_t st)
+cudaError_t launch_tip_class_query(const QueryArgs &a, int nLoci, cudaStream_t st)
 {
     const size_t smem = 8 * (size_t)a.maxNodes;
-    if (smem > 48 * 1024) {
-        if (smem > 227 * 1024) return -1;
-        cudaFuncSetAttribute(k_tip_class_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    static size_t configured[MAX_DEVICES] = {};
+    cudaError_t rc = ensure_dynamic_smem(k_tip_class_query, smem, configured);
+    if (rc != cudaSuccess) return rc;
     k_tip_class_query<<<nLoci, QUERY_THREADS, smem, st>>>(a);
-    return 0;
+    return cudaGetLastError();
 }
 
 }  // namespace sb2

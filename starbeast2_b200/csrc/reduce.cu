@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_xgpu(ReduceArgs A, CommA
 }
 
 template <typename K>
-static void launch_pdl(K kernel, const ReduceArgs &a, cudaStream_t st)
+static cudaError_t launch_pdl(K kernel, const ReduceArgs &a, cudaStream_t st)
 {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(1); cfg.blockDim = dim3(RED_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
@@ -96,16 +96,16 @@ static void launch_pdl(K kernel, const ReduceArgs &a, cudaStream_t st)
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, a);
+    return cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
-void launch_reduce_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches)
+cudaError_t launch_reduce_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches)
 {
-    launch_pdl(k_reduce_finish, a, st);
     ++*launches;
+    return launch_pdl(k_reduce_finish, a, st);
 }
 
-void launch_reduce_xgpu(const ReduceArgs &a, const CommArgs &c, cudaStream_t st, int64_t *launches)
+cudaError_t launch_reduce_xgpu(const ReduceArgs &a, const CommArgs &c, cudaStream_t st, int64_t *launches)
 {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(1); cfg.blockDim = dim3(RED_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
@@ -113,20 +113,21 @@ void launch_reduce_xgpu(const ReduceArgs &a, const CommArgs &c, cudaStream_t st,
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_reduce_xgpu, a, c);
     ++*launches;
+    return cudaLaunchKernelEx(&cfg, k_reduce_xgpu, a, c);
 }
 
-void launch_reduce_local(const ReduceArgs &a, cudaStream_t st, int64_t *launches)
+cudaError_t launch_reduce_local(const ReduceArgs &a, cudaStream_t st, int64_t *launches)
 {
-    launch_pdl(k_reduce_local, a, st);
     ++*launches;
+    return launch_pdl(k_reduce_local, a, st);
 }
 
-void launch_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches)
+cudaError_t launch_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches)
 {
     k_finish<<<1, RED_THREADS, 0, st>>>(a);
     ++*launches;
+    return cudaGetLastError();
 }
 
 }  // namespace sb2

@@ -199,7 +199,7 @@ struct CommArgs {
     uint32_t pad;
     unsigned long long seq;                         // evaluation sequence number (parity selects the buffer half)
 };
-void launch_reduce_xgpu(const ReduceArgs &a, const CommArgs &c, cudaStream_t st, int64_t *launches);
+cudaError_t launch_reduce_xgpu(const ReduceArgs &a, const CommArgs &c, cudaStream_t st, int64_t *launches);
 
 // Operator-side queries over the resident gene trees (query.cu)
 constexpr int QUERY_THREADS = 128;
@@ -214,13 +214,31 @@ struct QueryArgs {
     unsigned long long *result;      // {tipward, rootward, maxHeight} order-preserving encodings (pre-set to enc(+inf)), count
     int32_t mode, maxNodes;
 };
-int launch_tip_class_query(const QueryArgs &a, int nLoci, cudaStream_t st);
+cudaError_t launch_tip_class_query(const QueryArgs &a, int nLoci, cudaStream_t st);
 
-void launch_prepare(const PrepareArgs &a, int maxNodes, cudaStream_t st);
-void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st);
-void launch_reduce_local(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
-void launch_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
-void launch_reduce_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
+// Every launcher returns the launch's cudaError_t (cudaErrorInvalidValue for a geometry no instantiation covers) -- the
+// library lives inside a JVM, so nothing in here may abort() or drop an error.
+cudaError_t launch_prepare(const PrepareArgs &a, int maxNodes, cudaStream_t st);
+cudaError_t launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st);
+cudaError_t launch_reduce_local(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
+cudaError_t launch_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
+cudaError_t launch_reduce_finish(const ReduceArgs &a, cudaStream_t st, int64_t *launches);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: one host thread may drive one engine per GPU
+// (INTEGRATION.md section 4), so the opt-in above 48 KB is cached per (kernel instantiation, device), never per process.
+constexpr int MAX_DEVICES = 64;
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K kernel, size_t smem, size_t (&configured)[MAX_DEVICES])
+{
+    if (smem <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t st = cudaGetDevice(&dev);
+    if (st != cudaSuccess) return st;
+    if (dev < 0 || dev >= MAX_DEVICES) return cudaErrorInvalidDevice;
+    if (smem <= configured[dev]) return cudaSuccess;
+    st = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st == cudaSuccess) configured[dev] = smem;
+    return st;
+}
 size_t prepare_smem_bytes(int maxNodes, int S);
 size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, int maxTips, int workers);
 bool treewalk_tips_in_smem(int maxTips, int tilePat);

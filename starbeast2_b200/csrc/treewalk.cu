@@ -480,54 +480,50 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
 }
 
 template <bool EXACT, int R, int MINB, int NC, int CH, int DEPTH, int NW = 1>
-static void launch_one(const WalkArgs &a, int nTiles, size_t smem, int threads, cudaStream_t st)
+static cudaError_t launch_one(const WalkArgs &a, int nTiles, size_t smem, int threads, cudaStream_t st)
 {
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(k_treewalk<EXACT, R, MINB, NC, CH, DEPTH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static size_t configured[MAX_DEVICES] = {};
+    cudaError_t rc = ensure_dynamic_smem(k_treewalk<EXACT, R, MINB, NC, CH, DEPTH, NW>, smem, configured);
+    if (rc != cudaSuccess) return rc;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nTiles); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_treewalk<EXACT, R, MINB, NC, CH, DEPTH, NW>, a);
+    return cudaLaunchKernelEx(&cfg, k_treewalk<EXACT, R, MINB, NC, CH, DEPTH, NW>, a);
 }
 
 template <bool EXACT>
-static void launch_exact(const WalkArgs &a, int nTiles, size_t smem, int threads, cudaStream_t st)
+static cudaError_t launch_exact(const WalkArgs &a, int nTiles, size_t smem, int threads, cudaStream_t st)
 {
     static const bool forceGeneric = getenv("SB2_GENERIC") != nullptr;   // A/B knob
     const bool std4 = a.stackDepth == 4 && a.tipsInSmem == 1 && !forceGeneric;
     if (a.workers > 1) {   // tree-level parallelism: engine.cu only selects it for these shapes
-        if (a.nCat == 1 && a.workers == 4) launch_one<EXACT, 1, 4, 1, 1, 3, 4>(a, nTiles, smem, threads, st);
-        else if (a.nCat == 1 && a.workers == 2) launch_one<EXACT, 1, 4, 1, 1, 3, 2>(a, nTiles, smem, threads, st);
-        else if (a.nCat == 4 && a.workers == 2) launch_one<EXACT, 1, 4, 4, 1, 3, 2>(a, nTiles, smem, threads, st);
-        else abort();
-        return;
+        if (a.nCat == 1 && a.workers == 4) return launch_one<EXACT, 1, 4, 1, 1, 3, 4>(a, nTiles, smem, threads, st);
+        else if (a.nCat == 1 && a.workers == 2) return launch_one<EXACT, 1, 4, 1, 1, 3, 2>(a, nTiles, smem, threads, st);
+        else if (a.nCat == 4 && a.workers == 2) return launch_one<EXACT, 1, 4, 4, 1, 3, 2>(a, nTiles, smem, threads, st);
+        return cudaErrorInvalidValue;   // engine.cu only selects the shapes above; never abort() inside a JVM
     }
     if (a.patPerThread == 1) {
-        if (std4 && a.nCat == 4 && a.chunksPerTile == 1) launch_one<EXACT, 1, 4, 4, 1, 4>(a, nTiles, smem, threads, st);        // GTR+G4 shapes
-        else if (std4 && a.nCat == 1 && a.chunksPerTile == 2) launch_one<EXACT, 1, 4, 1, 2, 4>(a, nTiles, smem, threads, st);   // no rate heterogeneity
-        else launch_one<EXACT, 1, 4, 0, 0, 0>(a, nTiles, smem, threads, st);
+        if (std4 && a.nCat == 4 && a.chunksPerTile == 1) return launch_one<EXACT, 1, 4, 4, 1, 4>(a, nTiles, smem, threads, st);        // GTR+G4 shapes
+        else if (std4 && a.nCat == 1 && a.chunksPerTile == 2) return launch_one<EXACT, 1, 4, 1, 2, 4>(a, nTiles, smem, threads, st);   // no rate heterogeneity
+        else return launch_one<EXACT, 1, 4, 0, 0, 0>(a, nTiles, smem, threads, st);
     } else if (a.patPerThread == 2) {
-        if (a.stackDepth == 3 && a.tipsInSmem == 1 && a.nCat == 4 && a.chunksPerTile == 1) launch_one<EXACT, 2, 5, 4, 1, 3>(a, nTiles, smem, threads, st);   // 5 CTAs / SM
-        else if (std4 && a.nCat == 4 && a.chunksPerTile == 1) launch_one<EXACT, 2, 2, 4, 1, 4>(a, nTiles, smem, threads, st);
-        else if (std4 && a.nCat == 1 && a.chunksPerTile == 2) launch_one<EXACT, 2, 2, 1, 2, 4>(a, nTiles, smem, threads, st);
-        else launch_one<EXACT, 2, 2, 0, 0, 0>(a, nTiles, smem, threads, st);
+        if (a.stackDepth == 3 && a.tipsInSmem == 1 && a.nCat == 4 && a.chunksPerTile == 1) return launch_one<EXACT, 2, 5, 4, 1, 3>(a, nTiles, smem, threads, st);   // 5 CTAs / SM
+        else if (std4 && a.nCat == 4 && a.chunksPerTile == 1) return launch_one<EXACT, 2, 2, 4, 1, 4>(a, nTiles, smem, threads, st);
+        else if (std4 && a.nCat == 1 && a.chunksPerTile == 2) return launch_one<EXACT, 2, 2, 1, 2, 4>(a, nTiles, smem, threads, st);
+        else return launch_one<EXACT, 2, 2, 0, 0, 0>(a, nTiles, smem, threads, st);
     } else {
-        launch_one<EXACT, 4, 1, 0, 0, 0>(a, nTiles, smem, threads, st);
+        return launch_one<EXACT, 4, 1, 0, 0, 0>(a, nTiles, smem, threads, st);
     }
 }
 
-void launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st)
+cudaError_t launch_treewalk(const WalkArgs &a, int nTiles, bool exact, cudaStream_t st)
 {
     const size_t smem = treewalk_smem_bytes(a.nCat, a.chunksPerTile, a.patPerThread, a.stackDepth, a.maxTips, a.workers);
     const int threads = 32 * a.nCat * a.chunksPerTile * a.workers;
-    if (exact) launch_exact<true>(a, nTiles, smem, threads, st);
-    else launch_exact<false>(a, nTiles, smem, threads, st);
+    return exact ? launch_exact<true>(a, nTiles, smem, threads, st) : launch_exact<false>(a, nTiles, smem, threads, st);
 }
 
 }  // namespace sb2

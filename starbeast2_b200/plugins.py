@@ -379,6 +379,7 @@ class MultispeciesCoalescent(CompoundDistribution):
             raise ValueError("Either specify both population size prior parameters for analytical integration,"
                              "or neither for MCMC integration of population sizes.")
         self.alpha = self.beta = 0.0
+        self.storedAlpha = self.storedBeta = 0.0
         self.dontCalculate = shape is None
         for d in self.get("distribution"):
             if not isinstance(d, GeneTree):   # :116-118
@@ -411,12 +412,17 @@ class MultispeciesCoalescent(CompoundDistribution):
         self.logP = float(total)
         return self.logP
 
-    def store(self):
+    def store(self):   # MultispeciesCoalescent.java:50-61
         Distribution.store(self)
+        if not self.dontCalculate:
+            self.storedAlpha, self.storedBeta = self.alpha, self.beta
         self.session.store()
 
-    def restore(self):
+    def restore(self):   # MultispeciesCoalescent.java:63-88: (alpha, beta) swap back BEFORE the session re-derives its signature
         Distribution.restore(self)
+        if not self.dontCalculate:
+            self.alpha, self.storedAlpha = self.storedAlpha, self.alpha
+            self.beta, self.storedBeta = self.storedBeta, self.beta
         self.session.restore()
 
     def accept(self):

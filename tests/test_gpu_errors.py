@@ -103,3 +103,91 @@ def test_numerical_failure_is_minus_infinity_or_nan_never_an_error():
     e.restore()
     assert e.eval_posterior().total == base.total
     e.close()
+
+
+def test_malformed_trees_are_rejected_not_hung():
+    """A parent array with a cycle detached from the root, or child / parent arrays that disagree, would spin k_prepare's
+    rootward walks forever; the host-side check must refuse them."""
+    pb = synth.make_problem("C2", n_loci=1, n_sites=40)
+    e = Engine.from_problem(pb)
+    loc = pb.loci[0]
+    nT = loc.n_tips
+    t = loc.tree.copy()
+    # two internal non-root nodes that are each other's parent: indices stay in range and there is still exactly one root
+    a = next(i for i in range(nT, t.n_nodes) if t.parent[i] >= 0 and t.parent[t.parent[i]] >= 0)
+    b = int(t.parent[a])
+    t.parent[b] = a
+    with pytest.raises(Sb2Error, match="disagree|connected"):
+        e.set_gene_tree(0, t)
+    t = loc.tree.copy()
+    t.right[t.root] = t.left[t.root]                                   # the same child twice
+    with pytest.raises(Sb2Error):
+        e.set_gene_tree(0, t)
+    sp = pb.species.copy()
+    sp.right[sp.n_nodes - 1] = -1                                      # left >= 0 but right < 0
+    with pytest.raises(Sb2Error):
+        e.set_species_tree(sp)
+    sp = pb.species.copy()
+    i = next(i for i in range(sp.n_leaves, sp.n_nodes) if sp.parent[i] >= 0 and sp.parent[sp.parent[i]] >= 0)
+    sp.parent[int(sp.parent[i])] = i
+    with pytest.raises(Sb2Error):
+        e.set_species_tree(sp)
+    # nothing was staged by the refused calls: the engine still evaluates the original state
+    assert e.eval_posterior().total == pytest.approx(oracle.posterior(pb).total, rel=1e-9)
+    e.close()
+
+
+def test_restore_without_store_and_store_with_staged_inputs():
+    pb = synth.make_problem("C2", n_loci=3, n_sites=60)
+    e = Engine.from_problem(pb)
+    e.eval_posterior()
+    with pytest.raises(Sb2Error, match="without a prior"):
+        e.restore()
+    # stage a new gene tree, store WITHOUT evaluating, then propose something else and reject it:
+    # the stored state is the staged one (ADVICE r1: the staged values must not be lost by the restore)
+    rng = np.random.default_rng(5)
+    t1, _ = synth.perturb_gene_tree(rng, pb.loci[1].tree, pb.loci[1].n_tips)
+    e.set_gene_tree(1, t1)
+    e.store()
+    t2, _ = synth.perturb_gene_tree(rng, pb.loci[2].tree, pb.loci[2].n_tips)
+    e.set_gene_tree(2, t2)
+    e.eval_posterior()
+    e.restore()
+    pb.loci[1].tree = t1
+    got, want = e.eval_posterior(), oracle.posterior(pb)
+    assert got.total == pytest.approx(want.total, rel=1e-9)
+    np.testing.assert_allclose(got.per_locus_lik, want.per_locus_lik, rtol=1e-9)
+    e.close()
+
+
+def test_strict_protocol_two_coalescent_evaluations_without_a_likelihood(monkeypatch):
+    """SB2_NO_SPECULATION: eval_coalescent runs k_prepare but no pruning kernel.  A second staged input + evaluation must
+    first run the pending walk, or the nodes re-scheduled by the first k_prepare would be treated as clean."""
+    monkeypatch.setenv("SB2_NO_SPECULATION", "1")
+    pb = synth.make_problem("C2", n_loci=3, n_sites=60)
+    e = Engine.from_problem(pb)
+    e.eval_posterior()
+    rng = np.random.default_rng(9)
+    t0, _ = synth.perturb_gene_tree(rng, pb.loci[0].tree, pb.loci[0].n_tips)
+    e.set_gene_tree(0, t0)
+    e.eval_coalescent()
+    t1, _ = synth.perturb_gene_tree(rng, pb.loci[1].tree, pb.loci[1].n_tips)
+    e.set_gene_tree(1, t1)
+    e.eval_coalescent()
+    pb.loci[0].tree, pb.loci[1].tree = t0, t1
+    got, want = e.eval_likelihood(), oracle.posterior(pb)
+    np.testing.assert_allclose(got[1], want.per_locus_lik, rtol=1e-9)
+    e.close()
+
+
+def test_large_shared_memory_shapes_on_every_device():
+    """cudaFuncAttributeMaxDynamicSharedMemorySize is per device: an engine on EVERY visible GPU must be able to launch the
+    > 48 KB instantiations (many tips: big k_prepare / tip-state tiles), driven by one host thread."""
+    import torch
+    pb = synth.make_problem("C2", n_loci=2, n_sites=60, n_species=80, tips_per=4)   # 320 tips: k_prepare > 48 KB
+    want = oracle.posterior(pb)
+    engines = [Engine.from_problem(pb, device=d) for d in range(torch.cuda.device_count())]
+    for e in engines:
+        assert e.eval_posterior().total == pytest.approx(want.total, rel=1e-9)
+    for e in engines:
+        e.close()

@@ -92,6 +92,32 @@ def test_stale_alpha_quirk_q1():
     assert (msc.alpha, msc.beta) == (2.0, 5.0)
 
 
+def test_alpha_beta_are_stored_and_restored_like_the_reference():
+    """MultispeciesCoalescent.java:50-88: store() saves (alpha, beta), restore() swaps them back -- so after a REJECTED
+    populationShape move beta is recomputed from the restored alpha, not from the rejected one."""
+    class _Session:   # stands in for the device session: this test is about the host-side bookkeeping only
+        def store(self): pass
+        def restore(self): pass
+    alpha, mean = RealParameter(value="1.5"), RealParameter(value="5.0")
+    msc = MultispeciesCoalescent.__new__(MultispeciesCoalescent)
+    MultispeciesCoalescent.__init__(msc)
+    msc._inputs.update(populationShape=alpha, populationMean=mean)
+    msc.alpha = msc.beta = msc.storedAlpha = msc.storedBeta = 0.0
+    msc.dontCalculate, msc.session = False, _Session()
+    msc._check_hyperparameters(True)
+    msc._check_hyperparameters(False)
+    assert (msc.alpha, msc.beta) == (1.5, 2.5)
+    msc.store()
+    alpha.setValue(0.5)                                    # proposal: alpha < 1
+    msc._check_hyperparameters(False)
+    assert (msc.alpha, msc.beta) == (0.5, 2.5)
+    alpha.setValue(1.5)                                    # rejected: the state node goes back ...
+    msc.restore()                                          # ... and so do the cached hyperparameters
+    assert (msc.alpha, msc.beta) == (1.5, 2.5)
+    msc._check_hyperparameters(False)
+    assert (msc.alpha, msc.beta) == (1.5, 2.5)             # without the restore this would be (1.5, 5 * (0.5 - 1)) = (1.5, -2.5)
+
+
 # ---- through the GPU ------------------------------------------------------------------------------------------------
 
 def _gene_trees(speciesTree, newicks, popModel=None, ploidy=2.0):
@@ -151,6 +177,24 @@ def test_ConstantIOTest(genes, key):
     for gt in wrappers:
         assert gt.calculateLogP() == 0.0     # MissingDataConstantIOTest.java:97
     assert msc.calculateLogP() == pytest.approx(rf.EXPECTED[key], abs=allowedError)
+
+
+@pytest.mark.gpu
+def test_rejected_population_shape_move_restores_the_analytic_term():
+    alphaParameter, meanParameter = RealParameter(value="1.5"), RealParameter(value="5.0")
+    speciesTree = SpeciesTreeParser()
+    speciesTree.initByName("newick", rf.SPECIES_4, "IsLabelledNewick", True, "taxonset", generateSuperset())
+    msc = MultispeciesCoalescent()
+    msc.initByName("populationShape", alphaParameter, "populationMean", meanParameter, "distribution", _gene_trees(speciesTree, rf.GENES_4))
+    first = msc.calculateLogP()
+    assert first == pytest.approx(rf.EXPECTED["analytic"], abs=allowedError)
+    msc.store()
+    alphaParameter.setValue(0.5)                           # proposal with alpha < 1
+    msc.calculateLogP()
+    alphaParameter.setValue(1.5)                           # rejected
+    msc.restore()
+    assert msc.hyperparameters() == (1.5, 2.5)
+    assert msc.calculateLogP() == first                    # not NaN from beta = mean * (0.5 - 1)
 
 
 @pytest.mark.gpu
