@@ -235,6 +235,7 @@ ReduceArgs reduce_args(sb2_engine *e, bool coalOnly = false)
 }
 
 int do_walk(sb2_engine *e, int fuse = 0, bool *fused = nullptr);
+int flush_pending_walk(sb2_engine *e);
 
 // Structural check of a host-supplied binary tree in BEAST node numbering (leaves first): exactly one root, every
 // internal node has two distinct children that name it as their parent, leaves have none, and a walk from the root
@@ -279,7 +280,7 @@ int do_prepare(sb2_engine *e)
     if (!e->needPrepare) return SB2_OK;
     // A walk scheduled by an earlier k_prepare (strict two-phase protocol: coalescent evaluated, likelihood never asked for)
     // must run before the next k_prepare re-schedules: that one would treat the already-flipped nodes as clean.
-    if (e->walkPending) { int rc = do_walk(e); if (rc) return rc; }
+    if (e->walkPending) { int rc = flush_pending_walk(e); if (rc) return rc; }
     e->resultValid = false;
     cudaStream_t st = e->stream;
     const int L = e->L;
@@ -423,6 +424,19 @@ int do_walk(sb2_engine *e, int fuse, bool *fused)
     if (e->cfg.profile) CUDA_TRY(e, cudaEventRecord(ev.second, e->stream));
     CUDA_TRY(e, cudaGetLastError());
     if (fused) *fused = fuse != 0;
+    return SB2_OK;
+}
+
+int flush_pending_walk(sb2_engine *e)
+{
+    // k_prepare already flipped buffer indices for the scheduled nodes; make sure their partials exist before the
+    // state is frozen (only reachable when a host evaluates the coalescent but never the likelihood)
+    if (e->walkPending) {
+        int rc = do_walk(e);
+        if (rc) return rc;
+        // ... and that the cached per-locus log-likelihoods (cur.logL, what a clean locus reports) belong to them
+        CUDA_TRY(e, launch_reduce_local(reduce_args(e), e->stream, &e->launches));
+    }
     return SB2_OK;
 }
 
@@ -1005,17 +1019,6 @@ int sb2_set_stream(sb2_engine *e, void *cudaStream)
     return SB2_OK;
 }
 
-static int flush_pending_walk(sb2_engine *e)
-{
-    // k_prepare already flipped buffer indices for the scheduled nodes; make sure their partials exist before the
-    // state is frozen (only reachable when a host evaluates the coalescent but never the likelihood)
-    if (e->walkPending) {
-        int rc = do_walk(e, 1);
-        if (rc) return rc;
-    }
-    return SB2_OK;
-}
-
 int sb2_store(sb2_engine *e)
 {
     if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
@@ -1023,7 +1026,13 @@ int sb2_store(sb2_engine *e)
     // Inputs staged since the last evaluation belong to the state that is being stored (the host mirrors below include
     // them): bring the device state up to them first, or a later restore() would drop them without ever uploading them.
     int rc = SB2_OK;
-    if (e->needPrepare && (rc = do_prepare(e))) return rc;
+    if (e->needPrepare) {
+        if ((rc = do_prepare(e))) return rc;
+        if ((rc = do_walk(e))) return rc;
+        // the rank-local sums also refresh the cached per-locus values (cur.logL) that a restore() falls back on; no
+        // cross-GPU exchange here: ranks need not agree on whether they had anything staged
+        CUDA_TRY(e, launch_reduce_local(reduce_args(e), e->stream, &e->launches));
+    }
     if ((rc = flush_pending_walk(e))) return rc;
     e->hasStored = true;
     e->storePending = true;   // the device copy is owed to the next k_prepare (do_prepare), which knows how little differs
