@@ -3,9 +3,19 @@
 
 A "step" is one full posterior evaluation with every node dirty (SURVEY.md 8d regime A): multispecies-coalescent
 embedding + per-branch terms + species-clock rates + transition matrices + Felsenstein pruning of every gene tree
-+ root integration, for all loci of the workload.  N=1 workload: BASELINE.json configs[1] ("C2": 50 loci x
-1,000 bp x 30 individuals / 10 species, HKY, ConstantPopulations).  N>1: weak scaling, every rank holds its own
-50-locus shard of one 50*N-locus posterior and each step all-reduces the reduce vector over NCCL.
++ root integration, for all loci of the workload.
+
+Headline leg (value / e2e / roofline / cpu_baseline): BASELINE.json configs[1] ("C2": 50 loci x 1,000 bp x 30
+individuals / 10 species, HKY, ConstantPopulations).  N>1: weak scaling, every rank holds its own 50-locus shard of one
+50*N-locus posterior; the reduce vector is all-reduced inside the reduction kernel over peer memory (NVLink).
+
+North-star legs, run after the headline leg in the same process and carried in keys the driver's record keeps:
+  config.legs.C5_strong  BASELINE configs[4]: 2,000 loci x 500 bp x 120 tips, GTR+G4, UCLN -- STRONG scaling, 2,000/N loci per GPU
+  config.legs.C4_strong  BASELINE configs[3]: 500 loci, 24-species FBD-style tree, analytic populations -- 500/N per GPU
+  config.legs.C3         BASELINE configs[2]: 200 loci x 800 bp x 60 tips, GTR+G4, UCLN, LinearWithConstantRoot (N=1 only)
+  roofline.shapes.{C2,C3,C5s,C5}  the pruning kernel's CUDA-event time on each shape, same accounting as `roofline`
+Every leg is checked against the CPU oracle on the GLOBAL problem (rank 0, all host threads): the run FAILS (exit 1) when
+|logP_gpu - logP_oracle| / |logP_oracle| > 1e-9.
 
   value : pattern x node x category partials per second, whole job, inputs resident in HBM (device-timed)
   e2e   : the same metric through the C ABI with HOST buffers: species tree, all gene trees and parameters are
@@ -14,7 +24,7 @@ embedding + per-branch terms + species-clock rates + transition matrices + Felse
   cpu_baseline : the C restatement of the reference's Java path (oracle/), 1 thread, same workload, rank 0 only
 
 `--impl reference` times that CPU restatement on all host threads instead (no JVM exists in this image, so the
-reference's own code cannot run).
+reference's own code cannot run), on the same global problem the GPU arm evaluates at this N.
 """
 from __future__ import annotations
 
@@ -35,6 +45,8 @@ METRIC = "pattern·node·cat partials/sec (full multi-locus posterior evaluation
 UNIT = "partials/s"
 WORKLOAD = "C2"
 L2_FLUSH_BYTES = 512 << 20
+PARITY_TOL = 1e-9
+LEG_MIN_STEPS = 200
 
 
 def load_peaks():
@@ -48,14 +60,18 @@ def load_peaks():
 
 
 def design_bytes(pb) -> float:
-    """Compulsory HBM bytes of one full evaluation in THIS design (children are consumed from shared memory, so
+    """Compulsory HBM bytes of one full evaluation in THIS design (children are consumed from registers / shared memory, so
     partials are written once and never re-read): 32 B partials + 2 B exponent per unit, tip states once,
-    pattern log-likelihoods once.  DESIGN.md derives it."""
+    pattern log-likelihoods once.  DESIGN.md section 5 and BASELINE.md derive it."""
     b = 0.0
     for l in pb.loci:
         n_int = l.n_tips - 1
         b += 34.0 * l.n_pat * l.n_cat * n_int + l.n_pat * l.n_tips + 8.0 * l.n_pat
     return b
+
+
+def host_threads() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
 class ClockSampler:
@@ -67,7 +83,6 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.index = index
-        self.marks = []
 
     def start(self):
         try:
@@ -103,11 +118,53 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_problem(rank: int, world: int, loci_per_rank: int, workload: str):
-    from starbeast2_b200 import synth
-    total = loci_per_rank * world
-    return synth.make_problem(workload, n_loci=total, locus_range=(rank * loci_per_rank, (rank + 1) * loci_per_rank))
+# ----------------------------------------------------------------------------------------------------------------------
+# problems
+# ----------------------------------------------------------------------------------------------------------------------
 
+def rank_range(total: int, rank: int, world: int):
+    """Contiguous block of loci of rank `rank` (equal counts: the synthetic loci of one config are statistically alike)."""
+    return (total * rank) // world, (total * (rank + 1)) // world
+
+
+def build_problem(workload: str, total: int, lo: int, hi: int, procs: int):
+    from starbeast2_b200 import synth
+    return synth.make_problem_parallel(workload, n_loci=total, locus_range=(lo, hi), procs=procs)
+
+
+def canis_problem():
+    """BASELINE configs[0] (C1): the tutorial's 16 alignments (tests/golden/canis_c1.json, generated from the reference's FASTA
+    files by tests/golden/make_canis.py), 16 individuals / 8 species, HKY, constant populations, strict clock; the trees are
+    random MSC draws (the tutorial starts from random trees too)."""
+    from starbeast2_b200 import synth
+    from starbeast2_b200.problem import POP_CONSTANT, Locus, Problem, hky_params
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "canis_c1.json")))["loci"]
+    species = sorted({t[:-2] for v in fx.values() for t in v["taxa"]})
+    rng = np.random.Generator(np.random.PCG64(20260101))
+    sp = synth.yule_species_tree(rng, len(species))
+    pop = rng.gamma(2.0, 0.025, size=sp.n_nodes)
+    code = {c: i for i, c in enumerate("ACGT-")}
+    loci = []
+    for v in fx.values():
+        tree, tip_species = synth.simulate_gene_tree(rng, sp, pop * 2.0, np.array([2] * len(species)))
+        order = {}
+        for k, s in enumerate(tip_species):   # gene tip k belongs to species s: take that species' next individual of the alignment
+            order.setdefault(int(s), []).append(k)
+        rows = np.zeros((len(tip_species), len(v["weights"])), np.uint8)
+        seen = {}
+        for ti, taxon in enumerate(v["taxa"]):
+            s = species.index(taxon[:-2])
+            k = order[s][seen.get(s, 0)]
+            seen[s] = seen.get(s, 0) + 1
+            rows[k] = [code[c] for c in v["patterns"][ti]]
+        loci.append(Locus(tree=tree, tip_states=rows, weights=np.array(v["weights"], np.int32), tip_species=tip_species,
+                          subst_params=hky_params(2.0, [0.25] * 4), clock_rate=0.05))
+    return Problem(species=sp, loci=loci, pop_kind=POP_CONSTANT, pop_a=pop, species_rates=np.ones(sp.n_nodes))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU legs (the oracle as the reported baseline, never as the thing measured on the GPU side)
+# ----------------------------------------------------------------------------------------------------------------------
 
 def cpu_baseline(pb, n_threads: int, budget_s: float):
     import oracle
@@ -122,6 +179,56 @@ def cpu_baseline(pb, n_threads: int, budget_s: float):
             break
     return n, dt, r
 
+
+def cpu_incremental(pb, synth, n_steps=300):
+    """Regime B on the host: the C restatement of what the reference evaluates when one gene tree changed (oracle
+    IncrementalBaseline: embedding of EVERY locus -- GeneTree.requiresRecalculation() is always true --, population terms,
+    clock rates and incremental TreeLikelihood of the changed locus), 1 thread like the reference's MCMC."""
+    import oracle
+    if pb.pop_kind not in (0, 1):
+        return None
+    rng = np.random.default_rng(12345)
+    inc = oracle.IncrementalBaseline(pb)
+    moves = []
+    for _ in range(64):
+        l = int(rng.integers(0, pb.n_loci))
+        t, _ = synth.perturb_gene_tree(rng, pb.loci[l].tree, pb.loci[l].n_tips)
+        moves.append((l, t, pb.loci[l].tree))
+    for l, t, t0 in moves[:8]:
+        inc.step(l, t); inc.step(l, t0)
+    t_start = time.perf_counter()
+    for i in range(n_steps):
+        l, t, t0 = moves[i % len(moves)]
+        inc.step(l, t)          # propose + evaluate
+        inc.step(l, t0)         # the move back is an equally small update; both are counted as steps
+    dt = time.perf_counter() - t_start
+    inc.close()
+    return {"steps_per_sec": 2 * n_steps / dt, "us_per_step": 1e6 * dt / (2 * n_steps), "cores": 1, "kind": "port",
+            "note": "C restatement of the reference's per-step work (all-loci embedding + one-locus incremental likelihood), "
+                    "gcc -O2 -ffp-contract=off; not the JVM"}
+
+
+def cpu_operator_queries(pb, reps=20):
+    """The same walks by the C restatement of the Java recursions (1 thread; the Java adds HashSet<String> lookups per leaf)."""
+    import oracle
+    sp = pb.species
+    nodes = list(range(sp.n_leaves, sp.n_nodes - 1))
+    cmap = np.arange(sp.n_nodes, dtype=np.int32)
+    oracle.connecting_nodes(pb, nodes[0])
+    t0 = time.perf_counter()
+    for i in range(reps):
+        oracle.connecting_nodes(pb, nodes[i % len(nodes)])
+    t1 = time.perf_counter()
+    for i in range(reps):
+        oracle.max_height(pb, cmap, sp.n_leaves // 2)
+    t2 = time.perf_counter()
+    return {"connecting_nodes_us": 1e6 * (t1 - t0) / reps, "max_height_us": 1e6 * (t2 - t1) / reps,
+            "note": "ctypes call incl. concatenating the trees on the host; C port of the recursion, 1 thread"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU legs
+# ----------------------------------------------------------------------------------------------------------------------
 
 def bench_incremental(eng, pb, synth, n_steps=400):
     """Regime B of SURVEY.md 3.3: one MCMC step = store, move one node of one gene tree (BEAST's Uniform operator),
@@ -175,10 +282,12 @@ def bench_incremental(eng, pb, synth, n_steps=400):
 
     for i in range(20):
         one(i, count=True)
+    l0 = eng.launch_count()
     t0 = time.perf_counter()
     for i in range(n_steps):
         one(i)
     dt = time.perf_counter() - t0
+    launches = (eng.launch_count() - l0) / n_steps
     for i in range(20):
         one_call(i)
     t0 = time.perf_counter()
@@ -186,38 +295,11 @@ def bench_incremental(eng, pb, synth, n_steps=400):
         one_call(i)
     dt1 = time.perf_counter() - t0
     return {"steps_per_sec": n_steps / dt, "us_per_step": 1e6 * dt / n_steps, "mean_node_updates": float(np.mean(updates)),
+            "kernel_launches_per_step": launches,
             "protocol": "store, set_gene_tree(1 locus), eval_coalescent (likelihood evaluated speculatively in the same device pass), "
                         "eval_likelihood (cached), restore; host-timed",
             "single_round_trip": {"steps_per_sec": n_steps / dt1, "us_per_step": 1e6 * dt1 / n_steps,
                                   "protocol": "store, set_gene_tree, eval_posterior, restore"}}
-
-
-def cpu_incremental(pb, synth, n_steps=300):
-    """Regime B on the host: the C restatement of what the reference evaluates when one gene tree changed (oracle
-    IncrementalBaseline: embedding of EVERY locus -- GeneTree.requiresRecalculation() is always true --, population terms,
-    clock rates and incremental TreeLikelihood of the changed locus), 1 thread like the reference's MCMC."""
-    import oracle
-    if pb.pop_kind not in (0, 1):
-        return None
-    rng = np.random.default_rng(12345)
-    inc = oracle.IncrementalBaseline(pb)
-    moves = []
-    for _ in range(64):
-        l = int(rng.integers(0, pb.n_loci))
-        t, _ = synth.perturb_gene_tree(rng, pb.loci[l].tree, pb.loci[l].n_tips)
-        moves.append((l, t, pb.loci[l].tree))
-    for l, t, t0 in moves[:8]:
-        inc.step(l, t); inc.step(l, t0)
-    t_start = time.perf_counter()
-    for i in range(n_steps):
-        l, t, t0 = moves[i % len(moves)]
-        inc.step(l, t)          # propose + evaluate
-        inc.step(l, t0)         # the move back is an equally small update; both are counted as steps
-    dt = time.perf_counter() - t_start
-    inc.close()
-    return {"steps_per_sec": 2 * n_steps / dt, "us_per_step": 1e6 * dt / (2 * n_steps), "cores": 1, "kind": "port",
-            "note": "C restatement of the reference's per-step work (all-loci embedding + one-locus incremental likelihood), "
-                    "gcc -O2 -ffp-contract=off; not the JVM"}
 
 
 def bench_operator_queries(eng, pb, reps=200):
@@ -241,82 +323,251 @@ def bench_operator_queries(eng, pb, reps=200):
     return out
 
 
-def cpu_operator_queries(pb, reps=20):
-    """The same walks by the C restatement of the Java recursions (1 thread; the Java adds HashSet<String> lookups per leaf)."""
+class Ctx:
+    """Process-wide bench context: rank / world / torch handles / the L2-flush buffer."""
+
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: libsb2gpu has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        self.stream = torch.cuda.current_stream()
+        self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+        self.hbm_gbs, self.peak_src = load_peaks()
+        self.procs = max(1, min(16, host_threads() // self.world))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+    def sum_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+
+def stats(ms):
+    ms = np.asarray(ms, dtype=np.float64)
+    return {"min": float(ms.min()), "median": float(np.median(ms)), "mean": float(ms.mean()), "max": float(ms.max()),
+            "p90": float(np.percentile(ms, 90)), "n": int(ms.size)}
+
+
+class Leg:
+    """One workload on this rank's shard: engine, device-timed steps, e2e steps through the raw C ABI, roofline pass."""
+
+    def __init__(self, ctx: Ctx, workload: str, loci_total: int, lo: int, hi: int, pb=None):
+        from starbeast2_b200.engine import Engine
+        self.ctx, self.workload, self.loci_total = ctx, workload, loci_total
+        self.pb = pb if pb is not None else build_problem(workload, loci_total, lo, hi, ctx.procs)
+        pbs = self.pb
+        self.eng = Engine.from_problem(pbs, device=ctx.local, exact_order=ctx.args.exact, profile=False)
+        self.red = self.eng.bind_torch()
+        self.comm = "none"
+        if ctx.world > 1:
+            self.comm = "nccl"
+            if os.environ.get("SB2_COMM", "peer") == "peer" and self.eng.connect_peers():
+                self.comm = "peer-memory all-reduce inside the reduction kernel (NVLink stores, flag-in-data words)"
+        self.peers = ctx.world > 1 and self.comm != "nccl"
+        self.tot = np.zeros(3)
+        self.units_local = pbs.units
+        self._prepare_e2e()
+
+    def close(self):
+        self.eng.close()
+
+    def step_device(self):
+        ctx, eng = self.ctx, self.eng
+        eng.mark_all_dirty()
+        if ctx.world == 1 or self.peers:
+            eng.eval_posterior_total(self.tot)
+            return
+        eng.eval_begin()
+        ctx.dist.all_reduce(self.red)
+        eng.eval_end_total(self.tot)
+
+    def _prepare_e2e(self):
+        """Flat host copies of everything a step of the reference-facing API re-sends, addresses resolved once (as a JNI /
+        FFM caller would): species tree, species rates, population sizes, all gene trees in; per-locus + total logP out."""
+        from starbeast2_b200 import _lib as sblib
+        pb, eng = self.pb, self.eng
+        trees = [l.tree for l in pb.loci]
+        self._keep = [np.ascontiguousarray(np.concatenate([t.parent for t in trees]), np.int32),
+                      np.ascontiguousarray(np.concatenate([t.left for t in trees]), np.int32),
+                      np.ascontiguousarray(np.concatenate([t.right for t in trees]), np.int32),
+                      np.ascontiguousarray(np.concatenate([t.height for t in trees]), np.float64)]
+        n_nodes = int(self._keep[0].shape[0])
+        S = pb.species.n_nodes
+        self.h2d = 20 * n_nodes + 20 * S + 8 * S * 3 + 16 + pb.n_loci          # trees + species block + flags
+        self.d2h = 8 * (3 + 2 * pb.n_loci + S)
+        self._out = [np.zeros(pb.n_loci), np.zeros(pb.n_loci), np.zeros(S)]
+        sp = pb.species
+        self._keep2 = [np.ascontiguousarray(x) for x in (sp.parent, sp.left, sp.right, sp.height, pb.species_rates,
+                                                        pb.pop_a if pb.pop_a is not None else np.zeros(1),
+                                                        pb.pop_b if pb.pop_b is not None else np.zeros(1))]
+        self._raw, self._h = sblib.load_raw(), eng._h
+
+    def step_e2e(self):
+        raw, h, ctx = self._raw, self._h, self.ctx
+        ptr = [a.ctypes.data for a in self._keep2]
+        tp, tl, tr, th = (a.ctypes.data for a in self._keep)
+        oc, ol, ob = (a.ctypes.data for a in self._out)
+        ot = self.tot.ctypes.data
+        pb = self.pb
+        rc = raw.sb2_set_species_tree(h, ptr[0], ptr[1], ptr[2], ptr[3])
+        rc |= raw.sb2_set_species_rates(h, ptr[4])
+        rc |= raw.sb2_set_pop_model(h, pb.pop_kind, ptr[5], ptr[6], pb.alpha, pb.beta)
+        rc |= raw.sb2_set_gene_trees(h, 0, pb.n_loci, tp, tl, tr, th)
+        rc |= raw.sb2_mark_all_dirty(h)
+        if ctx.world == 1 or self.peers:
+            rc |= raw.sb2_eval_posterior(h, oc, ol, ob, ot)
+        else:
+            rc |= raw.sb2_eval_begin(h)
+            ctx.dist.all_reduce(self.red)
+            rc |= raw.sb2_eval_end(h, oc, ol, ob, ot)
+        if rc:
+            self.eng._ck(-1)
+
+    def timed(self, fn, steps, flush_l2=True, waits=None):
+        """Per-step device times (ms), CUDA events on the engine's stream, L2 flushed before every step (outside the events)."""
+        torch, ctx = self.ctx.torch, self.ctx
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            if flush_l2:
+                ctx.flush.fill_(1)          # evict the working set; outside the timed events
+            a.record(ctx.stream)
+            fn()
+            b.record(ctx.stream)
+            if waits is not None:
+                waits.append(self.eng.exchange_wait_us())
+        torch.cuda.synchronize()
+        return np.array([a.elapsed_time(b) for a, b in ev])
+
+    def measure(self, steps, warmup, e2e_steps=None, roofline_steps=50):
+        """Returns (per-step max-over-ranks device ms, e2e ms array, kernel us, launches, exchange-wait stats)."""
+        ctx, eng = self.ctx, self.eng
+        for _ in range(max(warmup, 3)):
+            ctx.flush.fill_(1)
+            self.step_device()
+        ctx.barrier()
+        l0 = eng.launch_count()
+        waits = [] if self.peers else None
+        ms = self.timed(self.step_device, steps, waits=waits)
+        launches = eng.launch_count() - l0
+        self.total_logp = float(self.tot[2])
+        ctx.barrier()
+        # roofline pass: the same steps with the pruning kernel bracketed by CUDA events on its own stream
+        eng.kernel_time()
+        eng.set_profile(True)
+        self.timed(self.step_device, min(steps, roofline_steps))
+        k_ms, k_n = eng.kernel_time()
+        eng.set_profile(False)
+        ctx.barrier()
+        e2e_steps = steps if e2e_steps is None else e2e_steps
+        for _ in range(3):
+            self.step_e2e()
+        ctx.barrier()
+        ms_e2e = self.timed(self.step_e2e, e2e_steps)
+        ctx.barrier()
+        ms = ctx.max_over_ranks(ms)
+        ms_e2e = ctx.max_over_ranks(ms_e2e)
+        wait = None
+        if waits:
+            w = ctx.max_over_ranks(waits)
+            wait = {"us_per_step": stats(w), "share_of_step": float(np.median(w) * 1e-3 / np.median(ms)),
+                    "note": "device time (globaltimer) the reduction kernel spends between publishing its words and having summed "
+                            "every peer's: rank skew + one NVLink trip; max over ranks per step"}
+        return ms, ms_e2e, 1e3 * k_ms / max(k_n, 1), int(k_n), launches, wait
+
+    def roofline(self, k_us, k_n):
+        ctx, pb = self.ctx, self.pb
+        dbytes, sbytes = design_bytes(pb), pb.algorithmic_bytes_survey()
+        achieved = dbytes / (k_us * 1e-6) / 1e9
+        return {"bound": "hbm", "kernel": "k_treewalk", "achieved": achieved, "peak": ctx.hbm_gbs, "unit": "GB/s", "frac": achieved / ctx.hbm_gbs,
+                "us_per_launch": k_us, "launches_timed": k_n, "algorithmic_bytes_per_launch": dbytes, "bytes_per_unit": dbytes / pb.units,
+                "survey_formula_bytes_per_launch": sbytes, "survey_formula_frac": sbytes / (k_us * 1e-6) / 1e9 / ctx.hbm_gbs,
+                "kernel_partials_per_sec": pb.units / (k_us * 1e-6), "loci_on_this_gpu": pb.n_loci, "units_on_this_gpu": pb.units}
+
+
+def oracle_total(workload, loci_total, pb_local, ctx):
+    """log posterior of the GLOBAL problem by the CPU oracle (rank 0 only; all host threads)."""
     import oracle
-    sp = pb.species
-    nodes = list(range(sp.n_leaves, sp.n_nodes - 1))
-    cmap = np.arange(sp.n_nodes, dtype=np.int32)
-    oracle.connecting_nodes(pb, nodes[0])
+    oracle.build()
+    pb = pb_local if ctx.world == 1 else build_problem(workload, loci_total, 0, loci_total, host_threads())
     t0 = time.perf_counter()
-    for i in range(reps):
-        oracle.connecting_nodes(pb, nodes[i % len(nodes)])
-    t1 = time.perf_counter()
-    for i in range(reps):
-        oracle.max_height(pb, cmap, sp.n_leaves // 2)
-    t2 = time.perf_counter()
-    return {"connecting_nodes_us": 1e6 * (t1 - t0) / reps, "max_height_us": 1e6 * (t2 - t1) / reps,
-            "note": "ctypes call incl. concatenating the trees on the host; C port of the recursion, 1 thread"}
+    r = oracle.posterior(pb, n_threads=host_threads())
+    return r, time.perf_counter() - t0, pb
 
 
-def bench_streaming(args, hbm_gbs, peak_src, flush, n_loci=250, steps=30):
-    """The pruning kernel where it actually streams HBM: a C5-shaped shard (GTR+G4, 120 individuals / 40 species, ~450
-    patterns per locus; 250 loci = the per-GPU shard of the 8-GPU config, 1.7 GB of partials per evaluation).  Same accounting as the headline `roofline`.
-    Not a bench line of its own (the C2 workload above is): it documents what bounds the kernel once the GPU is full."""
-    import torch
-    from starbeast2_b200 import synth
-    from starbeast2_b200.engine import Engine
-    pb = synth.make_problem("C5", n_loci=n_loci)
-    eng = Engine.from_problem(pb, device=torch.cuda.current_device(), exact_order=args.exact, profile=True)
-    eng.bind_torch()
-    tot = np.zeros(3)
-    for _ in range(3):
-        eng.mark_all_dirty(); eng.eval_posterior_total(tot)
-    eng.kernel_time()
-    stream = torch.cuda.current_stream()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for a, b in ev:
-        flush.fill_(1)
-        a.record(stream)
-        eng.mark_all_dirty(); eng.eval_posterior_total(tot)
-        b.record(stream)
-    torch.cuda.synchronize()
-    step_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
-    k_ms, k_n = eng.kernel_time()
-    k_us = 1e3 * k_ms / max(k_n, 1)
-    dbytes, sbytes = design_bytes(pb), pb.algorithmic_bytes_survey()
-    achieved = dbytes / (k_us * 1e-6) / 1e9
-    eng.set_profile(False)
-    incremental = bench_incremental(eng, pb, synth, n_steps=200)
-    queries = bench_operator_queries(eng, pb, reps=100)
-    if not args.no_cpu:
-        queries["cpu_port"] = cpu_operator_queries(pb, reps=5)
-        incremental["cpu_port"] = cpu_incremental(pb, synth, n_steps=60)
-    dev_bytes = eng.device_bytes()
-    eng.close()
-    return {"operator_queries": queries, "incremental": incremental, "device_bytes": dev_bytes, "workload": f"C5 shard, {n_loci} loci of the 2,000 (GTR+G4, UCLN species clock, 120 tips)", "kernel": "k_treewalk",
-            "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "peak_source": peak_src,
-            "us_per_launch": k_us, "launches_timed": k_n, "algorithmic_bytes_per_launch": dbytes, "bytes_per_unit": dbytes / pb.units,
-            "survey_formula_frac": sbytes / (k_us * 1e-6) / 1e9 / hbm_gbs, "kernel_partials_per_sec": pb.units / (k_us * 1e-6),
-            "step_ms": step_ms, "step_partials_per_sec": pb.units / (step_ms * 1e-3)}
+def run_leg(ctx: Ctx, name: str, workload: str, loci_total: int, steps: int, warmup: int, scaling: str, pb=None, check=True,
+            keep_open=False):
+    """One north-star leg: loci_total loci split over the ranks, device-timed per-step stats (max over ranks), e2e, the
+    pruning kernel's roofline on this rank's shard and the oracle check of the global log posterior."""
+    lo, hi = rank_range(loci_total, ctx.rank, ctx.world)
+    leg = Leg(ctx, workload, loci_total, lo, hi, pb=pb)
+    ms, ms_e2e, k_us, k_n, launches, wait = leg.measure(steps, warmup, e2e_steps=min(steps, 50))
+    units_total = float(ctx.sum_over_ranks([float(leg.units_local)])[0])
+    out = None
+    if ctx.rank == 0:
+        med = float(np.median(ms))
+        out = {"workload": workload, "loci_total": loci_total, "loci_per_gpu": hi - lo, "n_gpus": ctx.world, "scaling": scaling,
+               "units_per_step": units_total, "steps": int(len(ms)), "ms_per_step": stats(ms),
+               "partials_per_sec": units_total / (float(ms.mean()) * 1e-3), "posterior_evals_per_sec": 1e3 / float(ms.mean()),
+               "partials_per_sec_median_step": units_total / (med * 1e-3),
+               "e2e_ms_per_step": stats(ms_e2e), "e2e_partials_per_sec": units_total / (float(ms_e2e.mean()) * 1e-3),
+               "gpu_launches_per_step": launches / len(ms), "log_posterior": leg.total_logp,
+               "device_bytes_per_gpu": leg.eng.device_bytes(), "kernel": leg.roofline(k_us, k_n),
+               "timing": "CUDA events per step on the engine's stream, L2 flushed (512 MiB write) before every step, per-step max over ranks"}
+        if wait:
+            out["exchange_wait"] = wait
+        if check and not ctx.args.no_cpu:
+            r, dt, _ = oracle_total(workload, loci_total, leg.pb, ctx)
+            out["oracle_log_posterior"] = r.total
+            out["log_posterior_rel_diff"] = abs(r.total - leg.total_logp) / abs(r.total)
+            out["oracle_seconds"] = dt
+            out["parity_ok"] = bool(out["log_posterior_rel_diff"] <= PARITY_TOL)
+    if keep_open:
+        return out, leg
+    leg.close()
+    return out, None
 
 
 def run_reference(args):
-    """`--impl reference`: the CPU restatement of the reference path (oracle/, kind "port"), all host threads."""
+    """`--impl reference`: the CPU restatement of the reference path (oracle/, kind "port"), all host threads, on the same
+    global problem the GPU arm evaluates at this N (loci_per_gpu x N loci)."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     import oracle
     oracle.build()
-    pb = build_problem(0, 1, args.loci, args.workload)
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it is allowed to run on
-    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    total = args.loci * world
+    threads = host_threads()   # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it is allowed to run on
+    pb = build_problem(args.workload, total, 0, total, threads)
     fp = oracle.FlatProblem(pb)
     for _ in range(max(args.warmup, 1)):
         oracle.posterior(pb, n_threads=threads, flat=fp)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.posterior(pb, n_threads=threads, flat=fp)
+        r = oracle.posterior(pb, n_threads=threads, flat=fp)
     dt = time.perf_counter() - t0
     units = pb.units
     v = units * args.steps / dt
@@ -324,12 +575,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "loci": args.loci, "units_per_step": units,
-                   "note": "C restatement of the reference's Java path (no JVM in this image); one step = one full "
-                           "posterior evaluation of the N=1 workload on the host cores (rank 0 only)"},
-        "posterior_evals_per_sec": args.steps / dt,
+        "config": {"workload": args.workload, "loci_per_gpu": args.loci, "loci_total": total, "units_per_step": float(units),
+                   "regime": "A (every node of every locus dirty)",
+                   "note": "C restatement of the reference's Java path (no JVM in this image); one step = one full posterior "
+                           "evaluation of the same global problem as the GPU arm at this N, on the host cores (rank 0 only)"},
+        "posterior_evals_per_sec": args.steps / dt, "log_posterior": r.total,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} full evaluations of {args.workload} ({args.loci} loci), OpenMP over loci"},
+                         "sample": f"{args.steps} full evaluations of {args.workload} ({total} loci), OpenMP over loci"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -345,8 +597,9 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--loci", type=int, default=0, help="loci per GPU (default: the workload's own count)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the C5-shard streaming measurement of the pruning kernel")
+    ap.add_argument("--no-cpu", action="store_true", help="skip every CPU-oracle leg (baseline and parity checks)")
+    ap.add_argument("--no-extra", action="store_true", help="headline leg only: skip the north-star legs, regime B and the operator queries")
+    ap.add_argument("--legs", default="C5,C4,C3", help="north-star legs to run (comma separated subset of C5,C4,C3)")
     ap.add_argument("--exact", action="store_true")
     args = ap.parse_args()
     from starbeast2_b200 import synth
@@ -357,206 +610,175 @@ def main():
 
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
-    import torch
     from starbeast2_b200 import build as sbuild
-    from starbeast2_b200.engine import Engine
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: libsb2gpu has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Ctx(args)
     sbuild.build()
+    rank, world = ctx.rank, ctx.world
 
-    pb = build_problem(rank, world, args.loci, args.workload)
-    eng = Engine.from_problem(pb, device=local, exact_order=args.exact, profile=True)
-    red = eng.bind_torch()
-    comm = "none"
-    if world > 1:
-        comm = "nccl"
-        if os.environ.get("SB2_COMM", "peer") == "peer" and eng.connect_peers():
-            comm = "peer-memory all-reduce inside the reduction kernel (NVLink stores + flags)"
-    peers = world > 1 and comm != "nccl"
-    units_local = pb.units
-    stream = torch.cuda.current_stream()
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-    tot = np.zeros(3)
-
-    def step_device():
-        eng.mark_all_dirty()
-        if world == 1 or peers:
-            eng.eval_posterior_total(tot)
-            return
-        eng.eval_begin()
-        dist.all_reduce(red)
-        eng.eval_end_total(tot)
-
-    # flat host copies of everything a step of the reference-facing API re-sends
-    trees = [l.tree for l in pb.loci]
-    hp = np.ascontiguousarray(np.concatenate([t.parent for t in trees]), np.int32)
-    hl = np.ascontiguousarray(np.concatenate([t.left for t in trees]), np.int32)
-    hr = np.ascontiguousarray(np.concatenate([t.right for t in trees]), np.int32)
-    hh = np.ascontiguousarray(np.concatenate([t.height for t in trees]), np.float64)
-    n_nodes = int(hp.shape[0])
-    S = pb.species.n_nodes
-    h2d = 20 * n_nodes + 20 * S + 8 * S * 3 + 16 + pb.n_loci          # trees + species block + flags
-    d2h = 8 * (3 + 2 * pb.n_loci + S)
-    coal_buf, lik_buf, br_buf = np.zeros(pb.n_loci), np.zeros(pb.n_loci), np.zeros(S)
-
-    # the reference-facing call sequence of one step, through the C ABI with HOST buffers (addresses resolved once, as a
-    # JNI / FFM caller would): species tree, species rates, population sizes, all gene trees in; per-locus + total logP out
-    from starbeast2_b200 import _lib as sblib
-    raw, h = sblib.load_raw(), eng._h
-    sp = pb.species
-    keep = [np.ascontiguousarray(x) for x in (sp.parent, sp.left, sp.right, sp.height, pb.species_rates,
-                                              pb.pop_a if pb.pop_a is not None else np.zeros(1), pb.pop_b if pb.pop_b is not None else np.zeros(1))]
-    ptr = [a.ctypes.data for a in keep]
-    tp, tl, tr, th = hp.ctypes.data, hl.ctypes.data, hr.ctypes.data, hh.ctypes.data
-    oc, ol, ob, ot = coal_buf.ctypes.data, lik_buf.ctypes.data, br_buf.ctypes.data, tot.ctypes.data
-    n_loci, pop_kind, alpha, beta = pb.n_loci, pb.pop_kind, pb.alpha, pb.beta
-
-    def step_e2e():
-        rc = raw.sb2_set_species_tree(h, ptr[0], ptr[1], ptr[2], ptr[3])
-        rc |= raw.sb2_set_species_rates(h, ptr[4])
-        rc |= raw.sb2_set_pop_model(h, pop_kind, ptr[5], ptr[6], alpha, beta)
-        rc |= raw.sb2_set_gene_trees(h, 0, n_loci, tp, tl, tr, th)
-        rc |= raw.sb2_mark_all_dirty(h)
-        if world == 1 or peers:
-            rc |= raw.sb2_eval_posterior(h, oc, ol, ob, ot)
-        else:
-            rc |= raw.sb2_eval_begin(h)
-            dist.all_reduce(red)
-            rc |= raw.sb2_eval_end(h, oc, ol, ob, ot)
-        if rc:
-            eng._ck(-1)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, flush_l2=True):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for a, b in ev:
-            if flush_l2:
-                flush.fill_(1)          # evict the (L2-resident) working set; outside the timed events
-            a.record(stream)
-            fn()
-            b.record(stream)
-        torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in ev)   # ms
-
-    sampler = ClockSampler(local)
+    # ---- headline leg: C2, weak scaling ----------------------------------------------------------------------------------
+    total = args.loci * world
+    lo, hi = rank * args.loci, (rank + 1) * args.loci
+    sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        flush.fill_(1)
-        step_device()
-    eng.kernel_time()
-    eng.set_profile(False)        # no events between our launches in the timed region (they defeat dependent launch)
-    barrier()
-    l0 = eng.launch_count()
+    head = Leg(ctx, args.workload, total, lo, hi)
     t_wall0 = time.time()
-    ms = timed(step_device, args.steps)
-    launches = eng.launch_count() - l0
-    total_ref = float(tot[2])
-    barrier()
-    # roofline pass: the same steps with the pruning kernel bracketed by CUDA events on its own stream
-    eng.set_profile(True)
-    timed(step_device, min(args.steps, 100))
-    k_ms, k_n = eng.kernel_time()
-    eng.set_profile(False)
-    barrier()
-    # e2e
-    for _ in range(3):
-        step_e2e()
-    barrier()
-    ms_e2e = timed(step_e2e, args.steps)
-    barrier()
+    ms, ms_e2e, k_us, k_n, launches, wait = head.measure(args.steps, args.warmup)
     # keep the load up long enough for nvidia-smi to see it (100 ms sampling), same step, untimed
     t_probe = time.time()
     while time.time() - t_probe < 1.2:
-        step_device()
+        head.step_device()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    units_total = float(ctx.sum_over_ranks([float(head.units_local)])[0])
+    launches_total = int(ctx.sum_over_ranks([float(launches)])[0])
+    pb, eng = head.pb, head.eng
 
-    t = torch.tensor([ms, ms_e2e, float(units_local), float(launches)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, ms_e2e = float(tmax[0]), float(tmax[1])
-        units_total, launches_total = float(tsum[2]), int(tsum[3])
-    else:
-        units_total, launches_total = float(units_local), launches
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    line = None
+    failed = []
+    if rank == 0:
+        roof = head.roofline(k_us, k_n)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload)
+            except Exception:
+                traffic = None
+        roof.update({"traffic": traffic, "peak_source": ctx.peak_src,
+                     "accounting": "compulsory bytes of this design: 34 B per unit written once (32 B partials + 2 B exponent) + tip states + "
+                                   "pattern logL; SURVEY 8(d)'s 68.5-79.9 B/unit charges child re-reads that do not happen (survey_formula_*; "
+                                   "see BASELINE.md)"})
+        ms_sum = float(ms.sum())
+        line = {
+            "metric": METRIC, "value": units_total * len(ms) / (ms_sum * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_sum / len(ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "loci_per_gpu": args.loci, "loci_total": total,
+                       "units_per_step": units_total, "mean_patterns_per_locus": float(np.mean([l.n_pat for l in pb.loci])),
+                       "regime": "A (every node of every locus dirty)", "device_bytes": eng.device_bytes(), "exact_order": bool(args.exact),
+                       "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write; working set is L2-resident)",
+                       "ms_per_step_stats": stats(ms),
+                       "parallelism": f"loci sharded over {world} GPU(s), 1 all-reduce of {eng.reduce_vector_len()} doubles per step ({head.comm})" if world > 1 else "1 GPU"},
+            "posterior_evals_per_sec": len(ms) / (ms_sum * 1e-3),
+            "log_posterior": head.total_logp,
+            "e2e": {"value": units_total * len(ms_e2e) / (float(ms_e2e.sum()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": head.h2d * world,
+                    "d2h_bytes_per_step": head.d2h * world, "ms_per_step": float(ms_e2e.mean()), "ms_per_step_stats": stats(ms_e2e),
+                    "posterior_evals_per_sec": len(ms_e2e) / (float(ms_e2e.sum()) * 1e-3)},
+            "gpu_launches": launches_total,
+            "roofline": roof,
+            "clocks": clocks,
+        }
+        if wait:
+            line["config"]["exchange_wait"] = wait
+        # parity of the global log posterior at every N (the in-kernel all-reduce needs a driver-run check)
+        if not args.no_cpu:
+            r, dt, pb_glob = oracle_total(args.workload, total, pb, ctx)
+            rel = abs(r.total - head.total_logp) / abs(r.total)
+            line["e2e"]["log_posterior_rel_diff_vs_oracle"] = rel
+            line["config"]["log_posterior_rel_diff_vs_oracle"] = rel
+            line["config"]["oracle_log_posterior"] = r.total
+            if rel > PARITY_TOL:
+                failed.append(f"{args.workload} x{world}: rel diff {rel:.3e}")
+            if world == 1:
+                import oracle
+                n, dt, r1 = cpu_baseline(pb, 1, args.cpu_seconds)
+                line["cpu_baseline"] = {"value": pb.units * n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                        "sample": f"{n} full evaluations of {args.workload} ({args.loci} loci) in {dt:.1f} s, single thread "
+                                                  "(the reference runs threads: 1); C restatement of the Java path, gcc -O2 -ffp-contract=off",
+                                        "posterior_evals_per_sec": n / dt,
+                                        "log_posterior_rel_diff": abs(r1.total - head.total_logp) / abs(r1.total)}
+            else:
+                line["cpu_baseline"] = None
+        line["roofline"]["shapes"] = {args.workload: {k: roof[k] for k in ("frac", "achieved", "us_per_launch", "algorithmic_bytes_per_launch",
+                                                                            "bytes_per_unit", "loci_on_this_gpu", "kernel_partials_per_sec")}}
 
-    hbm_gbs, peak_src = load_peaks()
-    k_us = 1e3 * k_ms / max(k_n, 1)
-    dbytes = design_bytes(pb)
-    sbytes = pb.algorithmic_bytes_survey()
-    achieved = dbytes / (k_us * 1e-6) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.workload)
-        except Exception:
-            traffic = None
-    value = units_total * args.steps / (ms * 1e-3)
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "loci_per_gpu": args.loci, "loci_total": args.loci * world,
-                   "units_per_step": units_total, "mean_patterns_per_locus": float(np.mean([l.n_pat for l in pb.loci])),
-                   "regime": "A (every node of every locus dirty)", "device_bytes": eng.device_bytes(), "exact_order": bool(args.exact),
-                   "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write; working set is L2-resident)",
-                   "parallelism": f"loci sharded over {world} GPU(s), 1 all-reduce of {eng.reduce_vector_len()} doubles per step ({comm})" if world > 1 else "1 GPU"},
-        "posterior_evals_per_sec": args.steps / (ms * 1e-3),
-        "log_posterior": total_ref,
-        "e2e": {"value": units_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps, "posterior_evals_per_sec": args.steps / (ms_e2e * 1e-3)},
-        "gpu_launches": launches_total,
-        "roofline": {"bound": "hbm", "kernel": "k_treewalk", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                     "traffic": traffic, "peak_source": peak_src, "us_per_launch": k_us, "launches_timed": k_n,
-                     "algorithmic_bytes_per_launch": dbytes, "bytes_per_unit": dbytes / pb.units,
-                     "survey_formula_bytes_per_launch": sbytes, "survey_formula_GBps": sbytes / (k_us * 1e-6) / 1e9,
-                     "survey_formula_frac": sbytes / (k_us * 1e-6) / 1e9 / hbm_gbs,
-                     "kernel_partials_per_sec": pb.units / (k_us * 1e-6)},
-        "clocks": clocks,
-    }
-    if world == 1:
+    # ---- regime B + operator queries on the headline shape (N=1) ---------------------------------------------------------------
+    if world == 1 and not args.no_extra:
         line["incremental"] = bench_incremental(eng, pb, synth)
         line["operator_queries"] = bench_operator_queries(eng, pb)
         if not args.no_cpu:
             line["operator_queries"]["cpu_port"] = cpu_operator_queries(pb)
             line["incremental"]["cpu_port"] = cpu_incremental(pb, synth)
-        if not args.no_extra:
-            eng.close()
-            line["roofline_streaming"] = bench_streaming(args, hbm_gbs, peak_src, flush)
-    if not args.no_cpu and world == 1:
-        import oracle
-        oracle.build()
-        n, dt, r = cpu_baseline(pb, 1, args.cpu_seconds)
-        line["cpu_baseline"] = {"value": pb.units * n / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": f"{n} full evaluations of {args.workload} ({args.loci} loci) in {dt:.1f} s, single thread "
-                                          "(the reference runs threads: 1); C restatement of the Java path, gcc -O2 -ffp-contract=off",
-                                "posterior_evals_per_sec": n / dt,
-                                "log_posterior_rel_diff": abs(r.total - total_ref) / abs(r.total)}
-    print(json.dumps(line), flush=True)
+        line["config"]["regime_B"] = {args.workload: {k: line["incremental"][k] for k in ("us_per_step", "steps_per_sec", "mean_node_updates", "kernel_launches_per_step")}}
+        if "cpu_port" in line["incremental"] and line["incremental"]["cpu_port"]:
+            line["config"]["regime_B"][args.workload]["cpu_port_us_per_step"] = line["incremental"]["cpu_port"]["us_per_step"]
+    head.close()
+
+    # ---- north-star legs -----------------------------------------------------------------------------------------------------
+    if not args.no_extra:
+        legs = {}
+        want = [x.strip() for x in args.legs.split(",") if x.strip()]
+        leg_steps = max(args.steps, LEG_MIN_STEPS)
+        if "C5" in want:
+            n5 = synth.CONFIGS["C5"]["n_loci"]
+            out, leg = run_leg(ctx, "C5_strong", "C5", n5, leg_steps, 5, "strong", keep_open=(world == 1))
+            if rank == 0:
+                legs["C5_strong"] = out
+                line["roofline"]["shapes"]["C5" if world == 1 else f"C5/{world}"] = _shape(out["kernel"])
+            if world == 1:
+                # the per-GPU shard of the 8-GPU config (250 loci) on one GPU: the first 250 loci of the same problem
+                from starbeast2_b200.problem import Problem
+                pbs = leg.pb
+                shard = Problem(species=pbs.species, loci=pbs.loci[:n5 // 8], species_rates=pbs.species_rates, pop_kind=pbs.pop_kind,
+                                pop_a=pbs.pop_a, pop_b=pbs.pop_b, alpha=pbs.alpha, beta=pbs.beta)
+                leg.close()
+                out_s, leg_s = run_leg(ctx, "C5_shard", "C5", n5 // 8, leg_steps, 5, "n/a", pb=shard, keep_open=True)
+                legs["C5_shard_250"] = out_s
+                line["roofline"]["shapes"]["C5s"] = _shape(out_s["kernel"])
+                inc = bench_incremental(leg_s.eng, shard, synth, n_steps=200)
+                q = bench_operator_queries(leg_s.eng, shard, reps=100)
+                if not args.no_cpu:
+                    q["cpu_port"] = cpu_operator_queries(shard, reps=5)
+                    inc["cpu_port"] = cpu_incremental(shard, synth, n_steps=60)
+                line["roofline_streaming"] = {"incremental": inc, "operator_queries": q}
+                line["config"]["regime_B"]["C5s"] = {k: inc[k] for k in ("us_per_step", "steps_per_sec", "mean_node_updates", "kernel_launches_per_step")}
+                if inc.get("cpu_port"):
+                    line["config"]["regime_B"]["C5s"]["cpu_port_us_per_step"] = inc["cpu_port"]["us_per_step"]
+                leg_s.close()
+        if "C4" in want:
+            out, _ = run_leg(ctx, "C4_strong", "C4", synth.CONFIGS["C4"]["n_loci"], leg_steps, 5, "strong")
+            if rank == 0:
+                legs["C4_strong"] = out
+        if "C3" in want and world == 1:
+            out, _ = run_leg(ctx, "C3", "C3", synth.CONFIGS["C3"]["n_loci"], leg_steps, 5, "n/a")
+            legs["C3"] = out
+            line["roofline"]["shapes"]["C3"] = _shape(out["kernel"])
+        if world == 1:
+            # BASELINE configs[0]: the tutorial data, regime B (what the tutorial's 67-133 k steps/s on the JVM measure)
+            c1 = canis_problem()
+            from starbeast2_b200.engine import Engine
+            e1 = Engine.from_problem(c1, device=ctx.local)
+            inc = bench_incremental(e1, c1, synth, n_steps=400)
+            if not args.no_cpu:
+                inc["cpu_port"] = cpu_incremental(c1, synth, n_steps=300)
+                import oracle
+                inc["log_posterior_rel_diff"] = abs(oracle.posterior(c1).total - e1.eval_posterior().total) / abs(oracle.posterior(c1).total)
+            e1.close()
+            line["config"]["regime_B"]["C1"] = {k: inc[k] for k in ("us_per_step", "steps_per_sec", "mean_node_updates", "kernel_launches_per_step")}
+            line["config"]["regime_B"]["C1"]["reference_jvm_steps_per_sec"] = "67,000-133,000 (tutorial/StarBEAST2-tutorial.tex:378,419-421; other hardware, not measured here)"
+            if inc.get("cpu_port"):
+                line["config"]["regime_B"]["C1"]["cpu_port_us_per_step"] = inc["cpu_port"]["us_per_step"]
+            line["incremental_C1"] = inc
+        if rank == 0:
+            line["config"]["legs"] = legs
+            for k, v in legs.items():
+                if v and v.get("parity_ok") is False:
+                    failed.append(f"{k} x{world}: rel diff {v['log_posterior_rel_diff']:.3e}")
+
+    if rank == 0:
+        line["config"]["parity"] = {"tolerance": PARITY_TOL, "failed": failed,
+                                    "checked": "global log posterior of every leg vs the CPU oracle (rank 0)" if not args.no_cpu else "skipped (--no-cpu)"}
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
+    if failed:
+        raise SystemExit("parity check failed: " + "; ".join(failed))
+
+
+def _shape(k):
+    return {x: k[x] for x in ("frac", "achieved", "us_per_launch", "algorithmic_bytes_per_launch", "bytes_per_unit", "loci_on_this_gpu",
+                              "kernel_partials_per_sec")}
 
 
 if __name__ == "__main__":

@@ -206,6 +206,9 @@ SB2_API int sb2_kernel_time(sb2_engine *e, double *ms, int64_t *launches);
 SB2_API int sb2_set_profile(sb2_engine *e, int32_t on);
 /* device bytes held by the engine */
 SB2_API int64_t sb2_device_bytes(const sb2_engine *e);
+/* after sb2_comm_connect: microseconds the last evaluation's reduction kernel spent waiting for the peers' words
+ * (rank skew + one NVLink trip), measured on the device with %globaltimer; 0 without peers */
+SB2_API double sb2_exchange_wait_us(const sb2_engine *e);
 
 #ifdef __cplusplus
 }

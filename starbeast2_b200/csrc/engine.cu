@@ -699,9 +699,10 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     e->dRed = e->dRedOwn;
     if ((rc = dev_alloc(e, &e->dOut, e->nOut))) return rc;
     {   // result vector: host memory the kernels write directly (zero-copy), so a download is just a stream sync
-        cudaError_t st = cudaHostAlloc((void **)&e->hOut, sizeof(double) * e->nOut, cudaHostAllocMapped);
+        // (one extra slot behind the vector: the peer-exchange wait of the last evaluation, sb2_exchange_wait_us)
+        cudaError_t st = cudaHostAlloc((void **)&e->hOut, sizeof(double) * (e->nOut + 1), cudaHostAllocMapped);
         if (st != cudaSuccess) return e->fail(SB2_ERR_NOMEM, "cudaHostAlloc(mapped): %s", cudaGetErrorString(st));
-        memset(e->hOut, 0, sizeof(double) * e->nOut);
+        memset(e->hOut, 0, sizeof(double) * (e->nOut + 1));
         CUDA_TRY(e, cudaHostGetDevicePointer((void **)&e->hOutDev, e->hOut, 0));
     }
     if ((rc = dev_alloc(e, &e->dLaneOps, (size_t)L * (WALK_MAX_WORKERS + 1)))) return rc;
@@ -1307,5 +1308,7 @@ int sb2_set_profile(sb2_engine *e, int32_t on)
 }
 
 int64_t sb2_device_bytes(const sb2_engine *e) { return e ? e->devBytes : 0; }
+
+double sb2_exchange_wait_us(const sb2_engine *e) { return (e && e->finalized && e->commConnected) ? e->hOut[e->nOut] : 0.0; }
 
 }  // extern "C"

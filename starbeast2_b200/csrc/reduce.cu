@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_xgpu(ReduceArgs A, CommA
     __shared__ int s_poison;
     if (tid == 0) s_poison = 0;
     __syncthreads();
+    unsigned long long waitT0 = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(waitT0));
     for (int i = tid; i < n; i += nt) {
         double sum = 0.0;
         const long long t0 = clock64();
@@ -82,6 +84,11 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_xgpu(ReduceArgs A, CommA
     }
     __threadfence_block();
     __syncthreads();
+    if (tid == 0 && A.hostOut) {   // time spent waiting for the peers' words (rank skew + one NVLink trip), for sb2_exchange_wait_us
+        unsigned long long waitT1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(waitT1));
+        A.hostOut[3 + 2 * A.nLoci + A.S] = (double)(waitT1 - waitT0) * 1e-3;
+    }
     if (s_poison) { for (int i = tid; i < n; i += nt) A.red[i] = NAN; __threadfence_block(); __syncthreads(); }
     finish_body(A);
     publish_body(A);

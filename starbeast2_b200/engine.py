@@ -371,3 +371,6 @@ class Engine:
 
     def device_bytes(self) -> int:
         return int(self._L.sb2_device_bytes(self._h))
+
+    def exchange_wait_us(self) -> float:
+        return float(self._L.sb2_exchange_wait_us(self._h))

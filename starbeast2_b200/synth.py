@@ -288,6 +288,43 @@ def make_problem(name: str = "C2", n_loci: Optional[int] = None, n_sites: Option
                    alpha=alpha, beta=beta)
 
 
+def make_problem_parallel(name: str, n_loci: Optional[int] = None, locus_range: Optional[Tuple[int, int]] = None,
+                          procs: int = 1, **kw) -> Problem:
+    """make_problem with the loci generated by `procs` worker processes (every locus has its own (seed, index) stream, so
+    the result is identical to the serial one).  The workers are fresh interpreters (`python -m starbeast2_b200.synth`)
+    that send their chunk back pickled: safe after CUDA initialisation and under torchrun, and independent of __main__."""
+    import os
+    import pickle
+    import subprocess
+    import sys
+    total = n_loci if n_loci is not None else CONFIGS[name]["n_loci"]
+    lo, hi = locus_range if locus_range is not None else (0, total)
+    n = hi - lo
+    procs = max(1, min(procs, n // 16))
+    if procs <= 1:
+        return make_problem(name, n_loci=total, locus_range=(lo, hi), **kw)
+    cuts = [lo + (n * i) // procs for i in range(procs + 1)]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    workers = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        job = pickle.dumps((name, total, a, b, kw))
+        w = subprocess.Popen([sys.executable, "-m", "starbeast2_b200.synth"], stdin=subprocess.PIPE, stdout=subprocess.PIPE, cwd=root, env=env)
+        w.stdin.write(job)
+        w.stdin.close()
+        workers.append(w)
+    parts = []
+    for w in workers:
+        data = w.stdout.read()
+        if w.wait() != 0:
+            raise RuntimeError("synthetic-problem worker failed")
+        parts.append(pickle.loads(data))
+    pb = parts[0]
+    for q in parts[1:]:
+        pb.loci.extend(q.loci)
+    return pb
+
+
 def perturb_gene_tree(rng, tree: TreeArrays, n_tips: int) -> Tuple[TreeArrays, int]:
     """A BEAST 'Uniform'-operator style move: slide one internal non-root node between its oldest
     child and its parent.  Returns (new tree, moved node)."""
@@ -299,3 +336,10 @@ def perturb_gene_tree(rng, tree: TreeArrays, n_tips: int) -> Tuple[TreeArrays, i
     hi = t.height[t.parent[i]]
     t.height[i] = lo + (hi - lo) * rng.uniform(0.05, 0.95)
     return t, i
+
+
+if __name__ == "__main__":   # worker of make_problem_parallel: job on stdin, pickled Problem chunk on stdout
+    import pickle
+    import sys
+    _name, _total, _a, _b, _kw = pickle.loads(sys.stdin.buffer.read())
+    sys.stdout.buffer.write(pickle.dumps(make_problem(_name, n_loci=_total, locus_range=(_a, _b), **_kw)))
