@@ -1,10 +1,12 @@
 /*
  * sb2gpu_jni.c -- JNI shim between starbeast2.gpu.Sb2Gpu and libsb2gpu's C ABI (include/sb2gpu.h).
- * UNCOMPILED in the build image (no jni.h); see java/README.md.  Arrays are pinned with
+ * No JDK in the build image: compiled and executed there against tests/jni_stub (stand-in jni.h + mock JNIEnv,
+ * tests/test_jni_shim.py); see java/README.md.  Arrays are pinned with
  * GetPrimitiveArrayCritical for the duration of one C call: the engine copies inputs before returning
  * and writes outputs into the caller's buffers, so no reference outlives the call.
  */
 #include <jni.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "sb2gpu.h"

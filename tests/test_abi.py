@@ -81,6 +81,27 @@ def test_java_jni_sources_stay_consistent_with_the_header():
     assert called <= declared, sorted(called - declared)
     not_for_a_jvm = {"sb2_bind_reduce_vector", "sb2_comm_connect", "sb2_comm_handle", "sb2_set_stream",          # torch / one process per GPU
                      "sb2_device_bytes", "sb2_get_matrices", "sb2_get_partials", "sb2_get_pattern_logl", "sb2_kernel_time",
-                     "sb2_last_node_updates", "sb2_set_profile",                                                      # introspection for tests / bench
+                     "sb2_last_node_updates", "sb2_set_profile", "sb2_exchange_wait_us",                                                    # introspection for tests / bench
                      "sb2_compress_alignment", "sb2_compress_last_error"}                                             # BEAST's own Alignment compresses on the host
     assert declared - called == not_for_a_jvm, sorted((declared - called) ^ not_for_a_jvm)
+
+
+def test_java_ffm_twin_binds_the_same_surface_with_matching_arity():
+    """Sb2GpuFfm.java (Panama FFM, JDK >= 22; uncompiled here) must expose exactly the static methods of the JNI class
+    Sb2Gpu.java, bind only symbols include/sb2gpu.h declares, and give every downcall as many arguments as the C prototype."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    jni = open(os.path.join(root, "java", "src", "starbeast2", "gpu", "Sb2Gpu.java")).read()
+    ffm = open(os.path.join(root, "java", "src", "starbeast2", "gpu", "Sb2GpuFfm.java")).read()
+    hdr = open(os.path.join(root, "include", "sb2gpu.h")).read()
+    natives = set(re.findall(r"native\s+[\w\[\]]+\s+(\w+)\s*\(", jni))
+    publics = set(re.findall(r"public static [\w\[\]]+\s+(\w+)\s*\(", ffm))
+    assert natives == publics, sorted(natives ^ publics)
+    protos = {m.group(1): m.group(2) for m in re.finditer(r"SB2_API\s+[\w\s\*]+?\b(sb2_\w+)\s*\(([^;]*?)\)\s*;", hdr, re.S)}
+    binds = re.findall(r'bind\("(sb2_\w+)",\s*(\w+)((?:,\s*\w+)*)\)', ffm)
+    assert len(binds) >= 30
+    for name, _ret, args in binds:
+        assert name in protos, name
+        n_c = 0 if protos[name].strip() in ("", "void") else protos[name].count(",") + 1
+        n_j = len([a for a in args.split(",") if a.strip()])
+        assert n_c == n_j, (name, n_c, n_j)
