@@ -2,8 +2,9 @@
 
     python -m starbeast2_b200.build [--force]
 
-prepare.cu / reduce.cu carry the reference's scalar arithmetic and are compiled with -fmad=false so that sums
-and products associate exactly as in the Java; treewalk.cu selects fused or unfused arithmetic per template.
+prepare.cu / reduce.cu / step.cu carry the reference's scalar arithmetic and are compiled with -fmad=false so that sums
+and products associate exactly as in the Java; the pruning arithmetic (walk_common.cuh) uses explicit fma / rn intrinsics, so it
+is the same in every translation unit.
 """
 from __future__ import annotations
 
@@ -22,11 +23,12 @@ SOURCES = {
     "prepare.cu": ["-fmad=false"],
     "reduce.cu": ["-fmad=false"],
     "treewalk.cu": [],
+    "step.cu": ["-fmad=false"],
     "query.cu": ["-fmad=false"],
     "compress.cu": [],
     "engine.cu": [],
 }
-DEPS = ["sb2_device.cuh", "reduce_body.cuh", os.path.join("..", "..", "include", "sb2gpu.h")]
+DEPS = ["sb2_device.cuh", "reduce_body.cuh", "prepare_body.cuh", "walk_common.cuh", os.path.join("..", "..", "include", "sb2gpu.h")]
 
 
 def _newer(target: str, deps) -> bool:

@@ -43,6 +43,13 @@ struct sb2_engine {
     int64_t totalNodes = 0, totalTips = 0, totalPat = 0, totalCat = 0, totalInt = 0, totalTiles = 0;
     int maxNodes = 0, nCat = 0, chunksPerTile = 1, patPerThread = 1, stackDepth = 1, workers = 1;
     int32_t *dLaneOps = nullptr;
+    // fused one-launch step (step.cu)
+    bool fusedOk = false;            // shapes fit: cluster <= 16 CTAs per locus, shared memory, category count
+    int fusedMode = -1;              // SB2_FUSED: 0 never, 1 whenever eligible, -1 auto (single-locus steps; all-loci steps of small problems)
+    int64_t fusedMaxLanes = 150000;  // auto: all-loci evaluations go through k_step up to this many (pattern, category) lanes
+    int64_t totalLanes = 0;
+    int fusedCluster = 1;            // CTAs per cluster when every locus runs (widest locus)
+    int lastFusedSingle = -1;        // >= 0: the last evaluation ran this one locus through k_step (only its nOps entry is fresh)
     int64_t devBytes = 0;
     int64_t launches = 0;
     std::vector<void *> devAllocs;
@@ -52,7 +59,7 @@ struct sb2_engine {
     uint8_t *dStates = nullptr, *dConstMask = nullptr;
     int32_t *dWeights = nullptr, *dTipSpecies = nullptr, *dTileLocus = nullptr;
     // big dynamic device data
-    double *dPartials = nullptr, *dMats = nullptr, *dOpMats = nullptr, *dPatLogL = nullptr, *dTileSum = nullptr;
+    double *dPartials = nullptr, *dMats = nullptr, *dOpMats = nullptr, *dPatLogL = nullptr, *dChunkSum = nullptr;
     int16_t *dCumExp = nullptr;
     Op *dOps = nullptr;
     int32_t *dNOps = nullptr;
@@ -73,7 +80,7 @@ struct sb2_engine {
     int curIdx = 0;
     // outputs
     double *dRed = nullptr, *dRedOwn = nullptr, *dOut = nullptr, *hOut = nullptr, *hOutDev = nullptr;
-    uint32_t *dDone = nullptr, *dLocusDone = nullptr;
+    uint32_t *dDone = nullptr;
     // peer-memory all-reduce
     void *commBuf = nullptr;
     size_t commSlotsBytes = 0;
@@ -227,14 +234,14 @@ ReduceArgs reduce_args(sb2_engine *e, bool coalOnly = false)
 {
     ReduceArgs r;
     r.useTiles = (!coalOnly && e->tilesValid) ? 1 : 0;
-    r.loci = e->dLoci; r.nOps = e->dNOps; r.tileSum = e->dTileSum; r.patLogL = e->dPatLogL; r.weights = e->dWeights;
+    r.loci = e->dLoci; r.nOps = e->dNOps; r.chunkSum = e->dChunkSum; r.patLogL = e->dPatLogL; r.weights = e->dWeights;
     r.cur = cur(e); r.red = e->dRed; r.out = e->dOut;
     r.nLoci = e->L; r.S = e->S; r.popKind = e->popKind; r.exact = e->cfg.exact_order;
     r.hostOut = e->hOutDev;
     return r;
 }
 
-int do_walk(sb2_engine *e, int fuse = 0, bool *fused = nullptr);
+int do_walk(sb2_engine *e);
 int flush_pending_walk(sb2_engine *e);
 
 // Structural check of a host-supplied binary tree in BEAST node numbering (leaves first): exactly one root, every
@@ -274,9 +281,11 @@ const char *check_tree(int n, int nLeaves, const int32_t *parent, const int32_t 
     return nullptr;
 }
 
-// upload staged inputs and run k_prepare
-int do_prepare(sb2_engine *e)
+// upload staged inputs and run k_prepare -- or, when the caller wants a whole evaluation (allowFused) and the shapes are
+// latency-bound, the fused one-launch step k_step (*didFused: prepare, walk, reductions and publish are all in flight)
+int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
 {
+    if (didFused) *didFused = false;
     if (!e->needPrepare) return SB2_OK;
     // A walk scheduled by an earlier k_prepare (strict two-phase protocol: coalescent evaluated, likelihood never asked for)
     // must run before the next k_prepare re-schedules: that one would treat the already-flipped nodes as clean.
@@ -354,7 +363,59 @@ int do_prepare(sb2_engine *e)
     a.nSync = nSync;
     for (int j = 0; j < 8; j++) a.syncLoci[j] = syncLoci[j];
     a.pfTipStates = e->dStates; a.pfWeights = e->dWeights; a.pfTileLocus = e->dTileLocus; a.pfConstMask = e->dConstMask; a.pfCatProps = e->dCat + e->totalCat;
-    CUDA_TRY(e, launch_prepare(a, e->maxNodes, st));
+    // ---- one launch or three? ------------------------------------------------------------------------------------------
+    // k_step serves single-locus steps (the MCMC's common move) and, for small problems, steps in which every locus runs;
+    // streaming-size evaluations keep the three-kernel path, whose tile CTAs do not repeat the tree-shaped work.
+    bool fused = false;
+    int runCluster = e->fusedCluster;
+    if (allowFused && e->fusedOk && e->fusedMode != 0 && !e->cfg.exact_order) {
+        if (singleLocus >= 0) {
+            fused = true;
+            const LocusDesc &d = e->loci[singleLocus].d;
+            const int tilePat = (STEP_WARPS / e->nCat) * 32;
+            runCluster = (d.nPat + tilePat - 1) / tilePat;
+        } else {
+            fused = e->fusedMode == 1 || e->totalLanes <= e->fusedMaxLanes;
+        }
+    }
+    e->lastFusedSingle = -1;
+    if (fused) {
+        StepArgs sa;
+        sa.prep = a;
+        sa.prep.workers = 1;
+        sa.red = reduce_args(e, /*coalOnly=*/true);   // useTiles = 0: the leaders write the per-locus values into the state block
+        sa.comm = e->comm;
+        sa.useComm = e->commConnected ? 1 : 0;
+        if (e->commConnected) { e->comm.seq++; sa.comm.seq = e->comm.seq; }
+        sa.tipStates = e->dStates; sa.weights = e->dWeights; sa.constMask = e->dConstMask; sa.catProps = e->dCat + e->totalCat;
+        sa.partials = e->dPartials; sa.cumExp = e->dCumExp; sa.patLogL = e->dPatLogL; sa.doneCounter = e->dDone;
+        sa.maxNodes = e->maxNodes; sa.nCat = e->nCat; sa.stackDepth = e->stackDepth; sa.maxTips = (e->maxNodes + 1) / 2;
+        sa.nRun = 0; sa.runFlags = 0;
+        for (int j = 0; j < 9; j++) sa.runLoci[j] = 0;
+        int nClusters = L;
+        if (singleLocus >= 0) {
+            sa.runLoci[0] = singleLocus; sa.runFlags = e->hFlags[singleLocus]; sa.nRun = 1;
+            for (int j = 0; j < nSync; j++) if (syncLoci[j] != singleLocus) sa.runLoci[sa.nRun++] = syncLoci[j];
+            nClusters = sa.nRun;
+            e->lastFusedSingle = singleLocus;
+        }
+        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+        if (e->cfg.profile) {
+            if (e->evUsed == e->evPool.size()) {
+                cudaEvent_t x, y;
+                CUDA_TRY(e, cudaEventCreate(&x));
+                CUDA_TRY(e, cudaEventCreate(&y));
+                e->evPool.push_back({x, y});
+            }
+            ev = e->evPool[e->evUsed++];
+            CUDA_TRY(e, cudaEventRecord(ev.first, st));
+        }
+        CUDA_TRY(e, launch_step(sa, nClusters, runCluster, st));
+        if (e->cfg.profile) CUDA_TRY(e, cudaEventRecord(ev.second, st));
+    } else {
+        CUDA_TRY(e, launch_prepare(a, e->maxNodes, st));
+    }
+    if (didFused) *didFused = fused;
     e->launches++;
     std::fill(e->treeDirty.begin(), e->treeDirty.end(), 0);
     std::fill(e->modelDirty.begin(), e->modelDirty.end(), 0);
@@ -362,7 +423,7 @@ int do_prepare(sb2_engine *e)
     e->speciesDirty = e->catDirty = e->paramsDirty = e->explicitDirty = e->forceAll = false;
     e->needPrepare = false;
     e->everPrepared = true;
-    e->walkPending = true;
+    e->walkPending = !fused;
     e->tilesValid = false;
     (void)any;
     return SB2_OK;
@@ -384,27 +445,19 @@ int launch_final(sb2_engine *e, const ReduceArgs &r)
     return SB2_OK;
 }
 
-int do_walk(sb2_engine *e, int fuse, bool *fused)
+int do_walk(sb2_engine *e)
 {
-    if (fused) *fused = false;
     if (!e->walkPending) return SB2_OK;
     WalkArgs a;
     a.loci = e->dLoci; a.params = e->dParams; a.tileLocus = e->dTileLocus; a.ops = e->dOps; a.nOps = e->dNOps;
     a.tipStates = e->dStates; a.weights = e->dWeights; a.constMask = e->dConstMask; a.catProps = e->dCat + e->totalCat;
-    a.opMats = e->dOpMats; a.partials = e->dPartials; a.cumExp = e->dCumExp; a.patLogL = e->dPatLogL; a.tileSum = e->dTileSum;
+    a.opMats = e->dOpMats; a.partials = e->dPartials; a.cumExp = e->dCumExp; a.patLogL = e->dPatLogL; a.chunkSum = e->dChunkSum;
     a.nCat = e->nCat; a.chunksPerTile = e->chunksPerTile; a.patPerThread = e->patPerThread; a.stackDepth = e->stackDepth;
     a.maxTips = (e->maxNodes + 1) / 2;
     a.workers = e->workers; a.laneOps = e->dLaneOps;
     static const int debugMaxOps = getenv("SB2_DEBUG_MAX_OPS") ? atoi(getenv("SB2_DEBUG_MAX_OPS")) : -1;
     a.debugMaxOps = debugMaxOps;
-    // Folding the reductions into the walk's last CTA measured no faster end to end on B200 (69.5 vs 70.5 us at C2) and
-    // lengthens the roofline kernel, so it is opt-in (SB2_FUSE=1); never in exact mode (sequential pattern sums).
-    static const bool wantFuse = getenv("SB2_FUSE") != nullptr;
-    if (e->cfg.exact_order || !wantFuse || e->commConnected) fuse = 0;
-    a.fuseReduce = fuse; a.doneCounter = e->dDone; a.locusDone = e->dLocusDone;
     e->walkPending = false; e->tilesValid = true;
-    a.red = reduce_args(e);
-    a.red.useTiles = 0;                 // fused path: the last tile-CTA of each locus has already summed its tiles
     a.tipsInSmem = treewalk_tips_in_smem(a.maxTips, 32 * e->chunksPerTile * e->patPerThread) ? 1 : 0;
     if (a.tipsInSmem && getenv("SB2_TIP_STAGE_LEGACY")) a.tipsInSmem = 2;
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
@@ -423,7 +476,6 @@ int do_walk(sb2_engine *e, int fuse, bool *fused)
     e->launches++;
     if (e->cfg.profile) CUDA_TRY(e, cudaEventRecord(ev.second, e->stream));
     CUDA_TRY(e, cudaGetLastError());
-    if (fused) *fused = fuse != 0;
     return SB2_OK;
 }
 
@@ -461,13 +513,15 @@ void copy_out(sb2_engine *e, double *perLocusCoal, double *perLocusLik, double *
 static int eval_full(sb2_engine *e)
 {
     int rc;
-    bool fused;
-    if ((rc = do_prepare(e))) return rc;
+    bool fused = false;
+    if ((rc = do_prepare(e, /*allowFused=*/true, &fused))) return rc;
     // cached result: only without peers -- with a connected communicator EVERY evaluation call is one exchange on every
     // rank, whatever this rank's local state is (a rank whose loci did not change must still contribute)
-    if (e->resultValid && !e->walkPending && !e->commConnected) return SB2_OK;
-    if ((rc = do_walk(e, 2, &fused))) return rc;                                     // single GPU: no all-reduce in between
-    if (!fused && (rc = launch_final(e, reduce_args(e)))) return rc;
+    if (!fused && e->resultValid && !e->walkPending && !e->commConnected) return SB2_OK;
+    if (!fused) {
+        if ((rc = do_walk(e))) return rc;
+        if ((rc = launch_final(e, reduce_args(e)))) return rc;
+    }
     if ((rc = download(e))) return rc;
     e->resultValid = true;
     return SB2_OK;
@@ -582,7 +636,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
         if (e->chunksPerTile < 1 || 32 * e->nCat * e->chunksPerTile > 256) return e->fail(SB2_ERR_ARG, "nCat * chunks per tile must stay <= 8 warps");
     }
     const int tilePat = 32 * e->chunksPerTile * e->patPerThread;
-    int64_t nodeBase = 0, tipBase = 0, patBase = 0, catBase = 0, tileBase = 0, opBase = 0, stateBase = 0, partBase = 0, expBase = 0, matBase = 0, treeOff = 0;
+    int64_t nodeBase = 0, tipBase = 0, patBase = 0, catBase = 0, tileBase = 0, opBase = 0, stateBase = 0, partBase = 0, expBase = 0, matBase = 0, treeOff = 0, chunkBase = 0;
     e->stackDepth = 1;
     for (auto &hl : e->loci) {
         LocusDesc &d = hl.d;
@@ -591,6 +645,8 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
         d.nodeBase = (int32_t)nodeBase; d.tipBase = (int32_t)tipBase; d.patBase = (int32_t)patBase; d.catBase = (int32_t)catBase;
         d.tileBase = (int32_t)tileBase; d.nTiles = (d.nPat + tilePat - 1) / tilePat; d.opBase = (int32_t)opBase;
         d.stackDepth = floor_log2(d.nInt) + 1;
+        d.chunkBase = (int32_t)chunkBase; d.nChunks = (d.nPat + 31) / 32;
+        chunkBase += d.nChunks;
         d.stateBase = stateBase; d.partBase = partBase; d.expBase = expBase; d.matBase = matBase; d.treeOff = treeOff;
         e->stackDepth = std::max(e->stackDepth, d.stackDepth);
         e->maxNodes = std::max(e->maxNodes, d.nNodes);
@@ -649,7 +705,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if ((rc = dev_alloc(e, &e->dCumExp, (size_t)expBase))) return rc;
     if ((rc = dev_alloc(e, &e->dMats, (size_t)matBase))) return rc;
     if ((rc = dev_alloc(e, &e->dPatLogL, (size_t)patBase))) return rc;
-    if ((rc = dev_alloc(e, &e->dTileSum, (size_t)tileBase))) return rc;
+    if ((rc = dev_alloc(e, &e->dChunkSum, (size_t)chunkBase))) return rc;
     if ((rc = dev_alloc(e, &e->dOps, (size_t)opBase))) return rc;
     if ((rc = dev_alloc(e, &e->dOpMats, (size_t)opBase * e->nCat * 32))) return rc;
     if ((rc = dev_alloc(e, &e->dNOps, L))) return rc;
@@ -716,8 +772,6 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
         e->commBuf = cb;
         CUDA_TRY(e, cudaMemset(cb, 0, e->commSlotsBytes + sizeof(unsigned long long) * 2 * COMM_MAX_RANKS));
     }
-    if ((rc = dev_alloc(e, &e->dLocusDone, L))) return rc;
-    CUDA_TRY(e, cudaMemset(e->dLocusDone, 0, sizeof(uint32_t) * L));
     CUDA_TRY(e, cudaMemset(e->dOut, 0, sizeof(double) * e->nOut));
 
     e->treeDirty.assign(L, 0); e->modelDirty.assign(L, 0); e->clockDirty.assign(L, 0); e->touchedFlag.assign(L, 0);
@@ -725,6 +779,17 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     memcpy(e->hParamsStored, e->hParams, sizeof(LocusParams) * L);
     memcpy(e->hCatStored, e->hCat, 16 * (size_t)catBase);
     memcpy(e->hSpeciesStored, e->hSpecies, e->speciesBytes);
+    {   // the fused one-launch step: eligible when every locus fits a cluster and the CTA's shared memory holds a whole schedule
+        const int tilePat = e->nCat <= STEP_WARPS ? (STEP_WARPS / e->nCat) * 32 : 0;
+        int maxPat = 0;
+        e->totalLanes = 0;
+        for (auto &hl : e->loci) { maxPat = std::max(maxPat, hl.d.nPat); e->totalLanes += (int64_t)hl.d.nPat * hl.d.nCat; }
+        e->fusedCluster = tilePat ? (maxPat + tilePat - 1) / tilePat : 0;
+        e->fusedOk = tilePat > 0 && e->fusedCluster <= STEP_MAX_CLUSTER && e->workers == 1 &&
+                     step_smem_bytes(e->maxNodes, e->S, e->nCat, e->stackDepth, (e->maxNodes + 1) / 2) <= 227 * 1024;
+        if (const char *v = getenv("SB2_FUSED")) e->fusedMode = atoi(v) ? 1 : 0;
+        if (const char *v = getenv("SB2_FUSED_MAX_LANES")) e->fusedMaxLanes = atoll(v);
+    }
     e->finalized = true;
     e->forceAll = true;
     CUDA_TRY(e, cudaDeviceSynchronize());
@@ -870,10 +935,9 @@ int sb2_eval_begin(sb2_engine *e)
     if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     int rc;
-    bool fused;
     if ((rc = do_prepare(e))) return rc;
-    if ((rc = do_walk(e, 1, &fused))) return rc;
-    if (!fused) CUDA_TRY(e, launch_reduce_local(reduce_args(e), e->stream, &e->launches));
+    if ((rc = do_walk(e))) return rc;
+    CUDA_TRY(e, launch_reduce_local(reduce_args(e), e->stream, &e->launches));
     e->reduced = true;
     return SB2_OK;
 }
@@ -1277,6 +1341,7 @@ int64_t sb2_last_node_updates(sb2_engine *e)
     std::vector<int32_t> n(e->L);
     cudaStreamSynchronize(e->stream);
     if (cudaMemcpy(n.data(), e->dNOps, 4 * (size_t)e->L, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (e->lastFusedSingle >= 0) return n[e->lastFusedSingle];   // a single-locus k_step refreshes only that locus's entry
     int64_t t = 0;
     for (int v : n) t += v;
     return t;

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_finish(ReduceArgs A) { finish_b
 __global__ void __launch_bounds__(RED_THREADS) k_reduce_finish(ReduceArgs A)
 {
     int tb = -1, ntl = 0;
-    if ((int)threadIdx.x < A.nLoci) { tb = A.loci[threadIdx.x].tileBase; ntl = A.loci[threadIdx.x].nTiles; }   // static: fetched while the pruning kernel still runs
+    if ((int)threadIdx.x < A.nLoci) { tb = A.loci[threadIdx.x].chunkBase; ntl = A.loci[threadIdx.x].nChunks; }   // static: fetched while the pruning kernel still runs
     cudaGridDependencySynchronize();   // launched with programmatic serialization: wait for the pruning kernel's results
     reduce_local_body(A, tb, ntl);
     __threadfence_block();
@@ -44,52 +44,12 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_finish(ReduceArgs A)
 __global__ void __launch_bounds__(RED_THREADS) k_reduce_xgpu(ReduceArgs A, CommArgs Cm)
 {
     int tb = -1, ntl = 0;
-    if ((int)threadIdx.x < A.nLoci) { tb = A.loci[threadIdx.x].tileBase; ntl = A.loci[threadIdx.x].nTiles; }
+    if ((int)threadIdx.x < A.nLoci) { tb = A.loci[threadIdx.x].chunkBase; ntl = A.loci[threadIdx.x].nChunks; }
     cudaGridDependencySynchronize();
     reduce_local_body(A, tb, ntl);
     __threadfence_block();
     __syncthreads();
-    const int tid = threadIdx.x, nt = blockDim.x, nR = Cm.nRanks, n = Cm.nRed;
-    const int half = (int)(Cm.seq & 1ull);
-    // Flag-in-data exchange: every double travels as two 8-byte words {32 data bits | 32-bit sequence tag}.  An 8-byte store
-    // is atomic, so a receiver that sees the tag of this evaluation in a word also sees its data: no fence, no separate flag,
-    // one one-way NVLink trip between "my sums are ready" and "I can add yours".
-    const unsigned long long tag = (0x80000000ull | (Cm.seq & 0x7fffffffull)) << 32;
-    for (int idx = tid; idx < nR * n; idx += nt) {
-        const int r = idx / n, i = idx - r * n;
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(A.red[i]);
-        volatile unsigned long long *dst = Cm.peerSlots[r] + (((size_t)half * COMM_MAX_RANKS + Cm.rank) * n + i) * 2;
-        dst[0] = tag | (bits & 0xffffffffull);
-        dst[1] = tag | (bits >> 32);
-    }
-    __shared__ int s_poison;
-    if (tid == 0) s_poison = 0;
-    __syncthreads();
-    unsigned long long waitT0 = 0;
-    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(waitT0));
-    for (int i = tid; i < n; i += nt) {
-        double sum = 0.0;
-        const long long t0 = clock64();
-        for (int r = 0; r < nR; r++) {   // rank order: every rank adds the same numbers in the same order
-            const volatile unsigned long long *src = Cm.peerSlots[Cm.rank] + (((size_t)half * COMM_MAX_RANKS + r) * n + i) * 2;
-            unsigned long long w0, w1;
-            for (;;) {
-                w0 = src[0]; w1 = src[1];
-                if ((w0 & 0xffffffff00000000ull) == tag && (w1 & 0xffffffff00000000ull) == tag) break;
-                if (clock64() - t0 > 4000000000ll) { s_poison = 1; w0 = w1 = 0; break; }   // ~2 s at 2 GHz: a peer is gone
-            }
-            sum += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-        }
-        A.red[i] = sum;
-    }
-    __threadfence_block();
-    __syncthreads();
-    if (tid == 0 && A.hostOut) {   // time spent waiting for the peers' words (rank skew + one NVLink trip), for sb2_exchange_wait_us
-        unsigned long long waitT1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(waitT1));
-        A.hostOut[3 + 2 * A.nLoci + A.S] = (double)(waitT1 - waitT0) * 1e-3;
-    }
-    if (s_poison) { for (int i = tid; i < n; i += nt) A.red[i] = NAN; __threadfence_block(); __syncthreads(); }
+    xgpu_exchange_body(A, Cm);
     finish_body(A);
     publish_body(A);
 }

@@ -53,9 +53,9 @@ __device__ __forceinline__ void block_sum3(double &a, double &b, double &c, doub
     __syncthreads();
 }
 
-// preTileBase / preNTiles: tileBase / nTiles of locus threadIdx.x, fetched by the caller before it waited for the pruning
-// kernel (static data: one dependent round trip less on the latency path); preTileBase < 0 = not provided
-__device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preTileBase = -1, int preNTiles = 0)
+// preChunkBase / preNChunks: chunkBase / nChunks of locus threadIdx.x, fetched by the caller before it waited for the pruning
+// kernel (static data: one dependent round trip less on the latency path); preChunkBase < 0 = not provided
+__device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preChunkBase = -1, int preNChunks = 0)
 {
     __shared__ double scratch[96];
     const int tid = threadIdx.x, nt = blockDim.x, L = A.nLoci, S = A.S;
@@ -63,26 +63,28 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preTi
     double likPart = 0.0, coalPart = 0.0, incPart = 0.0;
     for (int l = tid; l < L; l += nt) {
         double lik;
-        const double coal = A.cur.coal[l];   // issued before the dependent tile loads
+        const double coal = __ldcg(A.cur.coal + l);   // issued before the dependent chunk-sum loads
         if (A.useTiles && A.nOps[l] > 0) {
             const LocusDesc &d = A.loci[l];
             lik = 0.0;
             if (A.exact) {
                 for (int p = 0; p < d.nPat; p++) lik = __dadd_rn(lik, __dmul_rn(__ldcg(A.patLogL + d.patBase + p), (double)A.weights[d.patBase + p]));   // calcLogP order
             } else {
-                const bool pre = preTileBase >= 0 && l == tid;
-                const int tileBase = pre ? preTileBase : d.tileBase, nTiles = pre ? preNTiles : d.nTiles;
-                for (int t0 = 0; t0 < nTiles; t0 += 8) {   // loads in flight together, adds in tile order
+                // the locus's 32-pattern chunk sums, added in pattern order (the order does not depend on the launch
+                // geometry, and the fused step of step.cu adds the same numbers the same way)
+                const bool pre = preChunkBase >= 0 && l == tid;
+                const int chunkBase = pre ? preChunkBase : d.chunkBase, nChunks = pre ? preNChunks : d.nChunks;
+                for (int t0 = 0; t0 < nChunks; t0 += 8) {   // loads in flight together, adds in chunk order
                     double v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) v[j] = (t0 + j < nTiles) ? __ldcg(A.tileSum + tileBase + t0 + j) : 0.0;
+                    for (int j = 0; j < 8; j++) v[j] = (t0 + j < nChunks) ? __ldcg(A.chunkSum + chunkBase + t0 + j) : 0.0;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) if (t0 + j < nTiles) lik += v[j];
+                    for (int j = 0; j < 8; j++) if (t0 + j < nChunks) lik += v[j];
                 }
             }
             A.cur.logL[l] = lik;
         } else {
-            lik = A.cur.logL[l];   // clean locus: cached value (CompoundDistribution uses getCurrentLogP)
+            lik = __ldcg(A.cur.logL + l);   // clean locus: cached value (CompoundDistribution uses getCurrentLogP)
         }
         perLocusLik[l] = lik;
         perLocusCoal[l] = coal;
@@ -119,12 +121,12 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preTi
                 if (lane == 0)
                     for (int l = 0; l < L; l++) {
                         const size_t o = (size_t)l * S + b;
-                        q += A.cur.brK[o]; g += A.cur.anG[o]; r += A.cur.anR[o];
+                        q += __ldcg(A.cur.brK + o); g += __ldcg(A.cur.anG + o); r += __ldcg(A.cur.anR + o);
                     }
             } else {
                 for (int l = lane; l < L; l += 32) {
                     const size_t o = (size_t)l * S + b;
-                    q += A.cur.brK[o]; g += A.cur.anG[o]; r += A.cur.anR[o];
+                    q += __ldcg(A.cur.brK + o); g += __ldcg(A.cur.anG + o); r += __ldcg(A.cur.anR + o);
                 }
                 for (int off = 16; off > 0; off >>= 1) {
                     q += __shfl_xor_sync(0xffffffffu, q, off);
@@ -179,6 +181,53 @@ __device__ __forceinline__ void finish_body(const ReduceArgs &A)
     }
 }
 
+
+// All-reduce of the reduce vector over peer memory (see reduce.cu:k_reduce_xgpu); called by every thread of ONE CTA after
+// reduce_local_body + __syncthreads; on return A.red holds the global sums (or NaN if a peer never showed up).
+__device__ __forceinline__ void xgpu_exchange_body(const ReduceArgs &A, const CommArgs &Cm)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, nR = Cm.nRanks, n = Cm.nRed;
+    const int half = (int)(Cm.seq & 1ull);
+    // Flag-in-data exchange: every double travels as two 8-byte words {32 data bits | 32-bit sequence tag}.  An 8-byte store
+    // is atomic, so a receiver that sees the tag of this evaluation in a word also sees its data: no fence, no separate flag,
+    // one one-way NVLink trip between "my sums are ready" and "I can add yours".
+    const unsigned long long tag = (0x80000000ull | (Cm.seq & 0x7fffffffull)) << 32;
+    for (int idx = tid; idx < nR * n; idx += nt) {
+        const int r = idx / n, i = idx - r * n;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(A.red[i]);
+        volatile unsigned long long *dst = Cm.peerSlots[r] + (((size_t)half * COMM_MAX_RANKS + Cm.rank) * n + i) * 2;
+        dst[0] = tag | (bits & 0xffffffffull);
+        dst[1] = tag | (bits >> 32);
+    }
+    __shared__ int s_poison;
+    if (tid == 0) s_poison = 0;
+    __syncthreads();
+    unsigned long long waitT0 = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(waitT0));
+    for (int i = tid; i < n; i += nt) {
+        double sum = 0.0;
+        const long long t0 = clock64();
+        for (int r = 0; r < nR; r++) {   // rank order: every rank adds the same numbers in the same order
+            const volatile unsigned long long *src = Cm.peerSlots[Cm.rank] + (((size_t)half * COMM_MAX_RANKS + r) * n + i) * 2;
+            unsigned long long w0, w1;
+            for (;;) {
+                w0 = src[0]; w1 = src[1];
+                if ((w0 & 0xffffffff00000000ull) == tag && (w1 & 0xffffffff00000000ull) == tag) break;
+                if (clock64() - t0 > 4000000000ll) { s_poison = 1; w0 = w1 = 0; break; }   // ~2 s at 2 GHz: a peer is gone
+            }
+            sum += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+        }
+        A.red[i] = sum;
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (tid == 0 && A.hostOut) {   // time spent waiting for the peers' words (rank skew + one NVLink trip), for sb2_exchange_wait_us
+        unsigned long long waitT1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(waitT1));
+        A.hostOut[3 + 2 * A.nLoci + A.S] = (double)(waitT1 - waitT0) * 1e-3;
+    }
+    if (s_poison) { for (int i = tid; i < n; i += nt) A.red[i] = NAN; __threadfence_block(); __syncthreads(); }
+}
 
 // The result vector lives twice: in device memory (`out`) and in host-mapped memory (`hostOut`, zero-copy download: the
 // host only has to synchronise the stream).  Both copies are written where the values are produced, so nothing is left to do

@@ -28,6 +28,8 @@ struct LocusDesc {
     int32_t opBase;     // into ops (sum of nInt)
     int32_t stackDepth; // floor(log2(nInt)) + 1
     int32_t stateStride;// bytes per tip row of tipStates: nPat rounded up to 128, padding = 4 (missing)
+    int32_t chunkBase;  // into chunkSum: first 32-pattern chunk of this locus
+    int32_t nChunks;    // ceil(nPat / 32)
     int64_t stateBase;  // into tipStates (bytes)
     int64_t partBase;   // into partials (doubles)
     int64_t expBase;    // into cumExp (int16)
@@ -147,7 +149,7 @@ struct PrepareArgs {
 struct ReduceArgs {
     const LocusDesc *loci;
     const int32_t *nOps;
-    const double *tileSum;
+    const double *chunkSum;   // [sum of nChunks] weighted log-likelihood of every 32-pattern chunk
     const double *patLogL;
     const int32_t *weights;
     StateBlock cur;
@@ -172,7 +174,7 @@ struct WalkArgs {
     double *partials;
     int16_t *cumExp;
     double *patLogL;             // by pattern
-    double *tileSum;             // [nTiles]
+    double *chunkSum;            // by 32-pattern chunk (LocusDesc::chunkBase)
     int32_t nCat;                // categories of every locus in this launch
     int32_t chunksPerTile;       // pattern chunks per tile (block = 32 * nCat * chunksPerTile threads)
     int32_t patPerThread;        // R: patterns per thread (a chunk is 32*R patterns)
@@ -182,12 +184,13 @@ struct WalkArgs {
     int32_t workers;             // worker warps per pattern chunk (tree-level parallelism), 1 = off
     int32_t debugMaxOps;         // timing experiments only (SB2_DEBUG_MAX_OPS): walk at most this many ops per worker; < 0 = all
     const int32_t *laneOps;      // [nLoci][WALK_MAX_WORKERS + 1]
-    int32_t fuseReduce;          // 0: none; 1: last CTA runs the local reduction; 2: ... and the closed forms + publish
-    uint32_t *doneCounter;       // CTAs finished so far (self-resetting)
-    uint32_t *locusDone;         // [nLoci] tile-CTAs finished per locus (self-resetting)
-    ReduceArgs red;
 };
 
+
+// The fused one-launch step (step.cu): one thread-block cluster per locus, one CTA of STEP_WARPS warps per pattern tile
+constexpr int STEP_THREADS = 256;       // == PREP_THREADS: the tree-shaped part is prepare_body.cuh's, warp-specialised in two halves
+constexpr int STEP_WARPS = STEP_THREADS / 32;
+constexpr int STEP_MAX_CLUSTER = 16;    // non-portable cluster size limit of sm_100
 
 // Peer-memory all-reduce of the reduce vector (one process per GPU, NVLink / NVSwitch; see reduce.cu:k_reduce_xgpu)
 constexpr int COMM_MAX_RANKS = 16;
@@ -200,6 +203,27 @@ struct CommArgs {
     unsigned long long seq;                         // evaluation sequence number (parity selects the buffer half)
 };
 cudaError_t launch_reduce_xgpu(const ReduceArgs &a, const CommArgs &c, cudaStream_t st, int64_t *launches);
+
+struct StepArgs {
+    PrepareArgs prep;            // ops / opMats / laneOps / pf* unused: schedule and matrices stay in shared memory
+    ReduceArgs red;              // useTiles = 0: the leaders write the per-locus values into the state block
+    CommArgs comm;
+    const uint8_t *tipStates;
+    const int32_t *weights;
+    const uint8_t *constMask;
+    const double *catProps;
+    double *partials;
+    int16_t *cumExp;
+    double *patLogL;
+    uint32_t *doneCounter;       // leaders finished so far (self-resetting), all-loci mode
+    int32_t nRun;                // > 0: only clusters runLoci[0..nRun) exist; [0] runs with runFlags, the others only owe the lazy
+                                 // store() copy.  0: one cluster per locus, flags as in PrepareArgs
+    int32_t runLoci[9];
+    int32_t runFlags;
+    int32_t maxNodes, nCat, stackDepth, maxTips, useComm;
+};
+size_t step_smem_bytes(int maxNodes, int S, int nCat, int stackDepth, int maxTips);
+cudaError_t launch_step(const StepArgs &a, int nClusters, int clusterSize, cudaStream_t st);
 
 // Operator-side queries over the resident gene trees (query.cu)
 constexpr int QUERY_THREADS = 128;

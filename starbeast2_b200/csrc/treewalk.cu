@@ -30,37 +30,13 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include "reduce_body.cuh"
+#include "walk_common.cuh"
 
 namespace sb2 {
-
-__device__ __forceinline__ void ld256_nc(const double *p, double &a, double &b, double &c, double &d)
-{
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-}
-__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d)
-{
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-}
 
 constexpr int OPS_BATCH = 32;   // ops staged in shared memory per half batch
 constexpr int MAT_RING = 4;     // transition-matrix pairs in flight per warp (cp.async ring)
 constexpr int TIP_SMEM_MAX = 48 * 1024;
-
-__device__ __forceinline__ void ld256_coherent(const double *p, double &a, double &b, double &c, double &d)
-{
-    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 bool treewalk_tips_in_smem(int maxTips, int tilePat) { return (size_t)maxTips * tilePat <= TIP_SMEM_MAX; }
 
@@ -73,7 +49,7 @@ size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, i
     b += (size_t)warps * MAT_RING * 2 * 16 * 8;            // per-warp matrix rings
     b += 2ull * OPS_BATCH * sizeof(Op);                    // op schedule, two half batches
     b += slots * warps * R * 32 * 2;                       // exponent stack (int16)
-    b += ((warps + 1) & ~size_t(1)) * 8 + 16 * 8;          // tile-sum scratch + the ones column
+    b += 16 * 8;                                           // the ones column
     if (workers > 1) b += ((slots * warps * 4 + 15) & ~size_t(15));   // mailbox flags
     if (treewalk_tips_in_smem(maxTips, (int)tilePat)) b += (size_t)maxTips * tilePat + 16;   // tip states of the tile
     return (b + 15) & ~size_t(15);
@@ -88,80 +64,6 @@ __device__ __forceinline__ unsigned ld_acquire_shared(const unsigned *p)
 __device__ __forceinline__ void st_release_shared(unsigned *p, unsigned v)
 {
     asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
-}
-
-// s[r][i] = sum_j M[i][j] a_r[j] for this thread's R patterns, folded into out (first operand: out = s, second: out *= s)
-template <bool EXACT, int R, bool FIRST>
-__device__ __forceinline__ void rows_times(const double *M, const double (&a)[R][4], double (&out)[R][4])
-{
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const double2 m01 = *reinterpret_cast<const double2 *>(M + i * 4);
-        const double2 m23 = *reinterpret_cast<const double2 *>(M + i * 4 + 2);
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            double s;
-            if (EXACT)   // the reference's order, no fused multiply-add: ((m0 a0 + m1 a1) + m2 a2) + m3 a3
-                s = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m01.x, a[r][0]), __dmul_rn(m01.y, a[r][1])), __dmul_rn(m23.x, a[r][2])), __dmul_rn(m23.y, a[r][3]));
-            else
-                s = fma(m23.y, a[r][3], fma(m23.x, a[r][2], fma(m01.y, a[r][1], m01.x * a[r][0])));
-            out[r][i] = FIRST ? s : out[r][i] * s;
-        }
-    }
-}
-
-// Reductions folded into the walk (one launch and its ramp fewer per evaluation), hierarchically:
-//   * the last tile-CTA of a locus sums that locus's tile sums in fixed tile order (parallel over loci, hidden in the tail);
-//   * the CTA that finishes last overall sums the per-locus values and, single-GPU, applies the closed forms and
-//     publishes the result vector.  Counters reset themselves.  Not used in exact_order mode (sequential pattern sums).
-__device__ __forceinline__ void walk_epilogue(const WalkArgs &A, int l, int tileBase, int nTiles, bool worked)
-{
-    if (!A.fuseReduce) return;
-    __shared__ unsigned s_last, s_lastOfLocus;
-    __threadfence();            // this CTA's tile sum is visible device-wide
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        s_lastOfLocus = 0;
-        if (worked) {
-            const unsigned t = atomicAdd(A.locusDone + l, 1u);
-            if (t == (unsigned)nTiles - 1) { A.locusDone[l] = 0; s_lastOfLocus = 1; }
-        }
-    }
-    __syncthreads();
-    if (s_lastOfLocus && threadIdx.x < 32) {
-        // the locus's tiles, loaded in parallel, summed in tile order (fixed order => deterministic)
-        __threadfence();
-        double lik = 0.0;
-        for (int base = 0; base < nTiles; base += 32) {
-            const int i = base + (int)threadIdx.x;
-            const double v = (i < nTiles) ? __ldcg(A.tileSum + tileBase + i) : 0.0;
-            const int cnt = min(32, nTiles - base);
-            for (int j = 0; j < cnt; j++) lik += __shfl_sync(0xffffffffu, v, j);
-        }
-        if (threadIdx.x == 0) { A.red.cur.logL[l] = lik; __threadfence(); }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned ticket = atomicAdd(A.doneCounter, 1u);
-        s_last = (ticket == gridDim.x - 1);
-        if (s_last) *A.doneCounter = 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    reduce_local_body(A.red);   // red.useTiles == 0: per-locus values are already summed
-    if (A.fuseReduce == 2) {
-        __threadfence_block();
-        __syncthreads();
-        finish_body(A.red);
-        publish_body(A.red);
-    }
 }
 
 // NC > 0: the launch geometry (categories, chunks per tile, stack depth, tips staged in shared memory) is a compile-time
@@ -193,9 +95,9 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
     // the accesses in the shared window (LDS/STS), never generic
     double2 *st2 = reinterpret_cast<double2 *>(smem_raw);                       // stack: [2 planes][depth][warps][R][32] double2
     const int planeStride = slots * warps * R * 32;                             //        plane 0 = states 0,1; plane 1 = states 2,3
-    double *smd = reinterpret_cast<double *>(st2 + 2 * planeStride);            // ring [warps][MAT_RING][32] | ones[16] | sred[warps]
-    const int onesIdx = warps * MAT_RING * 32, sredIdx = onesIdx + 16;
-    Op *sops = reinterpret_cast<Op *>(smd + sredIdx + ((warps + 1) & ~1));      // [2 * OPS_BATCH]
+    double *smd = reinterpret_cast<double *>(st2 + 2 * planeStride);            // ring [warps][MAT_RING][32] | ones[16]
+    const int onesIdx = warps * MAT_RING * 32;
+    Op *sops = reinterpret_cast<Op *>(smd + onesIdx + 16);                      // [2 * OPS_BATCH]
     int16_t *sexp = reinterpret_cast<int16_t *>(sops + 2 * OPS_BATCH);          // [slots][warps][R][32]
     unsigned *sflag = reinterpret_cast<unsigned *>(sexp + planeStride);         // [slots][warps] mailbox flags (NW > 1 only)
     uint8_t *sstate = reinterpret_cast<uint8_t *>(sflag + (NW > 1 ? ((slots * warps + 3) & ~3) : 0));   // [nTips][tilePat]; 16-byte aligned by construction
@@ -247,7 +149,6 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
     if (nOps == 0) {         // locus clean: cached logL stands
         cp_async_commit();
         cp_async_wait<0>();
-        walk_epilogue(A, l, 0, 0, false);
         return;
     }
     const bool incremental = nOps < d.nInt;         // only then can operands be clean nodes resident in HBM
@@ -388,13 +289,8 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
         const int so0 = outSlot * slotStride + stackIdx;
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            // partials are non-negative: the largest value has the largest high word; its exponent field is the scale
-            const int hmax = max(max(__double2hiint(out[r][0]), __double2hiint(out[r][1])), max(__double2hiint(out[r][2]), __double2hiint(out[r][3])));
-            int field = hmax >> 20;                                             // 0 for zero / denormal, >= 0x7ff for inf / nan
-            if (field <= 0 || field > 1023) field = 1023;                       // no scaling: nothing to scale / never scale down
-            const double scale = __hiloint2double((2046 - field) << 20, 0);     // 2^-(field-1023), exact
-            const double o0 = out[r][0] * scale, o1 = out[r][1] * scale, o2 = out[r][2] * scale, o3 = out[r][3] * scale;
-            const int ce = cum[r] + field - 1023;
+            double o0, o1, o2, o3;
+            const int ce = cum[r] + rescale4(out[r], o0, o1, o2, o3);
             if (toStack) {
                 st2[so0 + 32 * r] = make_double2(o0, o1);
                 st2[planeStride + so0 + 32 * r] = make_double2(o2, o3);
@@ -415,8 +311,10 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
     cp_async_wait<0>();
     __syncthreads();
 
-    // root: integratePartials over categories, (+pInv on constant patterns), frequencies, log, pattern weight
-    double contrib = 0.0;
+    // root: integratePartials over categories, (+pInv on constant patterns), frequencies, log, pattern weight; then the sum
+    // over each 32-pattern chunk (fixed-shape shuffle tree).  The locus's log-likelihood is the sum of its chunk sums in
+    // pattern order (k_reduce_*), whatever the launch geometry: the fused one-launch step (step.cu) adds the same numbers in
+    // the same order.
     if (c == 0 && worker == 0) {
         const LocusParams *prm = &A.params[l];
         const double *freqs = (prm->substKind == 0) ? prm->subst + 1 : prm->subst + 36;
@@ -424,59 +322,19 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
         const double pInv = prm->pInv;
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            if (!valid[r]) continue;
-            const int p = pbase + 32 * r;
-            // categories carry their own exponents: bring them to the largest one (exact)
-            int E = -32768;
-            for (int cc = 0; cc < C; cc++) E = max(E, (int)sexp[(chunk * C + cc) * R * 32 + 32 * r + lane]);
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int cc = 0; cc < C; cc++) {
-                const int si = (chunk * C + cc) * R * 32 + 32 * r + lane;   // slot 0 holds the root
-                const double2 lo = st2[si], hi = st2[planeStride + si];
-                const int diff = (int)sexp[si] - E;                          // <= 0
-                const double f = (diff < -1022) ? 0.0 : __hiloint2double((1023 + diff) << 20, 0);
-                const double pr = props[cc];
-                const double v0 = lo.x * f, v1 = lo.y * f, v2 = hi.x * f, v3 = hi.y * f;
-                if (cc == 0) {
-                    acc[0] = v0 * pr; acc[1] = v1 * pr; acc[2] = v2 * pr; acc[3] = v3 * pr;
-                } else if (EXACT) {
-                    acc[0] = __dadd_rn(acc[0], __dmul_rn(v0, pr)); acc[1] = __dadd_rn(acc[1], __dmul_rn(v1, pr));
-                    acc[2] = __dadd_rn(acc[2], __dmul_rn(v2, pr)); acc[3] = __dadd_rn(acc[3], __dmul_rn(v3, pr));
-                } else {
-                    acc[0] = fma(v0, pr, acc[0]); acc[1] = fma(v1, pr, acc[1]); acc[2] = fma(v2, pr, acc[2]); acc[3] = fma(v3, pr, acc[3]);
-                }
+            double contrib = 0.0;
+            if (valid[r]) {
+                const int p = pbase + 32 * r;
+                const int mask = (pInv > 0.0) ? A.constMask[d.patBase + p] : 0;
+                const double lk = root_pattern_logl<EXACT>(st2, planeStride, sexp, chunk * C * R * 32 + 32 * r + lane, R * 32, C, props, freqs, pInv, mask);
+                A.patLogL[d.patBase + p] = lk;
+                contrib = __dmul_rn(lk, (double)A.weights[d.patBase + p]);
             }
-            const int mask = (pInv > 0.0) ? A.constMask[d.patBase + p] : 0;
-            double lk;
-            if (mask) {
-                // unscale first (underflow here is harmless: pInv dominates), then add pInv on the constant states
-                double sum = 0.0;
-                for (int s = 0; s < 4; s++) {
-                    double v = ldexp(acc[s], E);
-                    if (mask & (1 << s)) v = __dadd_rn(v, pInv);
-                    sum = __dadd_rn(sum, __dmul_rn(freqs[s], v));
-                }
-                lk = log(sum);
-            } else {
-                double sum = 0.0;
-                for (int s = 0; s < 4; s++) sum = __dadd_rn(sum, __dmul_rn(freqs[s], acc[s]));
-                // 2^E is exact, so when the unscaled value is representable this is the reference's log(sum) bit for bit
-                lk = (E > -1000) ? log(ldexp(sum, E)) : (log(sum) + E * 0.6931471805599453);
-            }
-            A.patLogL[d.patBase + p] = lk;
-            contrib += __dmul_rn(lk, (double)A.weights[d.patBase + p]);
+            contrib = chunk_sum(contrib);
+            const int ch = (p0 >> 5) + chunk * R + r;   // 32-pattern chunk of the locus
+            if (lane == 0 && ch < d.nChunks) A.chunkSum[d.chunkBase + ch] = contrib;
         }
     }
-    // fixed-shape tile reduction (deterministic)
-    for (int off = 16; off > 0; off >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, off);
-    if (lane == 0) smd[sredIdx + w] = contrib;
-    __syncthreads();
-    if (tid == 0) {
-        double t = 0.0;
-        for (int ch = 0; ch < chunks; ch++) t += smd[sredIdx + ch * C];
-        A.tileSum[tile] = t;
-    }
-    walk_epilogue(A, l, d.tileBase, d.nTiles, true);
 }
 
 template <bool EXACT, int R, int MINB, int NC, int CH, int DEPTH, int NW = 1>
