@@ -204,6 +204,11 @@ SB2_API int sb2_kernel_time(sb2_engine *e, double *ms, int64_t *launches);
 /* switch the CUDA-event bracketing of the pruning kernel on/off (events between launches defeat programmatic
  * dependent launch, so latency measurements run with profiling off) */
 SB2_API int sb2_set_profile(sb2_engine *e, int32_t on);
+/* profile=1, after an evaluation that went through the fused one-launch step: microseconds since the start of that launch at
+ * its phase boundaries, read on the device (%globaltimer) by the leader CTA of the first cluster; n <= 16:
+ * [0] start (0), [1] tree-shaped work done, [2] walk done, [3] chunk sums gathered, [4] reductions entered, [5] result published,
+ * [8] state loaded, [9] embedding done, [10] coalescent terms done, [11] dirtiness known, [12] schedule built, [13] matrices done */
+SB2_API int sb2_step_phase_times(sb2_engine *e, double *us, int32_t n);
 /* device bytes held by the engine */
 SB2_API int64_t sb2_device_bytes(const sb2_engine *e);
 /* after sb2_comm_connect: microseconds the last evaluation's reduction kernel spent waiting for the peers' words

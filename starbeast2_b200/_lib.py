@@ -92,6 +92,7 @@ def load() -> C.CDLL:
         "sb2_kernel_time": (C.c_int, [E, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
         "sb2_set_profile": (C.c_int, [E, C.c_int32]),
         "sb2_device_bytes": (C.c_int64, [E]),
+        "sb2_step_phase_times": (C.c_int, [E, C.POINTER(C.c_double), C.c_int32]),
         "sb2_exchange_wait_us": (C.c_double, [E]),
     }
     for name, (res, args) in sig.items():

@@ -46,9 +46,11 @@ struct sb2_engine {
     // fused one-launch step (step.cu)
     bool fusedOk = false;            // shapes fit: cluster <= 16 CTAs per locus, shared memory, category count
     int fusedMode = -1;              // SB2_FUSED: 0 never, 1 whenever eligible, -1 auto (single-locus steps; all-loci steps of small problems)
-    int64_t fusedMaxLanes = 150000;  // auto: all-loci evaluations go through k_step up to this many (pattern, category) lanes
+    int64_t fusedMaxLanes = 0;       // auto: all-loci evaluations go through k_step up to this many (pattern, category) lanes; 0 = never:
+                                     // measured on B200, the three PDL-chained kernels win when every locus runs (C2: 37.7 vs 43.4 us per step)
     int64_t totalLanes = 0;
     int fusedCluster = 1;            // CTAs per cluster when every locus runs (widest locus)
+    unsigned long long *hStamps = nullptr, *hStampsDev = nullptr;   // profile mode: phase stamps of k_step (mapped host memory)
     int lastFusedSingle = -1;        // >= 0: the last evaluation ran this one locus through k_step (only its nOps entry is fresh)
     int64_t devBytes = 0;
     int64_t launches = 0;
@@ -81,6 +83,11 @@ struct sb2_engine {
     // outputs
     double *dRed = nullptr, *dRedOwn = nullptr, *dOut = nullptr, *hOut = nullptr, *hOutDev = nullptr;
     uint32_t *dDone = nullptr;
+    // polled download of the result vector (ReduceArgs::hostTag): mapped host words, the tag of the evaluation in flight
+    unsigned long long *hWords = nullptr, *hWordsDev = nullptr;
+    bool pollOk = false;
+    uint32_t pollSeq = 0;
+    unsigned long long pollTag = 0;   // != 0: the evaluation in flight publishes tagged words
     // peer-memory all-reduce
     void *commBuf = nullptr;
     size_t commSlotsBytes = 0;
@@ -238,7 +245,18 @@ ReduceArgs reduce_args(sb2_engine *e, bool coalOnly = false)
     r.cur = cur(e); r.red = e->dRed; r.out = e->dOut;
     r.nLoci = e->L; r.S = e->S; r.popKind = e->popKind; r.exact = e->cfg.exact_order;
     r.hostOut = e->hOutDev;
+    r.hostWords = e->hWordsDev; r.hostTag = 0;
     return r;
+}
+
+// a FULL evaluation (every entry of the result vector is rewritten) may publish tagged words that the host polls
+void arm_poll(sb2_engine *e, ReduceArgs &r)
+{
+    e->pollTag = 0;
+    if (!e->pollOk || e->commConnected) return;
+    e->pollSeq++;
+    e->pollTag = (0x80000000ull | (e->pollSeq & 0x7fffffffull)) << 32;
+    r.hostTag = e->pollTag;
 }
 
 int do_walk(sb2_engine *e);
@@ -384,13 +402,23 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
         sa.prep = a;
         sa.prep.workers = 1;
         sa.red = reduce_args(e, /*coalOnly=*/true);   // useTiles = 0: the leaders write the per-locus values into the state block
+        arm_poll(e, sa.red);
         sa.comm = e->comm;
         sa.useComm = e->commConnected ? 1 : 0;
         if (e->commConnected) { e->comm.seq++; sa.comm.seq = e->comm.seq; }
         sa.tipStates = e->dStates; sa.weights = e->dWeights; sa.constMask = e->dConstMask; sa.catProps = e->dCat + e->totalCat;
         sa.partials = e->dPartials; sa.cumExp = e->dCumExp; sa.patLogL = e->dPatLogL; sa.doneCounter = e->dDone;
         sa.maxNodes = e->maxNodes; sa.nCat = e->nCat; sa.stackDepth = e->stackDepth; sa.maxTips = (e->maxNodes + 1) / 2;
-        sa.nRun = 0; sa.runFlags = 0;
+        sa.dbg = nullptr;
+        if (e->cfg.profile) {
+            if (!e->hStamps) {
+                CUDA_TRY(e, cudaHostAlloc((void **)&e->hStamps, sizeof(unsigned long long) * STEP_STAMPS, cudaHostAllocMapped));
+                memset(e->hStamps, 0, sizeof(unsigned long long) * STEP_STAMPS);
+                CUDA_TRY(e, cudaHostGetDevicePointer((void **)&e->hStampsDev, e->hStamps, 0));
+            }
+            sa.dbg = e->hStampsDev;
+        }
+        sa.nRun = 0; sa.runFlags = 0; sa.inlineTreeBytes = 0; sa.pad0 = 0;
         for (int j = 0; j < 9; j++) sa.runLoci[j] = 0;
         int nClusters = L;
         if (singleLocus >= 0) {
@@ -398,6 +426,11 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
             for (int j = 0; j < nSync; j++) if (syncLoci[j] != singleLocus) sa.runLoci[sa.nRun++] = syncLoci[j];
             nClusters = sa.nRun;
             e->lastFusedSingle = singleLocus;
+            const LocusDesc &d1 = e->loci[singleLocus].d;
+            if ((sa.runFlags & LF_TREE_IN) && 20 * d1.nNodes <= STEP_INLINE_TREE_MAX) {   // the staged tree rides in the arguments
+                sa.inlineTreeBytes = 20 * d1.nNodes;
+                memcpy(sa.inlineTree, e->hInTree + d1.treeOff, (size_t)sa.inlineTreeBytes);
+            }
         }
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
         if (e->cfg.profile) {
@@ -435,7 +468,7 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
 int launch_final(sb2_engine *e, const ReduceArgs &r)
 {
     static const bool skip = getenv("SB2_DEBUG_SKIP_REDUCE") != nullptr;   // timing experiments only: results are stale
-    if (skip) return SB2_OK;
+    if (skip) { e->pollTag = 0; return SB2_OK; }
     if (e->commConnected) {
         e->comm.seq++;
         CUDA_TRY(e, launch_reduce_xgpu(r, e->comm, e->stream, &e->launches));
@@ -494,6 +527,32 @@ int flush_pending_walk(sb2_engine *e)
 
 int download(sb2_engine *e)
 {
+    if (e->pollTag) {
+        // the final kernel writes every double of the result as two tagged 8-byte words into mapped host memory: spin on the
+        // words themselves (no wait for the kernel to drain, no completion interrupt); the stream is queried now and then so
+        // that a failed launch surfaces as an error instead of a hang
+        const unsigned long long tag = e->pollTag;
+        e->pollTag = 0;
+        volatile unsigned long long *w = e->hWords;
+        const int n = e->nOut;
+        bool finished = false;
+        for (int i = 0; i < n; i++) {
+            unsigned long long w0, w1;
+            for (unsigned spins = 0;; spins++) {
+                w0 = w[2 * i]; w1 = w[2 * i + 1];
+                if ((w0 & 0xffffffff00000000ull) == tag && (w1 & 0xffffffff00000000ull) == tag) break;
+                if ((spins & 1023u) == 1023u) {
+                    if (finished) return e->fail(SB2_ERR_CUDA, "result word %d never arrived although the stream is idle", i);
+                    const cudaError_t st = cudaStreamQuery(e->stream);
+                    if (st == cudaSuccess) finished = true;   // one more look at the word, then give up
+                    else if (st != cudaErrorNotReady) return e->fail(SB2_ERR_CUDA, "evaluation failed: %s", cudaGetErrorString(st));
+                }
+            }
+            const unsigned long long bits = (w0 & 0xffffffffull) | (w1 << 32);
+            memcpy(&e->hOut[i], &bits, 8);
+        }
+        return SB2_OK;
+    }
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));   // k_finish already published the result vector into host memory
     return SB2_OK;
 }
@@ -520,7 +579,9 @@ static int eval_full(sb2_engine *e)
     if (!fused && e->resultValid && !e->walkPending && !e->commConnected) return SB2_OK;
     if (!fused) {
         if ((rc = do_walk(e))) return rc;
-        if ((rc = launch_final(e, reduce_args(e)))) return rc;
+        ReduceArgs r = reduce_args(e);
+        arm_poll(e, r);
+        if ((rc = launch_final(e, r))) return rc;
     }
     if ((rc = download(e))) return rc;
     e->resultValid = true;
@@ -557,7 +618,7 @@ void sb2_destroy(sb2_engine *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void *p : e->devAllocs) cudaFree(p);
     for (void *p : {(void *)e->hParams, (void *)e->hCat, (void *)e->hExplicit, (void *)e->hInTree, (void *)e->hFlags, (void *)e->hSpecies, (void *)e->hOut,
-                    (void *)e->hParamsStored, (void *)e->hCatStored, (void *)e->hExplicitStored, (void *)e->hSpeciesStored, (void *)e->hQuery})
+                    (void *)e->hStamps, (void *)e->hWords, (void *)e->hParamsStored, (void *)e->hCatStored, (void *)e->hExplicitStored, (void *)e->hSpeciesStored, (void *)e->hQuery})
         if (p) cudaFreeHost(p);
     for (void *p : e->commOpened) cudaIpcCloseMemHandle(p);
     for (auto &ev : e->evPool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -761,6 +822,16 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
         memset(e->hOut, 0, sizeof(double) * (e->nOut + 1));
         CUDA_TRY(e, cudaHostGetDevicePointer((void **)&e->hOutDev, e->hOut, 0));
     }
+    {   // polled download: two tagged words per double; small result vectors only (the host checks every word)
+        const char *v = getenv("SB2_POLL");
+        e->pollOk = (v ? atoi(v) != 0 : true) && e->nOut <= 4096;
+        if (e->pollOk) {
+            cudaError_t st = cudaHostAlloc((void **)&e->hWords, sizeof(unsigned long long) * 2 * (size_t)e->nOut, cudaHostAllocMapped);
+            if (st != cudaSuccess) return e->fail(SB2_ERR_NOMEM, "cudaHostAlloc(mapped words): %s", cudaGetErrorString(st));
+            memset(e->hWords, 0, sizeof(unsigned long long) * 2 * (size_t)e->nOut);
+            CUDA_TRY(e, cudaHostGetDevicePointer((void **)&e->hWordsDev, e->hWords, 0));
+        }
+    }
     if ((rc = dev_alloc(e, &e->dLaneOps, (size_t)L * (WALK_MAX_WORKERS + 1)))) return rc;
     CUDA_TRY(e, cudaMemset(e->dLaneOps, 0, sizeof(int32_t) * (size_t)L * (WALK_MAX_WORKERS + 1)));
     if ((rc = dev_alloc(e, &e->dDone, 1))) return rc;
@@ -948,6 +1019,7 @@ int sb2_eval_end(sb2_engine *e, double *perLocusCoal, double *perLocusLik, doubl
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (!e->reduced) return e->fail(SB2_ERR_STATE, "sb2_eval_end without sb2_eval_begin");
     CUDA_TRY(e, launch_finish(reduce_args(e), e->stream, &e->launches));
+    e->pollTag = 0;
     int rc = download(e);
     if (rc) return rc;
     copy_out(e, perLocusCoal, perLocusLik, perBranch, total3);
@@ -982,6 +1054,7 @@ int sb2_eval_coalescent(sb2_engine *e, double *perLocus, double *perBranch, doub
         // the pruning kernel has not run for the re-scheduled loci yet, so the likelihood entries of this pass are the
         // cached ones (coalOnly); sb2_eval_likelihood runs the walk
         ReduceArgs r = reduce_args(e, /*coalOnly=*/true);
+        e->pollTag = 0;
         if ((rc = launch_final(e, r))) return rc;
         if ((rc = download(e))) return rc;
     }
@@ -1373,6 +1446,17 @@ int sb2_set_profile(sb2_engine *e, int32_t on)
 }
 
 int64_t sb2_device_bytes(const sb2_engine *e) { return e ? e->devBytes : 0; }
+
+int sb2_step_phase_times(sb2_engine *e, double *us, int32_t n)
+{
+    if (e) cudaSetDevice(e->cfg.device);
+    if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
+    if (!us || n < 1) return e->fail(SB2_ERR_ARG, "null output");
+    if (!e->hStamps) return e->fail(SB2_ERR_STATE, "no fused step was launched in profile mode");
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < n; i++) us[i] = (i < STEP_STAMPS && e->hStamps[i] >= e->hStamps[0]) ? 1e-3 * (double)(e->hStamps[i] - e->hStamps[0]) : 0.0;
+    return SB2_OK;
+}
 
 double sb2_exchange_wait_us(const sb2_engine *e) { return (e && e->finalized && e->commConnected) ? e->hOut[e->nOut] : 0.0; }
 

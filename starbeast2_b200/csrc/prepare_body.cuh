@@ -223,18 +223,29 @@ struct PrepFused {
     Op *sops;          // [nInt]
     double *smats;     // [nInt][category][side][16]
     int *nOpsOut;      // shared-memory int
+    unsigned long long *dbg;   // profile mode, first cluster's leader only: %globaltimer stamps 8.. of the phases below; else nullptr
+    const uint8_t *treeSrc;    // the incoming gene tree when it travels in the kernel arguments (single-locus steps), else nullptr
+    bool splitReturn;          // see prepare_locus: the halves of the CTA return separately
 };
+// Return value of prepare_locus<true>: PREP_ALL = every thread returned together after a __syncthreads(); PREP_HALVES = the
+// likelihood half (threads >= PREP_THREADS/2) returned as soon as ITS work -- schedule and matrices -- was complete and has
+// signalled named barrier 4 (bar.arrive); the coalescent half returned after its own work and must bar.sync 4 before it reads
+// the schedule or the matrices.
+enum { PREP_ALL = 0, PREP_HALVES = 1 };
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // Must be called by all PREP_THREADS threads of the CTA, for a locus whose flags `fl` have LF_RUN set.  !FUSED: threads may
 // return early (group A when it has nothing left to do); FUSED: every thread returns, converged, after a __syncthreads().
 template <bool FUSED>
-__device__ __forceinline__ void prepare_locus(const PrepareArgs &A, int maxNodes, int l, uint8_t fl, unsigned char *smem_raw,
+__device__ __forceinline__ int prepare_locus(const PrepareArgs &A, int maxNodes, int l, uint8_t fl, unsigned char *smem_raw,
                                               LocusParams &sprm, const PrepFused &F)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     const bool owner = !FUSED || F.leader;   // writes the locus's state in HBM
+    auto stamp = [&](int i, int who) {
+        if (FUSED && F.dbg && tid == who) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); F.dbg[i] = t; }
+    };
     const LocusDesc d = A.loci[l];
     const LocusParams *prm = &sprm;
     const int G = d.nNodes, nT = d.nTips, nI = d.nInt, S = A.S, nb = d.nodeBase, C = d.nCat;
@@ -252,7 +263,7 @@ __device__ __forceinline__ void prepare_locus(const PrepareArgs &A, int maxNodes
         const double *prmSrc = reinterpret_cast<const double *>(&A.params[l]);
         double *prmDst = reinterpret_cast<double *>(&sprm);
         const bool treeIn = fl & LF_TREE_IN;
-        const double *inH = reinterpret_cast<const double *>(A.inTree + d.treeOff);
+        const double *inH = reinterpret_cast<const double *>((FUSED && F.treeSrc) ? F.treeSrc : A.inTree + d.treeOff);
         const int *inP = reinterpret_cast<const int *>(inH + G), *inL = inP + G, *inR = inL + G;
         const int span = max(max(G, S), NP);
         for (int base = 0; base < span; base += nt) {
@@ -300,6 +311,7 @@ __device__ __forceinline__ void prepare_locus(const PrepareArgs &A, int maxNodes
         warm(A.pfConstMask + d.patBase, (size_t)d.nPat);
     }
     __syncthreads();
+    stamp(8, 0);
     if (FUSED) {
         // every thread of the cluster has consumed the old state: from here on the leader may overwrite it
         cluster_arrive_release();
@@ -313,6 +325,7 @@ __device__ __forceinline__ void prepare_locus(const PrepareArgs &A, int maxNodes
     }
     for (int i = tid; i < G; i += nt) if (s.gP[i] < 0) s.misc[1] = i;
     for (int i = tid; i < nT; i += nt) atomicAdd(&s.n[s.assign[i]], 1);   // leafCoalescentLineageCounts, GeneTree.java:222
+    if (FUSED) asm volatile("cp.async.wait_all;" ::: "memory");   // the caller's asynchronous tile staging (static data, long landed)
     __syncthreads();
     const int root = s.misc[1];
 
@@ -357,6 +370,7 @@ __device__ __forceinline__ void prepare_locus(const PrepareArgs &A, int maxNodes
         }
     }
     gsync();
+    stamp(9, 0);
     if (wantRate) {   // the rates are complete: release group B (it waits on barrier 3 for them)
         if (gt == 0) s.rate[root] = clockRate;   // StarBeastClock.java:72
         __threadfence_block();
@@ -468,6 +482,7 @@ __device__ __forceinline__ void prepare_locus(const PrepareArgs &A, int maxNodes
         else for (int b = 0; b < S; b++) logP += s.sRate[b];  // GeneTree.java:185-196, node-number order
         A.cur.coal[l] = logP;
     }
+    stamp(10, 0);
     }
 
     } else {
@@ -511,6 +526,7 @@ __device__ __forceinline__ void prepare_locus(const PrepareArgs &A, int maxNodes
             while (a >= 0) { atomicAdd(&s.cnt[a], 1); a = s.gP[a]; }
         }
     gsync();
+    stamp(11, gn);
     if (gt == 0) {
         const int n = s.dirty[root] ? s.cnt[root] : 0;
         if (owner) A.nOps[l] = n;
@@ -630,12 +646,13 @@ __device__ __forceinline__ void prepare_locus(const PrepareArgs &A, int maxNodes
         else A.ops[d.opBase + pos] = o;
     }
     gsync();
+    stamp(12, gn);
 
     }
     // ---- 5. transition matrices: recompute the dirty branches; stream every scheduled op's pair in op order ----------------
     // few matrices: group B computes them alone, without waiting for group A; many: all threads, after a full barrier
-    const bool matsByB = !FUSED && G * C <= gn;
-    if (matsByB) { if (grpId == 0) return; }
+    const bool matsByB = (!FUSED || F.splitReturn) && G * C <= gn;
+    if (matsByB) { if (grpId == 0) return PREP_HALVES; }
     else __syncthreads();
     const int mt = matsByB ? gt : tid, mn = matsByB ? gn : nt;
     HkyTabs tabs;
@@ -670,7 +687,15 @@ __device__ __forceinline__ void prepare_locus(const PrepareArgs &A, int maxNodes
             for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(dst + q) = make_double2(m[q], m[q + 1]);
         }
     }
+    if (FUSED && matsByB) {   // this half is done: let the coalescent half know the schedule and the matrices are complete
+        gsync();
+        stamp(13, gn);
+        asm volatile("bar.arrive 4, %0;" ::"n"(PREP_THREADS) : "memory");
+        return PREP_HALVES;
+    }
     if (FUSED) __syncthreads();   // schedule and matrices are complete in this CTA's shared memory
+    stamp(13, 0);
+    return PREP_ALL;
 }
 
 }  // namespace sb2

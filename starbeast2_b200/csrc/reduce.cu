@@ -25,10 +25,10 @@ __global__ void __launch_bounds__(RED_THREADS) k_reduce_finish(ReduceArgs A)
     int tb = -1, ntl = 0;
     if ((int)threadIdx.x < A.nLoci) { tb = A.loci[threadIdx.x].chunkBase; ntl = A.loci[threadIdx.x].nChunks; }   // static: fetched while the pruning kernel still runs
     cudaGridDependencySynchronize();   // launched with programmatic serialization: wait for the pruning kernel's results
-    reduce_local_body(A, tb, ntl);
-    __threadfence_block();
-    __syncthreads();
-    finish_body(A);
+    double sums3[3];
+    reduce_local_body(A, tb, ntl, sums3);
+    if (A.popKind == 2) { __threadfence_block(); __syncthreads(); }   // the per-branch sums travel through the reduce vector
+    finish_body(A, sums3);
     publish_body(A);
 }
 

@@ -53,9 +53,24 @@ __device__ __forceinline__ void block_sum3(double &a, double &b, double &c, doub
     __syncthreads();
 }
 
+// one double of the result vector towards the host (see ReduceArgs::hostTag)
+__device__ __forceinline__ void host_put(const ReduceArgs &A, int idx, double v)
+{
+    if (A.hostTag) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+        volatile unsigned long long *w = A.hostWords + 2 * (size_t)idx;
+        w[0] = A.hostTag | (bits & 0xffffffffull);
+        w[1] = A.hostTag | (bits >> 32);
+    } else if (A.hostOut) {
+        A.hostOut[idx] = v;
+    }
+}
+
 // preChunkBase / preNChunks: chunkBase / nChunks of locus threadIdx.x, fetched by the caller before it waited for the pruning
 // kernel (static data: one dependent round trip less on the latency path); preChunkBase < 0 = not provided
-__device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preChunkBase = -1, int preNChunks = 0)
+// sums3 (optional): receives {coalescent, likelihood, nIncompatible} in EVERY thread, so that a finish_body in the same CTA
+// need not read them back from the reduce vector in HBM
+__device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preChunkBase = -1, int preNChunks = 0, double *sums3 = nullptr)
 {
     __shared__ double scratch[96];
     const int tid = threadIdx.x, nt = blockDim.x, L = A.nLoci, S = A.S;
@@ -88,7 +103,7 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preCh
         }
         perLocusLik[l] = lik;
         perLocusCoal[l] = coal;
-        if (A.hostOut) { A.hostOut[3 + L + l] = lik; A.hostOut[3 + l] = coal; }   // zero-copy result vector, written as soon as known
+        host_put(A, 3 + L + l, lik); host_put(A, 3 + l, coal);   // zero-copy result vector, written as soon as known
         likPart += lik;
         coalPart += coal;
         incPart += (coal == -INFINITY) ? 1.0 : 0.0;
@@ -111,6 +126,7 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preCh
     }
     const double inc = incPart;
     if (tid == 0) { A.red[0] = coalSum; A.red[1] = likSum; A.red[2] = inc; }
+    if (sums3) { sums3[0] = coalSum; sums3[1] = likSum; sums3[2] = inc; }
 
     // analytic integration: per-branch sums over this rank's loci
     if (A.popKind == 2) {
@@ -141,13 +157,14 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preCh
     }
 }
 
-__device__ __forceinline__ void finish_body(const ReduceArgs &A)
+// sums3 (optional): the three leading entries of the reduce vector, already in registers (single-GPU, same CTA)
+__device__ __forceinline__ void finish_body(const ReduceArgs &A, const double *sums3 = nullptr)
 {
     const int tid = threadIdx.x, nt = blockDim.x, L = A.nLoci, S = A.S;
     double *perBranch = A.out + 3 + 2 * L;
-    double coal = A.red[0];
-    const double lik = A.red[1];
-    const bool incompatible = A.red[2] > 0.0;
+    double coal = sums3 ? sums3[0] : A.red[0];
+    const double lik = sums3 ? sums3[1] : A.red[1];
+    const bool incompatible = (sums3 ? sums3[2] : A.red[2]) > 0.0;
     if (A.popKind == 2) {
         // one warp per species branch (no block barriers on this latency path); the per-branch terms are then added one by
         // one in node-number order (MultispeciesCoalescent.java:194)
@@ -167,17 +184,17 @@ __device__ __forceinline__ void finish_body(const ReduceArgs &A)
             // explicit roundings: this body is also inlined into k_treewalk, whose translation unit allows FMA contraction
             const double logP = __dadd_rn(__dsub_rn(__dadd_rn(branchLogR, __dmul_rn(alpha, log(beta))),
                                                     __dmul_rn(__dadd_rn(alpha, (double)q), log(__dadd_rn(beta, g)))), lgr);   // :232
-            if (lane == 0) { perBranch[b] = logP; if (A.hostOut) A.hostOut[3 + 2 * L + b] = logP; }
+            if (lane == 0) { perBranch[b] = logP; host_put(A, 3 + 2 * L + b, logP); }
         }
         __syncthreads();
         if (tid == 0) for (int b = 0; b < S; b++) coal += perBranch[b];
     } else {
-        for (int b = tid; b < S; b += nt) { perBranch[b] = 0.0; if (A.hostOut) A.hostOut[3 + 2 * L + b] = 0.0; }
+        for (int b = tid; b < S; b += nt) { perBranch[b] = 0.0; host_put(A, 3 + 2 * L + b, 0.0); }
     }
     if (incompatible) coal = -INFINITY;   // MultispeciesCoalescent.java:153
     if (tid == 0) {
         A.out[0] = coal; A.out[1] = lik; A.out[2] = coal + lik;
-        if (A.hostOut) { A.hostOut[0] = coal; A.hostOut[1] = lik; A.hostOut[2] = coal + lik; }
+        host_put(A, 0, coal); host_put(A, 1, lik); host_put(A, 2, coal + lik);
     }
 }
 
@@ -234,8 +251,7 @@ __device__ __forceinline__ void xgpu_exchange_body(const ReduceArgs &A, const Co
 // here but make sure the block's writes are ordered before the kernel ends.
 __device__ __forceinline__ void publish_body(const ReduceArgs &A)
 {
-    (void)A;
-    __threadfence_system();
+    if (!A.hostTag) __threadfence_system();   // tagged words need no fence: each carries its own proof of arrival
 }
 
 }  // namespace sb2

@@ -158,6 +158,12 @@ struct ReduceArgs {
     int32_t nLoci, S, popKind, exact;
     int32_t useTiles;   // 0: pruning results are stale or pending -> use the cached per-locus logL
     double *hostOut;    // host-mapped copy of `out` (zero-copy download), or nullptr
+    // Polled download (latency path): hostTag != 0 -> every double of the result goes to hostWords[2 i], [2 i + 1] as two
+    // 8-byte words {tag | 32 data bits} instead of into hostOut.  An aligned 8-byte store lands atomically, so a host that sees
+    // this evaluation's tag in a word also sees its data: no system-scope fence in the kernel, no wait for the kernel to
+    // drain on the host (the flag-in-data idea of the peer-memory all-reduce, pointed at the host).
+    unsigned long long *hostWords;
+    unsigned long long hostTag;
 };
 
 struct WalkArgs {
@@ -191,6 +197,7 @@ struct WalkArgs {
 constexpr int STEP_THREADS = 256;       // == PREP_THREADS: the tree-shaped part is prepare_body.cuh's, warp-specialised in two halves
 constexpr int STEP_WARPS = STEP_THREADS / 32;
 constexpr int STEP_MAX_CLUSTER = 16;    // non-portable cluster size limit of sm_100
+constexpr int STEP_INLINE_TREE_MAX = 3072;   // bytes of gene tree (20 per node) that fit the kernel arguments next to the rest
 
 // Peer-memory all-reduce of the reduce vector (one process per GPU, NVLink / NVSwitch; see reduce.cu:k_reduce_xgpu)
 constexpr int COMM_MAX_RANKS = 16;
@@ -221,7 +228,14 @@ struct StepArgs {
     int32_t runLoci[9];
     int32_t runFlags;
     int32_t maxNodes, nCat, stackDepth, maxTips, useComm;
+    unsigned long long *dbg;     // profile mode: %globaltimer stamps of cluster 0's leader at the phase boundaries, else nullptr
+    // single-locus steps: the staged gene tree of runLoci[0] rides in the kernel arguments (no PCIe round trip to the mapped
+    // host buffer, no copy-engine hop on the latency path); inlineTreeBytes == 0: read it from prep.inTree as usual
+    int32_t inlineTreeBytes;
+    int32_t pad0;
+    unsigned char inlineTree[STEP_INLINE_TREE_MAX];
 };
+constexpr int STEP_STAMPS = 16;
 size_t step_smem_bytes(int maxNodes, int S, int nCat, int stackDepth, int maxTips);
 cudaError_t launch_step(const StepArgs &a, int nClusters, int clusterSize, cudaStream_t st);
 

@@ -69,8 +69,8 @@ size_t step_smem_bytes(int maxNodes, int S, int nCat, int stackDepth, int maxTip
 }
 
 // The walk of one tile: the schedule and the matrices come from shared memory, everything else is k_treewalk's R = 1 walk.
-__device__ __forceinline__ void step_walk(const StepArgs &A, const LocusDesc &d, int l, int tile, int nOps, const StepSmem &m,
-                                          unsigned char *smem_raw, double *chunkOut)
+__device__ __forceinline__ void step_walk(const StepArgs &A, const LocusDesc &d, const LocusParams *prm, int tile, int nOps, const StepSmem &m,
+                                          unsigned char *smem_raw, double *chunkOut, int weight, int constMask)
 {
     const int C = A.nCat, chunks = STEP_WARPS / C, depth = A.stackDepth;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -92,12 +92,22 @@ __device__ __forceinline__ void step_walk(const StepArgs &A, const LocusDesc &d,
     int16_t *cumExp = A.cumExp + d.expBase + (size_t)c * nPat + p;
 
     if (active) {
-        if (nOps < d.nInt && valid)   // incremental: clean siblings live in HBM -- pull all of them in before the dependent chain starts
+        if (nOps < d.nInt && valid) {
+            // incremental: clean siblings live in HBM / L2 -- pull all of them into L1 before the dependent chain starts, and
+            // those of the partner warp in the other half of the CTA too (the halves reach the walk at different times: whoever
+            // comes first fetches for both)
+            const int dp = (C == 1 || C == 2 || C == 4) ? (((w ^ (STEP_WARPS / 2)) - w) / C) * 32 : 0;   // same category, partner chunk
             for (int k = 0; k < nOps; k++) {
                 const Op q = sops[k];
-                if ((q.ctl & 7) == OPK_GLOBAL) { prefetch_l1(partials + (size_t)q.aOff * 4); prefetch_l1(cumExp + (size_t)q.aOff); }
-                if (((q.ctl >> 3) & 7) == OPK_GLOBAL) { prefetch_l1(partials + (size_t)q.bOff * 4); prefetch_l1(cumExp + (size_t)q.bOff); }
+#pragma unroll
+                for (int side = 0; side < 2; side++) {
+                    if (((q.ctl >> (3 * side)) & 7) != OPK_GLOBAL) continue;
+                    const size_t off = side ? q.bOff : q.aOff;
+                    prefetch_l1(partials + off * 4); prefetch_l1(cumExp + off);
+                    if (dp != 0 && p + dp >= 0 && p + dp < nPat) prefetch_l1(partials + (off + dp) * 4);
+                }
             }
+        }
         double prev[1][4] = {{0.0, 0.0, 0.0, 0.0}};
         int prevCum = 0;
         for (int k = 0; k < nOps; k++) {
@@ -158,16 +168,15 @@ __device__ __forceinline__ void step_walk(const StepArgs &A, const LocusDesc &d,
     }
     __syncthreads();   // every category's root sits in stack slot 0
     if (active && c == 0) {
-        const LocusParams *prm = &A.prep.params[l];
-        const double *freqs = (prm->substKind == 0) ? prm->subst + 1 : prm->subst + 36;
+        const double *freqs = (prm->substKind == 0) ? prm->subst + 1 : prm->subst + 36;   // the CTA's shared-memory copy
         const double *props = A.catProps + d.catBase;
         const double pInv = prm->pInv;
         double contrib = 0.0;
         if (valid) {
-            const int mask = (pInv > 0.0) ? A.constMask[d.patBase + p] : 0;
+            const int mask = (pInv > 0.0) ? constMask : 0;
             const double lk = root_pattern_logl<false>(st2, planeStride, sexp, chunk * C * 32 + lane, 32, C, props, freqs, pInv, mask);
             A.patLogL[d.patBase + p] = lk;
-            contrib = __dmul_rn(lk, (double)A.weights[d.patBase + p]);
+            contrib = __dmul_rn(lk, (double)weight);
         }
         contrib = chunk_sum(contrib);
         const int ch = (p0 >> 5) + chunk;
@@ -175,7 +184,7 @@ __device__ __forceinline__ void step_walk(const StepArgs &A, const LocusDesc &d,
     }
 }
 
-__global__ void __launch_bounds__(STEP_THREADS, 1) k_step(StepArgs A)
+__global__ void __launch_bounds__(STEP_THREADS, 2) k_step(const __grid_constant__ StepArgs A)
 {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     __shared__ LocusParams sprm;
@@ -183,6 +192,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(StepArgs A)
     __shared__ unsigned s_last;
     const int tid = threadIdx.x;
     const unsigned rank = cluster_ctarank(), cid = cluster_id_x();
+    auto stamp = [&](int i) {   // profile mode only: where the time of one step goes (sb2_step_phase_times)
+        if (A.dbg && tid == 0 && rank == 0 && cid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); A.dbg[i] = t; }
+    };
+    stamp(0);
     const bool leader = rank == 0;
     const bool single = A.nRun > 0;
     const int l = single ? A.runLoci[cid] : (int)cid;
@@ -202,7 +215,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(StepArgs A)
         cluster_arrive_release(); cluster_wait_acquire();
         return;
     }
+    int weight = 0, constMask = 0;
     if (run) {
+        {   // static inputs of the root epilogue, per thread: fetched now, needed after the walk
+            const int C2 = A.nCat, w = tid >> 5, chunk = w / C2, p = (int)rank * tilePat + chunk * 32 + (tid & 31);
+            if (w % C2 == 0 && w < C2 * (STEP_WARPS / C2) && p < d.nPat) { weight = A.weights[d.patBase + p]; constMask = A.constMask[d.patBase + p]; }
+            if (tid < C2) prefetch_l1(A.catProps + d.catBase + tid);
+        }
         if (hasTile) {   // the tile's tip states (static input): asynchronous 16-byte copies that land while the tree work runs
             uint8_t *sstate = smem_raw + m.sstate;
             const uint8_t *states = A.tipStates + d.stateBase + (size_t)rank * tilePat;
@@ -220,15 +239,21 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(StepArgs A)
         F.sops = reinterpret_cast<Op *>(smem_raw + m.sops);
         F.smats = reinterpret_cast<double *>(smem_raw + m.smd);
         F.nOpsOut = &s_nOps;
-        prepare_locus<true>(A.prep, A.maxNodes, l, fl, smem_raw + m.prep, sprm, F);   // cluster barrier 1: all arrive, the leader waits
-        cp_async_wait<0>();
-        __syncthreads();
+        F.dbg = (leader && cid == 0) ? A.dbg : nullptr;
+        F.treeSrc = (single && cid == 0 && A.inlineTreeBytes > 0) ? A.inlineTree : nullptr;
+        F.splitReturn = true;
+        // cluster barrier 1 inside: all arrive, the leader waits
+        if (prepare_locus<true>(A.prep, A.maxNodes, l, fl, smem_raw + m.prep, sprm, F) == PREP_HALVES && tid < STEP_THREADS / 2)
+            asm volatile("bar.sync 4, %0;" ::"n"(STEP_THREADS) : "memory");   // the likelihood half's schedule and matrices
+        stamp(1);
         const int nOps = s_nOps;
-        if (hasTile && nOps > 0) step_walk(A, d, l, (int)rank, nOps, m, smem_raw, schunk);
+        if (hasTile && nOps > 0) step_walk(A, d, &sprm, (int)rank, nOps, m, smem_raw, schunk, weight, constMask);
+        stamp(2);
         if (!leader) cluster_wait_acquire();   // barrier 1 (completed long ago)
         cluster_arrive_release();              // barrier 2: the chunk sums are in the leader's shared memory
         cluster_wait_acquire();
         if (!leader) return;
+        stamp(3);
         if (nOps > 0 && tid == 0) {            // the locus's log-likelihood: chunk sums in pattern order, as k_reduce_* adds them
             double lik = 0.0;
             for (int ch = 0; ch < d.nChunks; ch++) lik += schunk[ch];
@@ -255,12 +280,16 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(StepArgs A)
         if (!s_last) return;
         __threadfence();
     }
-    reduce_local_body(A.red);                  // red.useTiles == 0: per-locus values come from the state block
-    __threadfence_block();
-    __syncthreads();
+    stamp(4);
+    double sums3[3];
+    reduce_local_body(A.red, -1, 0, sums3);    // red.useTiles == 0: per-locus values come from the state block
+    if (A.useComm || A.red.popKind == 2) { __threadfence_block(); __syncthreads(); }   // sums that travel through the reduce vector
+    stamp(6);
     if (A.useComm) xgpu_exchange_body(A.red, A.comm);
-    finish_body(A.red);
+    finish_body(A.red, A.useComm ? nullptr : sums3);
+    stamp(7);
     publish_body(A.red);
+    stamp(5);
 }
 
 cudaError_t launch_step(const StepArgs &a, int nClusters, int clusterSize, cudaStream_t st)

@@ -81,7 +81,7 @@ def test_java_jni_sources_stay_consistent_with_the_header():
     assert called <= declared, sorted(called - declared)
     not_for_a_jvm = {"sb2_bind_reduce_vector", "sb2_comm_connect", "sb2_comm_handle", "sb2_set_stream",          # torch / one process per GPU
                      "sb2_device_bytes", "sb2_get_matrices", "sb2_get_partials", "sb2_get_pattern_logl", "sb2_kernel_time",
-                     "sb2_last_node_updates", "sb2_set_profile", "sb2_exchange_wait_us",                                                    # introspection for tests / bench
+                     "sb2_last_node_updates", "sb2_set_profile", "sb2_exchange_wait_us", "sb2_step_phase_times",                                                    # introspection for tests / bench
                      "sb2_compress_alignment", "sb2_compress_last_error"}                                             # BEAST's own Alignment compresses on the host
     assert declared - called == not_for_a_jvm, sorted((declared - called) ^ not_for_a_jvm)
 

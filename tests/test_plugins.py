@@ -315,7 +315,9 @@ def test_posterior_protocol_with_tree_likelihoods():
             speciesTree.setHeight(child, speciesTree.arrays.height[root] * 0.9999)
             assert posterior.calculateLogP() == -math.inf
             eng = likelihoods[0].session.engine
-            assert eng.launch_count() - launches_lik == (2 if strict else 3)   # k_prepare (+ speculative pruning kernel) + the fused reduction
+            # strict: k_prepare + the reduction, the pruning kernel never launched; default: + the speculative pruning kernel
+            # (a species-tree move re-embeds every locus: the three-kernel path; single-locus moves take ONE launch, k_step)
+            assert eng.launch_count() - launches_lik == (2 if strict else 3)
             speciesTree.restore(); posterior.restore()
             assert posterior.calculateLogP() == before
         finally:
