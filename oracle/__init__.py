@@ -84,6 +84,11 @@ def lib():
         L.sb2o_tree_likelihood.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _f64p, _u8p, _i32p,
                                            C.c_int, _f64p, _f64p, _f64p, C.c_double, C.c_void_p, _f64p, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sb2o_eigen_matrix_k.restype = None
+        L.sb2o_eigen_matrix_k.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_double, _f64p]
+        L.sb2o_tree_likelihood_k.restype = C.c_double
+        L.sb2o_tree_likelihood_k.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _f64p, _u8p, _i32p,
+                                             _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.sb2o_posterior.restype = C.c_int
         L.sb2o_random_local_rates.restype = None
         L.sb2o_random_local_rates.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f64p, _u8p, _f64p, C.c_double, _f64p]
@@ -229,6 +234,32 @@ def tree_likelihood(locus, branch_rates, use_scaling: int = 2, want_details: boo
     return ll
 
 
+def split_eigen_k(K: int, sp):
+    sp = np.ascontiguousarray(sp, np.float64)
+    return sp[0:K].copy(), sp[K:K + K * K].copy(), sp[K + K * K:K + 2 * K * K].copy(), sp[K + 2 * K * K:K + 2 * K * K + K].copy()
+
+
+def eigen_matrix_k(K, evals, evec, ievc, distance) -> np.ndarray:
+    out = np.zeros(K * K)
+    lib().sb2o_eigen_matrix_k(K, np.ascontiguousarray(evals, np.float64), np.ascontiguousarray(evec, np.float64).reshape(K * K),
+                              np.ascontiguousarray(ievc, np.float64).reshape(K * K), distance, out)
+    return out.reshape(K, K)
+
+
+def tree_likelihood_k(part, tree, branch_rates=None, use_scaling: int = 2, want_patterns: bool = False):
+    """TreeLikelihood.calculateLogP of a K-state partition (starbeast2_b200.problem.MorphPartition) on `tree`, everything
+    dirty, with the ascertainment correction when part.excluded is not empty."""
+    K, G, nT, P, Cn = part.n_states, tree.n_nodes, part.n_tips, part.n_pat, part.n_cat
+    ev, vec, ivec, pi = split_eigen_k(K, part.subst_params)
+    br = np.full(G, part.clock_rate) if branch_rates is None else np.ascontiguousarray(branch_rates, np.float64)
+    pat = np.zeros(P) if want_patterns else None
+    exc = np.ascontiguousarray(part.excluded, np.int32)
+    ll = lib().sb2o_tree_likelihood_k(G, nT, P, Cn, K, tree.parent, tree.left, tree.right, tree.height, part.tip_states, part.weights,
+                                      ev, vec, ivec, pi, part.cat_rates, part.cat_props, br, use_scaling,
+                                      len(exc), exc.ctypes.data if len(exc) else None, pat.ctypes.data if pat is not None else None)
+    return (ll, pat) if want_patterns else ll
+
+
 class PosteriorResult:
     def __init__(self, per_locus_coal, per_locus_lik, per_branch, total):
         self.per_locus_coal = per_locus_coal
@@ -304,6 +335,13 @@ def posterior(pb, n_threads: int = 1, use_scaling: int = 2, flat: Optional[FlatP
     br = np.zeros(fp.S)
     tot = np.zeros(3)
     lib().sb2o_posterior(C.byref(fp.struct), n_threads, use_scaling, coal, lik, br, tot)
+    morph = getattr(pb, "morph", None) or []
+    if morph:   # K-state likelihoods on the species tree: appended after the loci, no coalescent term
+        extra = np.array([tree_likelihood_k(m, pb.species, use_scaling=use_scaling) for m in morph])
+        coal = np.concatenate([coal, np.zeros(len(morph))])
+        lik = np.concatenate([lik, extra])
+        tot[1] += extra.sum()
+        tot[2] = tot[0] + tot[1]
     return PosteriorResult(coal, lik, br, tot)
 
 

@@ -598,6 +598,159 @@ SB2O_API double sb2o_tree_likelihood(
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* (1c') K-state likelihoods: the morphological TreeLikelihoods of the FBD    */
+/*      configs -- /root/reference/tutorial/CanisFBD/Canis-FBD.xml:964-1033: TreeLikelihood on    */
+/*      tree="@Tree.t:Species", StandardData with nrOfStates 2..5, LewisMK, ascertained           */
+/*      FilteredAlignment.  The classes are BEAST.base's generic BeerLikelihoodCore /             */
+/*      GeneralSubstitutionModel / Alignment.getAscertainmentCorrection and the morph-models       */
+/*      package's LewisMK (neither under /root/reference): restated from the published            */
+/*      algorithm, the loops of the 4-state versions above with nrOfStates in place of 4.          */
+/*      PARITY UNPINNED like the rest of the BEAST.base half; pinned by brute force over internal  */
+/*      states and by the Mk closed form (tests/test_oracle_kstate.py).                            */
+/* ------------------------------------------------------------------------------------------ */
+
+/* GeneralSubstitutionModel.getTransitionProbabilities for K states: P = |V exp(d L) V^-1| */
+SB2O_API void sb2o_eigen_matrix_k(int K, const double *Eval, const double *Evec, const double *Ievc, double distance, double *matrix)
+{
+    double iexp[64];
+    for (int i = 0; i < K; i++) {
+        const double temp = exp(distance * Eval[i]);
+        for (int j = 0; j < K; j++) iexp[i * K + j] = Ievc[i * K + j] * temp;
+    }
+    int u = 0;
+    for (int i = 0; i < K; i++)
+        for (int j = 0; j < K; j++) {
+            double temp = 0.0;
+            for (int k = 0; k < K; k++) temp += Evec[i * K + k] * iexp[k * K + j];
+            matrix[u++] = fabs(temp);
+        }
+}
+
+typedef struct {
+    int G, nTips, nPat, nCat, K;
+    const int32_t *left, *right, *parent;
+    const double *height;
+    const uint8_t *tipStates;
+    const double *Eval, *Evec, *Ievc, *catRates, *branchRates;
+    double *partials; /* [G - nTips][nCat][nPat][K] */
+    double *matrices; /* [G][nCat][K*K] */
+    double *scaling;  /* [G - nTips][nPat] or NULL */
+} tlk_ctx;
+
+/* BeerLikelihoodCore.calculate{StatesStates,StatesPartials,PartialsPartials}Pruning + scalePartials, generic state count;
+ * a tip state >= K (gap / '?' / ambiguity with useAmbiguities=false) contributes the factor 1 */
+static void tlk_traverse(const tlk_ctx *c, int node)
+{
+    const int K = c->K, KK = K * K;
+    const int par = c->parent[node];
+    if (par >= 0)
+        for (int i = 0; i < c->nCat; i++) {
+            const double jointBranchRate = c->catRates[i] * c->branchRates[node];
+            sb2o_eigen_matrix_k(K, c->Eval, c->Evec, c->Ievc, (c->height[par] - c->height[node]) * jointBranchRate,
+                                c->matrices + ((size_t)node * c->nCat + i) * KK);
+        }
+    if (node < c->nTips) return;
+    const int c1 = c->left[node], c2 = c->right[node];
+    tlk_traverse(c, c1);
+    tlk_traverse(c, c2);
+    const size_t psz = (size_t)c->nCat * c->nPat * K;
+    double *p3 = c->partials + (size_t)(node - c->nTips) * psz;
+    const double *m1 = c->matrices + (size_t)c1 * c->nCat * KK, *m2 = c->matrices + (size_t)c2 * c->nCat * KK;
+    const uint8_t *s1 = c1 < c->nTips ? c->tipStates + (size_t)c1 * c->nPat : NULL;
+    const uint8_t *s2 = c2 < c->nTips ? c->tipStates + (size_t)c2 * c->nPat : NULL;
+    const double *p1 = s1 ? NULL : c->partials + (size_t)(c1 - c->nTips) * psz;
+    const double *p2 = s2 ? NULL : c->partials + (size_t)(c2 - c->nTips) * psz;
+    size_t u = 0, v = 0;
+    for (int l = 0; l < c->nCat; l++)
+        for (int k = 0; k < c->nPat; k++) {
+            int w = l * KK;
+            for (int i = 0; i < K; i++, w += K) {
+                double f1, f2;
+                if (s1) f1 = s1[k] < K ? m1[w + s1[k]] : 1.0;
+                else { f1 = 0.0; for (int j = 0; j < K; j++) f1 += m1[w + j] * p1[v + j]; }
+                if (s2) f2 = s2[k] < K ? m2[w + s2[k]] : 1.0;
+                else { f2 = 0.0; for (int j = 0; j < K; j++) f2 += m2[w + j] * p2[v + j]; }
+                p3[u++] = f1 * f2;
+            }
+            v += K;
+        }
+    if (c->scaling) {
+        double *scal = c->scaling + (size_t)(node - c->nTips) * c->nPat;
+        for (int i = 0; i < c->nPat; i++) {
+            double scaleFactor = 0.0;
+            for (int k = 0; k < c->nCat; k++)
+                for (int j = 0; j < K; j++) { const double x = p3[((size_t)k * c->nPat + i) * K + j]; if (x > scaleFactor) scaleFactor = x; }
+            if (scaleFactor < 1.0E-100) {
+                for (int k = 0; k < c->nCat; k++)
+                    for (int j = 0; j < K; j++) p3[((size_t)k * c->nPat + i) * K + j] /= scaleFactor;
+                scal[i] = log(scaleFactor);
+            } else scal[i] = 0.0;
+        }
+    }
+}
+
+/*
+ * TreeLikelihood.calculateLogP for K states (2..8), everything dirty, optionally with ascertainment correction:
+ * excluded[nExcluded] = the pattern indices Alignment puts in excludedPatterns (their weight is 0); then
+ *   correction = log(1 - sum_excluded exp(patternLogL))            (Alignment.getAscertainmentCorrection)
+ *   logP = sum_p (patternLogL[p] - correction) * weight[p]         (TreeLikelihood.calcLogP, useAscertainedSitePatterns)
+ * useScaling as in sb2o_tree_likelihood.  patternLogL (optional) receives the uncorrected values.
+ */
+SB2O_API double sb2o_tree_likelihood_k(
+    int G, int nTips, int nPat, int nCat, int K,
+    const int32_t *parent, const int32_t *left, const int32_t *right, const double *height,
+    const uint8_t *tipStates, const int32_t *weights,
+    const double *Eval, const double *Evec, const double *Ievc, const double *freqs,
+    const double *catRates, const double *catProps, const double *branchRates, int useScaling,
+    int nExcluded, const int32_t *excluded, double *patternLogL)
+{
+    const int nInt = G - nTips;
+    const size_t psz = (size_t)nCat * nPat * K;
+    double *partials = (double *)malloc(sizeof(double) * psz * nInt);
+    double *matrices = (double *)calloc((size_t)G * nCat * K * K, sizeof(double));
+    double *scaling = (double *)calloc((size_t)nInt * nPat, sizeof(double));
+    double *rootPartials = (double *)malloc(sizeof(double) * (size_t)nPat * K);
+    double *plog = (double *)malloc(sizeof(double) * (size_t)nPat);
+    int root = G - 1;
+    for (int i = 0; i < G; i++) if (parent[i] < 0) root = i;
+    double logP = 0.0;
+    for (int pass = 0; pass < 2; pass++) {
+        const int scaled = (useScaling == 1) || (useScaling == 2 && pass == 1);
+        tlk_ctx c = {G, nTips, nPat, nCat, K, left, right, parent, height, tipStates, Eval, Evec, Ievc, catRates, branchRates,
+                     partials, matrices, scaled ? scaling : NULL};
+        if (root < nTips) { logP = NAN; break; }
+        tlk_traverse(&c, root);
+        const double *rp = partials + (size_t)(root - nTips) * psz;
+        for (int k = 0; k < nPat; k++)
+            for (int i = 0; i < K; i++) rootPartials[k * K + i] = rp[k * K + i] * catProps[0];
+        for (int l = 1; l < nCat; l++)
+            for (int k = 0; k < nPat; k++)
+                for (int i = 0; i < K; i++) rootPartials[k * K + i] += rp[((size_t)l * nPat + k) * K + i] * catProps[l];
+        for (int k = 0; k < nPat; k++) {
+            double sum = 0.0;
+            for (int i = 0; i < K; i++) sum += freqs[i] * rootPartials[k * K + i];
+            double logScale = 0.0;
+            if (scaled) for (int nd = 0; nd < nInt; nd++) logScale += scaling[(size_t)nd * nPat + k];
+            plog[k] = log(sum) + logScale;
+        }
+        logP = 0.0;
+        if (nExcluded > 0) {
+            double excludeProb = 0.0, returnProb = 1.0;
+            for (int i = 0; i < nExcluded; i++) excludeProb += exp(plog[excluded[i]]);
+            returnProb -= excludeProb;
+            const double corr = log(returnProb);
+            for (int k = 0; k < nPat; k++) logP += (plog[k] - corr) * weights[k];
+        } else {
+            for (int k = 0; k < nPat; k++) logP += plog[k] * weights[k];
+        }
+        if (useScaling != 2 || pass == 1 || !(logP == -INFINITY)) break;
+    }
+    if (patternLogL) memcpy(patternLogL, plog, sizeof(double) * (size_t)nPat);
+    free(partials); free(matrices); free(scaling); free(rootPartials); free(plog);
+    return logP;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* (1d) operator-side walks over every gene tree -- PARITY UNPINNED: the    */
 /*      reference has no test of CoordinatedUniform / CoordinatedExponential / NodeReheight2,   */
 /*      so these follow the Java recursions literally and are checked by properties only.       */

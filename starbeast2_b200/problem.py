@@ -19,7 +19,8 @@ import numpy as np
 
 SUBST_HKY = 0
 SUBST_EIGEN = 1
-SUBST_STRIDE = 40
+SUBST_STRIDE = 40          # doubles of a 4-state model; K-state models take K + 2 K^2 + K (<= SUBST_STRIDE_MAX)
+SUBST_STRIDE_MAX = 64
 
 CLOCK_STRICT = 0
 CLOCK_SPECIES_RATES = 1
@@ -166,6 +167,64 @@ class Locus:
         return self.n_pat * (self.n_tips - 1) * self.n_cat
 
 
+def eigen_params_k(evals, evec, ievc, pi) -> np.ndarray:
+    """{eval[K], evec[K*K], ievc[K*K], pi[K]} (row-major), the K-state layout of SB2_SUBST_EIGEN; K = 4 gives eigen_params."""
+    K = len(evals)
+    sp = np.zeros(K + 2 * K * K + K)
+    sp[0:K] = evals
+    sp[K:K + K * K] = np.asarray(evec).reshape(K * K)
+    sp[K + K * K:K + 2 * K * K] = np.asarray(ievc).reshape(K * K)
+    sp[K + 2 * K * K:] = pi
+    return sp
+
+
+def lewis_mk_eigen(K: int) -> np.ndarray:
+    """LewisMK (morph-models package, named at tutorial/CanisFBD/Canis-FBD.xml:975): all K (K-1) rates equal, equal
+    frequencies, normalised to one expected change per unit time as GeneralSubstitutionModel does:
+    Q_ij = 1/(K-1) (i != j), Q_ii = -1.  Symmetric, so an orthonormal eigen system serves as (V, V^-1)."""
+    q = np.full((K, K), 1.0 / (K - 1))
+    np.fill_diagonal(q, -1.0)
+    w, u = np.linalg.eigh(q)
+    return eigen_params_k(w, u, u.T, np.full(K, 1.0 / K))
+
+
+@dataclass
+class MorphPartition:
+    """One morphological TreeLikelihood of the FBD configs: K-state characters scored on the SPECIES tree's tips
+    (tutorial/CanisFBD/Canis-FBD.xml:964-1033), a likelihood without a coalescent term.  `excluded` lists the ascertained
+    dummy patterns of an `ascertained="true"` FilteredAlignment (their weight is 0)."""
+    tip_states: np.ndarray          # uint8 [n species leaves, n_pat]; >= n_states: missing / ambiguous
+    weights: np.ndarray             # int32 [n_pat]
+    n_states: int
+    subst_params: np.ndarray        # eigen_params_k layout
+    cat_rates: np.ndarray = field(default_factory=lambda: np.ones(1))
+    cat_props: np.ndarray = field(default_factory=lambda: np.ones(1))
+    clock_rate: float = 1.0
+    excluded: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+
+    def __post_init__(self):
+        self.tip_states = np.ascontiguousarray(self.tip_states, dtype=np.uint8)
+        self.weights = _i32(self.weights)
+        self.subst_params = _f64(self.subst_params)
+        self.cat_rates = _f64(self.cat_rates)
+        self.cat_props = _f64(self.cat_props)
+        self.excluded = _i32(self.excluded)
+        K = self.n_states
+        assert 2 <= K <= 5 and self.subst_params.shape[0] == K + 2 * K * K + K
+
+    @property
+    def n_tips(self) -> int:
+        return int(self.tip_states.shape[0])
+
+    @property
+    def n_pat(self) -> int:
+        return int(self.weights.shape[0])
+
+    @property
+    def n_cat(self) -> int:
+        return int(self.cat_rates.shape[0])
+
+
 @dataclass
 class Problem:
     species: TreeArrays
@@ -176,6 +235,7 @@ class Problem:
     pop_b: Optional[np.ndarray] = None           # LWCR: top sizes [S-1]
     alpha: float = 0.0                           # ANALYTIC: populationShape
     beta: float = 0.0                            # ANALYTIC: mean*(alpha-1), by the reference rule (quirk Q1)
+    morph: List[MorphPartition] = field(default_factory=list)   # K-state likelihoods on the species tree (after the loci in every per-locus output)
 
     def __post_init__(self):
         S = self.species.n_nodes

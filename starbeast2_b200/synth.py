@@ -14,7 +14,7 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-from .problem import (CLOCK_SPECIES_RATES, CLOCK_STRICT, POP_ANALYTIC, POP_CONSTANT, POP_LWCR, SUBST_EIGEN,
+from .problem import (CLOCK_SPECIES_RATES, CLOCK_STRICT, POP_ANALYTIC, POP_CONSTANT, POP_LWCR, SUBST_EIGEN, MorphPartition, lewis_mk_eigen,
                       SUBST_HKY, Locus, Problem, TreeArrays, gtr_eigen_params, hky_params)
 
 
@@ -196,6 +196,44 @@ def simulate_alignment(rng, tree: TreeArrays, n_tips: int, n_sites: int, kind: i
     return np.ascontiguousarray(pats, np.uint8), weights.astype(np.int32)
 
 
+def simulate_morphology(rng, sp: TreeArrays, K: int, n_chars: int, clock_rate: float, missing_frac: float = 0.05):
+    """K-state characters evolved down the SPECIES tree under Lewis's Mk, kept only if variable (Mkv ascertainment), compressed
+    to patterns, with the K constant dummy patterns of an `ascertained="true"` alignment appended at weight 0 (the
+    excludefrom / excludeto columns of tutorial/CanisFBD/Canis-FBD.xml:969-971).  Returns (patterns, weights, excluded)."""
+    n_leaves, G = sp.n_leaves, sp.n_nodes
+
+    def mk(t):
+        e = np.exp(-K * t / (K - 1.0))
+        p = np.full((K, K), 1.0 / K - e / K)
+        np.fill_diagonal(p, 1.0 / K + (K - 1.0) * e / K)
+        return p
+
+    cols = []
+    while len(cols) < n_chars:
+        st = np.zeros(G, np.int64)
+        st[sp.root] = rng.integers(0, K)
+        stack = [sp.root]
+        while stack:
+            n = stack.pop()
+            for c in (sp.left[n], sp.right[n]):
+                if c < 0:
+                    continue
+                c = int(c)
+                st[c] = rng.choice(K, p=mk((sp.height[n] - sp.height[c]) * clock_rate)[st[n]])
+                stack.append(c)
+        col = st[:n_leaves].astype(np.uint8)
+        if len(np.unique(col)) > 1:
+            cols.append(col)
+    tips = np.stack(cols, axis=1)
+    tips[rng.uniform(size=tips.shape) < missing_frac] = K    # '?'
+    pats, weights = np.unique(tips, axis=1, return_counts=True)
+    dummies = np.stack([np.full(n_leaves, s, np.uint8) for s in range(K)], axis=1)
+    excluded = np.arange(pats.shape[1], pats.shape[1] + K, dtype=np.int32)
+    pats = np.concatenate([pats, dummies], axis=1)
+    weights = np.concatenate([weights, np.zeros(K, weights.dtype)])
+    return np.ascontiguousarray(pats, np.uint8), weights.astype(np.int32), excluded
+
+
 CONFIGS = {
     # name: loci, sites, species, tips/species, subst, n_cat, clock, pop model
     "C2": dict(n_loci=50, n_sites=1000, n_species=10, tips_per=3, subst="hky", n_cat=1, clock="strict", pop="constant", seed=2),
@@ -284,8 +322,17 @@ def make_problem(name: str = "C2", n_loci: Optional[int] = None, n_sites: Option
         loci.append(Locus(tree=tree, tip_states=pats, weights=w, tip_species=tip_species, ploidy=ploidy,
                           subst_kind=kind, subst_params=sparams, cat_rates=cat_rates, cat_props=cat_props,
                           clock_kind=clock_kind, clock_rate=clock_rate))
+    # morphological partitions on the species tree (CanisFBD-style: one TreeLikelihood per state count, LewisMK, ascertained)
+    morph = []
+    for mi in range(int(cfg.get("n_morph", 0))):
+        rng = np.random.Generator(np.random.PCG64([base_seed, 900000 + mi]))
+        K = 2 + mi % 4
+        rate = 0.6 / max(float(sp.height[sp.root]), 1e-6)
+        pats, w, excl = simulate_morphology(rng, sp, K, int(cfg.get("n_chars", 24)), rate)
+        morph.append(MorphPartition(tip_states=pats, weights=w, n_states=K, subst_params=lewis_mk_eigen(K),
+                                    clock_rate=rate * float(np.exp(rng.normal(0.0, 0.2))), excluded=excl))
     return Problem(species=sp, loci=loci, species_rates=srates, pop_kind=pop_kind, pop_a=pop_a, pop_b=pop_b,
-                   alpha=alpha, beta=beta)
+                   alpha=alpha, beta=beta, morph=morph)
 
 
 def make_problem_parallel(name: str, n_loci: Optional[int] = None, locus_range: Optional[Tuple[int, int]] = None,
