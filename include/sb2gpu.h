@@ -64,6 +64,20 @@ SB2_API int sb2_add_locus(sb2_engine *e, int32_t nTips, int32_t nPatterns, const
                           const int32_t *patternWeights, int32_t nCategories, const int32_t *tipToSpecies,
                           double ploidy);
 
+/* General form.  tipToSpecies != NULL: as sb2_add_locus (nStates must be 4, nExcluded 0).
+ * tipToSpecies == NULL: a LIKELIHOOD-ONLY locus -- a TreeLikelihood whose tree is not a GeneTree, i.e. the morphological
+ * partitions that the FBD configurations score on the species tree (tutorial/CanisFBD/Canis-FBD.xml:964-1033:
+ * spec="TreeLikelihood" tree="@Tree.t:Species", StandardData nrOfStates 2..5, LewisMK, ascertained FilteredAlignment).
+ * It has no embedding and no coalescent term (its perLocus coalescent entry is 0); nStates in 2..5, states >= nStates are
+ * gaps / '?'; its tree is staged with sb2_set_gene_tree like any other (for these partitions: the species tree's arrays, tips =
+ * the species tree's leaves), its model with sb2_set_subst_model(SB2_SUBST_EIGEN, {eval[K], evec[K*K], ievc[K*K], pi[K]}),
+ * its clock is STRICT or EXPLICIT, proportionInvariant must be 0.  excludedPatterns[nExcluded] = Alignment.excludedPatterns of
+ * an ascertained alignment (their weight is 0): logP = sum_p (patternLogL[p] - log(1 - sum_excluded exp(patternLogL))) * weight[p]
+ * (Alignment.getAscertainmentCorrection, TreeLikelihood.calcLogP; BEAST.base).  Returns the locus index or an error. */
+SB2_API int sb2_add_locus_k(sb2_engine *e, int32_t nTips, int32_t nPatterns, int32_t nStates, const uint8_t *tipStates,
+                            const int32_t *patternWeights, int32_t nCategories, const int32_t *tipToSpecies, double ploidy,
+                            int32_t nExcluded, const int32_t *excludedPatterns);
+
 /* Shards nothing (one engine = one GPU; the host shards loci over engines), allocates device state. */
 SB2_API int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves);
 

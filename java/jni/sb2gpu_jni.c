@@ -40,6 +40,16 @@ JNIEXPORT jint JNICALL FN(addLocus)(JNIEnv *env, jclass c, jlong h, jint nTips, 
     UNPIN(tipSp, t, JNI_ABORT); UNPIN(weights, w, JNI_ABORT); UNPIN(states, s, JNI_ABORT);
     return rc;
 }
+JNIEXPORT jint JNICALL FN(addLocusK)(JNIEnv *env, jclass c, jlong h, jint nTips, jint nPat, jint nStates, jbyteArray states, jintArray weights,
+                                     jint nCat, jintArray tipSp, jdouble ploidy, jintArray excluded)
+{
+    const jint nExcl = excluded ? (*env)->GetArrayLength(env, excluded) : 0;
+    void *s = PIN(states), *w = PIN(weights), *t = PIN(tipSp), *x = PIN(excluded);
+    int rc = sb2_add_locus_k(E(h), nTips, nPat, nStates, (const uint8_t *)s, (const int32_t *)w, nCat, (const int32_t *)t, ploidy,
+                             nExcl, (const int32_t *)x);
+    UNPIN(excluded, x, JNI_ABORT); UNPIN(tipSp, t, JNI_ABORT); UNPIN(weights, w, JNI_ABORT); UNPIN(states, s, JNI_ABORT);
+    return rc;
+}
 JNIEXPORT jint JNICALL FN(finalizeEngine)(JNIEnv *env, jclass c, jlong h, jint S, jint leaves) { return sb2_finalize(E(h), S, leaves); }
 
 static jint set_tree(JNIEnv *env, jlong h, jint locus, jintArray p, jintArray l, jintArray r, jdoubleArray ht)

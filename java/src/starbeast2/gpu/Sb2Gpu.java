@@ -18,6 +18,9 @@ public final class Sb2Gpu {
     public static native String lastError(long engine);                            // sb2_last_error
     public static native int addLocus(long engine, int nTips, int nPatterns, byte[] tipStates, int[] patternWeights,
                                       int nCategories, int[] tipToSpecies, double ploidy);   // sb2_add_locus
+    // likelihood-only K-state locus (tipToSpecies == null): the morphological TreeLikelihoods on the species tree; sb2_add_locus_k
+    public static native int addLocusK(long engine, int nTips, int nPatterns, int nStates, byte[] tipStates, int[] patternWeights,
+                                       int nCategories, int[] tipToSpeciesOrNull, double ploidy, int[] excludedPatternsOrNull);
     public static native int finalizeEngine(long engine, int nSpeciesNodes, int nSpeciesLeaves);   // sb2_finalize
     public static native int setSpeciesTree(long engine, int[] parent, int[] left, int[] right, double[] height);
     public static native int setGeneTree(long engine, int locus, int[] parent, int[] left, int[] right, double[] height);

@@ -58,6 +58,7 @@ public final class Sb2GpuFfm {
     private static final MethodHandle DESTROY = bind("sb2_destroy", null, ADDRESS);
     private static final MethodHandle LAST_ERROR = bind("sb2_last_error", ADDRESS, ADDRESS);
     private static final MethodHandle ADD_LOCUS = bind("sb2_add_locus", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_DOUBLE);
+    private static final MethodHandle ADD_LOCUS_K = bind("sb2_add_locus_k", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_DOUBLE, JAVA_INT, ADDRESS);
     private static final MethodHandle FINALIZE = bind("sb2_finalize", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT);
     private static final MethodHandle SET_SPECIES_TREE = bind("sb2_set_species_tree", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS);
     private static final MethodHandle SET_GENE_TREE = bind("sb2_set_gene_tree", JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS);
@@ -127,6 +128,12 @@ public final class Sb2GpuFfm {
 
     public static int addLocus(long engine, int nTips, int nPatterns, byte[] tipStates, int[] patternWeights, int nCategories, int[] tipToSpecies, double ploidy)
     { return rc(ADD_LOCUS, eng(engine), nTips, nPatterns, seg(tipStates), seg(patternWeights), nCategories, seg(tipToSpecies), ploidy); }
+    public static int addLocusK(long engine, int nTips, int nPatterns, int nStates, byte[] tipStates, int[] patternWeights, int nCategories,
+                                int[] tipToSpeciesOrNull, double ploidy, int[] excludedPatternsOrNull)
+    {
+        return rc(ADD_LOCUS_K, eng(engine), nTips, nPatterns, nStates, seg(tipStates), seg(patternWeights), nCategories, seg(tipToSpeciesOrNull), ploidy,
+                  excludedPatternsOrNull == null ? 0 : excludedPatternsOrNull.length, seg(excludedPatternsOrNull));
+    }
     public static int finalizeEngine(long engine, int nSpeciesNodes, int nSpeciesLeaves) { return rc(FINALIZE, eng(engine), nSpeciesNodes, nSpeciesLeaves); }
     public static int setSpeciesTree(long engine, int[] parent, int[] left, int[] right, double[] height)
     { return rc(SET_SPECIES_TREE, eng(engine), seg(parent), seg(left), seg(right), seg(height)); }

@@ -52,6 +52,7 @@ def load() -> C.CDLL:
         "sb2_destroy": (None, [E]),
         "sb2_last_error": (C.c_char_p, [E]),
         "sb2_add_locus": (C.c_int, [E, C.c_int32, C.c_int32, _u8p, _i32p, C.c_int32, _i32p, C.c_double]),
+        "sb2_add_locus_k": (C.c_int, [E, C.c_int32, C.c_int32, C.c_int32, _u8p, _i32p, C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_void_p]),
         "sb2_finalize": (C.c_int, [E, C.c_int32, C.c_int32]),
         "sb2_set_species_tree": (C.c_int, [E, _i32p, _i32p, _i32p, _f64p]),
         "sb2_set_gene_tree": (C.c_int, [E, C.c_int32, _i32p, _i32p, _i32p, _f64p]),

@@ -24,6 +24,7 @@ SOURCES = {
     "reduce.cu": ["-fmad=false"],
     "treewalk.cu": [],
     "step.cu": ["-fmad=false"],
+    "kstate.cu": ["-fmad=false"],
     "query.cu": ["-fmad=false"],
     "compress.cu": [],
     "engine.cu": [],

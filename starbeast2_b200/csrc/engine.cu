@@ -28,6 +28,7 @@ struct HostLocus {
     std::vector<int32_t> weights;
     std::vector<int32_t> tipSpecies;
     std::vector<uint8_t> constMask;
+    std::vector<int32_t> excluded;   // K-state loci: ascertained pattern indices
 };
 
 }  // namespace
@@ -43,6 +44,11 @@ struct sb2_engine {
     int64_t totalNodes = 0, totalTips = 0, totalPat = 0, totalCat = 0, totalInt = 0, totalTiles = 0;
     int maxNodes = 0, nCat = 0, chunksPerTile = 1, patPerThread = 1, stackDepth = 1, workers = 1;
     int32_t *dLaneOps = nullptr;
+    // K-state likelihood-only loci (kstate.cu)
+    int nK = 0, maxK = 0;
+    std::vector<int32_t> kLoci;
+    int32_t *dKLoci = nullptr, *dExcluded = nullptr, *dKExp = nullptr;
+    double *dKScratch = nullptr;
     // fused one-launch step (step.cu)
     bool fusedOk = false;            // shapes fit: cluster <= 16 CTAs per locus, shared memory, category count
     int fusedMode = -1;              // SB2_FUSED: 0 never, 1 whenever eligible, -1 auto (single-locus steps; all-loci steps of small problems)
@@ -388,12 +394,12 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
     int runCluster = e->fusedCluster;
     if (allowFused && e->fusedOk && e->fusedMode != 0 && !e->cfg.exact_order) {
         if (singleLocus >= 0) {
-            fused = true;
+            fused = e->loci[singleLocus].d.kStates == 0;   // a K-state locus goes through k_prepare + k_kstate
             const LocusDesc &d = e->loci[singleLocus].d;
             const int tilePat = (STEP_WARPS / e->nCat) * 32;
             runCluster = (d.nPat + tilePat - 1) / tilePat;
         } else {
-            fused = e->fusedMode == 1 || e->totalLanes <= e->fusedMaxLanes;
+            fused = e->nK == 0 && (e->fusedMode == 1 || e->totalLanes <= e->fusedMaxLanes);
         }
     }
     e->lastFusedSingle = -1;
@@ -447,6 +453,19 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
         if (e->cfg.profile) CUDA_TRY(e, cudaEventRecord(ev.second, st));
     } else {
         CUDA_TRY(e, launch_prepare(a, e->maxNodes, st));
+        bool kFlagged = false;
+        for (int32_t l : e->kLoci) kFlagged |= (e->hFlags[l] & LF_RUN) != 0;
+        if (kFlagged) {   // K-state likelihood-only loci: from scratch, on the tree k_prepare has just made current
+            KStateArgs k;
+            k.loci = e->dLoci; k.params = e->dParams; k.kLoci = e->dKLoci; k.flags = e->dFlags;
+            k.uniformFlags = uniformFlags; k.singleLocus = singleLocus; k.singleFlags = a.singleFlags;
+            k.tipStates = e->dStates; k.weights = e->dWeights; k.excluded = e->dExcluded;
+            k.catRates = e->dCat; k.catProps = e->dCat + e->totalCat; k.explicitRates = e->dExplicit ? e->dExplicit : e->dCat;
+            k.cur = cur(e); k.patLogL = e->dPatLogL; k.scratch = e->dKScratch; k.scratchExp = e->dKExp;
+            k.maxNodes = e->maxNodes; k.maxCat = e->nCat;
+            CUDA_TRY(e, launch_kstate(k, e->nK, e->maxK, st));
+            e->launches++;
+        }
     }
     if (didFused) *didFused = fused;
     e->launches++;
@@ -631,11 +650,27 @@ const char *sb2_last_error(const sb2_engine *e) { return e ? e->err.c_str() : "n
 int sb2_add_locus(sb2_engine *e, int32_t nTips, int32_t nPatterns, const uint8_t *tipStates, const int32_t *patternWeights,
                   int32_t nCategories, const int32_t *tipToSpecies, double ploidy)
 {
+    if (e && !tipToSpecies) return e->fail(SB2_ERR_ARG, "sb2_add_locus needs tipToSpecies (likelihood-only loci: sb2_add_locus_k)");
+    return sb2_add_locus_k(e, nTips, nPatterns, 4, tipStates, patternWeights, nCategories, tipToSpecies, ploidy, 0, nullptr);
+}
+
+int sb2_add_locus_k(sb2_engine *e, int32_t nTips, int32_t nPatterns, int32_t nStates, const uint8_t *tipStates, const int32_t *patternWeights,
+                    int32_t nCategories, const int32_t *tipToSpecies, double ploidy, int32_t nExcluded, const int32_t *excludedPatterns)
+{
     if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e) return SB2_ERR_ARG;
     if (e->finalized) return e->fail(SB2_ERR_STATE, "sb2_add_locus after sb2_finalize");
-    if (nTips < 2 || nPatterns < 1 || nCategories < 1 || nCategories > 32 || !tipStates || !patternWeights || !tipToSpecies)
+    if (nTips < 2 || nPatterns < 1 || nCategories < 1 || nCategories > 32 || !tipStates || !patternWeights)
         return e->fail(SB2_ERR_ARG, "bad locus shape: tips %d patterns %d categories %d (1..32)", nTips, nPatterns, nCategories);
+    // The 4-state pruning path pairs a TreeLikelihood with a GeneTree.  Anything else -- another state count, an ascertained
+    // alignment, a likelihood whose tree is not a gene tree -- is a K-state likelihood-only locus (kstate.cu).
+    const bool kstate = !tipToSpecies;
+    if (nStates < 2 || nStates > KSTATE_MAX) return e->fail(SB2_ERR_ARG, "nStates %d outside 2..%d", nStates, KSTATE_MAX);
+    if (!kstate && (nStates != 4 || nExcluded != 0))
+        return e->fail(SB2_ERR_ARG, "a locus with a gene-tree embedding (tipToSpecies) must be 4-state and not ascertained; K-state / ascertained data are likelihood-only (tipToSpecies = NULL)");
+    if (nExcluded < 0 || (nExcluded > 0 && !excludedPatterns)) return e->fail(SB2_ERR_ARG, "bad excluded-pattern list");
+    for (int i = 0; i < nExcluded; i++)
+        if (excludedPatterns[i] < 0 || excludedPatterns[i] >= nPatterns) return e->fail(SB2_ERR_ARG, "excluded pattern %d out of range", excludedPatterns[i]);
     if (nTips > 8192) return e->fail(SB2_ERR_ARG, "nTips %d > 8192: cumulative int16 exponents could overflow", nTips);
     if (!e->loci.empty() && e->loci[0].d.nCat != nCategories)
         return e->fail(SB2_ERR_ARG, "all loci of one engine must share the category count (%d vs %d)", e->loci[0].d.nCat, nCategories);
@@ -643,9 +678,12 @@ int sb2_add_locus(sb2_engine *e, int32_t nTips, int32_t nPatterns, const uint8_t
     memset(&hl.d, 0, sizeof hl.d);
     hl.d.nTips = nTips; hl.d.nNodes = 2 * nTips - 1; hl.d.nInt = nTips - 1; hl.d.nPat = nPatterns; hl.d.nCat = nCategories;
     hl.d.ploidy = ploidy;
+    hl.d.kStates = kstate ? nStates : 0; hl.d.nExcl = nExcluded;
     hl.states.assign(tipStates, tipStates + (size_t)nTips * nPatterns);
     hl.weights.assign(patternWeights, patternWeights + nPatterns);
-    hl.tipSpecies.assign(tipToSpecies, tipToSpecies + nTips);
+    if (tipToSpecies) hl.tipSpecies.assign(tipToSpecies, tipToSpecies + nTips);
+    else hl.tipSpecies.assign(nTips, 0);
+    if (nExcluded) hl.excluded.assign(excludedPatterns, excludedPatterns + nExcluded);
     // TreeLikelihood.calcConstantPatternIndices (useAmbiguities=false): states shared by every unambiguous tip
     hl.constMask.assign(nPatterns, 0xF);
     for (int t = 0; t < nTips; t++)
@@ -672,7 +710,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     // small ones are latency bound and want as many independent warps as possible (R=1).
     {
         int64_t threads1 = 0;
-        for (auto &hl : e->loci) threads1 += (int64_t)hl.d.nPat * hl.d.nCat;
+        for (auto &hl : e->loci) if (!hl.d.kStates) threads1 += (int64_t)hl.d.nPat * hl.d.nCat;
         // measured on B200 (same box A/B): R=2 is 1-6 % faster once the GPU is saturated (C3, C5 shard); small problems
         // (C2) are latency bound and want as many independent warps as possible
         e->patPerThread = threads1 > 150000 ? 2 : 1;
@@ -684,7 +722,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
         // k_prepare's worker assignment costs ~4 us -> the step gets slower (50.6 -> 54.9 us).  Kept for very short chains of
         // large trees; results are bit-identical either way (tests/test_gpu_parity.py).
         int maxInt = 0;
-        for (auto &hl : e->loci) maxInt = std::max(maxInt, hl.d.nTips - 1);
+        for (auto &hl : e->loci) if (!hl.d.kStates) maxInt = std::max(maxInt, hl.d.nTips - 1);
         e->workers = 1;
         if (const char *v = getenv("SB2_WORKERS")) {
             const int wv = atoi(v);
@@ -698,27 +736,38 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     }
     const int tilePat = 32 * e->chunksPerTile * e->patPerThread;
     int64_t nodeBase = 0, tipBase = 0, patBase = 0, catBase = 0, tileBase = 0, opBase = 0, stateBase = 0, partBase = 0, expBase = 0, matBase = 0, treeOff = 0, chunkBase = 0;
+    int64_t kBase = 0, exclBase = 0;
     e->stackDepth = 1;
     for (auto &hl : e->loci) {
         LocusDesc &d = hl.d;
-        for (int t = 0; t < d.nTips; t++)
+        for (int t = 0; t < d.nTips && !d.kStates; t++)
             if (hl.tipSpecies[t] < 0 || hl.tipSpecies[t] >= nSpeciesLeaves) return e->fail(SB2_ERR_ARG, "tipToSpecies must name a species LEAF (node number below the leaf count)");
         d.nodeBase = (int32_t)nodeBase; d.tipBase = (int32_t)tipBase; d.patBase = (int32_t)patBase; d.catBase = (int32_t)catBase;
-        d.tileBase = (int32_t)tileBase; d.nTiles = (d.nPat + tilePat - 1) / tilePat; d.opBase = (int32_t)opBase;
+        const bool ks = d.kStates != 0;   // K-state likelihood-only locus: no tiles, no schedule, no resident partials
+        d.tileBase = (int32_t)tileBase; d.nTiles = ks ? 0 : (d.nPat + tilePat - 1) / tilePat; d.opBase = (int32_t)opBase;
         d.stackDepth = floor_log2(d.nInt) + 1;
-        d.chunkBase = (int32_t)chunkBase; d.nChunks = (d.nPat + 31) / 32;
+        d.chunkBase = (int32_t)chunkBase; d.nChunks = ks ? 0 : (d.nPat + 31) / 32;
         chunkBase += d.nChunks;
         d.stateBase = stateBase; d.partBase = partBase; d.expBase = expBase; d.matBase = matBase; d.treeOff = treeOff;
-        e->stackDepth = std::max(e->stackDepth, d.stackDepth);
+        if (!ks) e->stackDepth = std::max(e->stackDepth, d.stackDepth);
         e->maxNodes = std::max(e->maxNodes, d.nNodes);
-        nodeBase += d.nNodes; tipBase += d.nTips; patBase += d.nPat; catBase += d.nCat; tileBase += d.nTiles; opBase += d.nInt;
+        nodeBase += d.nNodes; tipBase += d.nTips; patBase += d.nPat; catBase += d.nCat; tileBase += d.nTiles; opBase += ks ? 0 : d.nInt;
         d.stateStride = (d.nPat + 127) & ~127;
         stateBase += (int64_t)d.nTips * d.stateStride;
-        partBase += 2ll * d.nInt * d.nCat * d.nPat * 4;
-        expBase += 2ll * d.nInt * d.nCat * d.nPat;
-        expBase = (expBase + 7) & ~7ll;
-        if (2ll * d.nInt * d.nCat * d.nPat >= 0x7fffffffll) return e->fail(SB2_ERR_ARG, "locus too large for 32-bit element offsets");
-        matBase += 2ll * d.nNodes * d.nCat * 16;
+        if (ks) {
+            d.kBase = kBase; d.exclBase = (int32_t)exclBase;
+            kBase += (int64_t)d.nInt * d.nCat * d.nPat * d.kStates;
+            kBase = (kBase + 119) / 120 * 120;   // a multiple of every K: the exponent array is indexed by kBase / K
+            exclBase += d.nExcl;
+            e->kLoci.push_back((int32_t)(&hl - e->loci.data()));
+            e->maxK = std::max(e->maxK, d.kStates);
+        } else {
+            partBase += 2ll * d.nInt * d.nCat * d.nPat * 4;
+            expBase += 2ll * d.nInt * d.nCat * d.nPat;
+            expBase = (expBase + 7) & ~7ll;
+            if (2ll * d.nInt * d.nCat * d.nPat >= 0x7fffffffll) return e->fail(SB2_ERR_ARG, "locus too large for 32-bit element offsets");
+            matBase += 2ll * d.nNodes * d.nCat * 16;
+        }
         treeOff += 20ll * d.nNodes;
         treeOff = (treeOff + 7) & ~7ll;
     }
@@ -770,6 +819,18 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if ((rc = dev_alloc(e, &e->dOps, (size_t)opBase))) return rc;
     if ((rc = dev_alloc(e, &e->dOpMats, (size_t)opBase * e->nCat * 32))) return rc;
     if ((rc = dev_alloc(e, &e->dNOps, L))) return rc;
+    e->nK = (int)e->kLoci.size();
+    if (e->nK) {
+        if (kstate_smem_bytes(e->maxNodes, e->nCat, e->maxK) > 227 * 1024) return e->fail(SB2_ERR_ARG, "K-state locus too large for the per-locus shared-memory kernel");
+        std::vector<int32_t> excl((size_t)std::max<int64_t>(exclBase, 1), 0);
+        for (auto &hl : e->loci) if (hl.d.nExcl) memcpy(excl.data() + hl.d.exclBase, hl.excluded.data(), 4 * (size_t)hl.d.nExcl);
+        if ((rc = dev_alloc(e, &e->dKLoci, (size_t)e->nK))) return rc;
+        if ((rc = dev_alloc(e, &e->dExcluded, excl.size()))) return rc;
+        if ((rc = dev_alloc(e, &e->dKScratch, (size_t)kBase))) return rc;
+        if ((rc = dev_alloc(e, &e->dKExp, (size_t)kBase / 2 + 1))) return rc;
+        CUDA_TRY(e, cudaMemcpy(e->dKLoci, e->kLoci.data(), 4 * (size_t)e->nK, cudaMemcpyHostToDevice));
+        CUDA_TRY(e, cudaMemcpy(e->dExcluded, excl.data(), 4 * excl.size(), cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(e, cudaMemset(e->dNOps, 0, sizeof(int32_t) * L));
     CUDA_TRY(e, cudaMemset(e->dCumExp, 0, sizeof(int16_t) * (size_t)std::max<int64_t>(expBase, 1)));
     if ((rc = dev_alloc(e, &e->dParams, L))) return rc;
@@ -854,7 +915,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
         const int tilePat = e->nCat <= STEP_WARPS ? (STEP_WARPS / e->nCat) * 32 : 0;
         int maxPat = 0;
         e->totalLanes = 0;
-        for (auto &hl : e->loci) { maxPat = std::max(maxPat, hl.d.nPat); e->totalLanes += (int64_t)hl.d.nPat * hl.d.nCat; }
+        for (auto &hl : e->loci) if (!hl.d.kStates) { maxPat = std::max(maxPat, hl.d.nPat); e->totalLanes += (int64_t)hl.d.nPat * hl.d.nCat; }
         e->fusedCluster = tilePat ? (maxPat + tilePat - 1) / tilePat : 0;
         e->fusedOk = tilePat > 0 && e->fusedCluster <= STEP_MAX_CLUSTER && e->workers == 1 &&
                      step_smem_bytes(e->maxNodes, e->S, e->nCat, e->stackDepth, (e->maxNodes + 1) / 2) <= 227 * 1024;
@@ -917,10 +978,12 @@ int sb2_set_subst_model(sb2_engine *e, int32_t locus, int32_t kind, const double
     int rc = check_locus(e, locus);
     if (rc) return rc;
     if (!params || (kind != SB2_SUBST_HKY && kind != SB2_SUBST_EIGEN)) return e->fail(SB2_ERR_ARG, "bad substitution model");
+    const int K = e->loci[locus].d.kStates;
+    if (K && kind != SB2_SUBST_EIGEN) return e->fail(SB2_ERR_ARG, "a K-state locus takes an eigen system {eval[K], evec[K*K], ievc[K*K], pi[K]}");
     touch(e, locus);
     LocusParams &p = e->hParams[locus];
     p.substKind = kind;
-    memcpy(p.subst, params, sizeof(double) * (kind == SB2_SUBST_HKY ? 5 : 40));
+    memcpy(p.subst, params, sizeof(double) * (kind == SB2_SUBST_HKY ? 5 : (K ? 2 * K + 2 * K * K : 40)));
     e->modelDirty[locus] = 1; e->needPrepare = true;
     return SB2_OK;
 }
@@ -932,6 +995,7 @@ int sb2_set_site_model(sb2_engine *e, int32_t locus, const double *catRates, con
     int rc = check_locus(e, locus);
     if (rc) return rc;
     if (!catRates || !catProps) return e->fail(SB2_ERR_ARG, "null site model array");
+    if (e->loci[locus].d.kStates && pInv != 0.0) return e->fail(SB2_ERR_ARG, "proportionInvariant is not supported on K-state loci");
     touch(e, locus);
     const LocusDesc &d = e->loci[locus].d;
     memcpy(e->hCat + d.catBase, catRates, 8 * d.nCat);
@@ -948,6 +1012,8 @@ int sb2_set_clock(sb2_engine *e, int32_t locus, int32_t kind, double meanRate, c
     int rc = check_locus(e, locus);
     if (rc) return rc;
     if (kind < 0 || kind > 2) return e->fail(SB2_ERR_ARG, "bad clock kind %d", kind);
+    if (kind == SB2_CLOCK_SPECIES_RATES && e->loci[locus].d.kStates)
+        return e->fail(SB2_ERR_ARG, "StarBeastClock needs a gene-tree embedding: a likelihood-only locus takes a strict or explicit clock");
     if (kind == SB2_CLOCK_EXPLICIT) {
         if (!ratesOrNull) return e->fail(SB2_ERR_ARG, "explicit clock needs rates");
         if (!e->hExplicit) {
@@ -1273,6 +1339,7 @@ int sb2_get_partials(sb2_engine *e, int32_t locus, int32_t node, double *partial
     if (rc) return rc;
     const LocusDesc &d = e->loci[locus].d;
     if (node < d.nTips || node >= d.nNodes) return e->fail(SB2_ERR_ARG, "node %d is not an internal node", node);
+    if (d.kStates) return e->fail(SB2_ERR_ARG, "K-state loci keep no resident partials");
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     uint8_t buf;
     CUDA_TRY(e, cudaMemcpy(&buf, cur(e).curP + d.nodeBase + node, 1, cudaMemcpyDeviceToHost));
@@ -1296,6 +1363,7 @@ int sb2_get_matrices(sb2_engine *e, int32_t locus, int32_t node, double *matrice
     if (rc) return rc;
     const LocusDesc &d = e->loci[locus].d;
     if (node < 0 || node >= d.nNodes) return e->fail(SB2_ERR_ARG, "node %d out of range", node);
+    if (d.kStates) return e->fail(SB2_ERR_ARG, "K-state loci keep no resident matrices");
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     uint8_t buf;
     CUDA_TRY(e, cudaMemcpy(&buf, cur(e).curM + d.nodeBase + node, 1, cudaMemcpyDeviceToHost));

@@ -1,0 +1,221 @@
+// k_kstate: TreeLikelihood.calculateLogP for the K-state, likelihood-only loci -- the morphological partitions that the FBD
+// configurations score on the SPECIES tree (tutorial/CanisFBD/Canis-FBD.xml:964-1033: spec="TreeLikelihood"
+// tree="@Tree.t:Species", StandardData nrOfStates 2..5, LewisMK, ascertained FilteredAlignment, strict clock).
+//
+// Replaces, for K states: BeerLikelihoodCore.calculate{StatesStates,StatesPartials,PartialsPartials}Pruning, scalePartials,
+// integratePartials, calculateLogLikelihoods (BEAST.base, generic state count), GeneralSubstitutionModel.
+// getTransitionProbabilities, Alignment.getAscertainmentCorrection and TreeLikelihood.calcLogP's ascertained branch.
+//
+// These data are tiny (tens of characters x tens of tips) and hang off the species tree, which changes in a minority of the
+// MCMC steps; they are latency, not bandwidth.  One CTA per locus, everything from scratch whenever the locus is flagged:
+// the tree and all transition matrices in shared memory, one thread per site pattern walking the whole tree in post-order
+// for each rate category (partials in a small HBM scratch that only this thread touches), sums in the reference's order
+// (this translation unit is compiled with -fmad=false), exact power-of-two rescaling at every node.  The result goes into the
+// locus's cached log-likelihood in the state block, where the reductions, store() and restore() find it.
+#include <math.h>
+
+#include "sb2_device.cuh"
+
+namespace sb2 {
+
+constexpr int KS_THREADS = 128;
+
+struct KsSmem {
+    size_t gH, gP, gL, gR, order, stack, mats, total;
+};
+__host__ __device__ inline KsSmem ks_carve(int G, int C, int K)
+{
+    KsSmem m;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t r = o; o += (b + 15) & ~size_t(15); return r; };
+    m.gH = take(8ull * G); m.gP = take(4ull * G); m.gL = take(4ull * G); m.gR = take(4ull * G);
+    m.order = take(4ull * G); m.stack = take(4ull * G);
+    m.mats = take(8ull * G * C * K * K);
+    m.total = o;
+    return m;
+}
+size_t kstate_smem_bytes(int maxNodes, int maxCat, int K) { return ks_carve(maxNodes, maxCat, K).total; }
+
+template <int K>
+__device__ __forceinline__ void kstate_locus(const KStateArgs &A, int l, const LocusDesc &d, unsigned char *smem)
+{
+    constexpr int KK = K * K;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int G = d.nNodes, nT = d.nTips, nI = d.nInt, C = d.nCat, nPat = d.nPat, nb = d.nodeBase;
+    const KsSmem m = ks_carve(A.maxNodes, A.maxCat, K);
+    double *gH = reinterpret_cast<double *>(smem + m.gH);
+    int *gP = reinterpret_cast<int *>(smem + m.gP), *gL = reinterpret_cast<int *>(smem + m.gL), *gR = reinterpret_cast<int *>(smem + m.gR);
+    int *order = reinterpret_cast<int *>(smem + m.order), *stack = reinterpret_cast<int *>(smem + m.stack);
+    double *mats = reinterpret_cast<double *>(smem + m.mats);   // [node][category][K*K]
+    __shared__ LocusParams prm;
+    __shared__ int s_root;
+    {
+        constexpr int NP = (int)(sizeof(LocusParams) / 8);
+        const double *src = reinterpret_cast<const double *>(&A.params[l]);
+        double *dst = reinterpret_cast<double *>(&prm);
+        for (int i = tid; i < NP; i += nt) dst[i] = src[i];
+        for (int i = tid; i < G; i += nt) {   // the tree k_prepare has just made current
+            gH[i] = A.cur.gHeight[nb + i]; gP[i] = A.cur.gParent[nb + i]; gL[i] = A.cur.gLeft[nb + i]; gR[i] = A.cur.gRight[nb + i];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < G; i += nt) if (gP[i] < 0) s_root = i;
+    __syncthreads();
+    const int root = s_root;
+    if (tid == 0) {   // post-order of the internal nodes (TreeLikelihood.traverse's order: left subtree, right subtree, node)
+        int sp = 0, n = 0;
+        // two-stack iterative post-order: visit node, push left then right -> reverse pre-order (node, right, left) reversed
+        stack[sp++] = root;
+        while (sp > 0) {
+            const int v = stack[--sp];
+            if (v < nT) continue;
+            order[nI - 1 - n] = v; n++;
+            stack[sp++] = gL[v]; stack[sp++] = gR[v];
+        }
+    }
+    // GeneralSubstitutionModel.getTransitionProbabilities per (branch, category): |V exp(d L) V^-1|
+    const double *Eval = prm.subst, *Evec = prm.subst + K, *Ievc = prm.subst + K + KK, *freqs = prm.subst + K + 2 * KK;
+    for (int idx = tid; idx < G * C; idx += nt) {
+        const int i = idx / C, c = idx - i * C;
+        double *M = mats + (size_t)idx * KK;
+        if (gP[i] < 0) { for (int q = 0; q < KK; q++) M[q] = 0.0; continue; }
+        const double branchRate = (prm.clockKind == 2) ? A.explicitRates[nb + i] : prm.clockRate;   // StrictClockModel / explicit
+        const double jointBranchRate = A.catRates[d.catBase + c] * branchRate;
+        const double distance = (gH[gP[i]] - gH[i]) * jointBranchRate;
+        double iexp[KK];
+#pragma unroll
+        for (int a = 0; a < K; a++) {
+            const double temp = exp(distance * Eval[a]);
+#pragma unroll
+            for (int b = 0; b < K; b++) iexp[a * K + b] = Ievc[a * K + b] * temp;
+        }
+#pragma unroll
+        for (int a = 0; a < K; a++)
+#pragma unroll
+            for (int b = 0; b < K; b++) {
+                double temp = 0.0;
+#pragma unroll
+                for (int k = 0; k < K; k++) temp += Evec[a * K + k] * iexp[k * K + b];
+                M[a * K + b] = fabs(temp);
+            }
+    }
+    __syncthreads();
+
+    const uint8_t *states = A.tipStates + d.stateBase;
+    double *scr = A.scratch + d.kBase;                 // [internal][category][pattern][K]
+    int32_t *scrE = A.scratchExp + d.kBase / K;        // [internal][category][pattern]
+    const double *props = A.catProps + d.catBase;
+    for (int p = tid; p < nPat; p += nt) {
+        double acc[K];
+        int E = 0;
+        for (int c = 0; c < C; c++) {
+            // one post-order pass for this (pattern, category)
+            for (int oi = 0; oi < nI; oi++) {
+                const int v = order[oi], c1 = gL[v], c2 = gR[v];
+                const double *m1 = mats + ((size_t)c1 * C + c) * KK, *m2 = mats + ((size_t)c2 * C + c) * KK;
+                double out[K];
+                int cum = 0;
+#pragma unroll
+                for (int side = 0; side < 2; side++) {
+                    const int ch = side ? c2 : c1;
+                    const double *M = side ? m2 : m1;
+                    if (ch < nT) {
+                        const int st = states[(size_t)ch * d.stateStride + p];
+#pragma unroll
+                        for (int i = 0; i < K; i++) {
+                            const double f = (st < K) ? M[i * K + st] : 1.0;    // gap / '?': factor 1
+                            out[i] = side ? out[i] * f : f;
+                        }
+                    } else {
+                        const size_t e = ((size_t)(ch - nT) * C + c) * nPat + p;
+                        double a[K];
+#pragma unroll
+                        for (int j = 0; j < K; j++) a[j] = scr[e * K + j];
+                        cum += scrE[e];
+#pragma unroll
+                        for (int i = 0; i < K; i++) {
+                            double sum = 0.0;
+#pragma unroll
+                            for (int j = 0; j < K; j++) sum += M[i * K + j] * a[j];
+                            out[i] = side ? out[i] * sum : sum;
+                        }
+                    }
+                }
+                // exact power-of-two rescale (partials are non-negative: the largest has the largest high word)
+                int hmax = 0;
+#pragma unroll
+                for (int i = 0; i < K; i++) hmax = max(hmax, __double2hiint(out[i]));
+                int field = hmax >> 20;
+                if (field <= 0 || field > 1023) field = 1023;
+                const double scale = __hiloint2double((2046 - field) << 20, 0);
+                const size_t e = ((size_t)(v - nT) * C + c) * nPat + p;
+#pragma unroll
+                for (int i = 0; i < K; i++) scr[e * K + i] = out[i] * scale;
+                scrE[e] = cum + field - 1023;
+            }
+        }
+        // integratePartials over the categories at a common exponent, frequencies, log
+        const size_t r0 = (size_t)(root - nT) * C * nPat + p;
+        E = -2147483647;
+        for (int c = 0; c < C; c++) E = max(E, scrE[r0 + (size_t)c * nPat]);
+        for (int c = 0; c < C; c++) {
+            const size_t e = r0 + (size_t)c * nPat;
+            const int diff = scrE[e] - E;
+            const double f = (diff < -1022) ? 0.0 : __hiloint2double((1023 + diff) << 20, 0);
+#pragma unroll
+            for (int i = 0; i < K; i++) {
+                const double v = scr[e * K + i] * f * props[c];
+                acc[i] = (c == 0) ? v : acc[i] + v;
+            }
+        }
+        double sum = 0.0;
+#pragma unroll
+        for (int i = 0; i < K; i++) sum += freqs[i] * acc[i];
+        A.patLogL[d.patBase + p] = (E > -1000) ? log(ldexp(sum, E)) : (log(sum) + E * 0.6931471805599453);
+    }
+    __syncthreads();
+    if (tid == 0) {   // TreeLikelihood.calcLogP, with Alignment.getAscertainmentCorrection when patterns are excluded
+        const double *pl = A.patLogL + d.patBase;
+        const int32_t *w = A.weights + d.patBase;
+        double logP = 0.0;
+        if (d.nExcl > 0) {
+            double excludeProb = 0.0, returnProb = 1.0;
+            for (int i = 0; i < d.nExcl; i++) excludeProb += exp(pl[A.excluded[d.exclBase + i]]);
+            returnProb -= excludeProb;
+            const double corr = log(returnProb);
+            for (int k = 0; k < nPat; k++) logP += (pl[k] - corr) * w[k];
+        } else {
+            for (int k = 0; k < nPat; k++) logP += pl[k] * w[k];
+        }
+        A.cur.logL[l] = logP;
+    }
+}
+
+__global__ void __launch_bounds__(KS_THREADS) k_kstate(KStateArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int l = A.kLoci[blockIdx.x];
+    const uint8_t fl = A.uniformFlags >= 0 ? (uint8_t)A.uniformFlags
+                     : (A.singleLocus >= 0 ? (uint8_t)(l == A.singleLocus ? A.singleFlags : 0) : A.flags[l]);
+    if (!(fl & LF_RUN)) return;   // the cached log-likelihood stands
+    const LocusDesc d = A.loci[l];
+    switch (d.kStates) {
+    case 2: kstate_locus<2>(A, l, d, smem_raw); break;
+    case 3: kstate_locus<3>(A, l, d, smem_raw); break;
+    case 4: kstate_locus<4>(A, l, d, smem_raw); break;
+    case 5: kstate_locus<5>(A, l, d, smem_raw); break;
+    default: break;
+    }
+}
+
+cudaError_t launch_kstate(const KStateArgs &a, int nK, int maxK, cudaStream_t st)
+{
+    const size_t smem = kstate_smem_bytes(a.maxNodes, a.maxCat, maxK);
+    static size_t configured[MAX_DEVICES] = {};
+    cudaError_t rc = ensure_dynamic_smem(k_kstate, smem, configured);
+    if (rc != cudaSuccess) return rc;
+    k_kstate<<<nK, KS_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace sb2

@@ -28,6 +28,19 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
         if (tid == 0) A.nOps[l] = 0;
         return;
     }
+    if (A.loci[l].kStates) {   // K-state likelihood-only locus: no embedding, no schedule -- only its tree becomes current (k_kstate reads it)
+        const LocusDesc d = A.loci[l];
+        if (fl & LF_TREE_IN) {
+            const double *inH = reinterpret_cast<const double *>(A.inTree + d.treeOff);
+            const int *inP = reinterpret_cast<const int *>(inH + d.nNodes), *inL = inP + d.nNodes, *inR = inL + d.nNodes;
+            for (int i = tid; i < d.nNodes; i += blockDim.x) {
+                A.cur.gHeight[d.nodeBase + i] = inH[i]; A.cur.gParent[d.nodeBase + i] = inP[i];
+                A.cur.gLeft[d.nodeBase + i] = inL[i]; A.cur.gRight[d.nodeBase + i] = inR[i];
+            }
+        }
+        if (tid == 0) A.nOps[l] = 0;
+        return;
+    }
     __shared__ LocusParams sprm;
     prepare_locus<false>(A, maxNodes, l, fl, smem_raw, sprm, PrepFused{});
 }

@@ -15,7 +15,9 @@
 
 namespace sb2 {
 
-constexpr int SUBST_STRIDE = 40;
+constexpr int SUBST_STRIDE = 64;     // 4 states: HKY {kappa, pi[4]} or EIGEN {eval[4], evec[16], ievc[16], pi[4]} (40 doubles);
+                                     // K states (likelihood-only loci, kstate.cu): EIGEN {eval[K], evec[K*K], ievc[K*K], pi[K]}, K <= 5
+constexpr int KSTATE_MAX = 5;
 
 struct LocusDesc {
     int32_t nTips, nNodes, nInt, nPat, nCat;
@@ -30,6 +32,14 @@ struct LocusDesc {
     int32_t stateStride;// bytes per tip row of tipStates: nPat rounded up to 128, padding = 4 (missing)
     int32_t chunkBase;  // into chunkSum: first 32-pattern chunk of this locus
     int32_t nChunks;    // ceil(nPat / 32)
+    // K-state likelihood-only locus (kStates != 0): a TreeLikelihood that is not paired with a GeneTree -- the morphological
+    // partitions on the species tree, tutorial/CanisFBD/Canis-FBD.xml:964-1033.  No embedding, no coalescent term, no
+    // pruning schedule: k_kstate evaluates it from scratch whenever it is flagged.
+    int32_t kStates;    // 0, or the state count 2..KSTATE_MAX
+    int32_t nExcl;      // ascertained (excluded) patterns
+    int32_t exclBase;   // into the excluded-pattern index array
+    int32_t pad1;
+    int64_t kBase;      // into the K-state scratch: [internal node][category][pattern][K] doubles (exponents: the same / K)
     int64_t stateBase;  // into tipStates (bytes)
     int64_t partBase;   // into partials (doubles)
     int64_t expBase;    // into cumExp (int16)
@@ -238,6 +248,25 @@ struct StepArgs {
 constexpr int STEP_STAMPS = 16;
 size_t step_smem_bytes(int maxNodes, int S, int nCat, int stackDepth, int maxTips);
 cudaError_t launch_step(const StepArgs &a, int nClusters, int clusterSize, cudaStream_t st);
+
+// K-state likelihood-only loci (kstate.cu)
+struct KStateArgs {
+    const LocusDesc *loci;
+    const LocusParams *params;
+    const int32_t *kLoci;        // [grid] locus index of each K-state locus
+    const uint8_t *flags;
+    int32_t uniformFlags, singleLocus, singleFlags;
+    const uint8_t *tipStates;
+    const int32_t *weights, *excluded;
+    const double *catRates, *catProps, *explicitRates;
+    StateBlock cur;
+    double *patLogL;
+    double *scratch;             // partials, see LocusDesc::kBase
+    int32_t *scratchExp;         // power-of-two exponents per (node, category, pattern)
+    int32_t maxNodes, maxCat;
+};
+size_t kstate_smem_bytes(int maxNodes, int maxCat, int K);
+cudaError_t launch_kstate(const KStateArgs &a, int nK, int maxK, cudaStream_t st);
 
 // Operator-side queries over the resident gene trees (query.cu)
 constexpr int QUERY_THREADS = 128;

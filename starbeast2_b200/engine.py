@@ -91,6 +91,18 @@ class Engine:
         self.n_loci = idx + 1
         return idx
 
+    def add_locus_k(self, tip_states, weights, n_states, n_cat=1, excluded=()) -> int:
+        """A K-state LIKELIHOOD-ONLY locus (sb2_add_locus_k with tipToSpecies = NULL): a TreeLikelihood whose tree is not a
+        GeneTree, e.g. a morphological partition on the species tree.  Its tree is staged with set_gene_tree."""
+        ts = np.ascontiguousarray(tip_states, np.uint8)
+        w = np.ascontiguousarray(weights, np.int32)
+        ex = np.ascontiguousarray(excluded, np.int32)
+        idx = self._ck(self._L.sb2_add_locus_k(self._h, ts.shape[0], ts.shape[1], int(n_states), ts, w, int(n_cat), None, 2.0,
+                                               len(ex), ex.ctypes.data if len(ex) else None))
+        self._loci_shape.append((ts.shape[0], ts.shape[1], int(n_cat)))
+        self.n_loci = idx + 1
+        return idx
+
     def finalize(self, n_species_nodes: int, n_species_leaves: int):
         self._ck(self._L.sb2_finalize(self._h, n_species_nodes, n_species_leaves))
         self.S = n_species_nodes
@@ -105,6 +117,11 @@ class Engine:
         e.shard = (lo, hi)
         for loc in pb.loci[lo:hi]:
             e.add_locus(loc.tip_states, loc.weights, loc.n_cat, loc.tip_species, loc.ploidy)
+        # morphological partitions (K-state likelihoods on the species tree) follow the loci; sharded runs keep them on the
+        # rank that holds the last locus
+        e.morph = list(getattr(pb, "morph", None) or []) if hi == pb.n_loci else []
+        for m in e.morph:
+            e.add_locus_k(m.tip_states, m.weights, m.n_states, m.n_cat, m.excluded)
         e.finalize(pb.species.n_nodes, pb.species.n_leaves)
         e.set_problem_state(pb)
         return e
@@ -119,6 +136,12 @@ class Engine:
             self.set_subst_model(i, loc.subst_kind, loc.subst_params)
             self.set_site_model(i, loc.cat_rates, loc.cat_props, loc.p_inv)
             self.set_clock(i, loc.clock_kind, loc.clock_rate, loc.explicit_rates)
+        for j, m in enumerate(getattr(self, "morph", [])):
+            i = hi - lo + j
+            self.set_gene_tree(i, pb.species)            # tree="@Tree.t:Species"
+            self.set_subst_model(i, 1, m.subst_params)   # SB2_SUBST_EIGEN, K-state layout
+            self.set_site_model(i, m.cat_rates, m.cat_props, 0.0)
+            self.set_clock(i, 0, m.clock_rate, None)     # StrictClockModel
 
     # -- state input -----------------------------------------------------------------------------
     def set_species_tree(self, t: TreeArrays):
@@ -140,7 +163,7 @@ class Engine:
         self._ck(self._L.sb2_set_gene_trees(self._h, first, n, parent, left, right, height))
 
     def set_subst_model(self, locus: int, kind: int, params):
-        p = np.zeros(40)
+        p = np.zeros(64)
         src = np.asarray(params, np.float64).reshape(-1)
         p[: len(src)] = src
         self._ck(self._L.sb2_set_subst_model(self._h, locus, int(kind), p))

@@ -40,6 +40,7 @@ typedef const struct JNINativeInterface_ *JNIEnv;
 struct JNINativeInterface_ {
     jclass (JNICALL *FindClass)(JNIEnv *env, const char *name);
     jint (JNICALL *ThrowNew)(JNIEnv *env, jclass clazz, const char *msg);
+    jint (JNICALL *GetArrayLength)(JNIEnv *env, jarray array);
     jstring (JNICALL *NewStringUTF)(JNIEnv *env, const char *utf);
     void *(JNICALL *GetPrimitiveArrayCritical)(JNIEnv *env, jarray array, jboolean *isCopy);
     void (JNICALL *ReleasePrimitiveArrayCritical)(JNIEnv *env, jarray array, void *carray, jint mode);

@@ -13,6 +13,7 @@
 struct _jobject {
     int kind;            /* 1 array, 2 class, 3 string */
     void *data;
+    int length;
     int pins;
     char text[256];
 };
@@ -35,6 +36,7 @@ static jint JNICALL m_ThrowNew(JNIEnv *env, jclass clazz, const char *msg)
     strncpy(g_exMsg, msg ? msg : "", sizeof g_exMsg - 1);
     return 0;
 }
+static jint JNICALL m_GetArrayLength(JNIEnv *env, jarray a) { (void)env; return a->length; }
 static jstring JNICALL m_NewStringUTF(JNIEnv *env, const char *utf)
 {
     (void)env;
@@ -57,7 +59,7 @@ static void JNICALL m_ReleaseCritical(JNIEnv *env, jarray a, void *carray, jint 
     a->pins--; g_unpins++; g_live--;
 }
 
-static const struct JNINativeInterface_ g_table = {m_FindClass, m_ThrowNew, m_NewStringUTF, m_GetCritical, m_ReleaseCritical};
+static const struct JNINativeInterface_ g_table = {m_FindClass, m_ThrowNew, m_GetArrayLength, m_NewStringUTF, m_GetCritical, m_ReleaseCritical};
 static JNIEnv g_env = &g_table;
 
 JNIEXPORT JNIEnv *mock_env(void) { return &g_env; }
@@ -65,6 +67,12 @@ JNIEXPORT jarray mock_array(void *data)
 {
     struct _jobject *o = calloc(1, sizeof *o);
     o->kind = 1; o->data = data;
+    return o;
+}
+JNIEXPORT jarray mock_array_n(void *data, int length)
+{
+    jarray o = mock_array(data);
+    o->length = length;
     return o;
 }
 JNIEXPORT void mock_free(jobject o) { free(o); }
