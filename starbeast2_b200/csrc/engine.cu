@@ -524,6 +524,7 @@ int do_walk(sb2_engine *e)
         CUDA_TRY(e, cudaEventRecord(ev.first, e->stream));
     }
     static const bool skipWalk = getenv("SB2_DEBUG_SKIP_WALK") != nullptr;   // timing experiments only
+    if (e->totalTiles == 0) return SB2_OK;   // K-state likelihood-only loci only: nothing for the 4-state pruning kernel
     if (!skipWalk) CUDA_TRY(e, launch_treewalk(a, (int)e->totalTiles, e->cfg.exact_order != 0, e->stream));
     e->launches++;
     if (e->cfg.profile) CUDA_TRY(e, cudaEventRecord(ev.second, e->stream));

@@ -33,7 +33,7 @@ def test_c4_with_morphology_matches_the_oracle():
     # per-pattern values, and the ascertainment correction on top of them
     for j, m in enumerate(pb.morph):
         ll, pat = oracle.tree_likelihood_k(m, pb.species, want_patterns=True)
-        assert np.allclose(e.get_pattern_logl(6 + j), pat, rtol=1e-11, atol=1e-13)
+        assert np.allclose(e.pattern_logl(6 + j), pat, rtol=1e-11, atol=1e-13)
         assert got.per_locus_lik[6 + j] == pytest.approx(ll, rel=1e-11)
 
 
