@@ -53,6 +53,7 @@ public final class GpuSession {
     private final SpeciesTreeInterface speciesTree;
     private final List<GpuGeneTree> geneTrees = new ArrayList<>();
     private final Map<Integer, GpuTreeLikelihood> likelihoods = new java.util.HashMap<>();
+    private final List<GpuTreeLikelihood> morph = new ArrayList<>();   // TreeLikelihoods on the species tree itself (K-state, no GeneTree)
     private GpuMultispeciesCoalescent msc;
     private long engine = 0;
     private boolean coalValid = false, likValid = false, firstPush = true;
@@ -64,6 +65,8 @@ public final class GpuSession {
 
     public int register(GpuGeneTree gt) { geneTrees.add(gt); close(); return geneTrees.size() - 1; }
     public void register(int locus, GpuTreeLikelihood tl) { likelihoods.put(locus, tl); close(); }
+    public int registerMorph(GpuTreeLikelihood tl) { morph.add(tl); close(); return morph.size() - 1; }
+    public double morphLikelihood(int index) { evalLikelihood(); return perLocusLik[geneTrees.size() + index]; }
     public void setMsc(GpuMultispeciesCoalescent m) { msc = m; coalValid = false; }
     public int locusOf(TreeInterface tree) {
         for (int i = 0; i < geneTrees.size(); i++) if (geneTrees.get(i).treeInput.get() == tree) return i;
@@ -101,9 +104,27 @@ public final class GpuSession {
             }
             check(Sb2Gpu.addLocus(engine, nTips, nPat, states, weights, nCat, tipSpecies, gt.getPloidy()));
         }
+        // likelihoods on the species tree itself: K-state, likelihood-only loci after the gene loci (sb2_add_locus_k, tipToSpecies = null);
+        // tips in the species tree's own leaf numbering; the ascertained dummy patterns are Alignment's excludedPatterns
+        for (GpuTreeLikelihood tl : morph) {
+            final Alignment data = tl.dataInput.get();
+            final TreeInterface tree = (TreeInterface) speciesTree;
+            final int nTips = tree.getLeafNodeCount(), nPat = data.getPatternCount(), K = data.getDataType().getStateCount();
+            final byte[] states = new byte[nTips * nPat];
+            for (int t = 0; t < nTips; t++) {
+                final int taxon = data.getTaxonIndex(tree.getNode(t).getID());
+                for (int p = 0; p < nPat; p++) {
+                    final int code = data.getPattern(taxon, p);
+                    states[t * nPat + p] = (byte) (data.getDataType().isAmbiguousCode(code) || code >= K ? K : code);   // useAmbiguities=false
+                }
+            }
+            final int[] excluded = data.getExcludedPatternIndices().stream().mapToInt(Integer::intValue).toArray();
+            check(Sb2Gpu.addLocusK(engine, nTips, nPat, K, states, data.getWeights(), nCat, null, 2.0, excluded.length == 0 ? null : excluded));
+        }
         final int S = speciesTree.getNodeCount();
         check(Sb2Gpu.finalizeEngine(engine, S, speciesTree.getLeafNodeCount()));
-        perLocusCoal = new double[geneTrees.size()]; perLocusLik = new double[geneTrees.size()]; perBranch = new double[S];
+        final int nLoci = geneTrees.size() + morph.size();
+        perLocusCoal = new double[nLoci]; perLocusLik = new double[nLoci]; perBranch = new double[S];
         firstPush = true;
     }
 
@@ -185,6 +206,38 @@ public final class GpuSession {
                 final double r = clk == null ? 1.0 : ((RealParameter) clk.meanRateInput.get()).getValue();
                 if (firstPush || (clk != null && ((StrictClockModel) clk).isDirtyCalculation())) { check(Sb2Gpu.setClock(engine, l, Sb2Gpu.CLOCK_STRICT, r, null)); dirty = true; }
             } else {   // any other BranchRateModel: ship its per-node rates
+                final double[] r = new double[tree.getNodeCount()];
+                for (Node node : tree.getNodesAsArray()) r[node.getNr()] = clk.getRateForBranch(node);
+                check(Sb2Gpu.setClock(engine, l, Sb2Gpu.CLOCK_EXPLICIT, 1.0, r)); dirty = true;
+            }
+        }
+        for (int j = 0; j < morph.size(); j++) {   // likelihoods on the species tree: its arrays are their "gene tree"
+            final int l = geneTrees.size() + j;
+            final GpuTreeLikelihood tl = morph.get(j);
+            if (firstPush || speciesTree.getCurrent().somethingIsDirty()) { pushTree(engine, l, (TreeInterface) speciesTree); dirty = true; }
+            final SiteModel site = (SiteModel) tl.siteModelInput.get();
+            if (firstPush || site.isDirtyCalculation()) {
+                final GeneralSubstitutionModel sm = (GeneralSubstitutionModel) site.substModelInput.get();   // LewisMK extends it
+                final EigenDecomposition ed = sm.getEigenDecomposition(null);
+                final int K = sm.getStateCount();
+                final double[] p = new double[2 * K + 2 * K * K];   // {eval[K], evec[K*K], ievc[K*K], pi[K]}
+                System.arraycopy(ed.getEigenValues(), 0, p, 0, K);
+                System.arraycopy(ed.getEigenVectors(), 0, p, K, K * K);
+                System.arraycopy(ed.getInverseEigenVectors(), 0, p, K + K * K, K * K);
+                System.arraycopy(sm.getFrequencies(), 0, p, K + 2 * K * K, K);
+                check(Sb2Gpu.setSubstModel(engine, l, Sb2Gpu.SUBST_EIGEN, p));
+                final int C = site.getCategoryCount();
+                final double[] rates = new double[C];
+                for (int c = 0; c < C; c++) rates[c] = site.getRateForCategory(c, null);
+                check(Sb2Gpu.setSiteModel(engine, l, rates, site.getCategoryProportions(null), 0.0));
+                dirty = true;
+            }
+            final BranchRateModel clk = tl.branchRateModelInput.get();
+            if (clk == null || clk instanceof StrictClockModel) {
+                final double r = clk == null ? 1.0 : ((RealParameter) clk.meanRateInput.get()).getValue();
+                if (firstPush || (clk != null && ((StrictClockModel) clk).isDirtyCalculation())) { check(Sb2Gpu.setClock(engine, l, Sb2Gpu.CLOCK_STRICT, r, null)); dirty = true; }
+            } else {   // e.g. the species tree's relaxed clock applied to morphology: ship its per-node rates
+                final TreeInterface tree = (TreeInterface) speciesTree;
                 final double[] r = new double[tree.getNodeCount()];
                 for (Node node : tree.getNodesAsArray()) r[node.getNr()] = clk.getRateForBranch(node);
                 check(Sb2Gpu.setClock(engine, l, Sb2Gpu.CLOCK_EXPLICIT, 1.0, r)); dirty = true;

@@ -18,9 +18,18 @@ import starbeast2.StarBeastClock;
 public class GpuTreeLikelihood extends GenericTreeLikelihood {
     private GpuSession session;
     private int locus = -1;
+    private int morphIndex = -1;   // >= 0: a likelihood on the species tree itself (no GeneTree): K-state, likelihood-only locus
 
     @Override
     public void initAndValidate() {
+        if (treeInput.get() instanceof starbeast2.SpeciesTreeInterface) {
+            // tree="@Tree.t:Species": the morphological partitions of the FBD analyses (tutorial/CanisFBD/Canis-FBD.xml:964-1033);
+            // tested twin: starbeast2_b200/plugins.py:TreeLikelihood with a SpeciesTree (tests/test_plugins.py)
+            if (branchRateModelInput.get() instanceof StarBeastClock) throw new IllegalArgumentException("StarBeastClock needs a gene tree");
+            session = GpuSession.of((starbeast2.SpeciesTreeInterface) treeInput.get());
+            morphIndex = session.registerMorph(this);
+            return;
+        }
         if (branchRateModelInput.get() instanceof StarBeastClock) {
             final StarBeastClock clk = (StarBeastClock) branchRateModelInput.get();
             session = GpuSession.of(clk.geneTreeInput.get().speciesTreeInput.get());
@@ -32,7 +41,7 @@ public class GpuTreeLikelihood extends GenericTreeLikelihood {
         if (locus < 0) throw new IllegalArgumentException("GpuTreeLikelihood: tree " + treeInput.get().getID() + " is not embedded by any GpuGeneTree");
         session.register(locus, this);
     }
-    @Override public double calculateLogP() { logP = session.likelihood(locus); return logP; }
+    @Override public double calculateLogP() { logP = morphIndex >= 0 ? session.morphLikelihood(morphIndex) : session.likelihood(locus); return logP; }
     @Override protected boolean requiresRecalculation() { return true; }   // the engine decides on the device what is dirty
     @Override public List<String> getArguments() { return null; }
     @Override public List<String> getConditions() { return null; }

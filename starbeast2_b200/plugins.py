@@ -28,12 +28,12 @@ from .beast import (BEASTObject, BooleanParameter, CalculationNode, CompoundDist
                     Taxon, TaxonSet, Tree, TreeParser)
 from .engine import Engine
 from .problem import (CLOCK_SPECIES_RATES, CLOCK_STRICT, POP_ANALYTIC, POP_CONSTANT, POP_LWCR, SUBST_EIGEN, SUBST_HKY,
-                      gtr_eigen_params, hky_params)
+                      gtr_eigen_params, hky_params, lewis_mk_eigen)
 
 REQ = BEASTObject.REQUIRED
 __all__ = ["SpeciesTree", "SpeciesTreeParser", "GpuSession", "ConstantPopulations", "LinearWithConstantRoot",
            "UniformPopulations", "RandomLocalRates", "BooleanParameter", "PassthroughModel", "DummyModel", "GeneTree", "MultispeciesCoalescent", "StrictClockModel", "UncorrelatedRates",
-           "StarBeastClock", "Alignment", "Frequencies", "HKY", "GTR", "SiteModel", "TreeLikelihood", "RealParameter",
+           "StarBeastClock", "Alignment", "FilteredAlignment", "StandardData", "LewisMK", "Frequencies", "HKY", "GTR", "SiteModel", "TreeLikelihood", "RealParameter",
            "IntegerParameter", "Taxon", "TaxonSet", "Tree", "TreeParser", "CompoundDistribution"]
 
 
@@ -84,6 +84,7 @@ class GpuSession:
         self.species_tree = species_tree
         self.gene_trees: List["GeneTree"] = []
         self.likelihoods: Dict[int, "TreeLikelihood"] = {}     # locus -> TreeLikelihood
+        self.morph: List["TreeLikelihood"] = []                # TreeLikelihoods on the species tree itself (K-state, likelihood only)
         self.clocks: Dict[int, "StarBeastClock"] = {}          # locus -> StarBeastClock without a TreeLikelihood
         self.msc: Optional["MultispeciesCoalescent"] = None
         self.engine: Optional[Engine] = None
@@ -112,8 +113,13 @@ class GpuSession:
         self._coal_valid = self._lik_valid = False
 
     # -- build ------------------------------------------------------------------------------------------------------
+    def register_morph(self, tl: "TreeLikelihood") -> int:
+        self.morph.append(tl)
+        self._drop_engine()
+        return len(self.morph) - 1
+
     def _n_cat(self) -> int:
-        cats = {tl.get("siteModel").getCategoryCount() for tl in self.likelihoods.values()}
+        cats = {tl.get("siteModel").getCategoryCount() for tl in list(self.likelihoods.values()) + self.morph}
         if len(cats) > 1:
             raise ValueError("all TreeLikelihoods of one session must share the rate-category count")
         return cats.pop() if cats else 1
@@ -132,6 +138,12 @@ class GpuSession:
             else:   # a GeneTree with no TreeLikelihood: one all-missing pattern, log-likelihood exactly 0
                 states, weights = np.full((len(tree.labels), 1), 4, np.uint8), np.ones(1, np.int32)
             e.add_locus(states, weights, n_cat, tip_species, gt.getPloidy())
+        # TreeLikelihoods whose tree IS the species tree (Canis-FBD.xml:964-1033): K-state, likelihood-only loci after the gene loci,
+        # tips in the species tree's own leaf numbering
+        for tl in self.morph:
+            data = tl.get("data")
+            states, weights = data.patterns_for(sp.labels)
+            e.add_locus_k(states, weights, data.getStateCount(), n_cat, data.excluded_patterns())
         e.finalize(sp.getNodeCount(), sp.getLeafNodeCount())
         self.engine = e
         self._pushed.clear()
@@ -172,6 +184,21 @@ class GpuSession:
             clk = self._clock(i)
             if clk is not None:
                 yield ("clock", i), clk.signature(), (lambda i=i, clk=clk: e.set_clock(i, *clk.engine_clock()))
+
+        L = len(self.gene_trees)
+        for j, tl in enumerate(self.morph):
+            i = L + j
+            yield ("tree", i), sp._version, (lambda i=i: e.set_gene_tree(i, sp.arrays))
+            sm = tl.get("siteModel")
+
+            def push_msite(i=i, sm=sm):
+                kind, params = sm.get("substModel").engine_params()
+                e.set_subst_model(i, kind, params)
+                rates, props = sm.category_rates()
+                e.set_site_model(i, rates, props, sm.getProportionInvariant())
+            yield ("site", i), sm.signature(), push_msite
+            clk = tl.get("branchRateModel")
+            yield ("clock", i), clk.signature(), (lambda i=i, clk=clk: e.set_clock(i, *clk.engine_clock()))
 
     def _clock(self, i):
         tl = self.likelihoods.get(i)
@@ -602,6 +629,97 @@ class Alignment(BEASTObject):
         return counts / counts.sum()
 
 
+class StandardData(BEASTObject):
+    """beast.base.evolution.datatype.StandardData (userDataType of the morphological alignments, Canis-FBD.xml:973):
+    characters '0'..'9' are states 0..9; '?', '-' and anything else are missing (ambiguities="" in the reference's XML)."""
+    INPUTS = {"nrOfStates": REQ, "ambiguities": ""}
+
+    def getStateCount(self) -> int:
+        return int(self.get("nrOfStates"))
+
+    def encode(self, ch: str) -> int:
+        k = self.getStateCount()
+        return int(ch) if ch.isdigit() and int(ch) < k else k
+
+
+def _parse_filter(spec: str, n_sites: int) -> List[int]:
+    """FilteredAlignment's filter syntax: 1-based sites, comma separated, 'a-b' ranges, 'a-b\\c' every c-th, '-b', 'a-'."""
+    out: List[int] = []
+    for part in spec.split(","):
+        part = part.strip()
+        if not part:
+            continue
+        step = 1
+        if "\\" in part:
+            part, st = part.split("\\")
+            step = int(st)
+        if "-" in part:
+            a, b = part.split("-")
+            lo = int(a) if a.strip() else 1
+            hi = int(b) if b.strip() else n_sites
+            out.extend(range(lo - 1, hi, step))
+        else:
+            out.append(int(part) - 1)
+    return out
+
+
+class FilteredAlignment(BEASTObject):
+    """beast.base.evolution.alignment.FilteredAlignment with the ascertainment inputs of Alignment: a subset of the sites of
+    `data` (filter), re-typed by userDataType, optionally ascertained -- sites [excludefrom, excludeto) of the FILTERED
+    alignment are dummy columns whose patterns get weight 0 and form Alignment.excludedPatterns (Canis-FBD.xml:966-974)."""
+    INPUTS = {"data": REQ, "filter": REQ, "userDataType": None, "ascertained": False, "excludefrom": 0, "excludeto": 0, "excludeevery": 1}
+
+    def initAndValidate(self):
+        src = self.get("data")
+        seqs: Dict[str, str] = src.get("sequences")
+        if seqs is None:
+            raise ValueError("FilteredAlignment needs an Alignment built from sequences")
+        dt = self.get("userDataType")
+        self.taxa = sorted(seqs)
+        n_sites = len(seqs[self.taxa[0]])
+        sites = _parse_filter(str(self.get("filter")), n_sites)
+        enc = dt.encode if dt is not None else (lambda ch: Alignment.CODE.get(ch.upper(), 4))
+        self.n_states = dt.getStateCount() if dt is not None else 4
+        mat = np.array([[enc(seqs[t][s]) for s in sites] for t in self.taxa], np.uint8)
+        pats, index, w = np.unique(mat, axis=1, return_inverse=True, return_counts=True)
+        index = np.asarray(index).reshape(-1)
+        self.patterns, self.weights = np.ascontiguousarray(pats), w.astype(np.int32)
+        self.excluded = np.zeros(0, np.int32)
+        if self.get("ascertained"):
+            lo, hi, every = int(self.get("excludefrom")), int(self.get("excludeto")), int(self.get("excludeevery"))
+            if not (0 <= lo <= hi <= len(sites)):
+                raise ValueError("excludefrom / excludeto outside the filtered alignment")
+            ex = sorted({int(index[i]) for i in range(lo, hi, every)})
+            self.weights[ex] = 0                       # "reduce weight, so it does not confuse the tree likelihood"
+            self.excluded = np.array(ex, np.int32)
+
+    def patterns_for(self, labels: Sequence[str]):
+        idx = [self.taxa.index(l) for l in labels]
+        return np.ascontiguousarray(self.patterns[idx]), self.weights
+
+    def getPatternCount(self):
+        return self.patterns.shape[1]
+
+    def getStateCount(self) -> int:
+        return self.n_states
+
+    def excluded_patterns(self) -> np.ndarray:
+        return self.excluded
+
+
+class LewisMK(BEASTObject):
+    """morphmodels.evolution.substitutionmodel.LewisMK (Canis-FBD.xml:975): Lewis's Mk -- equal rates between all K states,
+    equal frequencies.  The engine takes its eigen system, as it does for every GeneralSubstitutionModel."""
+    INPUTS = {"datatype": None, "stateNumber": None}
+
+    def getStateCount(self) -> int:
+        dt = self.get("datatype")
+        return dt.getStateCount() if dt is not None else int(self.get("stateNumber"))
+
+    def engine_params(self):
+        return SUBST_EIGEN, lewis_mk_eigen(self.getStateCount())
+
+
 class Frequencies(BEASTObject):
     INPUTS = {"frequencies": None, "data": None, "estimate": True}
 
@@ -674,6 +792,17 @@ class TreeLikelihood(Distribution):
             clk = StrictClockModel()
             clk.initByName()
             self._inputs["branchRateModel"] = clk
+        if isinstance(tree, SpeciesTree):
+            # tree="@Tree.t:Species": a likelihood on the species tree itself (the morphological partitions of the FBD analyses,
+            # Canis-FBD.xml:964-1033) -- no GeneTree, no coalescent term; K-state, likelihood-only locus of the species tree's session
+            if not hasattr(self.get("data"), "excluded_patterns"):
+                raise ValueError("a TreeLikelihood on the species tree takes a FilteredAlignment (K-state data)")
+            if isinstance(clk, StarBeastClock):
+                raise ValueError("StarBeastClock needs a gene tree")
+            self.session = GpuSession.of(tree)
+            self.locus = None
+            self.morph_index = self.session.register_morph(self)
+            return
         session = None
         if isinstance(clk, StarBeastClock):
             session = clk.geneTree.session
@@ -691,9 +820,12 @@ class TreeLikelihood(Distribution):
 
     def calculateLogP(self) -> float:
         _, per_locus = self.session.likelihood()
-        self.logP = float(per_locus[self.locus])
+        self.logP = float(per_locus[self._index()])
         return self.logP
+
+    def _index(self) -> int:
+        return self.locus if self.locus is not None else len(self.session.gene_trees) + self.morph_index
 
     def getPatternLogLikelihoods(self):
         self.session.likelihood()
-        return self.session.engine.pattern_logl(self.locus)
+        return self.session.engine.pattern_logl(self._index())

@@ -532,3 +532,151 @@ def test_fasta_to_alignment_patterns_and_frequencies(tmp_path):
     f = aln.empirical_frequencies()
     counts = np.array([(full == s).sum() for s in range(4)], float)
     assert np.allclose(f, counts / counts.sum()) and abs(f.sum() - 1) < 1e-15
+
+
+# ---- morphological TreeLikelihoods on the species tree (tutorial/CanisFBD/Canis-FBD.xml:964-1033) -------------------------------
+
+def _morph_sequences(pb, rng, n_real=(9, 6, 5, 4)):
+    """A morphological matrix laid out like the reference's `morphology_canis`: real characters of mixed state counts in
+    arbitrary order, then dummy constant columns '0...', '1...', ... '4...' at the end.  Returns (sequences by species label,
+    {K: (1-based filter string, excludefrom, excludeto)})."""
+    from starbeast2_b200 import synth
+    sp = pb.species
+    names = [f"sp{i}" for i in range(sp.n_leaves)]
+    cols, kinds = [], []
+    for K, n in zip((2, 3, 4, 5), n_real):
+        pats, w, _ = synth.simulate_morphology(rng, sp, K, n, 0.6 / sp.height[sp.root], missing_frac=0.1)
+        real = np.repeat(pats[:, :-K], w[:-K], axis=1)
+        for c in range(real.shape[1]):
+            cols.append(real[:, c]); kinds.append(K)
+    order = rng.permutation(len(cols))
+    cols, kinds = [cols[i] for i in order], [kinds[i] for i in order]
+    n_chars = len(cols)
+    for s in range(5):
+        cols.append(np.full(sp.n_leaves, s, np.uint8)); kinds.append(-1)
+    seqs = {names[t]: "".join("?" if (k > 0 and c[t] >= k) else str(int(c[t])) for c, k in zip(cols, kinds)) for t in range(sp.n_leaves)}
+    filt = {}
+    for K in (2, 3, 4, 5):
+        mine = [i + 1 for i, k in enumerate(kinds) if k == K]
+        filt[K] = (",".join(map(str, mine)) + f",{n_chars + 1}-{n_chars + K}", len(mine), len(mine) + K)
+    return seqs, filt, names
+
+
+def test_filtered_alignment_ascertained_patterns():
+    from starbeast2_b200.plugins import FilteredAlignment, StandardData
+    seqs = {"a": "01?10" + "01", "b": "011-0" + "01", "c": "00100" + "01"}
+    data = Alignment(sequences=seqs)
+    fa = FilteredAlignment()
+    fa.initByName("data", data, "filter", "1-3,5,6-7", "userDataType", StandardData(nrOfStates=2), "ascertained", True,
+                  "excludefrom", 4, "excludeto", 6)
+    assert fa.getStateCount() == 2 and fa.taxa == ["a", "b", "c"]
+    cols = {tuple(fa.patterns[:, p]): int(fa.weights[p]) for p in range(fa.getPatternCount())}
+    # site 5 ("000") coincides with the dummy all-0 column: BEAST zeroes the pattern's weight ("so it does not confuse the tree likelihood")
+    assert cols == {(0, 0, 0): 0, (1, 1, 0): 1, (2, 1, 1): 1, (1, 1, 1): 0}
+    ex = {tuple(fa.patterns[:, p]) for p in fa.excluded_patterns()}
+    assert ex == {(0, 0, 0), (1, 1, 1)}
+    with pytest.raises(ValueError):
+        FilteredAlignment().initByName("data", data, "filter", "1-3", "ascertained", True, "excludefrom", 2, "excludeto", 9)
+
+
+@pytest.mark.gpu
+def test_posterior_with_morphological_likelihoods_on_the_species_tree():
+    """Canis-FBD.xml wiring: gene-tree likelihoods + four morphological TreeLikelihoods (K = 2..5, LewisMK, ascertained
+    FilteredAlignment, one shared strict clock) on tree="@Tree.t:Species" with fossil tips; species-tree moves, store / restore."""
+    import oracle
+    from starbeast2_b200 import synth
+    from starbeast2_b200.plugins import FilteredAlignment, LewisMK, StandardData
+    from starbeast2_b200.problem import MorphPartition, lewis_mk_eigen
+    pb = synth.make_problem("C4", n_loci=3, n_sites=100)
+    rng = np.random.default_rng(21)
+    seqs, filt, sp_names = _morph_sequences(pb, rng)
+    n_sp = pb.species.n_leaves
+    counts = np.bincount(np.concatenate([l.tip_species for l in pb.loci]), minlength=n_sp) // len(pb.loci)
+    superset = TaxonSet([TaxonSet(sp_names[i], [Taxon(f"sp{i}_{j}") for j in range(max(1, counts[i]))]) for i in range(n_sp)])
+    speciesTree = SpeciesTreeParser()
+    speciesTree.initByName("arrays", pb.species, "labels", sp_names, "taxonset", superset)
+    geneTrees, likelihoods, trees = [], [], []
+    for l, loc in enumerate(pb.loci):
+        seen = {}
+        labels = []
+        for t in range(loc.n_tips):
+            s = int(loc.tip_species[t]); j = seen.get(s, 0); seen[s] = j + 1
+            labels.append(f"sp{s}_{j}")
+        tree = TreeParser()
+        tree.initByName("arrays", loc.tree, "labels", labels)
+        trees.append(tree)
+        gt = GeneTree()
+        gt.initByName("tree", tree, "ploidy", loc.ploidy, "speciesTree", speciesTree)
+        geneTrees.append(gt)
+    for l, loc in enumerate(pb.loci):
+        data = Alignment()
+        data.initByName("patterns", loc.tip_states, "weights", loc.weights, "taxa", trees[l].labels)
+        freqs = Frequencies()
+        freqs.initByName("frequencies", RealParameter(value=" ".join(map(str, loc.subst_params[1:5])), dimension=4))
+        site = SiteModel()
+        site.initByName("substModel", HKY(kappa=RealParameter(value=str(loc.subst_params[0])), frequencies=freqs), "mutationRate", float(loc.cat_rates[0]))
+        clock = StrictClockModel()
+        clock.initByName("clock.rate", RealParameter(value=repr(float(loc.clock_rate))))
+        tl = TreeLikelihood()
+        tl.initByName("data", data, "tree", trees[l], "siteModel", site, "branchRateModel", clock)
+        likelihoods.append(tl)
+    morph = Alignment(sequences=seqs)
+    morphRate = RealParameter(value="0.7")
+    morphClock = StrictClockModel()
+    morphClock.initByName("clock.rate", morphRate)
+    morphLikelihoods, parts = [], []
+    for K in (2, 3, 4, 5):
+        f, lo, hi = filt[K]
+        dt = StandardData(nrOfStates=K)
+        fa = FilteredAlignment()
+        fa.initByName("data", morph, "filter", f, "userDataType", dt, "ascertained", True, "excludefrom", lo, "excludeto", hi)
+        site = SiteModel()
+        site.initByName("substModel", LewisMK(datatype=dt))
+        tl = TreeLikelihood()
+        tl.initByName("data", fa, "tree", speciesTree, "siteModel", site, "branchRateModel", morphClock)
+        morphLikelihoods.append(tl)
+        states, w = fa.patterns_for(sp_names)
+        parts.append(MorphPartition(tip_states=states, weights=w, n_states=K, subst_params=lewis_mk_eigen(K), clock_rate=0.7,
+                                    excluded=fa.excluded_patterns()))
+    speciescoalescent = MultispeciesCoalescent()
+    speciescoalescent.initByName("distribution", geneTrees, "populationShape", RealParameter(value=str(pb.alpha)),
+                                 "populationMean", RealParameter(value=str(pb.beta / (pb.alpha - 1.0))))
+    likelihood = CompoundDistribution()
+    likelihood.initByName("distribution", likelihoods + morphLikelihoods)
+    posterior = CompoundDistribution()
+    posterior.initByName("distribution", [speciescoalescent, likelihood])
+
+    def want_total():
+        pb.morph = parts
+        return oracle.posterior(pb)
+
+    w = want_total()
+    assert posterior.calculateLogP() == pytest.approx(w.total, rel=1e-9)
+    assert [tl.logP for tl in morphLikelihoods] == pytest.approx([oracle.tree_likelihood_k(m, pb.species) for m in parts], rel=1e-10)
+    assert len(morphLikelihoods[0].getPatternLogLikelihoods()) == parts[0].n_pat
+    # a species-tree height move: the coalescent AND the morphological likelihoods follow; reject brings everything back
+    before = posterior.logP
+    posterior.store(); speciesTree.store()
+    sp = speciesTree.arrays
+    node = next(i for i in range(sp.n_leaves, sp.n_nodes) if sp.parent[i] >= 0 and sp.height[sp.parent[i]] - sp.height[i] > 1e-4)
+    speciesTree.setHeight(node, sp.height[node] + 0.3 * (sp.height[sp.parent[node]] - sp.height[node]))
+    pb.species = speciesTree.arrays
+    proposed = posterior.calculateLogP()
+    w2 = want_total()
+    if math.isfinite(w2.coalescent):
+        assert proposed == pytest.approx(w2.total, rel=1e-9)
+        assert [tl.logP for tl in morphLikelihoods] == pytest.approx(list(w2.per_locus_lik[3:]), rel=1e-10)
+        assert morphLikelihoods[0].logP != pytest.approx(w.per_locus_lik[3], rel=1e-12)
+    else:
+        assert proposed == -math.inf
+    speciesTree.restore(); posterior.restore()
+    pb.species = speciesTree.arrays
+    assert posterior.calculateLogP() == before
+    # the morphological clock rate moves: only the four partitions change
+    posterior.store()
+    morphRate.setValue(0, 1.1)
+    for m in parts:
+        m.clock_rate = 1.1
+    w3 = want_total()
+    assert posterior.calculateLogP() == pytest.approx(w3.total, rel=1e-9)
+    assert [tl.logP for tl in likelihoods] == pytest.approx(list(w.per_locus_lik[:3]), rel=1e-12)
