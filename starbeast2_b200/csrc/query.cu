@@ -38,6 +38,10 @@ __global__ void __launch_bounds__(QUERY_THREADS) k_tip_class_query(QueryArgs A)
     extern __shared__ int sm[];
     const LocusDesc &d = A.loci[blockIdx.x];
     const int G = d.nNodes, nTips = d.nTips, nb = d.nodeBase, tid = threadIdx.x;
+    if (d.kStates) {   // a likelihood-only locus is not a gene tree: the co-ordinated operators do not see it
+        if (A.mask) for (int i = tid; i < G; i += QUERY_THREADS) A.mask[nb + i] = 0;
+        return;
+    }
     int *par = sm;
     unsigned *state = reinterpret_cast<unsigned *>(sm + A.maxNodes);
     for (int i = tid; i < G; i += QUERY_THREADS) { par[i] = A.gParent[nb + i]; state[i] = 0u; }

@@ -238,8 +238,10 @@ CONFIGS = {
     # name: loci, sites, species, tips/species, subst, n_cat, clock, pop model
     "C2": dict(n_loci=50, n_sites=1000, n_species=10, tips_per=3, subst="hky", n_cat=1, clock="strict", pop="constant", seed=2),
     "C3": dict(n_loci=200, n_sites=800, n_species=20, tips_per=3, subst="gtr", n_cat=4, clock="ucln", pop="lwcr", seed=3),
+    # CanisFBD-style (tutorial/CanisFBD/Canis-FBD.xml): fossil tips in the species tree, analytic population sizes, and -- like the
+    # reference's four morphTreeLikelihoods (:964-1033) -- four ascertained LewisMK partitions (K = 2..5) on the species tree
     "C4": dict(n_loci=500, n_sites=600, n_species=8, tips_per=2, subst="hky", n_cat=1, clock="strict", pop="analytic", seed=4,
-               n_fossils=16),
+               n_fossils=16, n_morph=4, n_chars=24),
     "C5": dict(n_loci=2000, n_sites=500, n_species=40, tips_per=3, subst="gtr", n_cat=4, clock="ucln", pop="constant", seed=5),
 }
 
@@ -324,7 +326,8 @@ def make_problem(name: str = "C2", n_loci: Optional[int] = None, n_sites: Option
                           clock_kind=clock_kind, clock_rate=clock_rate))
     # morphological partitions on the species tree (CanisFBD-style: one TreeLikelihood per state count, LewisMK, ascertained)
     morph = []
-    for mi in range(int(cfg.get("n_morph", 0))):
+    # (they travel with the shard that holds the last locus, so that every rank of a sharded run sees each partition once)
+    for mi in range(int(cfg.get("n_morph", 0)) if hi == cfg["n_loci"] else 0):
         rng = np.random.Generator(np.random.PCG64([base_seed, 900000 + mi]))
         K = 2 + mi % 4
         rate = 0.6 / max(float(sp.height[sp.root]), 1e-6)
@@ -369,6 +372,7 @@ def make_problem_parallel(name: str, n_loci: Optional[int] = None, locus_range: 
     pb = parts[0]
     for q in parts[1:]:
         pb.loci.extend(q.loci)
+        pb.morph.extend(q.morph)   # only the chunk with the last locus carries them
     return pb
 
 

@@ -158,7 +158,7 @@ def test_posterior_adds_the_morphological_partitions():
     assert len(pb.morph) == 3 and {m.n_states for m in pb.morph} <= {2, 3, 4, 5}
     r = oracle.posterior(pb)
     assert len(r.per_locus_lik) == 3 + 3 and np.all(r.per_locus_coal[3:] == 0.0)
-    pb2 = synth.make_problem("C4", n_loci=3, n_sites=80)
+    pb2 = synth.make_problem("C4", n_loci=3, n_sites=80, n_morph=0)
     r2 = oracle.posterior(pb2)
     extra = sum(oracle.tree_likelihood_k(m, pb.species) for m in pb.morph)
     assert r.likelihood == pytest.approx(r2.likelihood + extra, rel=1e-13)
