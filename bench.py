@@ -254,7 +254,7 @@ def bench_incremental(eng, pb, synth, n_steps=400):
                 np.ascontiguousarray(t.height, np.float64)]
         keep.append(arrs)
         ptrs.append((l, arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data))
-    coal_buf, lik_buf, br_buf = np.zeros(pb.n_loci), np.zeros(pb.n_loci), np.zeros(pb.species.n_nodes)
+    coal_buf, lik_buf, br_buf = np.zeros(eng.n_loci), np.zeros(eng.n_loci), np.zeros(pb.species.n_nodes)   # eng.n_loci: + the morphological partitions
     c1, l1, tot = np.zeros(1), np.zeros(1), np.zeros(3)
     pc, pl, pbr, pc1, pl1, pt = (a.ctypes.data for a in (coal_buf, lik_buf, br_buf, c1, l1, tot))
 
@@ -417,8 +417,10 @@ class Leg:
         n_nodes = int(self._keep[0].shape[0])
         S = pb.species.n_nodes
         self.h2d = 20 * n_nodes + 20 * S + 8 * S * 3 + 16 + pb.n_loci          # trees + species block + flags
-        self.d2h = 8 * (3 + 2 * pb.n_loci + S)
-        self._out = [np.zeros(pb.n_loci), np.zeros(pb.n_loci), np.zeros(S)]
+        self.n_morph = len(getattr(eng, "morph", []))
+        self.h2d += 20 * S * self.n_morph
+        self.d2h = 8 * (3 + 2 * eng.n_loci + S)
+        self._out = [np.zeros(eng.n_loci), np.zeros(eng.n_loci), np.zeros(S)]   # per-locus outputs cover the morphological partitions too
         sp = pb.species
         self._keep2 = [np.ascontiguousarray(x) for x in (sp.parent, sp.left, sp.right, sp.height, pb.species_rates,
                                                         pb.pop_a if pb.pop_a is not None else np.zeros(1),
@@ -436,6 +438,8 @@ class Leg:
         rc |= raw.sb2_set_species_rates(h, ptr[4])
         rc |= raw.sb2_set_pop_model(h, pb.pop_kind, ptr[5], ptr[6], pb.alpha, pb.beta)
         rc |= raw.sb2_set_gene_trees(h, 0, pb.n_loci, tp, tl, tr, th)
+        for j in range(self.n_morph):   # the morphological partitions live on the species tree: re-stage it for each of them
+            rc |= raw.sb2_set_gene_trees(h, pb.n_loci + j, 1, ptr[0], ptr[1], ptr[2], ptr[3])
         rc |= raw.sb2_mark_all_dirty(h)
         if ctx.world == 1 or self.peers:
             rc |= raw.sb2_eval_posterior(h, oc, ol, ob, ot)

@@ -46,6 +46,7 @@ struct sb2_engine {
     int32_t *dLaneOps = nullptr;
     // K-state likelihood-only loci (kstate.cu)
     int nK = 0, maxK = 0;
+    size_t kSmemScratch = 0;         // shared-memory partials scratch of k_kstate: the largest K-state locus that fits 96 KB
     std::vector<int32_t> kLoci;
     int32_t *dKLoci = nullptr, *dExcluded = nullptr, *dKExp = nullptr;
     double *dKScratch = nullptr;
@@ -462,7 +463,7 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
             k.tipStates = e->dStates; k.weights = e->dWeights; k.excluded = e->dExcluded;
             k.catRates = e->dCat; k.catProps = e->dCat + e->totalCat; k.explicitRates = e->dExplicit ? e->dExplicit : e->dCat;
             k.cur = cur(e); k.patLogL = e->dPatLogL; k.scratch = e->dKScratch; k.scratchExp = e->dKExp;
-            k.maxNodes = e->maxNodes; k.maxCat = e->nCat;
+            k.maxNodes = e->maxNodes; k.maxCat = e->nCat; k.smemScratch = e->kSmemScratch;
             CUDA_TRY(e, launch_kstate(k, e->nK, e->maxK, st));
             e->launches++;
         }
@@ -822,7 +823,16 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if ((rc = dev_alloc(e, &e->dNOps, L))) return rc;
     e->nK = (int)e->kLoci.size();
     if (e->nK) {
-        if (kstate_smem_bytes(e->maxNodes, e->nCat, e->maxK) > 227 * 1024) return e->fail(SB2_ERR_ARG, "K-state locus too large for the per-locus shared-memory kernel");
+        for (int32_t l : e->kLoci) {
+            const LocusDesc &d = e->loci[l].d;
+            const size_t b = kstate_scratch_bytes(d.nInt, d.nCat, d.nPat, d.kStates);
+            if (b <= 96 * 1024) e->kSmemScratch = std::max(e->kSmemScratch, b);
+        }
+        e->kSmemScratch = (e->kSmemScratch + 15) & ~size_t(15);
+        if (kstate_smem_bytes(e->maxNodes, e->nCat, e->maxK, e->kSmemScratch) > 227 * 1024) {
+            e->kSmemScratch = 0;   // trees this large leave no room: every K-state locus uses the HBM scratch
+            if (kstate_smem_bytes(e->maxNodes, e->nCat, e->maxK, 0) > 227 * 1024) return e->fail(SB2_ERR_ARG, "K-state locus too large for the per-locus shared-memory kernel");
+        }
         std::vector<int32_t> excl((size_t)std::max<int64_t>(exclBase, 1), 0);
         for (auto &hl : e->loci) if (hl.d.nExcl) memcpy(excl.data() + hl.d.exclBase, hl.excluded.data(), 4 * (size_t)hl.d.nExcl);
         if ((rc = dev_alloc(e, &e->dKLoci, (size_t)e->nK))) return rc;

@@ -20,21 +20,29 @@ namespace sb2 {
 
 constexpr int KS_THREADS = 128;
 
+constexpr size_t KS_SCRATCH_SMEM_MAX = 96 * 1024;   // per-locus partials + exponents up to this size live in shared memory
+
 struct KsSmem {
-    size_t gH, gP, gL, gR, order, stack, mats, total;
+    size_t gH, gP, gL, gR, order, stack, mats, scr, total;
 };
-__host__ __device__ inline KsSmem ks_carve(int G, int C, int K)
+// scratchBytes: size of the shared-memory partials scratch (the largest locus that fits KS_SCRATCH_SMEM_MAX, see
+// kstate_scratch_bytes); the carve is the same for every K of one launch except for the two trailing regions
+__host__ __device__ inline KsSmem ks_carve(int G, int C, int K, size_t scratchBytes)
 {
     KsSmem m;
     size_t o = 0;
     auto take = [&](size_t b) { size_t r = o; o += (b + 15) & ~size_t(15); return r; };
     m.gH = take(8ull * G); m.gP = take(4ull * G); m.gL = take(4ull * G); m.gR = take(4ull * G);
     m.order = take(4ull * G); m.stack = take(4ull * G);
+    m.scr = take(scratchBytes);
     m.mats = take(8ull * G * C * K * K);
     m.total = o;
     return m;
 }
-size_t kstate_smem_bytes(int maxNodes, int maxCat, int K) { return ks_carve(maxNodes, maxCat, K).total; }
+// bytes of partials [internal][category][pattern][K] + int32 exponents [internal][category][pattern] of one locus
+__host__ __device__ inline size_t ks_locus_scratch(int nInt, int C, int nPat, int K) { return (size_t)nInt * C * nPat * (8 * K + 4); }
+size_t kstate_scratch_bytes(int nInt, int nCat, int nPat, int K) { return ks_locus_scratch(nInt, nCat, nPat, K); }
+size_t kstate_smem_bytes(int maxNodes, int maxCat, int K, size_t scratchBytes) { return ks_carve(maxNodes, maxCat, K, scratchBytes).total; }
 
 template <int K>
 __device__ __forceinline__ void kstate_locus(const KStateArgs &A, int l, const LocusDesc &d, unsigned char *smem)
@@ -42,7 +50,7 @@ __device__ __forceinline__ void kstate_locus(const KStateArgs &A, int l, const L
     constexpr int KK = K * K;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int G = d.nNodes, nT = d.nTips, nI = d.nInt, C = d.nCat, nPat = d.nPat, nb = d.nodeBase;
-    const KsSmem m = ks_carve(A.maxNodes, A.maxCat, K);
+    const KsSmem m = ks_carve(A.maxNodes, A.maxCat, K, A.smemScratch);
     double *gH = reinterpret_cast<double *>(smem + m.gH);
     int *gP = reinterpret_cast<int *>(smem + m.gP), *gL = reinterpret_cast<int *>(smem + m.gL), *gR = reinterpret_cast<int *>(smem + m.gR);
     int *order = reinterpret_cast<int *>(smem + m.order), *stack = reinterpret_cast<int *>(smem + m.stack);
@@ -102,8 +110,12 @@ __device__ __forceinline__ void kstate_locus(const KStateArgs &A, int l, const L
     __syncthreads();
 
     const uint8_t *states = A.tipStates + d.stateBase;
-    double *scr = A.scratch + d.kBase;                 // [internal][category][pattern][K]
-    int32_t *scrE = A.scratchExp + d.kBase / K;        // [internal][category][pattern]
+    // partials [internal][category][pattern][K] and exponents [internal][category][pattern]: in shared memory when the locus
+    // fits (the usual case: tens of characters x tens of tips), else in the HBM scratch; only this thread touches its pattern's
+    const size_t nElem = (size_t)nI * C * nPat;
+    const bool inSmem = ks_locus_scratch(nI, C, nPat, K) <= A.smemScratch;
+    double *scr = inSmem ? reinterpret_cast<double *>(smem + m.scr) : A.scratch + d.kBase;
+    int32_t *scrE = inSmem ? reinterpret_cast<int32_t *>(smem + m.scr + 8 * K * nElem) : A.scratchExp + d.kBase / K;
     const double *props = A.catProps + d.catBase;
     for (int p = tid; p < nPat; p += nt) {
         double acc[K];
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(KS_THREADS) k_kstate(KStateArgs A)
 
 cudaError_t launch_kstate(const KStateArgs &a, int nK, int maxK, cudaStream_t st)
 {
-    const size_t smem = kstate_smem_bytes(a.maxNodes, a.maxCat, maxK);
+    const size_t smem = kstate_smem_bytes(a.maxNodes, a.maxCat, maxK, a.smemScratch);
     static size_t configured[MAX_DEVICES] = {};
     cudaError_t rc = ensure_dynamic_smem(k_kstate, smem, configured);
     if (rc != cudaSuccess) return rc;

@@ -264,8 +264,10 @@ struct KStateArgs {
     double *scratch;             // partials, see LocusDesc::kBase
     int32_t *scratchExp;         // power-of-two exponents per (node, category, pattern)
     int32_t maxNodes, maxCat;
+    size_t smemScratch;          // bytes of shared memory set aside for a locus's partials (loci that do not fit use `scratch`)
 };
-size_t kstate_smem_bytes(int maxNodes, int maxCat, int K);
+size_t kstate_smem_bytes(int maxNodes, int maxCat, int K, size_t scratchBytes);
+size_t kstate_scratch_bytes(int nInt, int nCat, int nPat, int K);
 cudaError_t launch_kstate(const KStateArgs &a, int nK, int maxK, cudaStream_t st);
 
 // Operator-side queries over the resident gene trees (query.cu)

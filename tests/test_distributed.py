@@ -138,13 +138,15 @@ def test_engine_distributed_two_ranks(name):
     node_off = np.concatenate([[0], np.cumsum([l.tree.n_nodes for l in pb.loci])])
     for rank, coal, lik, total, per_locus, per_branch, q in got:
         lo, hi = shard_loci([1.0] * n_loci, world)[rank]
-        assert q[0] == w_mask[node_off[lo]:node_off[hi]].tolist()
+        n_gene = int(node_off[hi] - node_off[lo])   # the rank with the last locus also holds the morphological partitions: never connecting
+        assert q[0][:n_gene] == w_mask[node_off[lo]:node_off[hi]].tolist() and not any(q[0][n_gene:])
         assert q[1:] == (w_tip, w_root, w_cnt, w_mh)
         assert coal == pytest.approx(full.coalescent, rel=1e-9)      # every rank ends with the global totals
         assert lik == pytest.approx(full.likelihood, rel=1e-9)
         assert total == pytest.approx(full.total, rel=1e-9)
         lo, hi = shard_loci([1.0] * n_loci, world)[rank]
-        np.testing.assert_allclose(per_locus, full.per_locus_lik[lo:hi], rtol=1e-9)
+        hi_out = len(full.per_locus_lik) if hi == n_loci else hi      # + the morphological partitions on the last rank
+        np.testing.assert_allclose(per_locus, full.per_locus_lik[lo:hi_out], rtol=1e-9)
         if pb.pop_kind == POP_ANALYTIC:
             np.testing.assert_allclose(per_branch, full.per_branch, rtol=1e-9)
 
@@ -253,7 +255,8 @@ def test_one_host_thread_several_engines(name):
             assert r.coalescent == pytest.approx(full.coalescent, rel=1e-9)
             assert r.likelihood == pytest.approx(full.likelihood, rel=1e-9)
             assert r.total == pytest.approx(full.total, rel=1e-9)
-            np.testing.assert_allclose(r.per_locus_lik, full.per_locus_lik[lo:hi], rtol=1e-9)
+            hi_out = len(full.per_locus_lik) if hi == n_loci else hi      # + the morphological partitions on the last shard
+            np.testing.assert_allclose(r.per_locus_lik, full.per_locus_lik[lo:hi_out], rtol=1e-9)
             if pb.pop_kind == POP_ANALYTIC:
                 np.testing.assert_allclose(r.per_branch, full.per_branch, rtol=1e-9)
         assert res[0].total == res[1].total == res[2].total          # same summation order everywhere

@@ -147,3 +147,30 @@ def test_k_state_argument_errors():
         e.set_site_model(i, [1.0], [1.0], 0.1)
     with pytest.raises(Sb2Error, match="StarBeastClock"):
         e.set_clock(i, 1, 1.0, None)
+
+
+def test_a_partition_too_large_for_shared_memory_uses_the_hbm_scratch():
+    """k_kstate keeps a locus's partials in shared memory up to 96 KB; a larger partition (here ~1 MB) takes the HBM scratch,
+    next to a small one in the same launch."""
+    rng = np.random.default_rng(6)
+    sp = synth.yule_species_tree(rng, 40)
+    parts = []
+    for K, n_chars in ((5, 400), (3, 12)):
+        pats, w, excl = synth.simulate_morphology(rng, sp, K, n_chars, 1.5)
+        parts.append(MorphPartition(tip_states=pats, weights=w, n_states=K, subst_params=lewis_mk_eigen(K), clock_rate=1.2, excluded=excl,
+                                    cat_rates=[0.4, 1.6], cat_props=[0.5, 0.5]))
+    assert parts[0].n_pat * 39 * 2 * 44 > 96 * 1024 > parts[1].n_pat * 39 * 2 * 28
+    e = Engine()
+    for m in parts:
+        e.add_locus_k(m.tip_states, m.weights, m.n_states, m.n_cat, m.excluded)
+    e.finalize(sp.n_nodes, sp.n_leaves)
+    e.set_species_tree(sp)
+    e.set_pop_model(0, np.ones(sp.n_nodes))
+    for i, m in enumerate(parts):
+        e.set_gene_tree(i, sp)
+        e.set_subst_model(i, 1, m.subst_params)
+        e.set_site_model(i, m.cat_rates, m.cat_props, 0.0)
+        e.set_clock(i, 0, m.clock_rate, None)
+    r = e.eval_posterior()
+    want = [oracle.tree_likelihood_k(m, sp) for m in parts]
+    assert np.allclose(r.per_locus_lik, want, rtol=1e-11, atol=0)
