@@ -186,7 +186,8 @@ SB2_API int sb2_get_pattern_logl(sb2_engine *e, int32_t locus, double *patternLo
  * CoordinatedUniform.getConnectingNodes + findConnectingNodes (CoordinatedUniform.java:94-177) and the
  * CoordinatedExponential twins (CoordinatedExponential.java:92-160), for every gene tree at once:
  *   mask[sum of (2*nTips-1)]  1 where the gene node belongs to a connected component of `speciesNode` (loci concatenated in
- *                             engine order, node-number order inside a locus), may be NULL;
+ *                             engine order, node-number order inside a locus; likelihood-only loci added with
+ *                             sb2_add_locus_k have no gene tree: their slots stay 0), may be NULL;
  *   freedoms[0] tipwardFreedom, freedoms[1] rootwardFreedom as accumulated by the gene-tree walk (+inf if unconstrained;
  *   the caller adds the species-branch constraints of :76-81; CoordinatedExponential ignores freedoms[1]);
  *   count       number of connecting nodes, may be NULL. */

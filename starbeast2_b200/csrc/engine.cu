@@ -384,6 +384,8 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
     a.cur = cur(e); a.stored = stored(e); a.ops = e->dOps; a.nOps = e->dNOps; a.mats = e->dMats; a.opMats = e->dOpMats;
     a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L; a.stackDepth = e->stackDepth; a.uniformFlags = uniformFlags;
     a.workers = e->workers; a.laneOps = e->dLaneOps;
+    static const bool noRegPark = getenv("SB2_NO_REGPARK") != nullptr;   // A/B knob: every park goes to the shared-memory stack
+    a.regPark = (e->workers == 1 && !noRegPark) ? 1 : 0;
     a.singleLocus = singleLocus; a.singleFlags = singleLocus >= 0 ? e->hFlags[singleLocus] : 0;
     a.nSync = nSync;
     for (int j = 0; j < 8; j++) a.syncLoci[j] = syncLoci[j];
@@ -408,6 +410,7 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
         StepArgs sa;
         sa.prep = a;
         sa.prep.workers = 1;
+        sa.prep.regPark = 0;   // k_step's walk keeps every park in its shared-memory stack
         sa.red = reduce_args(e, /*coalOnly=*/true);   // useTiles = 0: the leaders write the per-locus values into the state block
         arm_poll(e, sa.red);
         sa.comm = e->comm;
@@ -791,8 +794,12 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     for (int l = 0; l < L; l++) {
         const HostLocus &hl = e->loci[l];
         descs[l] = hl.d;
-        for (int t = 0; t < hl.d.nTips; t++)
-            memcpy(states.data() + hl.d.stateBase + (size_t)t * hl.d.stateStride, hl.states.data() + (size_t)t * hl.d.nPat, hl.d.nPat);
+        for (int t = 0; t < hl.d.nTips; t++) {
+            uint8_t *row = states.data() + hl.d.stateBase + (size_t)t * hl.d.stateStride;
+            memcpy(row, hl.states.data() + (size_t)t * hl.d.nPat, hl.d.nPat);
+            // 4-state loci: every missing / ambiguous code becomes 4, the index of the ones column k_treewalk reads for it
+            if (!hl.d.kStates) for (int p = 0; p < hl.d.nPat; p++) if (row[p] > 4) row[p] = 4;
+        }
         memcpy(cmask.data() + hl.d.patBase, hl.constMask.data(), hl.constMask.size());
         memcpy(weights.data() + hl.d.patBase, hl.weights.data(), hl.weights.size() * 4);
         memcpy(tipsp.data() + hl.d.tipBase, hl.tipSpecies.data(), hl.tipSpecies.size() * 4);
@@ -819,7 +826,8 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if ((rc = dev_alloc(e, &e->dPatLogL, (size_t)patBase))) return rc;
     if ((rc = dev_alloc(e, &e->dChunkSum, (size_t)chunkBase))) return rc;
     if ((rc = dev_alloc(e, &e->dOps, (size_t)opBase))) return rc;
-    if ((rc = dev_alloc(e, &e->dOpMats, (size_t)opBase * e->nCat * 32))) return rc;
+    if ((rc = dev_alloc(e, &e->dOpMats, (size_t)opBase * e->nCat * 2 * OPMAT_STRIDE))) return rc;
+    CUDA_TRY(e, cudaMemset(e->dOpMats, 0, sizeof(double) * (size_t)opBase * e->nCat * 2 * OPMAT_STRIDE));
     if ((rc = dev_alloc(e, &e->dNOps, L))) return rc;
     e->nK = (int)e->kLoci.size();
     if (e->nK) {

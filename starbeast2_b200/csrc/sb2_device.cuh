@@ -8,7 +8,7 @@
 //   mats        f64 [locus][buf][node][cat][16]                P = exp(Q d) per branch x category
 //   StateBlock (x2: current / stored)  small per-node and per-locus state, see below
 //   ops         Op  [locus][internal node]                      post-order pruning schedule built on device
-//   opMats      f64 [locus][op][cat][side][16]                  the scheduled ops' matrix pairs, in schedule order
+//   opMats      f64 [locus][op][cat][side][20]                  the scheduled ops' matrix pairs, in schedule order (OPMAT_STRIDE)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -74,8 +74,11 @@ enum : uint8_t {
 // REMOTE: (latency-bound shapes only, see WALK_MAX_WORKERS) the result of a side subtree that another worker warp of the
 // same CTA evaluates concurrently; it arrives in that warp's mailbox slot (slot field) and the operand's offset field holds
 // the worker number
-enum : uint8_t { OPK_TIP = 0, OPK_STACK = 1, OPK_GLOBAL = 2, OPK_SPILL = 3, OPK_PREV = 4, OPK_REMOTE = 5 };
+// REG: a parked result that waits in the walking thread's registers (k_treewalk only, PrepareArgs::regPark): chosen when the
+// sibling subtree parks nothing itself, so one register slot per thread is enough -- most parks of a random tree qualify
+enum : uint8_t { OPK_TIP = 0, OPK_STACK = 1, OPK_GLOBAL = 2, OPK_SPILL = 3, OPK_PREV = 4, OPK_REMOTE = 5, OPK_REG = 6 };
 constexpr unsigned OP_NO_SLOT = 255;   // outSlot: result is not parked (forwarded in registers, or spilled)
+constexpr unsigned OP_REG_SLOT = 254;  // outSlot: parked in the register slot (OPK_REG)
 constexpr unsigned OP_SIGNAL = 1u << 22;   // ctl: the parked result is awaited by another worker: publish the mailbox flag
 // Tree-level parallelism for latency-bound shapes: the walk of one pattern chunk is split over up to WALK_MAX_WORKERS warps.
 // Worker 0 walks the main (heavy-child) path; side subtrees hanging off it go to the helpers, whose results come back through
@@ -84,6 +87,10 @@ constexpr int WALK_MAX_WORKERS = 4;
 constexpr int WALK_MAILBOX = 2;
 constexpr int WALK_MAX_WORKER_OPS = 64;    // multi-worker walks keep the whole op list in shared memory
 
+// Doubles per matrix of the op-ordered stream `opMats` that k_treewalk reads: 16 for the matrix (row-major for an internal
+// operand; TRANSPOSED for a tip, whose factor is a column) + 4: a fifth column of ones behind a tip's four, so that the tip's
+// state byte (0..3, 4 = missing / ambiguous) is the column index.  k_step's shared-memory stream keeps 16 (+ a separate ones column).
+constexpr int OPMAT_STRIDE = 20;
 struct __align__(16) Op {
     // offsets are pre-multiplied by k_prepare so that the pruning kernel needs one IMAD.WIDE per address:
     uint32_t outOff;  // (buf*nInt + internal index) * nCat*nPat   -> (pattern, category) element of the output
@@ -154,6 +161,7 @@ struct PrepareArgs {
     const double *pfCatProps;
     int32_t workers;             // worker warps per pattern chunk of k_treewalk (1 = single walk)
     int32_t *laneOps;            // [nLoci][WALK_MAX_WORKERS + 1] first op of each worker's list (workers > 1)
+    int32_t regPark;             // 1: parks whose sibling subtree parks nothing use the register slot (OPK_REG); k_treewalk only
 };
 
 struct ReduceArgs {

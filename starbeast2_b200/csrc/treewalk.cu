@@ -35,7 +35,8 @@
 namespace sb2 {
 
 constexpr int OPS_BATCH = 32;   // ops staged in shared memory per half batch
-constexpr int MAT_RING = 4;     // transition-matrix pairs in flight per warp (cp.async ring)
+constexpr int MAT_RING = 4;     // transition-matrix pairs in flight per warp (bulk-copy ring)
+constexpr int MAT_STRIDE = OPMAT_STRIDE;   // doubles per matrix of the op-ordered stream (sb2_device.cuh)
 constexpr int TIP_SMEM_MAX = 48 * 1024;
 
 bool treewalk_tips_in_smem(int maxTips, int tilePat) { return (size_t)maxTips * tilePat <= TIP_SMEM_MAX; }
@@ -46,7 +47,8 @@ size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, i
     const size_t tilePat = (size_t)chunksPerTile * 32 * R;
     const size_t slots = (size_t)stackDepth + (workers > 1 ? WALK_MAILBOX : 0);
     size_t b = slots * warps * R * 32 * 32;                // partials stack (two double2 planes)
-    b += (size_t)warps * MAT_RING * 2 * 16 * 8;            // per-warp matrix rings
+    b += (size_t)warps * MAT_RING * 2 * MAT_STRIDE * 8;    // per-warp matrix rings
+    b += (size_t)warps * MAT_RING * 8 + 32;                // their mbarriers (one per ring slot) + the tip-state tile's
     b += 2ull * OPS_BATCH * sizeof(Op);                    // op schedule, two half batches
     b += slots * warps * R * 32 * 2;                       // exponent stack (int16)
     b += 16 * 8;                                           // the ones column
@@ -95,9 +97,11 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
     // the accesses in the shared window (LDS/STS), never generic
     double2 *st2 = reinterpret_cast<double2 *>(smem_raw);                       // stack: [2 planes][depth][warps][R][32] double2
     const int planeStride = slots * warps * R * 32;                             //        plane 0 = states 0,1; plane 1 = states 2,3
-    double *smd = reinterpret_cast<double *>(st2 + 2 * planeStride);            // ring [warps][MAT_RING][32] | ones[16]
-    const int onesIdx = warps * MAT_RING * 32;
-    Op *sops = reinterpret_cast<Op *>(smd + onesIdx + 16);                      // [2 * OPS_BATCH]
+    double *smd = reinterpret_cast<double *>(st2 + 2 * planeStride);            // ring [warps][MAT_RING][2 * MAT_STRIDE] | ones[16]
+    const int onesIdx = warps * MAT_RING * 2 * MAT_STRIDE;
+    unsigned long long *sbar = reinterpret_cast<unsigned long long *>(smd + onesIdx + 16);   // [warps][MAT_RING] ring-slot mbarriers | [4]: tip tile
+    unsigned long long *tipBar = sbar + warps * MAT_RING;
+    Op *sops = reinterpret_cast<Op *>(tipBar + 4);                              // [2 * OPS_BATCH]
     int16_t *sexp = reinterpret_cast<int16_t *>(sops + 2 * OPS_BATCH);          // [slots][warps][R][32]
     unsigned *sflag = reinterpret_cast<unsigned *>(sexp + planeStride);         // [slots][warps] mailbox flags (NW > 1 only)
     uint8_t *sstate = reinterpret_cast<uint8_t *>(sflag + (NW > 1 ? ((slots * warps + 3) & ~3) : 0));   // [nTips][tilePat]; 16-byte aligned by construction
@@ -106,39 +110,51 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
     // ---- static inputs first: under programmatic dependent launch this part overlaps k_prepare's tail ----
     if (tid < 16) smd[onesIdx + tid] = 1.0;
     if (NW > 1) for (int i = tid; i < slots * warps; i += blockDim.x) sflag[i] = 0u;
+    // mbarriers: one per matrix-ring slot of every warp (one arrival: the elected lane's expect_tx), one for the tip-state tile
+    // (every thread arrives with the bytes of the rows it copies)
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < MAT_RING; j++) mbar_init(sbar + w * MAT_RING + j, 1);
+        if (tid == 0) mbar_init(tipBar, blockDim.x);
+    }
+    mbar_init_fence();
+    __syncthreads();
     if (tipsInSmem) {
-        // the tile's tip states, every tip, as one burst of asynchronous 16-byte copies (rows are padded to 128 bytes with
-        // 'missing', so a tile never leaves its row); they ride in the first cp.async group, which the first op waits for
+        // the tile's tip states: one bulk copy per tip row (rows are padded to 128 bytes with 'missing', so a tile never
+        // leaves its row), all completing on one mbarrier that every thread waits for before its first op
         if (A.tipsInSmem == 2) {   // A/B knob: plain byte loads
             const int total = d.nTips * tilePat;
             for (int idx = tid; idx < total; idx += blockDim.x) {
                 const int t = idx / tilePat, pp = idx - t * tilePat;
                 sstate[idx] = states[(size_t)t * d.stateStride + p0 + pp];
             }
+            mbar_arrive_expect_tx(tipBar, 0);
         } else {
-            const int per = tilePat >> 4, total = d.nTips * per;
-            for (int idx = tid; idx < total; idx += blockDim.x) {
-                const int t = idx / per, q = idx - t * per;
-                cp_async16(sstate + t * tilePat + q * 16, states + (size_t)t * d.stateStride + p0 + q * 16);
-            }
+            const int mine = tid < d.nTips ? (d.nTips - tid + (int)blockDim.x - 1) / (int)blockDim.x : 0;
+            mbar_arrive_expect_tx(tipBar, (unsigned)(mine * tilePat));
+            for (int t = tid; t < d.nTips; t += blockDim.x)
+                bulk_g2s(sstate + t * tilePat, states + (size_t)t * d.stateStride + p0, (unsigned)tilePat, tipBar);
         }
     }
     // nOps / ops / opMats are k_prepare's outputs: they must not be touched before that grid has completed
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();   // the (single-CTA) reduction kernel may queue up behind us already
     const Op *ops = A.ops + d.opBase;
-    const double *matStream = A.opMats + ((size_t)d.opBase * C + c) * 32 + lane;   // + k * C*32: this lane's 8 bytes of op k's pair
-    const int ringIdx = w * MAT_RING * 32;
-    const int matStride = C * 32;
+    const double *matStream = A.opMats + ((size_t)d.opBase * C + c) * (2 * MAT_STRIDE);   // + k * matStride: op k's matrix pair of this category
+    unsigned long long *myBar = sbar + w * MAT_RING;
+    const int ringIdx = w * MAT_RING * (2 * MAT_STRIDE);
+    const int matStride = C * (2 * MAT_STRIDE);
+    constexpr unsigned PAIR_BYTES = 2 * MAT_STRIDE * 8;
     // Single-worker walks start at op 0 whatever nOps turns out to be: fetch the first batch of the schedule and the first
     // matrix pairs in the same wave of loads as nOps itself (bounded by the locus's allocation, so a clean locus merely
     // reads stale entries) instead of one dependent round trip later.
     int4 specOp = make_int4(0, 0, 0, 0);
     if (NW == 1) {
         if (tid < OPS_BATCH && tid < d.nInt) specOp = reinterpret_cast<const int4 *>(ops)[tid];
-        for (int j = 0; j < MAT_RING - 1; j++) {
-            if (j < d.nInt) cp_async8(smd + ringIdx + j * 32 + lane, matStream + (size_t)j * matStride);
-            cp_async_commit();
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < MAT_RING; j++)
+                if (j < d.nInt) { mbar_arrive_expect_tx(myBar + j, PAIR_BYTES); bulk_g2s(smd + ringIdx + j * (2 * MAT_STRIDE), matStream + (size_t)j * matStride, PAIR_BYTES, myBar + j); }
         }
     }
     const int nOps = A.nOps[l];
@@ -146,9 +162,12 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
     const int kBeg = NW > 1 ? A.laneOps[l * (WALK_MAX_WORKERS + 1) + worker] : 0;
     int kEnd = NW > 1 ? A.laneOps[l * (WALK_MAX_WORKERS + 1) + worker + 1] : nOps;
     if (A.debugMaxOps >= 0 && NW == 1) kEnd = min(kEnd, kBeg + A.debugMaxOps);   // timing experiments only: results are garbage
-    if (nOps == 0) {         // locus clean: cached logL stands
-        cp_async_commit();
-        cp_async_wait<0>();
+    if (nOps == 0) {         // locus clean: cached logL stands; the copies in flight must land before the CTA's shared memory goes away
+        if (tipsInSmem) mbar_wait(tipBar, 0);
+        if (NW == 1) {
+#pragma unroll
+            for (int j = 0; j < MAT_RING; j++) if (j < d.nInt) mbar_wait(myBar + j, 0);
+        }
         return;
     }
     const bool incremental = nOps < d.nInt;         // only then can operands be clean nodes resident in HBM
@@ -173,16 +192,22 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
         int4 *dst = reinterpret_cast<int4 *>(sops + (b & 1) * OPS_BATCH);
         for (int t = tid; t < cnt; t += blockDim.x) dst[t] = src[t];
     };
-    // this warp's matrix pair of op k (256 contiguous bytes of the op-ordered stream) -> ring slot k % MAT_RING
+    // this warp's matrix pair of op k (256 contiguous bytes of the op-ordered stream) -> ring slot (k - kBeg) % MAT_RING: one bulk
+    // copy by the elected lane, completing on the slot's mbarrier (phase parity = ((k - kBeg) / MAT_RING) & 1)
     auto issue_mats = [&](int k) {
-        if (k < kEnd) cp_async8(smd + ringIdx + (k & (MAT_RING - 1)) * 32 + lane, matStream + (size_t)k * matStride);
-        cp_async_commit();
+        if (lane == 0 && k < kEnd) {
+            const int j = (k - kBeg) & (MAT_RING - 1);
+            mbar_arrive_expect_tx(myBar + j, PAIR_BYTES);
+            bulk_g2s(smd + ringIdx + j * (2 * MAT_STRIDE), matStream + (size_t)k * matStride, PAIR_BYTES, myBar + j);
+        }
     };
 
-    double prev[R][4];   // result of the previous op (scaled) and its cumulative exponent
-    int prevCum[R];
+    // two register sets: one receives every op's result (and forwards it to the next op), the other is the register parking
+    // slot; they swap roles whenever a result is parked in registers (flip)
+    double xv[R][4], yv[R][4];
+    int xc[R], yc[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) { prev[r][0] = prev[r][1] = prev[r][2] = prev[r][3] = 0.0; prevCum[r] = 0; }
+    for (int r = 0; r < R; r++) { xv[r][0] = xv[r][1] = xv[r][2] = xv[r][3] = 0.0; yv[r][0] = yv[r][1] = yv[r][2] = yv[r][3] = 0.0; xc[r] = yc[r] = 0; }
 
     if (c == 0 && worker == 0) {   // what the root epilogue will read, pulled into L1 while the walk runs
         const LocusParams *prm = &A.params[l];
@@ -197,88 +222,93 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
     } else {
         load_batch(0);
         if (nOps > OPS_BATCH) load_batch(1);   // multi-worker walks are limited to 2 * OPS_BATCH ops: all resident, no reloads
-        for (int j = 0; j < MAT_RING - 1; j++) issue_mats(kBeg + j);
+        for (int j = 0; j < MAT_RING; j++) issue_mats(kBeg + j);
     }
-    cp_async_wait<MAT_RING - 2>();   // group 0 (tip states + op 0's matrices) has landed for this thread ...
-    __syncthreads();                 // ... and for everybody else; the op schedule is visible too
+    __syncthreads();                 // the op schedule is visible
+    if (tipsInSmem) mbar_wait(tipBar, 0);   // the tip-state tile has landed
 
-    for (int k = kBeg; k < kEnd; k++) {
-        if (NW == 1 && (k & (OPS_BATCH - 1)) == OPS_BATCH / 2 && (k / OPS_BATCH + 1) * OPS_BATCH < nOps) {
-            __syncthreads();                       // every warp has left the previous batch's half
-            load_batch(k / OPS_BATCH + 1);
-            __syncthreads();
-        }
-        cp_async_wait<MAT_RING - 2>();             // this lane's pieces of op k's matrices have landed
-        __syncwarp();                              // ... and the other lanes'; the warp is also done with op k-1
-        issue_mats(k + MAT_RING - 1);              // reuses the ring slot of op k-1
-        if (incremental && k + 2 < kEnd) {         // clean children live in HBM: pull their sectors towards L2 two ops ahead
-            const Op q = sops[(k + 2) & (2 * OPS_BATCH - 1)];
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                if ((q.ctl & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.aOff * 4 + r * 128);
-                if (((q.ctl >> 3) & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.bOff * 4 + r * 128);
-            }
-        }
-
-        const Op o = sops[k & (2 * OPS_BATCH - 1)];
-        const int mIdx = ringIdx + (k & (MAT_RING - 1)) * 32;
+    // One pruning op.  `fwd` holds the previous op's (scaled) result and receives this op's; `park` is the register parking
+    // slot (OPK_REG).  Returns true when the result is parked in registers (OP_REG_SLOT): the caller swaps the sets' roles.
+    auto op_body = [&](const Op &o, int mIdx, double (&fwd)[R][4], int (&fwdCum)[R], double (&park)[R][4], int (&parkCum)[R]) -> bool {
+        const unsigned aKind = o.ctl & 7, bKind = (o.ctl >> 3) & 7;
         double out[R][4];
         int cum[R];
 #pragma unroll
         for (int r = 0; r < R; r++) cum[r] = 0;
 
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            const unsigned kind = (o.ctl >> (3 * side)) & 7;
-            const unsigned off = side ? o.bOff : o.aOff;
-            const int m = mIdx + side * 16;
-            if (kind == OPK_TIP) {
+        // a tip's factor: column `state` of its matrix.  k_prepare stores a tip's matrix transposed (a column = 32 contiguous
+        // bytes = two LDS.128 that the whole warp shares bank-conflict free) with a fifth column of ones for missing /
+        // ambiguous data (state 4: the engine normalises every such code to 4), so the state byte IS the column index.
+        auto tip_column = [&](unsigned tip, int m, int r, double2 &v01, double2 &v23) {
+            const int st = tipsInSmem ? sstate[tip * tilePat + stateIdx + 32 * r]
+                                      : states[(size_t)tip * d.stateStride + pbase + 32 * r];
+            v01 = *reinterpret_cast<const double2 *>(smd + m + st * 4);
+            v23 = *reinterpret_cast<const double2 *>(smd + m + st * 4 + 2);
+        };
+        // a parked (shared-memory stack / helper mailbox) or resident (HBM) operand
+        auto fetch = [&](unsigned kind, unsigned off, unsigned slot, double (&a)[R][4]) {
+            if (kind == OPK_STACK || (NW > 1 && kind == OPK_REMOTE)) {
+                int si0 = slot * slotStride + stackIdx;
+                if (NW > 1 && kind == OPK_REMOTE) {   // a helper's finished subtree: wait for its mailbox flag, read its slot
+                    const int src = (int)off * inner + wi;
+                    const unsigned *flag = sflag + slot * warps + src;
+                    while (ld_acquire_shared(flag) == 0u) { }
+                    si0 += (src - w) * R * 32;
+                }
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const int st = tipsInSmem ? sstate[off * tilePat + stateIdx + 32 * r]
-                                              : states[(size_t)off * d.stateStride + pbase + 32 * r];
-                    const int col = (st < 4) ? (m + st) : onesIdx;   // missing / ambiguous: factor 1
-                    if (side == 0) { out[r][0] = smd[col]; out[r][1] = smd[col + 4]; out[r][2] = smd[col + 8]; out[r][3] = smd[col + 12]; }
-                    else { out[r][0] *= smd[col]; out[r][1] *= smd[col + 4]; out[r][2] *= smd[col + 8]; out[r][3] *= smd[col + 12]; }
+                    const double2 lo = st2[si0 + 32 * r], hi = st2[planeStride + si0 + 32 * r];
+                    a[r][0] = lo.x; a[r][1] = lo.y; a[r][2] = hi.x; a[r][3] = hi.y;
+                    cum[r] += sexp[si0 + 32 * r];
                 }
             } else {
-                if (kind == OPK_PREV) {   // the previous op's result, forwarded in registers
 #pragma unroll
-                    for (int r = 0; r < R; r++) cum[r] += prevCum[r];
-                    if (side == 0) rows_times<EXACT, R, true>(smd + m, prev, out);
-                    else rows_times<EXACT, R, false>(smd + m, prev, out);
-                    continue;
-                }
-                double a[R][4];
-                if (kind == OPK_STACK || (NW > 1 && kind == OPK_REMOTE)) {
-                    int si0 = ((o.ctl >> (6 + 4 * side)) & 15) * slotStride + stackIdx;
-                    if (NW > 1 && kind == OPK_REMOTE) {   // a helper's finished subtree: wait for its mailbox flag, read its slot
-                        const int src = (int)off * inner + wi;
-                        const unsigned *flag = sflag + ((o.ctl >> (6 + 4 * side)) & 15) * warps + src;
-                        while (ld_acquire_shared(flag) == 0u) { }
-                        si0 += (src - w) * R * 32;
-                    }
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        const double2 lo = st2[si0 + 32 * r], hi = st2[planeStride + si0 + 32 * r];
-                        a[r][0] = lo.x; a[r][1] = lo.y; a[r][2] = hi.x; a[r][3] = hi.y;
-                        cum[r] += sexp[si0 + 32 * r];
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0.0;
-                        if (valid[r]) {
-                            const double *src = partials + (size_t)off * 4 + r * 128;
-                            if (kind == OPK_GLOBAL) ld256_nc(src, a[r][0], a[r][1], a[r][2], a[r][3]);
-                            else ld256_coherent(src, a[r][0], a[r][1], a[r][2], a[r][3]);   // OPK_SPILL: written by this thread in this launch
-                            cum[r] += cumExp[(size_t)off + 32 * r];
-                        }
+                for (int r = 0; r < R; r++) {
+                    a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0.0;
+                    if (valid[r]) {
+                        const double *src = partials + (size_t)off * 4 + r * 128;
+                        if (kind == OPK_GLOBAL) ld256_nc(src, a[r][0], a[r][1], a[r][2], a[r][3]);
+                        else ld256_coherent(src, a[r][0], a[r][1], a[r][2], a[r][3]);   // OPK_SPILL: written by this thread in this launch
+                        cum[r] += cumExp[(size_t)off + 32 * r];
                     }
                 }
-                if (side == 0) rows_times<EXACT, R, true>(smd + m, a, out);
-                else rows_times<EXACT, R, false>(smd + m, a, out);
             }
+        };
+
+        // ---- operand a (canonical order: a tip whenever the op has one; never the register-forwarded result) ----
+        if (aKind == OPK_TIP) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                double2 v01, v23;
+                tip_column(o.aOff, mIdx, r, v01, v23);
+                out[r][0] = v01.x; out[r][1] = v01.y; out[r][2] = v23.x; out[r][3] = v23.y;
+            }
+        } else if (aKind == OPK_REG) {
+#pragma unroll
+            for (int r = 0; r < R; r++) cum[r] += parkCum[r];
+            rows_times<EXACT, R, true>(smd + mIdx, park, out);
+        } else {
+            double a[R][4];
+            fetch(aKind, o.aOff, (o.ctl >> 6) & 15, a);
+            rows_times<EXACT, R, true>(smd + mIdx, a, out);
+        }
+        // ---- operand b: the previous op's result forwarded in registers, or a second tip, or (incremental walks) a clean node ----
+        if (bKind == OPK_PREV) {
+#pragma unroll
+            for (int r = 0; r < R; r++) cum[r] += fwdCum[r];
+            rows_times<EXACT, R, false>(smd + mIdx + MAT_STRIDE, fwd, out);
+        } else if (bKind == OPK_TIP) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                double2 v01, v23;
+                tip_column(o.bOff, mIdx + MAT_STRIDE, r, v01, v23);
+                out[r][0] = __dmul_rn(out[r][0], v01.x); out[r][1] = __dmul_rn(out[r][1], v01.y);
+                out[r][2] = __dmul_rn(out[r][2], v23.x); out[r][3] = __dmul_rn(out[r][3], v23.y);
+            }
+        } else {
+            double a[R][4];
+            fetch(bKind, o.bOff, (o.ctl >> 10) & 15, a);
+            rows_times<EXACT, R, false>(smd + mIdx + MAT_STRIDE, a, out);
         }
 
         // ---- exact power-of-two rescale, store ----
@@ -300,15 +330,46 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
                 st256(dst + r * 128, o0, o1, o2, o3);
                 dstE[32 * r] = (int16_t)ce;
             }
-            prev[r][0] = o0; prev[r][1] = o1; prev[r][2] = o2; prev[r][3] = o3;
-            prevCum[r] = ce;
+            fwd[r][0] = o0; fwd[r][1] = o1; fwd[r][2] = o2; fwd[r][3] = o3;
+            fwdCum[r] = ce;
         }
+        return outSlot == (int)OP_REG_SLOT;
+    };
+    bool flip = false;
+
+    for (int k = kBeg; k < kEnd; k++) {
+        if (NW == 1 && (k & (OPS_BATCH - 1)) == OPS_BATCH / 2 && (k / OPS_BATCH + 1) * OPS_BATCH < nOps) {
+            __syncthreads();                       // every warp has left the previous batch's half
+            load_batch(k / OPS_BATCH + 1);
+            __syncthreads();
+        }
+        mbar_wait(myBar + ((k - kBeg) & (MAT_RING - 1)), ((k - kBeg) / MAT_RING) & 1);   // op k's matrix pair has landed
+        if (incremental && k + 2 < kEnd) {         // clean children live in HBM: pull their sectors towards L2 two ops ahead
+            const Op q = sops[(k + 2) & (2 * OPS_BATCH - 1)];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if ((q.ctl & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.aOff * 4 + r * 128);
+                if (((q.ctl >> 3) & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.bOff * 4 + r * 128);
+            }
+        }
+
+        const Op o = sops[k & (2 * OPS_BATCH - 1)];
+        const int mIdx = ringIdx + ((k - kBeg) & (MAT_RING - 1)) * (2 * MAT_STRIDE);
+        // the op itself, on (forward, parked) = (X, Y) or (Y, X): a result parked in registers simply stays where it was
+        // written and the two register sets swap roles -- no copies
+        const bool parked = flip ? op_body(o, mIdx, yv, yc, xv, xc) : op_body(o, mIdx, xv, xc, yv, yc);
+        flip ^= parked;
+        __syncwarp();                              // every lane has consumed op k's matrices: its ring slot is free
+        issue_mats(k + MAT_RING);
         if (NW > 1 && (o.ctl & OP_SIGNAL)) {   // hand the finished subtree to worker 0
             __syncwarp();
-            if (lane == 0) st_release_shared(sflag + outSlot * warps + w, 1u);
+            if (lane == 0) st_release_shared(sflag + ((o.ctl >> 14) & 255) * warps + w, 1u);
         }
     }
-    cp_async_wait<0>();
+    if (NW == 1) {   // speculative first fetches beyond a short op list: they must land before the CTA's shared memory goes away
+#pragma unroll
+        for (int j = 0; j < MAT_RING; j++) if (j >= kEnd && j < d.nInt) mbar_wait(myBar + j, 0);
+    }
     __syncthreads();
 
     // root: integratePartials over categories, (+pInv on constant patterns), frequencies, log, pattern weight; then the sum
@@ -369,7 +430,7 @@ static cudaError_t launch_exact(const WalkArgs &a, int nTiles, size_t smem, int 
         else return launch_one<EXACT, 1, 4, 0, 0, 0>(a, nTiles, smem, threads, st);
     } else if (a.patPerThread == 2) {
         if (a.stackDepth == 3 && a.tipsInSmem == 1 && a.nCat == 4 && a.chunksPerTile == 1) return launch_one<EXACT, 2, 5, 4, 1, 3>(a, nTiles, smem, threads, st);   // 5 CTAs / SM
-        else if (std4 && a.nCat == 4 && a.chunksPerTile == 1) return launch_one<EXACT, 2, 2, 4, 1, 4>(a, nTiles, smem, threads, st);
+        else if (std4 && a.nCat == 4 && a.chunksPerTile == 1) return launch_one<EXACT, 2, 4, 4, 1, 4>(a, nTiles, smem, threads, st);
         else if (std4 && a.nCat == 1 && a.chunksPerTile == 2) return launch_one<EXACT, 2, 2, 1, 2, 4>(a, nTiles, smem, threads, st);
         else return launch_one<EXACT, 2, 2, 0, 0, 0>(a, nTiles, smem, threads, st);
     } else {

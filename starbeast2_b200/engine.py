@@ -62,6 +62,7 @@ class Engine:
         self.n_loci = 0
         self.S = 0
         self._loci_shape: List[Tuple[int, int, int]] = []
+        self._locus_is_k: List[bool] = []   # likelihood-only (K-state) loci: no gene tree, no part in the operator queries
         self._bound_tensor = None
 
     # -- helpers ---------------------------------------------------------------------------------
@@ -88,6 +89,7 @@ class Engine:
         sp = np.ascontiguousarray(tip_species, np.int32)
         idx = self._ck(self._L.sb2_add_locus(self._h, ts.shape[0], ts.shape[1], ts, w, int(n_cat), sp, float(ploidy)))
         self._loci_shape.append((ts.shape[0], ts.shape[1], int(n_cat)))
+        self._locus_is_k.append(False)
         self.n_loci = idx + 1
         return idx
 
@@ -99,6 +101,7 @@ class Engine:
         ex = np.ascontiguousarray(excluded, np.int32)
         idx = self._ck(self._L.sb2_add_locus_k(self._h, ts.shape[0], ts.shape[1], int(n_states), ts, w, int(n_cat), None, 2.0,
                                                len(ex), ex.ctypes.data if len(ex) else None))
+        self._locus_is_k.append(True)
         self._loci_shape.append((ts.shape[0], ts.shape[1], int(n_cat)))
         self.n_loci = idx + 1
         return idx
@@ -315,6 +318,11 @@ class Engine:
         fr = np.zeros(2)
         cnt = C.c_int64(0)
         self._ck(self._L.sb2_connecting_nodes(self._h, int(species_node), mask.ctypes.data if want_mask else None, fr, C.byref(cnt)))
+        if want_mask and any(self._locus_is_k):
+            # the C ABI's mask runs over every locus in engine order (likelihood-only loci: zeros); the reference's walk only
+            # knows gene trees, so their slots are cut out here
+            keep = np.concatenate([np.full(2 * sh[0] - 1, not k) for sh, k in zip(self._loci_shape, self._locus_is_k)])
+            mask = mask[keep]
         return mask, float(fr[0]), float(fr[1]), int(cnt.value)
 
     def connecting_nodes_distributed(self, species_node: int, group=None):

@@ -64,7 +64,7 @@ CASES = [
     ("C2", dict(n_loci=7, n_sites=700)),                                   # HKY, strict clock, 3 CTAs per cluster
     ("C3", dict(n_loci=5, n_sites=300)),                                   # GTR+G4, species-tree clock (followers embed too), LWCR
     ("C3", dict(n_loci=4, n_sites=40)),                                    # single-CTA clusters
-    ("C4", dict(n_loci=6, n_sites=200)),                                   # fossil species tree
+    ("C4", dict(n_loci=6, n_sites=200, n_morph=0)),                        # fossil species tree (gene loci only: K-state partitions keep the k_prepare + k_kstate path)
     ("C5", dict(n_loci=3, n_sites=260)),                                   # 120 tips, 4 categories: the large-schedule shared-memory carve
     ("C2", dict(n_loci=4, n_sites=500, missing_frac=0.2)),
     ("C2", dict(n_loci=3, n_sites=300, n_cat=3)),                          # a category count that leaves warps idle
