@@ -68,9 +68,9 @@ struct sb2_engine {
     uint8_t *dStates = nullptr, *dConstMask = nullptr;
     int32_t *dWeights = nullptr, *dTipSpecies = nullptr, *dTileLocus = nullptr;
     // big dynamic device data
-    double *dPartials = nullptr, *dMats = nullptr, *dOpMats = nullptr, *dPatLogL = nullptr, *dChunkSum = nullptr;
+    double *dPartials = nullptr, *dMats = nullptr, *dPatLogL = nullptr, *dChunkSum = nullptr;
     int16_t *dCumExp = nullptr;
-    Op *dOps = nullptr;
+    OpRec *dOpStream = nullptr;
     int32_t *dNOps = nullptr;
     // staged inputs: pinned host mirror + device copy
     LocusParams *hParams = nullptr, *dParams = nullptr;
@@ -381,7 +381,7 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
     PrepareArgs a;
     a.loci = e->dLoci; a.params = e->dParams; a.flags = e->dFlags; a.inTree = zeroCopyTrees ? e->hInTreeDev : e->dInTree; a.tipSpecies = e->dTipSpecies;
     a.catRates = e->dCat; a.explicitRates = e->dExplicit ? e->dExplicit : e->dCat;
-    a.cur = cur(e); a.stored = stored(e); a.ops = e->dOps; a.nOps = e->dNOps; a.mats = e->dMats; a.opMats = e->dOpMats;
+    a.cur = cur(e); a.stored = stored(e); a.opStream = e->dOpStream; a.nOps = e->dNOps; a.mats = e->dMats;
     a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L; a.stackDepth = e->stackDepth; a.uniformFlags = uniformFlags;
     a.workers = e->workers; a.laneOps = e->dLaneOps;
     static const bool noRegPark = getenv("SB2_NO_REGPARK") != nullptr;   // A/B knob: every park goes to the shared-memory stack
@@ -505,9 +505,9 @@ int do_walk(sb2_engine *e)
 {
     if (!e->walkPending) return SB2_OK;
     WalkArgs a;
-    a.loci = e->dLoci; a.params = e->dParams; a.tileLocus = e->dTileLocus; a.ops = e->dOps; a.nOps = e->dNOps;
+    a.loci = e->dLoci; a.params = e->dParams; a.tileLocus = e->dTileLocus; a.opStream = e->dOpStream; a.nOps = e->dNOps;
     a.tipStates = e->dStates; a.weights = e->dWeights; a.constMask = e->dConstMask; a.catProps = e->dCat + e->totalCat;
-    a.opMats = e->dOpMats; a.partials = e->dPartials; a.cumExp = e->dCumExp; a.patLogL = e->dPatLogL; a.chunkSum = e->dChunkSum;
+    a.partials = e->dPartials; a.cumExp = e->dCumExp; a.patLogL = e->dPatLogL; a.chunkSum = e->dChunkSum;
     a.nCat = e->nCat; a.chunksPerTile = e->chunksPerTile; a.patPerThread = e->patPerThread; a.stackDepth = e->stackDepth;
     a.maxTips = (e->maxNodes + 1) / 2;
     a.workers = e->workers; a.laneOps = e->dLaneOps;
@@ -825,9 +825,8 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if ((rc = dev_alloc(e, &e->dMats, (size_t)matBase))) return rc;
     if ((rc = dev_alloc(e, &e->dPatLogL, (size_t)patBase))) return rc;
     if ((rc = dev_alloc(e, &e->dChunkSum, (size_t)chunkBase))) return rc;
-    if ((rc = dev_alloc(e, &e->dOps, (size_t)opBase))) return rc;
-    if ((rc = dev_alloc(e, &e->dOpMats, (size_t)opBase * e->nCat * 2 * OPMAT_STRIDE))) return rc;
-    CUDA_TRY(e, cudaMemset(e->dOpMats, 0, sizeof(double) * (size_t)opBase * e->nCat * 2 * OPMAT_STRIDE));
+    if ((rc = dev_alloc(e, &e->dOpStream, (size_t)std::max<int64_t>(opBase, 1) * e->nCat))) return rc;
+    CUDA_TRY(e, cudaMemset(e->dOpStream, 0, sizeof(OpRec) * (size_t)std::max<int64_t>(opBase, 1) * e->nCat));
     if ((rc = dev_alloc(e, &e->dNOps, L))) return rc;
     e->nK = (int)e->kLoci.size();
     if (e->nK) {

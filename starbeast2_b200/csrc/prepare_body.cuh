@@ -665,7 +665,7 @@ __device__ __forceinline__ int prepare_locus(const PrepareArgs &A, int maxNodes,
         o.ctl = op_ctl(aKind, bKind, aSlot, bSlot, outSlot) | signal;
 
         if (FUSED) F.sops[pos] = o;
-        else A.ops[d.opBase + pos] = o;
+        else for (int cc = 0; cc < C; cc++) A.opStream[(size_t)d.opBase * C + (size_t)cc * nI + pos].op = o;   // one stream per category
     }
     gsync();
     stamp(12, gn);
@@ -704,7 +704,7 @@ __device__ __forceinline__ int prepare_locus(const PrepareArgs &A, int maxNodes,
         if (used) {   // [op][category][side][16]: the pruning kernel's warp (one category) reads 256 contiguous bytes per op
             const int side = ((s.gR[par] == i) ? 1 : 0) ^ (int)s.swp[par];
             double *dst = FUSED ? F.smats + (((size_t)s.pos[par] * C + c) * 2 + side) * 16
-                                : A.opMats + (((size_t)(d.opBase + s.pos[par]) * C + c) * 2 + side) * OPMAT_STRIDE;
+                                : A.opStream[(size_t)d.opBase * C + (size_t)c * nI + s.pos[par]].m[side];
             if (i < nT) {   // a tip's matrix is read by COLUMN (the tip's state): stored transposed, a column = 32 contiguous bytes
 #pragma unroll
                 for (int q = 0; q < 4; q++) {

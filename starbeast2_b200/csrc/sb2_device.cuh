@@ -7,8 +7,8 @@
 //   cumExp      i16 [locus][buf][internal node][cat][pattern]  power-of-two scale exponent, cumulative over subtree
 //   mats        f64 [locus][buf][node][cat][16]                P = exp(Q d) per branch x category
 //   StateBlock (x2: current / stored)  small per-node and per-locus state, see below
-//   ops         Op  [locus][internal node]                      post-order pruning schedule built on device
-//   opMats      f64 [locus][op][cat][side][20]                  the scheduled ops' matrix pairs, in schedule order (OPMAT_STRIDE)
+//   opStream    OpRec [locus][cat][op]                          post-order pruning schedule built on device, one stream per category:
+//                                                               op descriptor + the op's two transition matrices (OPMAT_STRIDE doubles each)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -87,7 +87,7 @@ constexpr int WALK_MAX_WORKERS = 4;
 constexpr int WALK_MAILBOX = 2;
 constexpr int WALK_MAX_WORKER_OPS = 64;    // multi-worker walks keep the whole op list in shared memory
 
-// Doubles per matrix of the op-ordered stream `opMats` that k_treewalk reads: 16 for the matrix (row-major for an internal
+// Doubles per matrix of the op stream (OpRec) that k_treewalk reads: 16 for the matrix (row-major for an internal
 // operand; TRANSPOSED for a tip, whose factor is a column) + 4: a fifth column of ones behind a tip's four, so that the tip's
 // state byte (0..3, 4 = missing / ambiguous) is the column index.  k_step's shared-memory stream keeps 16 (+ a separate ones column).
 constexpr int OPMAT_STRIDE = 20;
@@ -99,6 +99,16 @@ struct __align__(16) Op {
     uint32_t ctl;     // bits 0-2 aKind, 3-5 bKind, 6-9 aSlot, 10-13 bSlot, 14-21 outSlot (>= slot count: not parked), 22 OP_SIGNAL
 };
 static_assert(sizeof(Op) == 16, "Op must stay 16 bytes (one LDS.128)");
+// k_treewalk's input: the schedule as ONE stream per (locus, category), [locus][category][op] -- a warp (one category) walks
+// consecutive records, so a chunk of OPREC_CHUNK ops (descriptors AND matrix pairs) is one contiguous bulk copy into the warp's
+// own shared-memory ring: no CTA-wide staging of the schedule, no barrier between the warps of a CTA during the walk.
+struct __align__(16) OpRec {
+    Op op;
+    uint32_t pad[4];
+    double m[2][OPMAT_STRIDE];   // operand a's and operand b's matrix (see OPMAT_STRIDE)
+};
+static_assert(sizeof(OpRec) == 32 + 16 * OPMAT_STRIDE, "OpRec layout");
+constexpr int OPREC_CHUNK = 4;
 __host__ __device__ inline uint32_t op_ctl(unsigned aKind, unsigned bKind, unsigned aSlot, unsigned bSlot, unsigned outSlot)
 {
     return aKind | (bKind << 3) | (aSlot << 6) | (bSlot << 10) | (outSlot << 14);
@@ -139,10 +149,9 @@ struct PrepareArgs {
     const double *explicitRates; // by node
     StateBlock cur;
     StateBlock stored;
-    Op *ops;
+    OpRec *opStream;             // [locus][category][op]: k_treewalk's schedule + matrices (record (opBase * nCat + c * nInt + k))
     int32_t *nOps;               // [nLoci]
     double *mats;
-    double *opMats;              // [op][category][side][16]: each scheduled op's two matrices, in schedule order
     int32_t S, nSpeciesLeaves, popKind, nLoci;
     int32_t stackDepth;          // shared-memory stack slots of k_treewalk
     int32_t uniformFlags;        // >= 0: every locus uses these flags (no per-step flags upload); < 0: read `flags`
@@ -188,13 +197,12 @@ struct WalkArgs {
     const LocusDesc *loci;
     const LocusParams *params;
     const int32_t *tileLocus;    // [nTiles]
-    const Op *ops;
+    const OpRec *opStream;
     const int32_t *nOps;
     const uint8_t *tipStates;
     const int32_t *weights;
     const uint8_t *constMask;
     const double *catProps;
-    const double *opMats;
     double *partials;
     int16_t *cumExp;
     double *patLogL;             // by pattern
@@ -230,7 +238,7 @@ struct CommArgs {
 cudaError_t launch_reduce_xgpu(const ReduceArgs &a, const CommArgs &c, cudaStream_t st, int64_t *launches);
 
 struct StepArgs {
-    PrepareArgs prep;            // ops / opMats / laneOps / pf* unused: schedule and matrices stay in shared memory
+    PrepareArgs prep;            // opStream / laneOps / pf* unused: schedule and matrices stay in shared memory
     ReduceArgs red;              // useTiles = 0: the leaders write the per-locus values into the state block
     CommArgs comm;
     const uint8_t *tipStates;

@@ -20,8 +20,14 @@
 //
 // Thread mapping: a warp owns 32*R consecutive patterns of ONE rate category, a thread R of them (stride 32, so
 // every global / shared access is coalesced / conflict free).  Warps never wait for each other inside the walk:
-// each warp streams its own category's transition matrices through a private cp.async ring, the op schedule and
-// the tile's tip states are staged in shared memory once, and rescaling is per (pattern, category).
+// each warp streams its own category's schedule -- op descriptors AND transition-matrix pairs, one OpRec per op, laid out
+// [locus][category][op] by k_prepare -- through a private double-buffered ring of OPREC_CHUNK-op chunks, each chunk ONE
+// bulk asynchronous copy (cp.async.bulk, issued by an elected lane, completing on the buffer's mbarrier); the tile's
+// tip states arrive the same way, one bulk copy per tip row; rescaling is per (pattern, category).
+//
+// Parked results: a first-evaluated child waits for its sibling's subtree either in the thread's REGISTERS (OPK_REG: whenever
+// that subtree parks nothing itself -- most parks of a random tree; the two register sets then simply swap roles, nothing is
+// copied) or in the shared-memory stack.
 //
 // Rescaling: every node, every (pattern, category), by an exact power of two (the exponent of the largest of
 // the 4 values); scaled values keep their mantissas, so rescaling never perturbs a result and evaluation is
@@ -34,9 +40,8 @@
 
 namespace sb2 {
 
-constexpr int OPS_BATCH = 32;   // ops staged in shared memory per half batch
-constexpr int MAT_RING = 4;     // transition-matrix pairs in flight per warp (bulk-copy ring)
-constexpr int MAT_STRIDE = OPMAT_STRIDE;   // doubles per matrix of the op-ordered stream (sb2_device.cuh)
+constexpr int CHUNK = OPREC_CHUNK;          // ops per bulk copy
+constexpr int MAT_STRIDE = OPMAT_STRIDE;    // doubles per matrix of an OpRec (sb2_device.cuh)
 constexpr int TIP_SMEM_MAX = 48 * 1024;
 
 bool treewalk_tips_in_smem(int maxTips, int tilePat) { return (size_t)maxTips * tilePat <= TIP_SMEM_MAX; }
@@ -47,14 +52,12 @@ size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, i
     const size_t tilePat = (size_t)chunksPerTile * 32 * R;
     const size_t slots = (size_t)stackDepth + (workers > 1 ? WALK_MAILBOX : 0);
     size_t b = slots * warps * R * 32 * 32;                // partials stack (two double2 planes)
-    b += (size_t)warps * MAT_RING * 2 * MAT_STRIDE * 8;    // per-warp matrix rings
-    b += (size_t)warps * MAT_RING * 8 + 32;                // their mbarriers (one per ring slot) + the tip-state tile's
-    b += 2ull * OPS_BATCH * sizeof(Op);                    // op schedule, two half batches
+    b += warps * 2 * CHUNK * sizeof(OpRec);                // per-warp schedule rings: two chunk buffers
+    b += warps * 2 * 8 + 32;                               // their mbarriers + the tip-state tile's
     b += slots * warps * R * 32 * 2;                       // exponent stack (int16)
-    b += 16 * 8;                                           // the ones column
     if (workers > 1) b += ((slots * warps * 4 + 15) & ~size_t(15));   // mailbox flags
     if (treewalk_tips_in_smem(maxTips, (int)tilePat)) b += (size_t)maxTips * tilePat + 16;   // tip states of the tile
-    return (b + 15) & ~size_t(15);
+    return (b + 31) & ~size_t(15);
 }
 
 __device__ __forceinline__ unsigned ld_acquire_shared(const unsigned *p)
@@ -97,24 +100,23 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
     // the accesses in the shared window (LDS/STS), never generic
     double2 *st2 = reinterpret_cast<double2 *>(smem_raw);                       // stack: [2 planes][depth][warps][R][32] double2
     const int planeStride = slots * warps * R * 32;                             //        plane 0 = states 0,1; plane 1 = states 2,3
-    double *smd = reinterpret_cast<double *>(st2 + 2 * planeStride);            // ring [warps][MAT_RING][2 * MAT_STRIDE] | ones[16]
-    const int onesIdx = warps * MAT_RING * 2 * MAT_STRIDE;
-    unsigned long long *sbar = reinterpret_cast<unsigned long long *>(smd + onesIdx + 16);   // [warps][MAT_RING] ring-slot mbarriers | [4]: tip tile
-    unsigned long long *tipBar = sbar + warps * MAT_RING;
-    Op *sops = reinterpret_cast<Op *>(tipBar + 4);                              // [2 * OPS_BATCH]
-    int16_t *sexp = reinterpret_cast<int16_t *>(sops + 2 * OPS_BATCH);          // [slots][warps][R][32]
+    OpRec *ring = reinterpret_cast<OpRec *>(st2 + 2 * planeStride);             // [warps][2][CHUNK]
+    unsigned long long *sbar = reinterpret_cast<unsigned long long *>(ring + warps * 2 * CHUNK);   // [warps][2] chunk-buffer mbarriers | [4]: tip tile
+    unsigned long long *tipBar = sbar + warps * 2;
+    int16_t *sexp = reinterpret_cast<int16_t *>(tipBar + 4);                    // [slots][warps][R][32]
     unsigned *sflag = reinterpret_cast<unsigned *>(sexp + planeStride);         // [slots][warps] mailbox flags (NW > 1 only)
-    uint8_t *sstate = reinterpret_cast<uint8_t *>(sflag + (NW > 1 ? ((slots * warps + 3) & ~3) : 0));   // [nTips][tilePat]; 16-byte aligned by construction
+    const int stateOff = (int)(((reinterpret_cast<unsigned char *>(sflag + (NW > 1 ? slots * warps : 0)) - smem_raw) + 15) & ~15);
+    uint8_t *sstate = smem_raw + stateOff;                                      // [nTips][tilePat], 16-byte aligned
     const uint8_t *states = A.tipStates + d.stateBase;
+    OpRec *myRing = ring + w * 2 * CHUNK;
+    unsigned long long *myBar = sbar + w * 2;
 
     // ---- static inputs first: under programmatic dependent launch this part overlaps k_prepare's tail ----
-    if (tid < 16) smd[onesIdx + tid] = 1.0;
     if (NW > 1) for (int i = tid; i < slots * warps; i += blockDim.x) sflag[i] = 0u;
-    // mbarriers: one per matrix-ring slot of every warp (one arrival: the elected lane's expect_tx), one for the tip-state tile
+    // mbarriers: one per chunk buffer of every warp (one arrival: the elected lane's expect_tx), one for the tip-state tile
     // (every thread arrives with the bytes of the rows it copies)
     if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < MAT_RING; j++) mbar_init(sbar + w * MAT_RING + j, 1);
+        mbar_init(myBar, 1); mbar_init(myBar + 1, 1);
         if (tid == 0) mbar_init(tipBar, blockDim.x);
     }
     mbar_init_fence();
@@ -136,71 +138,51 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
                 bulk_g2s(sstate + t * tilePat, states + (size_t)t * d.stateStride + p0, (unsigned)tilePat, tipBar);
         }
     }
-    // nOps / ops / opMats are k_prepare's outputs: they must not be touched before that grid has completed
+    // the schedule is k_prepare's output: it must not be touched before that grid has completed
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();   // the (single-CTA) reduction kernel may queue up behind us already
-    const Op *ops = A.ops + d.opBase;
-    const double *matStream = A.opMats + ((size_t)d.opBase * C + c) * (2 * MAT_STRIDE);   // + k * matStride: op k's matrix pair of this category
-    unsigned long long *myBar = sbar + w * MAT_RING;
-    const int ringIdx = w * MAT_RING * (2 * MAT_STRIDE);
-    const int matStride = C * (2 * MAT_STRIDE);
-    constexpr unsigned PAIR_BYTES = 2 * MAT_STRIDE * 8;
-    // Single-worker walks start at op 0 whatever nOps turns out to be: fetch the first batch of the schedule and the first
-    // matrix pairs in the same wave of loads as nOps itself (bounded by the locus's allocation, so a clean locus merely
-    // reads stale entries) instead of one dependent round trip later.
-    int4 specOp = make_int4(0, 0, 0, 0);
-    if (NW == 1) {
-        if (tid < OPS_BATCH && tid < d.nInt) specOp = reinterpret_cast<const int4 *>(ops)[tid];
-        if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < MAT_RING; j++)
-                if (j < d.nInt) { mbar_arrive_expect_tx(myBar + j, PAIR_BYTES); bulk_g2s(smd + ringIdx + j * (2 * MAT_STRIDE), matStream + (size_t)j * matStride, PAIR_BYTES, myBar + j); }
+    const OpRec *stream = A.opStream + (size_t)d.opBase * C + (size_t)c * d.nInt;   // this category's records of the locus
+    // chunk j of this warp's list (ops kBeg + j*CHUNK ...) -> chunk buffer j & 1, one bulk copy by the elected lane completing
+    // on the buffer's mbarrier (phase parity (j >> 1) & 1).  A chunk is copied whole, up to the locus's allocation (nInt
+    // records): entries past the op count are stale but harmless, so the first chunks can be fetched before nOps is known.
+    auto issue_chunk = [&](int kFirst, int j) {
+        const int first = kFirst + j * CHUNK;
+        if (lane == 0 && first < d.nInt) {
+            const unsigned bytes = (unsigned)(min(CHUNK, d.nInt - first) * (int)sizeof(OpRec));
+            mbar_arrive_expect_tx(myBar + (j & 1), bytes);
+            bulk_g2s(myRing + (j & 1) * CHUNK, stream + first, bytes, myBar + (j & 1));
         }
-    }
+    };
+    // Single-worker walks start at op 0 whatever nOps turns out to be: fetch the first two chunks in the same wave of loads as
+    // nOps itself instead of one dependent round trip later.
+    if (NW == 1) { issue_chunk(0, 0); issue_chunk(0, 1); }
     const int nOps = A.nOps[l];
     // this worker's share of the schedule: ops [kBeg, kEnd) of the locus's list
     const int kBeg = NW > 1 ? A.laneOps[l * (WALK_MAX_WORKERS + 1) + worker] : 0;
     int kEnd = NW > 1 ? A.laneOps[l * (WALK_MAX_WORKERS + 1) + worker + 1] : nOps;
     if (A.debugMaxOps >= 0 && NW == 1) kEnd = min(kEnd, kBeg + A.debugMaxOps);   // timing experiments only: results are garbage
+    if (NW > 1) { issue_chunk(kBeg, 0); issue_chunk(kBeg, 1); }
+    const int nChunks = (kEnd - kBeg + CHUNK - 1) / CHUNK;
+    const int issued = min(2, (d.nInt - kBeg + CHUNK - 1) / CHUNK);   // chunk copies in flight so far
     if (nOps == 0) {         // locus clean: cached logL stands; the copies in flight must land before the CTA's shared memory goes away
         if (tipsInSmem) mbar_wait(tipBar, 0);
-        if (NW == 1) {
-#pragma unroll
-            for (int j = 0; j < MAT_RING; j++) if (j < d.nInt) mbar_wait(myBar + j, 0);
-        }
+        for (int j = 0; j < issued; j++) mbar_wait(myBar + j, 0);
         return;
     }
     const bool incremental = nOps < d.nInt;         // only then can operands be clean nodes resident in HBM
 
     double *partials = A.partials + d.partBase + ((size_t)c * nPat + pbase) * 4;   // + idx*4 (+ r*128)
     int16_t *cumExp = A.cumExp + d.expBase + (size_t)c * nPat + pbase;              // + idx   (+ r*32)
-    // keep the three per-thread base pointers in registers: under the 64-register cap ptxas otherwise re-derives them
-    // (64-bit multiplies) inside every iteration of the walk
+    // keep the per-thread base pointers in registers: ptxas otherwise re-derives them (64-bit multiplies) inside every
+    // iteration of the walk
     asm volatile("" : "+l"(partials));
     asm volatile("" : "+l"(cumExp));
-    asm volatile("" : "+l"(matStream));
     const int stateIdx = chunk * 32 * R + lane;
     const int stackIdx = w * R * 32 + lane;                 // + slot*slotStride + r*32
     const int slotStride = warps * R * 32;
     bool valid[R];
 #pragma unroll
     for (int r = 0; r < R; r++) valid[r] = pbase + 32 * r < nPat;
-
-    auto load_batch = [&](int b) {
-        const int first = b * OPS_BATCH, cnt = min(OPS_BATCH, nOps - first);
-        const int4 *src = reinterpret_cast<const int4 *>(ops + first);
-        int4 *dst = reinterpret_cast<int4 *>(sops + (b & 1) * OPS_BATCH);
-        for (int t = tid; t < cnt; t += blockDim.x) dst[t] = src[t];
-    };
-    // this warp's matrix pair of op k (256 contiguous bytes of the op-ordered stream) -> ring slot (k - kBeg) % MAT_RING: one bulk
-    // copy by the elected lane, completing on the slot's mbarrier (phase parity = ((k - kBeg) / MAT_RING) & 1)
-    auto issue_mats = [&](int k) {
-        if (lane == 0 && k < kEnd) {
-            const int j = (k - kBeg) & (MAT_RING - 1);
-            mbar_arrive_expect_tx(myBar + j, PAIR_BYTES);
-            bulk_g2s(smd + ringIdx + j * (2 * MAT_STRIDE), matStream + (size_t)k * matStride, PAIR_BYTES, myBar + j);
-        }
-    };
 
     // two register sets: one receives every op's result (and forwards it to the next op), the other is the register parking
     // slot; they swap roles whenever a result is parked in registers (flip)
@@ -217,19 +199,24 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
 #pragma unroll
         for (int r = 0; r < R; r++) if (valid[r]) prefetch_l1(A.weights + d.patBase + pbase + 32 * r);
     }
-    if (NW == 1) {
-        if (tid < OPS_BATCH) reinterpret_cast<int4 *>(sops)[tid] = specOp;   // batch 0, fetched above
-    } else {
-        load_batch(0);
-        if (nOps > OPS_BATCH) load_batch(1);   // multi-worker walks are limited to 2 * OPS_BATCH ops: all resident, no reloads
-        for (int j = 0; j < MAT_RING; j++) issue_mats(kBeg + j);
-    }
-    __syncthreads();                 // the op schedule is visible
     if (tipsInSmem) mbar_wait(tipBar, 0);   // the tip-state tile has landed
 
     // One pruning op.  `fwd` holds the previous op's (scaled) result and receives this op's; `park` is the register parking
     // slot (OPK_REG).  Returns true when the result is parked in registers (OP_REG_SLOT): the caller swaps the sets' roles.
-    auto op_body = [&](const Op &o, int mIdx, double (&fwd)[R][4], int (&fwdCum)[R], double (&park)[R][4], int (&parkCum)[R]) -> bool {
+    // Software pipelining across ops: the op's descriptor `o` and the state bytes of its tip operands (sa, sb) were fetched
+    // while the previous op was computing; this op in turn fetches the state bytes of `on`, the next op of the chunk.
+    auto tip_states = [&](const Op &q, int (&ta)[R], int (&tb)[R]) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if ((q.ctl & 7) == OPK_TIP)
+                ta[r] = tipsInSmem ? sstate[q.aOff * tilePat + stateIdx + 32 * r] : states[(size_t)q.aOff * d.stateStride + pbase + 32 * r];
+            if (((q.ctl >> 3) & 7) == OPK_TIP)
+                tb[r] = tipsInSmem ? sstate[q.bOff * tilePat + stateIdx + 32 * r] : states[(size_t)q.bOff * d.stateStride + pbase + 32 * r];
+        }
+    };
+    auto op_body = [&](const Op &o, const OpRec *rec, const Op &on, int (&sa)[R], int (&sb)[R],
+                       double (&fwd)[R][4], int (&fwdCum)[R], double (&park)[R][4], int (&parkCum)[R]) -> bool {
+        const double *mA = rec->m[0], *mB = rec->m[1];
         const unsigned aKind = o.ctl & 7, bKind = (o.ctl >> 3) & 7;
         double out[R][4];
         int cum[R];
@@ -239,11 +226,9 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
         // a tip's factor: column `state` of its matrix.  k_prepare stores a tip's matrix transposed (a column = 32 contiguous
         // bytes = two LDS.128 that the whole warp shares bank-conflict free) with a fifth column of ones for missing /
         // ambiguous data (state 4: the engine normalises every such code to 4), so the state byte IS the column index.
-        auto tip_column = [&](unsigned tip, int m, int r, double2 &v01, double2 &v23) {
-            const int st = tipsInSmem ? sstate[tip * tilePat + stateIdx + 32 * r]
-                                      : states[(size_t)tip * d.stateStride + pbase + 32 * r];
-            v01 = *reinterpret_cast<const double2 *>(smd + m + st * 4);
-            v23 = *reinterpret_cast<const double2 *>(smd + m + st * 4 + 2);
+        auto tip_column = [&](int st, const double *m, double2 &v01, double2 &v23) {
+            v01 = *reinterpret_cast<const double2 *>(m + st * 4);
+            v23 = *reinterpret_cast<const double2 *>(m + st * 4 + 2);
         };
         // a parked (shared-memory stack / helper mailbox) or resident (HBM) operand
         auto fetch = [&](unsigned kind, unsigned off, unsigned slot, double (&a)[R][4]) {
@@ -280,35 +265,39 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 double2 v01, v23;
-                tip_column(o.aOff, mIdx, r, v01, v23);
+                tip_column(sa[r], mA, v01, v23);
                 out[r][0] = v01.x; out[r][1] = v01.y; out[r][2] = v23.x; out[r][3] = v23.y;
             }
         } else if (aKind == OPK_REG) {
 #pragma unroll
             for (int r = 0; r < R; r++) cum[r] += parkCum[r];
-            rows_times<EXACT, R, true>(smd + mIdx, park, out);
+            rows_times<EXACT, R, true>(mA, park, out);
         } else {
             double a[R][4];
             fetch(aKind, o.aOff, (o.ctl >> 6) & 15, a);
-            rows_times<EXACT, R, true>(smd + mIdx, a, out);
+            rows_times<EXACT, R, true>(mA, a, out);
         }
+        int na[R], nb[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) { na[r] = 4; nb[r] = 4; }
+        tip_states(on, na, nb);   // the next op's tip states: in flight while this op finishes
         // ---- operand b: the previous op's result forwarded in registers, or a second tip, or (incremental walks) a clean node ----
         if (bKind == OPK_PREV) {
 #pragma unroll
             for (int r = 0; r < R; r++) cum[r] += fwdCum[r];
-            rows_times<EXACT, R, false>(smd + mIdx + MAT_STRIDE, fwd, out);
+            rows_times<EXACT, R, false>(mB, fwd, out);
         } else if (bKind == OPK_TIP) {
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 double2 v01, v23;
-                tip_column(o.bOff, mIdx + MAT_STRIDE, r, v01, v23);
+                tip_column(sb[r], mB, v01, v23);
                 out[r][0] = __dmul_rn(out[r][0], v01.x); out[r][1] = __dmul_rn(out[r][1], v01.y);
                 out[r][2] = __dmul_rn(out[r][2], v23.x); out[r][3] = __dmul_rn(out[r][3], v23.y);
             }
         } else {
             double a[R][4];
             fetch(bKind, o.bOff, (o.ctl >> 10) & 15, a);
-            rows_times<EXACT, R, false>(smd + mIdx + MAT_STRIDE, a, out);
+            rows_times<EXACT, R, false>(mB, a, out);
         }
 
         // ---- exact power-of-two rescale, store ----
@@ -333,43 +322,48 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
             fwd[r][0] = o0; fwd[r][1] = o1; fwd[r][2] = o2; fwd[r][3] = o3;
             fwdCum[r] = ce;
         }
-        return outSlot == (int)OP_REG_SLOT;
-    };
-    bool flip = false;
-
-    for (int k = kBeg; k < kEnd; k++) {
-        if (NW == 1 && (k & (OPS_BATCH - 1)) == OPS_BATCH / 2 && (k / OPS_BATCH + 1) * OPS_BATCH < nOps) {
-            __syncthreads();                       // every warp has left the previous batch's half
-            load_batch(k / OPS_BATCH + 1);
-            __syncthreads();
-        }
-        mbar_wait(myBar + ((k - kBeg) & (MAT_RING - 1)), ((k - kBeg) / MAT_RING) & 1);   // op k's matrix pair has landed
-        if (incremental && k + 2 < kEnd) {         // clean children live in HBM: pull their sectors towards L2 two ops ahead
-            const Op q = sops[(k + 2) & (2 * OPS_BATCH - 1)];
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                if ((q.ctl & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.aOff * 4 + r * 128);
-                if (((q.ctl >> 3) & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.bOff * 4 + r * 128);
-            }
-        }
-
-        const Op o = sops[k & (2 * OPS_BATCH - 1)];
-        const int mIdx = ringIdx + ((k - kBeg) & (MAT_RING - 1)) * (2 * MAT_STRIDE);
-        // the op itself, on (forward, parked) = (X, Y) or (Y, X): a result parked in registers simply stays where it was
-        // written and the two register sets swap roles -- no copies
-        const bool parked = flip ? op_body(o, mIdx, yv, yc, xv, xc) : op_body(o, mIdx, xv, xc, yv, yc);
-        flip ^= parked;
-        __syncwarp();                              // every lane has consumed op k's matrices: its ring slot is free
-        issue_mats(k + MAT_RING);
         if (NW > 1 && (o.ctl & OP_SIGNAL)) {   // hand the finished subtree to worker 0
             __syncwarp();
-            if (lane == 0) st_release_shared(sflag + ((o.ctl >> 14) & 255) * warps + w, 1u);
+            if (lane == 0) st_release_shared(sflag + outSlot * warps + w, 1u);
         }
-    }
-    if (NW == 1) {   // speculative first fetches beyond a short op list: they must land before the CTA's shared memory goes away
 #pragma unroll
-        for (int j = 0; j < MAT_RING; j++) if (j >= kEnd && j < d.nInt) mbar_wait(myBar + j, 0);
+        for (int r = 0; r < R; r++) { sa[r] = na[r]; sb[r] = nb[r]; }
+        return outSlot == (int)OP_REG_SLOT;
+    };
+
+    bool flip = false;
+    for (int j = 0; j < nChunks; j++) {
+        mbar_wait(myBar + (j & 1), (j >> 1) & 1);          // chunk j (descriptors and matrix pairs of up to CHUNK ops) has landed
+        const OpRec *recs = myRing + (j & 1) * CHUNK;
+        const int n = min(CHUNK, kEnd - kBeg - j * CHUNK);
+        if (incremental) {                                  // clean children live in HBM: pull the chunk's sectors towards L2
+            for (int i = 0; i < n; i++) {
+                const Op q = recs[i].op;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if ((q.ctl & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.aOff * 4 + r * 128);
+                    if (((q.ctl >> 3) & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.bOff * 4 + r * 128);
+                }
+            }
+        }
+        Op o = recs[0].op;
+        int sa[R], sb[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) { sa[r] = 4; sb[r] = 4; }
+        tip_states(o, sa, sb);
+#pragma unroll 1
+        for (int i = 0; i < n; i++) {
+            const Op on = recs[min(i + 1, n - 1)].op;       // the next op's descriptor (the last op of a chunk re-reads its own)
+            // the op itself, on (forward, parked) = (X, Y) or (Y, X): a result parked in registers simply stays where it was
+            // written and the two register sets swap roles -- no copies
+            const bool parked = flip ? op_body(o, recs + i, on, sa, sb, yv, yc, xv, xc) : op_body(o, recs + i, on, sa, sb, xv, xc, yv, yc);
+            flip ^= parked;
+            o = on;
+        }
+        __syncwarp();                                       // every lane is done with chunk j: its buffer is free
+        if (j + 2 < nChunks) issue_chunk(kBeg, j + 2);
     }
+    for (int j = nChunks; j < issued; j++) mbar_wait(myBar + j, 0);   // speculative fetches beyond a short op list must land before the CTA retires
     __syncthreads();
 
     // root: integratePartials over categories, (+pInv on constant patterns), frequencies, log, pattern weight; then the sum
