@@ -68,9 +68,9 @@ struct sb2_engine {
     uint8_t *dStates = nullptr, *dConstMask = nullptr;
     int32_t *dWeights = nullptr, *dTipSpecies = nullptr, *dTileLocus = nullptr;
     // big dynamic device data
-    double *dPartials = nullptr, *dMats = nullptr, *dPatLogL = nullptr, *dChunkSum = nullptr;
+    double *dPartials = nullptr, *dMats = nullptr, *dOpMats = nullptr, *dPatLogL = nullptr, *dChunkSum = nullptr;
     int16_t *dCumExp = nullptr;
-    OpRec *dOpStream = nullptr;
+    Op *dOps = nullptr;
     int32_t *dNOps = nullptr;
     // staged inputs: pinned host mirror + device copy
     LocusParams *hParams = nullptr, *dParams = nullptr;
@@ -381,11 +381,9 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
     PrepareArgs a;
     a.loci = e->dLoci; a.params = e->dParams; a.flags = e->dFlags; a.inTree = zeroCopyTrees ? e->hInTreeDev : e->dInTree; a.tipSpecies = e->dTipSpecies;
     a.catRates = e->dCat; a.explicitRates = e->dExplicit ? e->dExplicit : e->dCat;
-    a.cur = cur(e); a.stored = stored(e); a.opStream = e->dOpStream; a.nOps = e->dNOps; a.mats = e->dMats;
+    a.cur = cur(e); a.stored = stored(e); a.ops = e->dOps; a.nOps = e->dNOps; a.mats = e->dMats; a.opMats = e->dOpMats;
     a.S = e->S; a.nSpeciesLeaves = e->nSpeciesLeaves; a.popKind = e->popKind; a.nLoci = L; a.stackDepth = e->stackDepth; a.uniformFlags = uniformFlags;
     a.workers = e->workers; a.laneOps = e->dLaneOps;
-    static const bool noRegPark = getenv("SB2_NO_REGPARK") != nullptr;   // A/B knob: every park goes to the shared-memory stack
-    a.regPark = (e->workers == 1 && !noRegPark) ? 1 : 0;
     a.singleLocus = singleLocus; a.singleFlags = singleLocus >= 0 ? e->hFlags[singleLocus] : 0;
     a.nSync = nSync;
     for (int j = 0; j < 8; j++) a.syncLoci[j] = syncLoci[j];
@@ -410,7 +408,6 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
         StepArgs sa;
         sa.prep = a;
         sa.prep.workers = 1;
-        sa.prep.regPark = 0;   // k_step's walk keeps every park in its shared-memory stack
         sa.red = reduce_args(e, /*coalOnly=*/true);   // useTiles = 0: the leaders write the per-locus values into the state block
         arm_poll(e, sa.red);
         sa.comm = e->comm;
@@ -505,12 +502,14 @@ int do_walk(sb2_engine *e)
 {
     if (!e->walkPending) return SB2_OK;
     WalkArgs a;
-    a.loci = e->dLoci; a.params = e->dParams; a.tileLocus = e->dTileLocus; a.opStream = e->dOpStream; a.nOps = e->dNOps;
+    a.loci = e->dLoci; a.params = e->dParams; a.tileLocus = e->dTileLocus; a.ops = e->dOps; a.nOps = e->dNOps;
     a.tipStates = e->dStates; a.weights = e->dWeights; a.constMask = e->dConstMask; a.catProps = e->dCat + e->totalCat;
-    a.partials = e->dPartials; a.cumExp = e->dCumExp; a.patLogL = e->dPatLogL; a.chunkSum = e->dChunkSum;
+    a.opMats = e->dOpMats; a.partials = e->dPartials; a.cumExp = e->dCumExp; a.patLogL = e->dPatLogL; a.chunkSum = e->dChunkSum;
     a.nCat = e->nCat; a.chunksPerTile = e->chunksPerTile; a.patPerThread = e->patPerThread; a.stackDepth = e->stackDepth;
     a.maxTips = (e->maxNodes + 1) / 2;
     a.workers = e->workers; a.laneOps = e->dLaneOps;
+    static const int walkCtas = getenv("SB2_WALK_CTAS") ? atoi(getenv("SB2_WALK_CTAS")) : 0;   // A/B knob
+    a.ctasPerSM = walkCtas;
     static const int debugMaxOps = getenv("SB2_DEBUG_MAX_OPS") ? atoi(getenv("SB2_DEBUG_MAX_OPS")) : -1;
     a.debugMaxOps = debugMaxOps;
     e->walkPending = false; e->tilesValid = true;
@@ -758,6 +757,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
         e->maxNodes = std::max(e->maxNodes, d.nNodes);
         nodeBase += d.nNodes; tipBase += d.nTips; patBase += d.nPat; catBase += d.nCat; tileBase += d.nTiles; opBase += ks ? 0 : d.nInt;
         d.stateStride = (d.nPat + 127) & ~127;
+        d.patStride = (d.nPat + 63) & ~63;
         stateBase += (int64_t)d.nTips * d.stateStride;
         if (ks) {
             d.kBase = kBase; d.exclBase = (int32_t)exclBase;
@@ -767,10 +767,10 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
             e->kLoci.push_back((int32_t)(&hl - e->loci.data()));
             e->maxK = std::max(e->maxK, d.kStates);
         } else {
-            partBase += 2ll * d.nInt * d.nCat * d.nPat * 4;
-            expBase += 2ll * d.nInt * d.nCat * d.nPat;
-            expBase = (expBase + 7) & ~7ll;
-            if (2ll * d.nInt * d.nCat * d.nPat >= 0x7fffffffll) return e->fail(SB2_ERR_ARG, "locus too large for 32-bit element offsets");
+            partBase += 2ll * d.nInt * d.nCat * d.patStride * 4;
+            expBase += 2ll * d.nInt * d.nCat * d.patStride;
+            expBase = (expBase + 63) & ~63ll;
+            if (2ll * d.nInt * d.nCat * d.patStride >= 0x7fffffffll) return e->fail(SB2_ERR_ARG, "locus too large for 32-bit element offsets");
             matBase += 2ll * d.nNodes * d.nCat * 16;
         }
         treeOff += 20ll * d.nNodes;
@@ -794,12 +794,8 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     for (int l = 0; l < L; l++) {
         const HostLocus &hl = e->loci[l];
         descs[l] = hl.d;
-        for (int t = 0; t < hl.d.nTips; t++) {
-            uint8_t *row = states.data() + hl.d.stateBase + (size_t)t * hl.d.stateStride;
-            memcpy(row, hl.states.data() + (size_t)t * hl.d.nPat, hl.d.nPat);
-            // 4-state loci: every missing / ambiguous code becomes 4, the index of the ones column k_treewalk reads for it
-            if (!hl.d.kStates) for (int p = 0; p < hl.d.nPat; p++) if (row[p] > 4) row[p] = 4;
-        }
+        for (int t = 0; t < hl.d.nTips; t++)
+            memcpy(states.data() + hl.d.stateBase + (size_t)t * hl.d.stateStride, hl.states.data() + (size_t)t * hl.d.nPat, hl.d.nPat);
         memcpy(cmask.data() + hl.d.patBase, hl.constMask.data(), hl.constMask.size());
         memcpy(weights.data() + hl.d.patBase, hl.weights.data(), hl.weights.size() * 4);
         memcpy(tipsp.data() + hl.d.tipBase, hl.tipSpecies.data(), hl.tipSpecies.size() * 4);
@@ -825,8 +821,8 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if ((rc = dev_alloc(e, &e->dMats, (size_t)matBase))) return rc;
     if ((rc = dev_alloc(e, &e->dPatLogL, (size_t)patBase))) return rc;
     if ((rc = dev_alloc(e, &e->dChunkSum, (size_t)chunkBase))) return rc;
-    if ((rc = dev_alloc(e, &e->dOpStream, (size_t)std::max<int64_t>(opBase, 1) * e->nCat))) return rc;
-    CUDA_TRY(e, cudaMemset(e->dOpStream, 0, sizeof(OpRec) * (size_t)std::max<int64_t>(opBase, 1) * e->nCat));
+    if ((rc = dev_alloc(e, &e->dOps, (size_t)opBase))) return rc;
+    if ((rc = dev_alloc(e, &e->dOpMats, (size_t)opBase * e->nCat * 32))) return rc;
     if ((rc = dev_alloc(e, &e->dNOps, L))) return rc;
     e->nK = (int)e->kLoci.size();
     if (e->nK) {
@@ -1362,13 +1358,16 @@ int sb2_get_partials(sb2_engine *e, int32_t locus, int32_t node, double *partial
     uint8_t buf;
     CUDA_TRY(e, cudaMemcpy(&buf, cur(e).curP + d.nodeBase + node, 1, cudaMemcpyDeviceToHost));
     const size_t idx = (size_t)buf * d.nInt + (node - d.nTips);
+    // device rows are padded to patStride patterns; the caller's buffers are compact [category][pattern]
+    const size_t rowElems = (size_t)d.nCat * d.patStride;
     if (partials)
-        CUDA_TRY(e, cudaMemcpy(partials, e->dPartials + d.partBase + idx * d.nCat * d.nPat * 4, 8 * (size_t)d.nCat * d.nPat * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(e, cudaMemcpy2D(partials, 32 * (size_t)d.nPat, e->dPartials + d.partBase + idx * rowElems * 4, 32 * (size_t)d.patStride,
+                                 32 * (size_t)d.nPat, (size_t)d.nCat, cudaMemcpyDeviceToHost));
     if (exponents) {
-        const size_t n = (size_t)d.nCat * d.nPat;
-        std::vector<int16_t> tmp(n);
-        CUDA_TRY(e, cudaMemcpy(tmp.data(), e->dCumExp + d.expBase + idx * n, 2 * n, cudaMemcpyDeviceToHost));
-        for (size_t p = 0; p < n; p++) exponents[p] = tmp[p];
+        std::vector<int16_t> tmp(rowElems);
+        CUDA_TRY(e, cudaMemcpy(tmp.data(), e->dCumExp + d.expBase + idx * rowElems, 2 * rowElems, cudaMemcpyDeviceToHost));
+        for (int c = 0; c < d.nCat; c++)
+            for (int p = 0; p < d.nPat; p++) exponents[(size_t)c * d.nPat + p] = tmp[(size_t)c * d.patStride + p];
     }
     return SB2_OK;
 }

@@ -40,8 +40,6 @@ struct PrepSmem {
     uint8_t *wk, *mbx;
     int *woff, *path;
     int *pos;     // schedule position of each dirty internal node
-    int *pk;      // number of parking nodes (two dirty internal children) in the subtree of each node (register parking)
-    uint8_t *swp; // per scheduled node: its operands were swapped into the canonical order (see the op emission)
 };
 
 __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, int G, int S)
@@ -55,9 +53,8 @@ __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, i
     size_t misc = take(4ull * 8), first = take(4ull * G);
     size_t md = take(G), di = take(G), to = take(G), stM = take(G), stP = take(G), cuP = take(G), cuM = take(G);
     size_t wk = take(G), mbx = take(G), woff = take(4ull * G), path = take(4ull * G), pos = take(4ull * G);
-    size_t pk = take(4ull * G), swp = take(G);
     if (s) {
-        s->pos = (int *)(base + pos); s->pk = (int *)(base + pk); s->swp = base + swp;
+        s->pos = (int *)(base + pos);
         s->wk = base + wk; s->mbx = base + mbx; s->woff = (int *)(base + woff); s->path = (int *)(base + path);
         s->gH = (double *)(base + gH); s->rate = (double *)(base + rate); s->times = (double *)(base + times);
         s->sH = (double *)(base + sH); s->sRate = (double *)(base + sRate);
@@ -294,7 +291,7 @@ __device__ __forceinline__ int prepare_locus(const PrepareArgs &A, int maxNodes,
                 s.topo[i] = treeIn && ((L != curL) || (R != curR));
                 if (!FUSED && treeIn) { A.cur.gHeight[nb + i] = h; A.cur.gParent[nb + i] = p; A.cur.gLeft[nb + i] = L; A.cur.gRight[nb + i] = R; }
                 s.assign[i] = (i < nT) ? tipSp : -1;   // GeneTree.java:243,247
-                s.cnt[i] = 0; s.pk[i] = 0;
+                s.cnt[i] = 0;
                 s.btOld[i] = bt; s.stM[i] = stM; s.stP[i] = stP; s.curP[i] = cuP; s.curM[i] = cuM;
             }
             if (i < NP) prmDst[i] = pv;
@@ -522,14 +519,11 @@ __device__ __forceinline__ int prepare_locus(const PrepareArgs &A, int maxNodes,
             while (a >= 0 && s.dirty[a] == 0) { s.dirty[a] = 2; a = s.gP[a]; }
         }
     gsync();
-    // cnt[i] = number of dirty internal nodes in the subtree of i; pk[i] = how many of them have two dirty internal children
-    // (i.e. park a result while their other subtree is walked)
+    // cnt[i] = number of dirty internal nodes in the subtree of i
     for (int i = nT + gt; i < G; i += gn)
         if (s.dirty[i]) {
-            const int Lc = s.gL[i], Rc = s.gR[i];
-            const bool parks = A.regPark && Lc >= nT && Rc >= nT && s.dirty[Lc] && s.dirty[Rc];
             int a = i;
-            while (a >= 0) { atomicAdd(&s.cnt[a], 1); if (parks) atomicAdd(&s.pk[a], 1); a = s.gP[a]; }
+            while (a >= 0) { atomicAdd(&s.cnt[a], 1); a = s.gP[a]; }
         }
     gsync();
     stamp(11, gn);
@@ -611,7 +605,7 @@ __device__ __forceinline__ int prepare_locus(const PrepareArgs &A, int maxNodes,
         const int Lc = s.gL[i], Rc = s.gR[i];
         const bool dl = Lc >= nT && s.dirty[Lc], dr = Rc >= nT && s.dirty[Rc];
         const int first = (dl && dr) ? s.first[i] : (dl ? Lc : Rc);
-        const unsigned cp = (unsigned)C * d.nPat;   // (pattern, category) elements per node buffer
+        const unsigned cp = (unsigned)C * d.patStride;   // (pattern, category) elements per node buffer (rows padded to 64 patterns)
         // the child evaluated last (the second of two dirty children, or the only dirty one) is consumed straight from
         // registers; only a first-evaluated child is parked: in stack slot `base`, or, beyond the shared-memory stack, in
         // its own global buffer
@@ -619,16 +613,12 @@ __device__ __forceinline__ int prepare_locus(const PrepareArgs &A, int maxNodes,
         // first-evaluated child is then the op right before this one in worker 0's list (register forwarding)
         const int second = (dl && dr) ? ((first == Lc) ? Rc : Lc) : -1;
         const bool remote = W > 1 && second >= 0 && s.wk[second] != 0;
-        // Register parking: while the second subtree of this node is walked nothing else is parked (pk == 0), so the first child's
-        // result can wait in the walking thread's registers instead of the shared-memory stack.
-        const bool regParkHere = A.regPark && W == 1 && second >= 0 && s.pk[second] == 0;
         auto operand = [&](int c, bool cd, uint32_t &off, unsigned &kind, unsigned &slot) {
             slot = 0; off = 0;
             if (c < nT) { kind = OPK_TIP; off = c; }
             else if (cd) {
                 if (remote && c == second) { kind = OPK_REMOTE; slot = A.stackDepth + s.mbx[c]; off = s.wk[c]; }
                 else if (remote || !(dl && dr && c == first)) { kind = OPK_PREV; }
-                else if (regParkHere) { kind = OPK_REG; }        // parked in registers: nothing else parks before the parent runs
                 else if (base < A.stackDepth) { kind = OPK_STACK; slot = base; }
                 else { kind = OPK_SPILL; off = ((1 - s.stP[c]) * nI + (c - nT)) * cp; }   // the buffer the child is being written to
             }
@@ -646,26 +636,14 @@ __device__ __forceinline__ int prepare_locus(const PrepareArgs &A, int maxNodes,
         unsigned signal = 0;
         if (par < 0) outSlot = 0;
         else if (W > 1 && s.wk[i]) { outSlot = A.stackDepth + s.mbx[i]; signal = OP_SIGNAL; }   // a helper's finished subtree
-        else if (s.first[par] == i) {
+        else if (s.first[par] == i && base < A.stackDepth) {
             const int sib = (s.gL[par] == i) ? s.gR[par] : s.gL[par];
-            if (A.regPark && W == 1 && s.pk[sib] == 0) outSlot = OP_REG_SLOT;
-            else if (base < A.stackDepth && !(W > 1 && s.wk[sib])) outSlot = base;     // sibling evaluated elsewhere: the parent takes this result from registers
+            if (!(W > 1 && s.wk[sib])) outSlot = base;     // sibling evaluated elsewhere: the parent takes this result from registers
         }
-        // Canonical operand order (a product of two factors: the order cannot change a bit): the register-forwarded operand
-        // is always b, a tip is a whenever the other operand is not a tip.  The op-ordered matrix stream follows (swp).
-        bool swp = false;
-        if (aKind == OPK_PREV) swp = true;
-        else if (bKind == OPK_TIP && aKind != OPK_TIP && bKind != OPK_PREV) swp = true;
-        if (swp) {
-            const uint32_t to = o.aOff; o.aOff = o.bOff; o.bOff = to;
-            const unsigned tk = aKind; aKind = bKind; bKind = tk;
-            const unsigned ts = aSlot; aSlot = bSlot; bSlot = ts;
-        }
-        s.swp[i] = swp ? 1 : 0;
         o.ctl = op_ctl(aKind, bKind, aSlot, bSlot, outSlot) | signal;
 
         if (FUSED) F.sops[pos] = o;
-        else for (int cc = 0; cc < C; cc++) A.opStream[(size_t)d.opBase * C + (size_t)cc * nI + pos].op = o;   // one stream per category
+        else A.ops[d.opBase + pos] = o;
     }
     gsync();
     stamp(12, gn);
@@ -702,23 +680,11 @@ __device__ __forceinline__ int prepare_locus(const PrepareArgs &A, int maxNodes,
             for (int q = 0; q < 16; q += 2) { const double2 v = *reinterpret_cast<const double2 *>(store + q); m[q] = v.x; m[q + 1] = v.y; }
         }
         if (used) {   // [op][category][side][16]: the pruning kernel's warp (one category) reads 256 contiguous bytes per op
-            const int side = ((s.gR[par] == i) ? 1 : 0) ^ (int)s.swp[par];
+            const int side = (s.gR[par] == i) ? 1 : 0;
             double *dst = FUSED ? F.smats + (((size_t)s.pos[par] * C + c) * 2 + side) * 16
-                                : A.opStream[(size_t)d.opBase * C + (size_t)c * nI + s.pos[par]].m[side];
-            if (i < nT) {   // a tip's matrix is read by COLUMN (the tip's state): stored transposed, a column = 32 contiguous bytes
+                                : A.opMats + (((size_t)(d.opBase + s.pos[par]) * C + c) * 2 + side) * 16;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    *reinterpret_cast<double2 *>(dst + 4 * q) = make_double2(m[q], m[4 + q]);
-                    *reinterpret_cast<double2 *>(dst + 4 * q + 2) = make_double2(m[8 + q], m[12 + q]);
-                }
-                if (!FUSED) {   // k_treewalk's fifth column: missing / ambiguous data (state 4) contributes a factor 1
-                    *reinterpret_cast<double2 *>(dst + 16) = make_double2(1.0, 1.0);
-                    *reinterpret_cast<double2 *>(dst + 18) = make_double2(1.0, 1.0);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(dst + q) = make_double2(m[q], m[q + 1]);
-            }
+            for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(dst + q) = make_double2(m[q], m[q + 1]);
         }
     }
     if (FUSED && matsByB) {   // this half is done: let the coalescent half know the schedule and the matrices are complete

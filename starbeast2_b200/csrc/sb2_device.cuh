@@ -2,13 +2,13 @@
 //
 // HBM layout (one engine = one GPU = one shard of loci), all arrays locus-major:
 //   tipStates   u8  [locus][tip][stateStride]                  static; rows padded to 128 B with 'missing'
-//   partials    f64 [locus][buf 0/1][internal node][cat][pattern][4]   (BEAST layout per node, two buffers
+//   partials    f64 [locus][buf 0/1][internal node][cat][patStride][4] (BEAST layout per node, rows padded to 64 patterns, two buffers
 //                                                               per node for store/restore, index flip only)
-//   cumExp      i16 [locus][buf][internal node][cat][pattern]  power-of-two scale exponent, cumulative over subtree
+//   cumExp      i16 [locus][buf][internal node][cat][patStride] power-of-two scale exponent, cumulative over subtree
 //   mats        f64 [locus][buf][node][cat][16]                P = exp(Q d) per branch x category
 //   StateBlock (x2: current / stored)  small per-node and per-locus state, see below
-//   opStream    OpRec [locus][cat][op]                          post-order pruning schedule built on device, one stream per category:
-//                                                               op descriptor + the op's two transition matrices (OPMAT_STRIDE doubles each)
+//   ops         Op  [locus][internal node]                      post-order pruning schedule built on device
+//   opMats      f64 [locus][op][cat][side][16]                  the scheduled ops' matrix pairs, in schedule order
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -38,7 +38,8 @@ struct LocusDesc {
     int32_t kStates;    // 0, or the state count 2..KSTATE_MAX
     int32_t nExcl;      // ascertained (excluded) patterns
     int32_t exclBase;   // into the excluded-pattern index array
-    int32_t pad1;
+    int32_t patStride;  // patterns per (node, category) row of partials / cumExp: nPat rounded up to 64, so that every row starts on a
+                        // 128-byte line in both arrays (a misaligned scattered row costs 14-50 % of HBM write bandwidth, measured)
     int64_t kBase;      // into the K-state scratch: [internal node][category][pattern][K] doubles (exponents: the same / K)
     int64_t stateBase;  // into tipStates (bytes)
     int64_t partBase;   // into partials (doubles)
@@ -74,11 +75,8 @@ enum : uint8_t {
 // REMOTE: (latency-bound shapes only, see WALK_MAX_WORKERS) the result of a side subtree that another worker warp of the
 // same CTA evaluates concurrently; it arrives in that warp's mailbox slot (slot field) and the operand's offset field holds
 // the worker number
-// REG: a parked result that waits in the walking thread's registers (k_treewalk only, PrepareArgs::regPark): chosen when the
-// sibling subtree parks nothing itself, so one register slot per thread is enough -- most parks of a random tree qualify
-enum : uint8_t { OPK_TIP = 0, OPK_STACK = 1, OPK_GLOBAL = 2, OPK_SPILL = 3, OPK_PREV = 4, OPK_REMOTE = 5, OPK_REG = 6 };
+enum : uint8_t { OPK_TIP = 0, OPK_STACK = 1, OPK_GLOBAL = 2, OPK_SPILL = 3, OPK_PREV = 4, OPK_REMOTE = 5 };
 constexpr unsigned OP_NO_SLOT = 255;   // outSlot: result is not parked (forwarded in registers, or spilled)
-constexpr unsigned OP_REG_SLOT = 254;  // outSlot: parked in the register slot (OPK_REG)
 constexpr unsigned OP_SIGNAL = 1u << 22;   // ctl: the parked result is awaited by another worker: publish the mailbox flag
 // Tree-level parallelism for latency-bound shapes: the walk of one pattern chunk is split over up to WALK_MAX_WORKERS warps.
 // Worker 0 walks the main (heavy-child) path; side subtrees hanging off it go to the helpers, whose results come back through
@@ -87,28 +85,14 @@ constexpr int WALK_MAX_WORKERS = 4;
 constexpr int WALK_MAILBOX = 2;
 constexpr int WALK_MAX_WORKER_OPS = 64;    // multi-worker walks keep the whole op list in shared memory
 
-// Doubles per matrix of the op stream (OpRec) that k_treewalk reads: 16 for the matrix (row-major for an internal
-// operand; TRANSPOSED for a tip, whose factor is a column) + 4: a fifth column of ones behind a tip's four, so that the tip's
-// state byte (0..3, 4 = missing / ambiguous) is the column index.  k_step's shared-memory stream keeps 16 (+ a separate ones column).
-constexpr int OPMAT_STRIDE = 20;
 struct __align__(16) Op {
     // offsets are pre-multiplied by k_prepare so that the pruning kernel needs one IMAD.WIDE per address:
-    uint32_t outOff;  // (buf*nInt + internal index) * nCat*nPat   -> (pattern, category) element of the output
-    uint32_t aOff;    // TIP: tip index; GLOBAL / SPILL: (buf*nInt + internal index) * nCat*nPat
+    uint32_t outOff;  // (buf*nInt + internal index) * nCat*patStride -> (pattern, category) element of the output
+    uint32_t aOff;    // TIP: tip index; GLOBAL / SPILL: (buf*nInt + internal index) * nCat*patStride
     uint32_t bOff;
     uint32_t ctl;     // bits 0-2 aKind, 3-5 bKind, 6-9 aSlot, 10-13 bSlot, 14-21 outSlot (>= slot count: not parked), 22 OP_SIGNAL
 };
 static_assert(sizeof(Op) == 16, "Op must stay 16 bytes (one LDS.128)");
-// k_treewalk's input: the schedule as ONE stream per (locus, category), [locus][category][op] -- a warp (one category) walks
-// consecutive records, so a chunk of OPREC_CHUNK ops (descriptors AND matrix pairs) is one contiguous bulk copy into the warp's
-// own shared-memory ring: no CTA-wide staging of the schedule, no barrier between the warps of a CTA during the walk.
-struct __align__(16) OpRec {
-    Op op;
-    uint32_t pad[4];
-    double m[2][OPMAT_STRIDE];   // operand a's and operand b's matrix (see OPMAT_STRIDE)
-};
-static_assert(sizeof(OpRec) == 32 + 16 * OPMAT_STRIDE, "OpRec layout");
-constexpr int OPREC_CHUNK = 4;
 __host__ __device__ inline uint32_t op_ctl(unsigned aKind, unsigned bKind, unsigned aSlot, unsigned bSlot, unsigned outSlot)
 {
     return aKind | (bKind << 3) | (aSlot << 6) | (bSlot << 10) | (outSlot << 14);
@@ -149,9 +133,10 @@ struct PrepareArgs {
     const double *explicitRates; // by node
     StateBlock cur;
     StateBlock stored;
-    OpRec *opStream;             // [locus][category][op]: k_treewalk's schedule + matrices (record (opBase * nCat + c * nInt + k))
+    Op *ops;
     int32_t *nOps;               // [nLoci]
     double *mats;
+    double *opMats;              // [op][category][side][16]: each scheduled op's two matrices, in schedule order
     int32_t S, nSpeciesLeaves, popKind, nLoci;
     int32_t stackDepth;          // shared-memory stack slots of k_treewalk
     int32_t uniformFlags;        // >= 0: every locus uses these flags (no per-step flags upload); < 0: read `flags`
@@ -170,7 +155,6 @@ struct PrepareArgs {
     const double *pfCatProps;
     int32_t workers;             // worker warps per pattern chunk of k_treewalk (1 = single walk)
     int32_t *laneOps;            // [nLoci][WALK_MAX_WORKERS + 1] first op of each worker's list (workers > 1)
-    int32_t regPark;             // 1: parks whose sibling subtree parks nothing use the register slot (OPK_REG); k_treewalk only
 };
 
 struct ReduceArgs {
@@ -197,12 +181,13 @@ struct WalkArgs {
     const LocusDesc *loci;
     const LocusParams *params;
     const int32_t *tileLocus;    // [nTiles]
-    const OpRec *opStream;
+    const Op *ops;
     const int32_t *nOps;
     const uint8_t *tipStates;
     const int32_t *weights;
     const uint8_t *constMask;
     const double *catProps;
+    const double *opMats;
     double *partials;
     int16_t *cumExp;
     double *patLogL;             // by pattern
@@ -216,6 +201,7 @@ struct WalkArgs {
     int32_t workers;             // worker warps per pattern chunk (tree-level parallelism), 1 = off
     int32_t debugMaxOps;         // timing experiments only (SB2_DEBUG_MAX_OPS): walk at most this many ops per worker; < 0 = all
     const int32_t *laneOps;      // [nLoci][WALK_MAX_WORKERS + 1]
+    int32_t ctasPerSM;           // > 0: cap on resident CTAs per SM (see engine.cu: walk_ctas_per_sm)
 };
 
 
@@ -238,7 +224,7 @@ struct CommArgs {
 cudaError_t launch_reduce_xgpu(const ReduceArgs &a, const CommArgs &c, cudaStream_t st, int64_t *launches);
 
 struct StepArgs {
-    PrepareArgs prep;            // opStream / laneOps / pf* unused: schedule and matrices stay in shared memory
+    PrepareArgs prep;            // ops / opMats / laneOps / pf* unused: schedule and matrices stay in shared memory
     ReduceArgs red;              // useTiles = 0: the leaders write the per-locus values into the state block
     CommArgs comm;
     const uint8_t *tipStates;

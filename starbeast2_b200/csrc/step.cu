@@ -88,8 +88,8 @@ __device__ __forceinline__ void step_walk(const StepArgs &A, const LocusDesc &d,
     const int planeStride = m.planeStride, onesIdx = m.onesIdx;
     constexpr int slotStride = STEP_WARPS * 32;
     const int stackIdx = w * 32 + lane, stateIdx = chunk * 32 + lane;
-    double *partials = A.partials + d.partBase + ((size_t)c * nPat + p) * 4;
-    int16_t *cumExp = A.cumExp + d.expBase + (size_t)c * nPat + p;
+    double *partials = A.partials + d.partBase + ((size_t)c * d.patStride + p) * 4;
+    int16_t *cumExp = A.cumExp + d.expBase + (size_t)c * d.patStride + p;
 
     if (active) {
         if (nOps < d.nInt && valid) {
@@ -122,12 +122,11 @@ __device__ __forceinline__ void step_walk(const StepArgs &A, const LocusDesc &d,
                 const int mm = mIdx + side * 16;
                 if (kind == OPK_TIP) {
                     const int st = sstate[off * tilePat + stateIdx];
-                    const int col = (st < 4) ? (mm + st * 4) : onesIdx;   // a tip's matrix is stored transposed; missing / ambiguous: factor 1
-                    const double2 v01 = *reinterpret_cast<const double2 *>(smd + col), v23 = *reinterpret_cast<const double2 *>(smd + col + 2);
-                    if (side == 0) { out[0][0] = v01.x; out[0][1] = v01.y; out[0][2] = v23.x; out[0][3] = v23.y; }
+                    const int col = (st < 4) ? (mm + st) : onesIdx;   // missing / ambiguous: factor 1
+                    if (side == 0) { out[0][0] = smd[col]; out[0][1] = smd[col + 4]; out[0][2] = smd[col + 8]; out[0][3] = smd[col + 12]; }
                     else {
-                        out[0][0] = __dmul_rn(out[0][0], v01.x); out[0][1] = __dmul_rn(out[0][1], v01.y);
-                        out[0][2] = __dmul_rn(out[0][2], v23.x); out[0][3] = __dmul_rn(out[0][3], v23.y);
+                        out[0][0] = __dmul_rn(out[0][0], smd[col]); out[0][1] = __dmul_rn(out[0][1], smd[col + 4]);
+                        out[0][2] = __dmul_rn(out[0][2], smd[col + 8]); out[0][3] = __dmul_rn(out[0][3], smd[col + 12]);
                     }
                 } else if (kind == OPK_PREV) {
                     cum += prevCum;

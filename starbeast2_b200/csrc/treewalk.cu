@@ -20,14 +20,8 @@
 //
 // Thread mapping: a warp owns 32*R consecutive patterns of ONE rate category, a thread R of them (stride 32, so
 // every global / shared access is coalesced / conflict free).  Warps never wait for each other inside the walk:
-// each warp streams its own category's schedule -- op descriptors AND transition-matrix pairs, one OpRec per op, laid out
-// [locus][category][op] by k_prepare -- through a private double-buffered ring of OPREC_CHUNK-op chunks, each chunk ONE
-// bulk asynchronous copy (cp.async.bulk, issued by an elected lane, completing on the buffer's mbarrier); the tile's
-// tip states arrive the same way, one bulk copy per tip row; rescaling is per (pattern, category).
-//
-// Parked results: a first-evaluated child waits for its sibling's subtree either in the thread's REGISTERS (OPK_REG: whenever
-// that subtree parks nothing itself -- most parks of a random tree; the two register sets then simply swap roles, nothing is
-// copied) or in the shared-memory stack.
+// each warp streams its own category's transition matrices through a private cp.async ring, the op schedule and
+// the tile's tip states are staged in shared memory once, and rescaling is per (pattern, category).
 //
 // Rescaling: every node, every (pattern, category), by an exact power of two (the exponent of the largest of
 // the 4 values); scaled values keep their mantissas, so rescaling never perturbs a result and evaluation is
@@ -36,12 +30,14 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "walk_common.cuh"
 
 namespace sb2 {
 
-constexpr int CHUNK = OPREC_CHUNK;          // ops per bulk copy
-constexpr int MAT_STRIDE = OPMAT_STRIDE;    // doubles per matrix of an OpRec (sb2_device.cuh)
+constexpr int OPS_BATCH = 32;   // ops staged in shared memory per half batch
+constexpr int MAT_RING = 4;     // transition-matrix pairs in flight per warp (cp.async ring)
 constexpr int TIP_SMEM_MAX = 48 * 1024;
 
 bool treewalk_tips_in_smem(int maxTips, int tilePat) { return (size_t)maxTips * tilePat <= TIP_SMEM_MAX; }
@@ -52,12 +48,13 @@ size_t treewalk_smem_bytes(int nCat, int chunksPerTile, int R, int stackDepth, i
     const size_t tilePat = (size_t)chunksPerTile * 32 * R;
     const size_t slots = (size_t)stackDepth + (workers > 1 ? WALK_MAILBOX : 0);
     size_t b = slots * warps * R * 32 * 32;                // partials stack (two double2 planes)
-    b += warps * 2 * CHUNK * sizeof(OpRec);                // per-warp schedule rings: two chunk buffers
-    b += warps * 2 * 8 + 32;                               // their mbarriers + the tip-state tile's
+    b += (size_t)warps * MAT_RING * 2 * 16 * 8;            // per-warp matrix rings
+    b += 2ull * OPS_BATCH * sizeof(Op);                    // op schedule, two half batches
     b += slots * warps * R * 32 * 2;                       // exponent stack (int16)
+    b += 16 * 8;                                           // the ones column
     if (workers > 1) b += ((slots * warps * 4 + 15) & ~size_t(15));   // mailbox flags
     if (treewalk_tips_in_smem(maxTips, (int)tilePat)) b += (size_t)maxTips * tilePat + 16;   // tip states of the tile
-    return (b + 31) & ~size_t(15);
+    return (b + 15) & ~size_t(15);
 }
 
 __device__ __forceinline__ unsigned ld_acquire_shared(const unsigned *p)
@@ -100,83 +97,71 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
     // the accesses in the shared window (LDS/STS), never generic
     double2 *st2 = reinterpret_cast<double2 *>(smem_raw);                       // stack: [2 planes][depth][warps][R][32] double2
     const int planeStride = slots * warps * R * 32;                             //        plane 0 = states 0,1; plane 1 = states 2,3
-    OpRec *ring = reinterpret_cast<OpRec *>(st2 + 2 * planeStride);             // [warps][2][CHUNK]
-    unsigned long long *sbar = reinterpret_cast<unsigned long long *>(ring + warps * 2 * CHUNK);   // [warps][2] chunk-buffer mbarriers | [4]: tip tile
-    unsigned long long *tipBar = sbar + warps * 2;
-    int16_t *sexp = reinterpret_cast<int16_t *>(tipBar + 4);                    // [slots][warps][R][32]
+    double *smd = reinterpret_cast<double *>(st2 + 2 * planeStride);            // ring [warps][MAT_RING][32] | ones[16]
+    const int onesIdx = warps * MAT_RING * 32;
+    Op *sops = reinterpret_cast<Op *>(smd + onesIdx + 16);                      // [2 * OPS_BATCH]
+    int16_t *sexp = reinterpret_cast<int16_t *>(sops + 2 * OPS_BATCH);          // [slots][warps][R][32]
     unsigned *sflag = reinterpret_cast<unsigned *>(sexp + planeStride);         // [slots][warps] mailbox flags (NW > 1 only)
-    const int stateOff = (int)(((reinterpret_cast<unsigned char *>(sflag + (NW > 1 ? slots * warps : 0)) - smem_raw) + 15) & ~15);
-    uint8_t *sstate = smem_raw + stateOff;                                      // [nTips][tilePat], 16-byte aligned
+    uint8_t *sstate = reinterpret_cast<uint8_t *>(sflag + (NW > 1 ? ((slots * warps + 3) & ~3) : 0));   // [nTips][tilePat]; 16-byte aligned by construction
     const uint8_t *states = A.tipStates + d.stateBase;
-    OpRec *myRing = ring + w * 2 * CHUNK;
-    unsigned long long *myBar = sbar + w * 2;
 
     // ---- static inputs first: under programmatic dependent launch this part overlaps k_prepare's tail ----
+    if (tid < 16) smd[onesIdx + tid] = 1.0;
     if (NW > 1) for (int i = tid; i < slots * warps; i += blockDim.x) sflag[i] = 0u;
-    // mbarriers: one per chunk buffer of every warp (one arrival: the elected lane's expect_tx), one for the tip-state tile
-    // (every thread arrives with the bytes of the rows it copies)
-    if (lane == 0) {
-        mbar_init(myBar, 1); mbar_init(myBar + 1, 1);
-        if (tid == 0) mbar_init(tipBar, blockDim.x);
-    }
-    mbar_init_fence();
-    __syncthreads();
     if (tipsInSmem) {
-        // the tile's tip states: one bulk copy per tip row (rows are padded to 128 bytes with 'missing', so a tile never
-        // leaves its row), all completing on one mbarrier that every thread waits for before its first op
+        // the tile's tip states, every tip, as one burst of asynchronous 16-byte copies (rows are padded to 128 bytes with
+        // 'missing', so a tile never leaves its row); they ride in the first cp.async group, which the first op waits for
         if (A.tipsInSmem == 2) {   // A/B knob: plain byte loads
             const int total = d.nTips * tilePat;
             for (int idx = tid; idx < total; idx += blockDim.x) {
                 const int t = idx / tilePat, pp = idx - t * tilePat;
                 sstate[idx] = states[(size_t)t * d.stateStride + p0 + pp];
             }
-            mbar_arrive_expect_tx(tipBar, 0);
         } else {
-            const int mine = tid < d.nTips ? (d.nTips - tid + (int)blockDim.x - 1) / (int)blockDim.x : 0;
-            mbar_arrive_expect_tx(tipBar, (unsigned)(mine * tilePat));
-            for (int t = tid; t < d.nTips; t += blockDim.x)
-                bulk_g2s(sstate + t * tilePat, states + (size_t)t * d.stateStride + p0, (unsigned)tilePat, tipBar);
+            const int per = tilePat >> 4, total = d.nTips * per;
+            for (int idx = tid; idx < total; idx += blockDim.x) {
+                const int t = idx / per, q = idx - t * per;
+                cp_async16(sstate + t * tilePat + q * 16, states + (size_t)t * d.stateStride + p0 + q * 16);
+            }
         }
     }
-    // the schedule is k_prepare's output: it must not be touched before that grid has completed
+    // nOps / ops / opMats are k_prepare's outputs: they must not be touched before that grid has completed
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();   // the (single-CTA) reduction kernel may queue up behind us already
-    const OpRec *stream = A.opStream + (size_t)d.opBase * C + (size_t)c * d.nInt;   // this category's records of the locus
-    // chunk j of this warp's list (ops kBeg + j*CHUNK ...) -> chunk buffer j & 1, one bulk copy by the elected lane completing
-    // on the buffer's mbarrier (phase parity (j >> 1) & 1).  A chunk is copied whole, up to the locus's allocation (nInt
-    // records): entries past the op count are stale but harmless, so the first chunks can be fetched before nOps is known.
-    auto issue_chunk = [&](int kFirst, int j) {
-        const int first = kFirst + j * CHUNK;
-        if (lane == 0 && first < d.nInt) {
-            const unsigned bytes = (unsigned)(min(CHUNK, d.nInt - first) * (int)sizeof(OpRec));
-            mbar_arrive_expect_tx(myBar + (j & 1), bytes);
-            bulk_g2s(myRing + (j & 1) * CHUNK, stream + first, bytes, myBar + (j & 1));
+    const Op *ops = A.ops + d.opBase;
+    const double *matStream = A.opMats + ((size_t)d.opBase * C + c) * 32 + lane;   // + k * C*32: this lane's 8 bytes of op k's pair
+    const int ringIdx = w * MAT_RING * 32;
+    const int matStride = C * 32;
+    // Single-worker walks start at op 0 whatever nOps turns out to be: fetch the first batch of the schedule and the first
+    // matrix pairs in the same wave of loads as nOps itself (bounded by the locus's allocation, so a clean locus merely
+    // reads stale entries) instead of one dependent round trip later.
+    int4 specOp = make_int4(0, 0, 0, 0);
+    if (NW == 1) {
+        if (tid < OPS_BATCH && tid < d.nInt) specOp = reinterpret_cast<const int4 *>(ops)[tid];
+        for (int j = 0; j < MAT_RING - 1; j++) {
+            if (j < d.nInt) cp_async8(smd + ringIdx + j * 32 + lane, matStream + (size_t)j * matStride);
+            cp_async_commit();
         }
-    };
-    // Single-worker walks start at op 0 whatever nOps turns out to be: fetch the first two chunks in the same wave of loads as
-    // nOps itself instead of one dependent round trip later.
-    if (NW == 1) { issue_chunk(0, 0); issue_chunk(0, 1); }
+    }
     const int nOps = A.nOps[l];
     // this worker's share of the schedule: ops [kBeg, kEnd) of the locus's list
     const int kBeg = NW > 1 ? A.laneOps[l * (WALK_MAX_WORKERS + 1) + worker] : 0;
     int kEnd = NW > 1 ? A.laneOps[l * (WALK_MAX_WORKERS + 1) + worker + 1] : nOps;
     if (A.debugMaxOps >= 0 && NW == 1) kEnd = min(kEnd, kBeg + A.debugMaxOps);   // timing experiments only: results are garbage
-    if (NW > 1) { issue_chunk(kBeg, 0); issue_chunk(kBeg, 1); }
-    const int nChunks = (kEnd - kBeg + CHUNK - 1) / CHUNK;
-    const int issued = min(2, (d.nInt - kBeg + CHUNK - 1) / CHUNK);   // chunk copies in flight so far
-    if (nOps == 0) {         // locus clean: cached logL stands; the copies in flight must land before the CTA's shared memory goes away
-        if (tipsInSmem) mbar_wait(tipBar, 0);
-        for (int j = 0; j < issued; j++) mbar_wait(myBar + j, 0);
+    if (nOps == 0) {         // locus clean: cached logL stands
+        cp_async_commit();
+        cp_async_wait<0>();
         return;
     }
     const bool incremental = nOps < d.nInt;         // only then can operands be clean nodes resident in HBM
 
-    double *partials = A.partials + d.partBase + ((size_t)c * nPat + pbase) * 4;   // + idx*4 (+ r*128)
-    int16_t *cumExp = A.cumExp + d.expBase + (size_t)c * nPat + pbase;              // + idx   (+ r*32)
-    // keep the per-thread base pointers in registers: ptxas otherwise re-derives them (64-bit multiplies) inside every
-    // iteration of the walk
+    double *partials = A.partials + d.partBase + ((size_t)c * d.patStride + pbase) * 4;   // + idx*4 (+ r*128)
+    int16_t *cumExp = A.cumExp + d.expBase + (size_t)c * d.patStride + pbase;              // + idx   (+ r*32)
+    // keep the three per-thread base pointers in registers: under the 64-register cap ptxas otherwise re-derives them
+    // (64-bit multiplies) inside every iteration of the walk
     asm volatile("" : "+l"(partials));
     asm volatile("" : "+l"(cumExp));
+    asm volatile("" : "+l"(matStream));
     const int stateIdx = chunk * 32 * R + lane;
     const int stackIdx = w * R * 32 + lane;                 // + slot*slotStride + r*32
     const int slotStride = warps * R * 32;
@@ -184,12 +169,22 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
 #pragma unroll
     for (int r = 0; r < R; r++) valid[r] = pbase + 32 * r < nPat;
 
-    // two register sets: one receives every op's result (and forwards it to the next op), the other is the register parking
-    // slot; they swap roles whenever a result is parked in registers (flip)
-    double xv[R][4], yv[R][4];
-    int xc[R], yc[R];
+    auto load_batch = [&](int b) {
+        const int first = b * OPS_BATCH, cnt = min(OPS_BATCH, nOps - first);
+        const int4 *src = reinterpret_cast<const int4 *>(ops + first);
+        int4 *dst = reinterpret_cast<int4 *>(sops + (b & 1) * OPS_BATCH);
+        for (int t = tid; t < cnt; t += blockDim.x) dst[t] = src[t];
+    };
+    // this warp's matrix pair of op k (256 contiguous bytes of the op-ordered stream) -> ring slot k % MAT_RING
+    auto issue_mats = [&](int k) {
+        if (k < kEnd) cp_async8(smd + ringIdx + (k & (MAT_RING - 1)) * 32 + lane, matStream + (size_t)k * matStride);
+        cp_async_commit();
+    };
+
+    double prev[R][4];   // result of the previous op (scaled) and its cumulative exponent
+    int prevCum[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) { xv[r][0] = xv[r][1] = xv[r][2] = xv[r][3] = 0.0; yv[r][0] = yv[r][1] = yv[r][2] = yv[r][3] = 0.0; xc[r] = yc[r] = 0; }
+    for (int r = 0; r < R; r++) { prev[r][0] = prev[r][1] = prev[r][2] = prev[r][3] = 0.0; prevCum[r] = 0; }
 
     if (c == 0 && worker == 0) {   // what the root epilogue will read, pulled into L1 while the walk runs
         const LocusParams *prm = &A.params[l];
@@ -199,105 +194,93 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
 #pragma unroll
         for (int r = 0; r < R; r++) if (valid[r]) prefetch_l1(A.weights + d.patBase + pbase + 32 * r);
     }
-    if (tipsInSmem) mbar_wait(tipBar, 0);   // the tip-state tile has landed
+    if (NW == 1) {
+        if (tid < OPS_BATCH) reinterpret_cast<int4 *>(sops)[tid] = specOp;   // batch 0, fetched above
+    } else {
+        load_batch(0);
+        if (nOps > OPS_BATCH) load_batch(1);   // multi-worker walks are limited to 2 * OPS_BATCH ops: all resident, no reloads
+        for (int j = 0; j < MAT_RING - 1; j++) issue_mats(kBeg + j);
+    }
+    cp_async_wait<MAT_RING - 2>();   // group 0 (tip states + op 0's matrices) has landed for this thread ...
+    __syncthreads();                 // ... and for everybody else; the op schedule is visible too
 
-    // One pruning op.  `fwd` holds the previous op's (scaled) result and receives this op's; `park` is the register parking
-    // slot (OPK_REG).  Returns true when the result is parked in registers (OP_REG_SLOT): the caller swaps the sets' roles.
-    // Software pipelining across ops: the op's descriptor `o` and the state bytes of its tip operands (sa, sb) were fetched
-    // while the previous op was computing; this op in turn fetches the state bytes of `on`, the next op of the chunk.
-    auto tip_states = [&](const Op &q, int (&ta)[R], int (&tb)[R]) {
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            if ((q.ctl & 7) == OPK_TIP)
-                ta[r] = tipsInSmem ? sstate[q.aOff * tilePat + stateIdx + 32 * r] : states[(size_t)q.aOff * d.stateStride + pbase + 32 * r];
-            if (((q.ctl >> 3) & 7) == OPK_TIP)
-                tb[r] = tipsInSmem ? sstate[q.bOff * tilePat + stateIdx + 32 * r] : states[(size_t)q.bOff * d.stateStride + pbase + 32 * r];
+    for (int k = kBeg; k < kEnd; k++) {
+        if (NW == 1 && (k & (OPS_BATCH - 1)) == OPS_BATCH / 2 && (k / OPS_BATCH + 1) * OPS_BATCH < nOps) {
+            __syncthreads();                       // every warp has left the previous batch's half
+            load_batch(k / OPS_BATCH + 1);
+            __syncthreads();
         }
-    };
-    auto op_body = [&](const Op &o, const OpRec *rec, const Op &on, int (&sa)[R], int (&sb)[R],
-                       double (&fwd)[R][4], int (&fwdCum)[R], double (&park)[R][4], int (&parkCum)[R]) -> bool {
-        const double *mA = rec->m[0], *mB = rec->m[1];
-        const unsigned aKind = o.ctl & 7, bKind = (o.ctl >> 3) & 7;
+        cp_async_wait<MAT_RING - 2>();             // this lane's pieces of op k's matrices have landed
+        __syncwarp();                              // ... and the other lanes'; the warp is also done with op k-1
+        issue_mats(k + MAT_RING - 1);              // reuses the ring slot of op k-1
+        if (incremental && k + 2 < kEnd) {         // clean children live in HBM: pull their sectors towards L2 two ops ahead
+            const Op q = sops[(k + 2) & (2 * OPS_BATCH - 1)];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if ((q.ctl & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.aOff * 4 + r * 128);
+                if (((q.ctl >> 3) & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.bOff * 4 + r * 128);
+            }
+        }
+
+        const Op o = sops[k & (2 * OPS_BATCH - 1)];
+        const int mIdx = ringIdx + (k & (MAT_RING - 1)) * 32;
         double out[R][4];
         int cum[R];
 #pragma unroll
         for (int r = 0; r < R; r++) cum[r] = 0;
 
-        // a tip's factor: column `state` of its matrix.  k_prepare stores a tip's matrix transposed (a column = 32 contiguous
-        // bytes = two LDS.128 that the whole warp shares bank-conflict free) with a fifth column of ones for missing /
-        // ambiguous data (state 4: the engine normalises every such code to 4), so the state byte IS the column index.
-        auto tip_column = [&](int st, const double *m, double2 &v01, double2 &v23) {
-            v01 = *reinterpret_cast<const double2 *>(m + st * 4);
-            v23 = *reinterpret_cast<const double2 *>(m + st * 4 + 2);
-        };
-        // a parked (shared-memory stack / helper mailbox) or resident (HBM) operand
-        auto fetch = [&](unsigned kind, unsigned off, unsigned slot, double (&a)[R][4]) {
-            if (kind == OPK_STACK || (NW > 1 && kind == OPK_REMOTE)) {
-                int si0 = slot * slotStride + stackIdx;
-                if (NW > 1 && kind == OPK_REMOTE) {   // a helper's finished subtree: wait for its mailbox flag, read its slot
-                    const int src = (int)off * inner + wi;
-                    const unsigned *flag = sflag + slot * warps + src;
-                    while (ld_acquire_shared(flag) == 0u) { }
-                    si0 += (src - w) * R * 32;
-                }
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const unsigned kind = (o.ctl >> (3 * side)) & 7;
+            const unsigned off = side ? o.bOff : o.aOff;
+            const int m = mIdx + side * 16;
+            if (kind == OPK_TIP) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const double2 lo = st2[si0 + 32 * r], hi = st2[planeStride + si0 + 32 * r];
-                    a[r][0] = lo.x; a[r][1] = lo.y; a[r][2] = hi.x; a[r][3] = hi.y;
-                    cum[r] += sexp[si0 + 32 * r];
+                    const int st = tipsInSmem ? sstate[off * tilePat + stateIdx + 32 * r]
+                                              : states[(size_t)off * d.stateStride + pbase + 32 * r];
+                    const int col = (st < 4) ? (m + st) : onesIdx;   // missing / ambiguous: factor 1
+                    if (side == 0) { out[r][0] = smd[col]; out[r][1] = smd[col + 4]; out[r][2] = smd[col + 8]; out[r][3] = smd[col + 12]; }
+                    else { out[r][0] *= smd[col]; out[r][1] *= smd[col + 4]; out[r][2] *= smd[col + 8]; out[r][3] *= smd[col + 12]; }
                 }
             } else {
+                if (kind == OPK_PREV) {   // the previous op's result, forwarded in registers
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0.0;
-                    if (valid[r]) {
-                        const double *src = partials + (size_t)off * 4 + r * 128;
-                        if (kind == OPK_GLOBAL) ld256_nc(src, a[r][0], a[r][1], a[r][2], a[r][3]);
-                        else ld256_coherent(src, a[r][0], a[r][1], a[r][2], a[r][3]);   // OPK_SPILL: written by this thread in this launch
-                        cum[r] += cumExp[(size_t)off + 32 * r];
+                    for (int r = 0; r < R; r++) cum[r] += prevCum[r];
+                    if (side == 0) rows_times<EXACT, R, true>(smd + m, prev, out);
+                    else rows_times<EXACT, R, false>(smd + m, prev, out);
+                    continue;
+                }
+                double a[R][4];
+                if (kind == OPK_STACK || (NW > 1 && kind == OPK_REMOTE)) {
+                    int si0 = ((o.ctl >> (6 + 4 * side)) & 15) * slotStride + stackIdx;
+                    if (NW > 1 && kind == OPK_REMOTE) {   // a helper's finished subtree: wait for its mailbox flag, read its slot
+                        const int src = (int)off * inner + wi;
+                        const unsigned *flag = sflag + ((o.ctl >> (6 + 4 * side)) & 15) * warps + src;
+                        while (ld_acquire_shared(flag) == 0u) { }
+                        si0 += (src - w) * R * 32;
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const double2 lo = st2[si0 + 32 * r], hi = st2[planeStride + si0 + 32 * r];
+                        a[r][0] = lo.x; a[r][1] = lo.y; a[r][2] = hi.x; a[r][3] = hi.y;
+                        cum[r] += sexp[si0 + 32 * r];
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0.0;
+                        if (valid[r]) {
+                            const double *src = partials + (size_t)off * 4 + r * 128;
+                            if (kind == OPK_GLOBAL) ld256_nc(src, a[r][0], a[r][1], a[r][2], a[r][3]);
+                            else ld256_coherent(src, a[r][0], a[r][1], a[r][2], a[r][3]);   // OPK_SPILL: written by this thread in this launch
+                            cum[r] += cumExp[(size_t)off + 32 * r];
+                        }
                     }
                 }
+                if (side == 0) rows_times<EXACT, R, true>(smd + m, a, out);
+                else rows_times<EXACT, R, false>(smd + m, a, out);
             }
-        };
-
-        // ---- operand a (canonical order: a tip whenever the op has one; never the register-forwarded result) ----
-        if (aKind == OPK_TIP) {
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                double2 v01, v23;
-                tip_column(sa[r], mA, v01, v23);
-                out[r][0] = v01.x; out[r][1] = v01.y; out[r][2] = v23.x; out[r][3] = v23.y;
-            }
-        } else if (aKind == OPK_REG) {
-#pragma unroll
-            for (int r = 0; r < R; r++) cum[r] += parkCum[r];
-            rows_times<EXACT, R, true>(mA, park, out);
-        } else {
-            double a[R][4];
-            fetch(aKind, o.aOff, (o.ctl >> 6) & 15, a);
-            rows_times<EXACT, R, true>(mA, a, out);
-        }
-        int na[R], nb[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) { na[r] = 4; nb[r] = 4; }
-        tip_states(on, na, nb);   // the next op's tip states: in flight while this op finishes
-        // ---- operand b: the previous op's result forwarded in registers, or a second tip, or (incremental walks) a clean node ----
-        if (bKind == OPK_PREV) {
-#pragma unroll
-            for (int r = 0; r < R; r++) cum[r] += fwdCum[r];
-            rows_times<EXACT, R, false>(mB, fwd, out);
-        } else if (bKind == OPK_TIP) {
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                double2 v01, v23;
-                tip_column(sb[r], mB, v01, v23);
-                out[r][0] = __dmul_rn(out[r][0], v01.x); out[r][1] = __dmul_rn(out[r][1], v01.y);
-                out[r][2] = __dmul_rn(out[r][2], v23.x); out[r][3] = __dmul_rn(out[r][3], v23.y);
-            }
-        } else {
-            double a[R][4];
-            fetch(bKind, o.bOff, (o.ctl >> 10) & 15, a);
-            rows_times<EXACT, R, false>(mB, a, out);
         }
 
         // ---- exact power-of-two rescale, store ----
@@ -319,51 +302,15 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
                 st256(dst + r * 128, o0, o1, o2, o3);
                 dstE[32 * r] = (int16_t)ce;
             }
-            fwd[r][0] = o0; fwd[r][1] = o1; fwd[r][2] = o2; fwd[r][3] = o3;
-            fwdCum[r] = ce;
+            prev[r][0] = o0; prev[r][1] = o1; prev[r][2] = o2; prev[r][3] = o3;
+            prevCum[r] = ce;
         }
         if (NW > 1 && (o.ctl & OP_SIGNAL)) {   // hand the finished subtree to worker 0
             __syncwarp();
             if (lane == 0) st_release_shared(sflag + outSlot * warps + w, 1u);
         }
-#pragma unroll
-        for (int r = 0; r < R; r++) { sa[r] = na[r]; sb[r] = nb[r]; }
-        return outSlot == (int)OP_REG_SLOT;
-    };
-
-    bool flip = false;
-    for (int j = 0; j < nChunks; j++) {
-        mbar_wait(myBar + (j & 1), (j >> 1) & 1);          // chunk j (descriptors and matrix pairs of up to CHUNK ops) has landed
-        const OpRec *recs = myRing + (j & 1) * CHUNK;
-        const int n = min(CHUNK, kEnd - kBeg - j * CHUNK);
-        if (incremental) {                                  // clean children live in HBM: pull the chunk's sectors towards L2
-            for (int i = 0; i < n; i++) {
-                const Op q = recs[i].op;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    if ((q.ctl & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.aOff * 4 + r * 128);
-                    if (((q.ctl >> 3) & 7) == OPK_GLOBAL && valid[r]) prefetch_l2(partials + (size_t)q.bOff * 4 + r * 128);
-                }
-            }
-        }
-        Op o = recs[0].op;
-        int sa[R], sb[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) { sa[r] = 4; sb[r] = 4; }
-        tip_states(o, sa, sb);
-#pragma unroll 1
-        for (int i = 0; i < n; i++) {
-            const Op on = recs[min(i + 1, n - 1)].op;       // the next op's descriptor (the last op of a chunk re-reads its own)
-            // the op itself, on (forward, parked) = (X, Y) or (Y, X): a result parked in registers simply stays where it was
-            // written and the two register sets swap roles -- no copies
-            const bool parked = flip ? op_body(o, recs + i, on, sa, sb, yv, yc, xv, xc) : op_body(o, recs + i, on, sa, sb, xv, xc, yv, yc);
-            flip ^= parked;
-            o = on;
-        }
-        __syncwarp();                                       // every lane is done with chunk j: its buffer is free
-        if (j + 2 < nChunks) issue_chunk(kBeg, j + 2);
     }
-    for (int j = nChunks; j < issued; j++) mbar_wait(myBar + j, 0);   // speculative fetches beyond a short op list must land before the CTA retires
+    cp_async_wait<0>();
     __syncthreads();
 
     // root: integratePartials over categories, (+pInv on constant patterns), frequencies, log, pattern weight; then the sum
@@ -395,6 +342,8 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
 template <bool EXACT, int R, int MINB, int NC, int CH, int DEPTH, int NW = 1>
 static cudaError_t launch_one(const WalkArgs &a, int nTiles, size_t smem, int threads, cudaStream_t st)
 {
+    // resident CTAs per SM can be capped by padding the dynamic shared memory (WalkArgs::ctasPerSM, 0 = whatever fits)
+    if (a.ctasPerSM > 0) smem = std::max(smem, (size_t)(227 * 1024 / a.ctasPerSM - 1024) & ~size_t(15));
     static size_t configured[MAX_DEVICES] = {};
     cudaError_t rc = ensure_dynamic_smem(k_treewalk<EXACT, R, MINB, NC, CH, DEPTH, NW>, smem, configured);
     if (rc != cudaSuccess) return rc;
@@ -424,7 +373,7 @@ static cudaError_t launch_exact(const WalkArgs &a, int nTiles, size_t smem, int 
         else return launch_one<EXACT, 1, 4, 0, 0, 0>(a, nTiles, smem, threads, st);
     } else if (a.patPerThread == 2) {
         if (a.stackDepth == 3 && a.tipsInSmem == 1 && a.nCat == 4 && a.chunksPerTile == 1) return launch_one<EXACT, 2, 5, 4, 1, 3>(a, nTiles, smem, threads, st);   // 5 CTAs / SM
-        else if (std4 && a.nCat == 4 && a.chunksPerTile == 1) return launch_one<EXACT, 2, 4, 4, 1, 4>(a, nTiles, smem, threads, st);
+        else if (std4 && a.nCat == 4 && a.chunksPerTile == 1) return launch_one<EXACT, 2, 2, 4, 1, 4>(a, nTiles, smem, threads, st);
         else if (std4 && a.nCat == 1 && a.chunksPerTile == 2) return launch_one<EXACT, 2, 2, 1, 2, 4>(a, nTiles, smem, threads, st);
         else return launch_one<EXACT, 2, 2, 0, 0, 0>(a, nTiles, smem, threads, st);
     } else {
