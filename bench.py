@@ -612,8 +612,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG")            # both print "NCCL version ..." on stdout: keep stdout to the one JSON line
     from starbeast2_b200 import build as sbuild
     ctx = Ctx(args)
     sbuild.build()

@@ -38,6 +38,11 @@ struct sb2_engine {
     std::string err;
     bool finalized = false;
     cudaStream_t stream = nullptr;
+    // K-state likelihood-only loci run on a side stream, concurrently with the 4-state pruning kernel (they only depend on
+    // k_prepare); every reduction -- and anything else that touches their inputs or outputs -- joins it first (join_kstate)
+    cudaStream_t kStream = nullptr;
+    cudaEvent_t evPrepared = nullptr, evKDone = nullptr;
+    bool kPending = false;
     bool ownStream = false;
     std::vector<HostLocus> loci;
     int S = 0, nSpeciesLeaves = 0, L = 0;
@@ -308,8 +313,18 @@ const char *check_tree(int n, int nLeaves, const int32_t *parent, const int32_t 
 
 // upload staged inputs and run k_prepare -- or, when the caller wants a whole evaluation (allowFused) and the shapes are
 // latency-bound, the fused one-launch step k_step (*didFused: prepare, walk, reductions and publish are all in flight)
+int join_kstate(sb2_engine *e)
+{
+    if (e->kPending) {
+        CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->evKDone, 0));
+        e->kPending = false;
+    }
+    return SB2_OK;
+}
+
 int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
 {
+    { int jrc = join_kstate(e); if (jrc) return jrc; }   // a K-state kernel still in flight reads what is about to be uploaded
     if (didFused) *didFused = false;
     if (!e->needPrepare) return SB2_OK;
     // A walk scheduled by an earlier k_prepare (strict two-phase protocol: coalescent evaluated, likelihood never asked for)
@@ -464,7 +479,15 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
             k.catRates = e->dCat; k.catProps = e->dCat + e->totalCat; k.explicitRates = e->dExplicit ? e->dExplicit : e->dCat;
             k.cur = cur(e); k.patLogL = e->dPatLogL; k.scratch = e->dKScratch; k.scratchExp = e->dKExp;
             k.maxNodes = e->maxNodes; k.maxCat = e->nCat; k.smemScratch = e->kSmemScratch;
-            CUDA_TRY(e, launch_kstate(k, e->nK, e->maxK, st));
+            if (e->kStream) {   // concurrently with the pruning kernel of the gene loci
+                CUDA_TRY(e, cudaEventRecord(e->evPrepared, st));
+                CUDA_TRY(e, cudaStreamWaitEvent(e->kStream, e->evPrepared, 0));
+                CUDA_TRY(e, launch_kstate(k, e->nK, e->maxK, e->kStream));
+                CUDA_TRY(e, cudaEventRecord(e->evKDone, e->kStream));
+                e->kPending = true;
+            } else {
+                CUDA_TRY(e, launch_kstate(k, e->nK, e->maxK, st));
+            }
             e->launches++;
         }
     }
@@ -487,6 +510,7 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
 // final reduction of the single-call evaluations: across GPUs over peer memory when connected, else local
 int launch_final(sb2_engine *e, const ReduceArgs &r)
 {
+    { int jrc = join_kstate(e); if (jrc) return jrc; }
     static const bool skip = getenv("SB2_DEBUG_SKIP_REDUCE") != nullptr;   // timing experiments only: results are stale
     if (skip) { e->pollTag = 0; return SB2_OK; }
     if (e->commConnected) {
@@ -543,6 +567,7 @@ int flush_pending_walk(sb2_engine *e)
         int rc = do_walk(e);
         if (rc) return rc;
         // ... and that the cached per-locus log-likelihoods (cur.logL, what a clean locus reports) belong to them
+        { int jrc = join_kstate(e); if (jrc) return jrc; }
         CUDA_TRY(e, launch_reduce_local(reduce_args(e), e->stream, &e->launches));
     }
     return SB2_OK;
@@ -638,7 +663,11 @@ void sb2_destroy(sb2_engine *e)
 {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
+    if (e->kStream) cudaStreamSynchronize(e->kStream);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->kStream) cudaStreamDestroy(e->kStream);
+    if (e->evPrepared) cudaEventDestroy(e->evPrepared);
+    if (e->evKDone) cudaEventDestroy(e->evKDone);
     for (void *p : e->devAllocs) cudaFree(p);
     for (void *p : {(void *)e->hParams, (void *)e->hCat, (void *)e->hExplicit, (void *)e->hInTree, (void *)e->hFlags, (void *)e->hSpecies, (void *)e->hOut,
                     (void *)e->hStamps, (void *)e->hWords, (void *)e->hParamsStored, (void *)e->hCatStored, (void *)e->hExplicitStored, (void *)e->hSpeciesStored, (void *)e->hQuery})
@@ -825,6 +854,11 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if ((rc = dev_alloc(e, &e->dOpMats, (size_t)opBase * e->nCat * 32))) return rc;
     if ((rc = dev_alloc(e, &e->dNOps, L))) return rc;
     e->nK = (int)e->kLoci.size();
+    if (e->nK && e->totalTiles > 0 && !getenv("SB2_KSTATE_INLINE")) {   // SB2_KSTATE_INLINE: A/B knob, k_kstate in the main stream
+        CUDA_TRY(e, cudaStreamCreateWithFlags(&e->kStream, cudaStreamNonBlocking));
+        CUDA_TRY(e, cudaEventCreateWithFlags(&e->evPrepared, cudaEventDisableTiming));
+        CUDA_TRY(e, cudaEventCreateWithFlags(&e->evKDone, cudaEventDisableTiming));
+    }
     if (e->nK) {
         for (int32_t l : e->kLoci) {
             const LocusDesc &d = e->loci[l].d;
@@ -1088,6 +1122,7 @@ int sb2_eval_begin(sb2_engine *e)
     int rc;
     if ((rc = do_prepare(e))) return rc;
     if ((rc = do_walk(e))) return rc;
+    { int jrc = join_kstate(e); if (jrc) return jrc; }
     CUDA_TRY(e, launch_reduce_local(reduce_args(e), e->stream, &e->launches));
     e->reduced = true;
     return SB2_OK;
@@ -1239,6 +1274,7 @@ int sb2_set_stream(sb2_engine *e, void *cudaStream)
 
 int sb2_store(sb2_engine *e)
 {
+    if (e && e->finalized) { int jrc = join_kstate(e); if (jrc) return jrc; }
     if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     // Inputs staged since the last evaluation belong to the state that is being stored (the host mirrors below include
@@ -1249,6 +1285,7 @@ int sb2_store(sb2_engine *e)
         if ((rc = do_walk(e))) return rc;
         // the rank-local sums also refresh the cached per-locus values (cur.logL) that a restore() falls back on; no
         // cross-GPU exchange here: ranks need not agree on whether they had anything staged
+        { int jrc = join_kstate(e); if (jrc) return jrc; }
         CUDA_TRY(e, launch_reduce_local(reduce_args(e), e->stream, &e->launches));
     }
     if ((rc = flush_pending_walk(e))) return rc;
@@ -1271,6 +1308,7 @@ int sb2_store(sb2_engine *e)
 
 int sb2_restore(sb2_engine *e)
 {
+    if (e && e->finalized) { int jrc = join_kstate(e); if (jrc) return jrc; }
     if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (!e->hasStored) return e->fail(SB2_ERR_STATE, "sb2_restore without a prior sb2_store");

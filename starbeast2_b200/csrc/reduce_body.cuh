@@ -129,28 +129,53 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preCh
     if (sums3) { sums3[0] = coalSum; sums3[1] = likSum; sums3[2] = inc; }
 
     // analytic integration: per-branch sums over this rank's loci
-    if (A.popKind == 2) {
+    if (A.popKind == 2 && A.exact) {   // the reference's order: loci in list order, one branch at a time
         const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
         for (int b = warp; b < S; b += nw) {
             double q = 0.0, g = 0.0, r = 0.0;
-            if (A.exact) {
-                if (lane == 0)
-                    for (int l = 0; l < L; l++) {
-                        const size_t o = (size_t)l * S + b;
-                        q += __ldcg(A.cur.brK + o); g += __ldcg(A.cur.anG + o); r += __ldcg(A.cur.anR + o);
-                    }
-            } else {
-                for (int l = lane; l < L; l += 32) {
+            if (lane == 0) {
+                for (int l = 0; l < L; l++) {
                     const size_t o = (size_t)l * S + b;
                     q += __ldcg(A.cur.brK + o); g += __ldcg(A.cur.anG + o); r += __ldcg(A.cur.anR + o);
                 }
-                for (int off = 16; off > 0; off >>= 1) {
-                    q += __shfl_xor_sync(0xffffffffu, q, off);
-                    g += __shfl_xor_sync(0xffffffffu, g, off);
-                    r += __shfl_xor_sync(0xffffffffu, r, off);
+                A.red[3 + 3 * b] = q; A.red[3 + 3 * b + 1] = g; A.red[3 + 3 * b + 2] = r;
+            }
+        }
+    } else if (A.popKind == 2) {
+        // The three arrays are [locus][branch]: a warp reads whole rows (lanes = 32 consecutive branches: coalesced), warp w
+        // the loci l = w (mod warps), several rows in flight; the warps' partial sums then meet in shared memory and are
+        // added in warp order.  Fixed shape: deterministic, whatever runs before or after.
+        __shared__ double part[3][8][32];
+        const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;   // nw <= 8 (RED_THREADS / STEP_THREADS = 256)
+        for (int b0 = 0; b0 < S; b0 += 32) {
+            const int b = b0 + lane;
+            double q = 0.0, g = 0.0, r = 0.0;
+            if (b < S) {
+                int l = warp;
+                for (; l + 3 * nw < L; l += 4 * nw) {   // four rows in flight
+                    double vq[4], vg[4], vr[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const size_t o = (size_t)(l + j * nw) * S + b;
+                        vq[j] = (double)__ldcg(A.cur.brK + o); vg[j] = __ldcg(A.cur.anG + o); vr[j] = __ldcg(A.cur.anR + o);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { q += vq[j]; g += vg[j]; r += vr[j]; }
+                }
+                for (; l < L; l += nw) {
+                    const size_t o = (size_t)l * S + b;
+                    q += (double)__ldcg(A.cur.brK + o); g += __ldcg(A.cur.anG + o); r += __ldcg(A.cur.anR + o);
                 }
             }
-            if (lane == 0) { A.red[3 + 3 * b] = q; A.red[3 + 3 * b + 1] = g; A.red[3 + 3 * b + 2] = r; }
+            __syncthreads();   // the previous block of branches has been consumed
+            part[0][warp][lane] = q; part[1][warp][lane] = g; part[2][warp][lane] = r;
+            __syncthreads();
+            if (tid < 96) {
+                const int a = tid >> 5, bb = b0 + (tid & 31);
+                double sum = 0.0;
+                for (int w = 0; w < nw; w++) sum += part[a][w][tid & 31];
+                if (bb < S) A.red[3 + 3 * bb + a] = sum;
+            }
         }
     } else {
         for (int i = tid; i < 3 * S; i += nt) A.red[3 + i] = 0.0;

@@ -120,9 +120,15 @@ class Engine:
         e.shard = (lo, hi)
         for loc in pb.loci[lo:hi]:
             e.add_locus(loc.tip_states, loc.weights, loc.n_cat, loc.tip_species, loc.ploidy)
-        # morphological partitions (K-state likelihoods on the species tree) follow the loci; sharded runs keep them on the
-        # rank that holds the last locus
-        e.morph = list(getattr(pb, "morph", None) or []) if hi == pb.n_loci else []
+        # morphological partitions (K-state likelihoods on the species tree) follow the loci.  A shard built by
+        # synth.make_problem(locus_range=...) already carries only the partitions that travel with it; when a range of a
+        # whole Problem is registered here instead, the same rule applies (synth.morph_owner_locus)
+        allm = list(getattr(pb, "morph", None) or [])
+        if (lo, hi) == (0, pb.n_loci):
+            e.morph = allm
+        else:
+            from .synth import morph_owner_locus
+            e.morph = [m for mi, m in enumerate(allm) if lo <= morph_owner_locus(mi, pb.n_loci, len(allm)) < hi]
         for m in e.morph:
             e.add_locus_k(m.tip_states, m.weights, m.n_states, m.n_cat, m.excluded)
         e.finalize(pb.species.n_nodes, pb.species.n_leaves)

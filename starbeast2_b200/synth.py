@@ -246,6 +246,11 @@ CONFIGS = {
 }
 
 
+def morph_owner_locus(mi: int, n_loci: int, n_morph: int) -> int:
+    """Sharded runs: morphological partition mi travels with the shard that holds this locus index."""
+    return ((2 * mi + 1) * n_loci) // (2 * n_morph)
+
+
 def make_problem(name: str = "C2", n_loci: Optional[int] = None, n_sites: Optional[int] = None,
                  seed_offset: int = 0, missing_frac: float = 0.0, locus_range: Optional[Tuple[int, int]] = None,
                  **override) -> Problem:
@@ -326,8 +331,12 @@ def make_problem(name: str = "C2", n_loci: Optional[int] = None, n_sites: Option
                           clock_kind=clock_kind, clock_rate=clock_rate))
     # morphological partitions on the species tree (CanisFBD-style: one TreeLikelihood per state count, LewisMK, ascertained)
     morph = []
-    # (they travel with the shard that holds the last locus, so that every rank of a sharded run sees each partition once)
-    for mi in range(int(cfg.get("n_morph", 0)) if hi == cfg["n_loci"] else 0):
+    # (sharded runs: partition mi travels with the shard that holds locus (2 mi + 1) n / (2 n_morph) -- spread evenly along the
+    # locus axis, so that every rank sees each partition once and no rank carries all of them)
+    n_morph = int(cfg.get("n_morph", 0))
+    for mi in range(n_morph):
+        if not (lo <= morph_owner_locus(mi, cfg["n_loci"], n_morph) < hi):
+            continue
         rng = np.random.Generator(np.random.PCG64([base_seed, 900000 + mi]))
         K = 2 + mi % 4
         rate = 0.6 / max(float(sp.height[sp.root]), 1e-6)
@@ -372,7 +381,7 @@ def make_problem_parallel(name: str, n_loci: Optional[int] = None, locus_range: 
     pb = parts[0]
     for q in parts[1:]:
         pb.loci.extend(q.loci)
-        pb.morph.extend(q.morph)   # only the chunk with the last locus carries them
+        pb.morph.extend(q.morph)   # every partition travels with exactly one chunk, in partition order
     return pb
 
 

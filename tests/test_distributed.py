@@ -95,6 +95,13 @@ def test_sharded_reduce_vector_protocol_gloo_cpu(name):
     assert lik == pytest.approx(full.likelihood, rel=1e-12)
 
 
+def _shard_values(per_locus, pb, n_loci, lo, hi):
+    """The shard's slice of a global per-locus vector: its loci, then the morphological partitions that travel with it."""
+    n_morph = len(pb.morph)
+    mine = [n_loci + mi for mi in range(n_morph) if lo <= synth.morph_owner_locus(mi, n_loci, n_morph) < hi]
+    return np.concatenate([np.asarray(per_locus)[lo:hi], np.asarray(per_locus)[mine]])
+
+
 def _gpu_worker(rank, world, port, name, n_loci, n_sites, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)   # both ranks share cuda:0, so gloo (NCCL wants 1 GPU per rank)
@@ -138,15 +145,14 @@ def test_engine_distributed_two_ranks(name):
     node_off = np.concatenate([[0], np.cumsum([l.tree.n_nodes for l in pb.loci])])
     for rank, coal, lik, total, per_locus, per_branch, q in got:
         lo, hi = shard_loci([1.0] * n_loci, world)[rank]
-        n_gene = int(node_off[hi] - node_off[lo])   # the rank with the last locus also holds the morphological partitions: never connecting
-        assert q[0][:n_gene] == w_mask[node_off[lo]:node_off[hi]].tolist() and not any(q[0][n_gene:])
+        n_gene = int(node_off[hi] - node_off[lo])   # the mask covers gene trees only (morphological partitions have none)
+        assert q[0] == w_mask[node_off[lo]:node_off[hi]].tolist() and len(q[0]) == n_gene
         assert q[1:] == (w_tip, w_root, w_cnt, w_mh)
         assert coal == pytest.approx(full.coalescent, rel=1e-9)      # every rank ends with the global totals
         assert lik == pytest.approx(full.likelihood, rel=1e-9)
         assert total == pytest.approx(full.total, rel=1e-9)
         lo, hi = shard_loci([1.0] * n_loci, world)[rank]
-        hi_out = len(full.per_locus_lik) if hi == n_loci else hi      # + the morphological partitions on the last rank
-        np.testing.assert_allclose(per_locus, full.per_locus_lik[lo:hi_out], rtol=1e-9)
+        np.testing.assert_allclose(per_locus, _shard_values(full.per_locus_lik, pb, n_loci, lo, hi), rtol=1e-9)
         if pb.pop_kind == POP_ANALYTIC:
             np.testing.assert_allclose(per_branch, full.per_branch, rtol=1e-9)
 
@@ -255,8 +261,7 @@ def test_one_host_thread_several_engines(name):
             assert r.coalescent == pytest.approx(full.coalescent, rel=1e-9)
             assert r.likelihood == pytest.approx(full.likelihood, rel=1e-9)
             assert r.total == pytest.approx(full.total, rel=1e-9)
-            hi_out = len(full.per_locus_lik) if hi == n_loci else hi      # + the morphological partitions on the last shard
-            np.testing.assert_allclose(r.per_locus_lik, full.per_locus_lik[lo:hi_out], rtol=1e-9)
+            np.testing.assert_allclose(r.per_locus_lik, _shard_values(full.per_locus_lik, pb, n_loci, lo, hi), rtol=1e-9)
             if pb.pop_kind == POP_ANALYTIC:
                 np.testing.assert_allclose(r.per_branch, full.per_branch, rtol=1e-9)
         assert res[0].total == res[1].total == res[2].total          # same summation order everywhere
