@@ -202,7 +202,8 @@ SB2_API int sb2_max_height(sb2_engine *e, const uint8_t *leafIsRight, double *ma
  * Canis-Phylogeny.xml:3-23): sequences[tip][site] (0-3, >= 4 missing / ambiguous) -> the unique site columns in
  * lexicographic order (taxon 0 most significant) as patterns[tip][*nPatterns] (compact rows), their multiplicities
  * weights[*nPatterns] and, optionally, siteToPattern[nSites].  Buffers must hold nSites entries per row / array.
- * Feed the result to sb2_add_locus.  At most 16384 sites per call.  Errors: sb2_compress_last_error(). */
+ * Feed the result to sb2_add_locus.  Alignments longer than 16384 sites are sorted in blocks of 16384 columns on the device
+ * and the blocks' pattern lists merged on the host (same result).  Errors: sb2_compress_last_error(). */
 SB2_API int sb2_compress_alignment(int32_t device, int32_t nTips, int32_t nSites, const uint8_t *sequences, uint8_t *patterns,
                                    int32_t *weights, int32_t *siteToPattern, int32_t *nPatterns);
 SB2_API const char *sb2_compress_last_error(void);

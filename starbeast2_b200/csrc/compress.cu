@@ -11,6 +11,8 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
+#include <algorithm>
 
 #include "../../include/sb2gpu.h"
 
@@ -108,16 +110,12 @@ extern "C" {
 
 const char *sb2_compress_last_error(void) { return g_err.c_str(); }
 
-int sb2_compress_alignment(int32_t device, int32_t nTips, int32_t nSites, const uint8_t *sequences, uint8_t *patterns,
-                           int32_t *weights, int32_t *siteToPattern, int32_t *nPatterns)
+// One block of at most MAX_SITES site columns [s0, s0 + nSites) of an alignment whose rows have nSitesTotal entries.
+// patterns: compact rows [tip][*nPatterns] in a buffer whose rows hold patRowCap entries.
+static int compress_block(int32_t device, int32_t nTips, int32_t nSitesTotal, int32_t s0, int32_t nSites, const uint8_t *sequences,
+                          uint8_t *patterns, int32_t *weights, int32_t *siteToPattern, int32_t *nPatterns)
 {
     auto fail = [&](int code, const std::string &m) { g_err = m; return code; };
-    if (nTips < 1 || nSites < 1 || !sequences || !patterns || !weights || !nPatterns) return fail(SB2_ERR_ARG, "bad argument");
-    if (nSites > MAX_SITES) return fail(SB2_ERR_ARG, "alignment longer than 16384 sites: split it or compress on the host");
-    int nDev = 0;
-    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) return fail(SB2_ERR_CUDA, "no CUDA device; libsb2gpu has no CPU fallback");
-    if (device < 0 || device >= nDev) return fail(SB2_ERR_ARG, "device out of range");
-    cudaSetDevice(device);
     const int W = (nTips + 7) / 8;
     int P2 = 2;
     while (P2 < nSites) P2 <<= 1;
@@ -141,7 +139,9 @@ int sb2_compress_alignment(int32_t device, int32_t nTips, int32_t nSites, const 
     int32_t *dW = reinterpret_cast<int32_t *>(arena.base + oW), *dMap = reinterpret_cast<int32_t *>(arena.base + oMap),
             *dN = reinterpret_cast<int32_t *>(arena.base + oN);
     int rc = SB2_OK;
-    if (st == cudaSuccess) st = cudaMemcpy(dSeq, sequences, seqBytes, cudaMemcpyHostToDevice);
+    // the block's columns of every row: host rows have nSitesTotal entries, device rows nSites
+    if (st == cudaSuccess)
+        st = cudaMemcpy2D(dSeq, (size_t)nSites, sequences + s0, (size_t)nSitesTotal, (size_t)nSites, (size_t)nTips, cudaMemcpyHostToDevice);
     if (st == cudaSuccess) {
         const int total = nSites * W;
         k_pack_columns<<<(total + 255) / 256, 256>>>(dSeq, nTips, nSites, W, dKeys);
@@ -162,6 +162,71 @@ int sb2_compress_alignment(int32_t device, int32_t nTips, int32_t nSites, const 
     }
     if (st != cudaSuccess) rc = fail(SB2_ERR_CUDA, cudaGetErrorString(st));
     return rc;
+}
+
+int sb2_compress_alignment(int32_t device, int32_t nTips, int32_t nSites, const uint8_t *sequences, uint8_t *patterns,
+                           int32_t *weights, int32_t *siteToPattern, int32_t *nPatterns)
+{
+    auto fail = [&](int code, const std::string &m) { g_err = m; return code; };
+    if (nTips < 1 || nSites < 1 || !sequences || !patterns || !weights || !nPatterns) return fail(SB2_ERR_ARG, "bad argument");
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) return fail(SB2_ERR_CUDA, "no CUDA device; libsb2gpu has no CPU fallback");
+    if (device < 0 || device >= nDev) return fail(SB2_ERR_ARG, "device out of range");
+    cudaSetDevice(device);
+    if (nSites <= MAX_SITES) return compress_block(device, nTips, nSites, 0, nSites, sequences, patterns, weights, siteToPattern, nPatterns);
+
+    // Long alignments (phylogenomic concatenations): blocks of MAX_SITES columns are sorted and made unique on the device, the
+    // blocks' sorted pattern lists are then merged here (the unique patterns of a block are few next to its sites, and this
+    // is set-up time).  Same result as one pass: sorted unique columns, summed multiplicities, site -> pattern map.
+    const int nBlocks = (nSites + MAX_SITES - 1) / MAX_SITES;
+    std::vector<std::vector<uint8_t>> bPat(nBlocks);
+    std::vector<std::vector<int32_t>> bW(nBlocks), bMap(nBlocks), bGlobal(nBlocks);
+    std::vector<int32_t> bN(nBlocks, 0);
+    for (int b = 0; b < nBlocks; b++) {
+        const int s0 = b * MAX_SITES, n = std::min(MAX_SITES, nSites - s0);
+        bPat[b].resize((size_t)nTips * n); bW[b].resize(n); bMap[b].resize(n);
+        const int rc = compress_block(device, nTips, nSites, s0, n, sequences, bPat[b].data(), bW[b].data(), bMap[b].data(), &bN[b]);
+        if (rc != SB2_OK) return rc;
+        bGlobal[b].resize(bN[b]);
+    }
+    // column i of block b: bPat[b][t * bN[b] + i]; lexicographic order with taxon 0 most significant
+    auto cmp = [&](int b1, int i1, int b2, int i2) {
+        for (int t = 0; t < nTips; t++) {
+            const uint8_t x = bPat[b1][(size_t)t * bN[b1] + i1], y = bPat[b2][(size_t)t * bN[b2] + i2];
+            if (x != y) return x < y ? -1 : 1;
+        }
+        return 0;
+    };
+    std::vector<int32_t> head(nBlocks, 0);
+    std::vector<std::pair<int, int>> order;   // (block, index) of the first occurrence of every global pattern
+    std::vector<int32_t> gW;
+    for (;;) {
+        int best = -1;
+        for (int b = 0; b < nBlocks; b++)
+            if (head[b] < bN[b] && (best < 0 || cmp(b, head[b], best, head[best]) < 0)) best = b;
+        if (best < 0) break;
+        const int bi = head[best];
+        const int32_t g = (int32_t)order.size();
+        order.push_back({best, bi});
+        int32_t w = 0;
+        for (int b = 0; b < nBlocks; b++)
+            if (head[b] < bN[b] && cmp(b, head[b], best, bi) == 0) { w += bW[b][head[b]]; bGlobal[b][head[b]] = g; if (b != best) head[b]++; }
+        head[best]++;
+        gW.push_back(w);
+    }
+    const int32_t nPat = (int32_t)order.size();
+    *nPatterns = nPat;
+    for (int32_t g = 0; g < nPat; g++) {
+        weights[g] = gW[g];
+        const int b = order[g].first, i = order[g].second;
+        for (int t = 0; t < nTips; t++) patterns[(size_t)t * nPat + g] = bPat[b][(size_t)t * bN[b] + i];
+    }
+    if (siteToPattern)
+        for (int b = 0; b < nBlocks; b++) {
+            const int s0 = b * MAX_SITES, n = std::min(MAX_SITES, nSites - s0);
+            for (int j = 0; j < n; j++) siteToPattern[s0 + j] = bGlobal[b][bMap[b][j]];
+        }
+    return SB2_OK;
 }
 
 }  // extern "C"

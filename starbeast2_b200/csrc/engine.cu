@@ -744,9 +744,11 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     {
         int64_t threads1 = 0;
         for (auto &hl : e->loci) if (!hl.d.kStates) threads1 += (int64_t)hl.d.nPat * hl.d.nCat;
-        // measured on B200 (same box A/B): R=2 is 1-6 % faster once the GPU is saturated (C3, C5 shard); small problems
-        // (C2) are latency bound and want as many independent warps as possible
-        e->patPerThread = threads1 > 150000 ? 2 : 1;
+        // measured on B200 (same box A/B, round 2 with aligned rows): R=2 wins from ~100k (pattern, category) lanes up
+        // (C2 x 200 loci = 112k: 30.7 vs 36.9 us; C5 x 103 = 139k: 122.6 vs 134.6; C5 x 2000: 1,961 vs 2,109), R=1 below
+        // (C3 x 50 = 91k: 43.2 vs 44.2; C2 x 100 = 56k: 20.6 vs 21.8; C2 = 28k: 16.7 vs 18.4): small problems are latency
+        // bound and want as many independent warps as possible
+        e->patPerThread = threads1 > 100000 ? 2 : 1;
         e->chunksPerTile = std::max(1, 2 / e->nCat);
         if (const char *v = getenv("SB2_PATTERNS_PER_THREAD")) e->patPerThread = atoi(v);
         if (const char *v = getenv("SB2_CHUNKS_PER_TILE")) e->chunksPerTile = atoi(v);

@@ -24,7 +24,8 @@ def check(mat):
 
 
 @pytest.mark.parametrize("n_tips,n_sites,alphabet", [(1, 1, 4), (2, 7, 2), (16, 1000, 5), (30, 1000, 5), (120, 500, 5), (120, 4097, 3),
-                                                     (9, 16384, 2), (257, 300, 5)])
+                                                     (9, 16384, 2), (257, 300, 5),
+                                                     (2, 16385, 4), (30, 40000, 5), (12, 100000, 3)])   # longer than one block: block sort + merge
 def test_random_alignments_match_numpy_unique(n_tips, n_sites, alphabet):
     rng = np.random.default_rng(n_tips * 100003 + n_sites)
     mat = rng.integers(0, alphabet, size=(n_tips, n_sites)).astype(np.uint8)
@@ -37,8 +38,10 @@ def test_random_alignments_match_numpy_unique(n_tips, n_sites, alphabet):
 def test_degenerate_and_error_cases():
     check(np.zeros((5, 64), np.uint8))                           # every column identical: one pattern of weight 64
     check(np.arange(200, dtype=np.uint8)[None, :].repeat(3, 0))  # every column distinct, bytes above the state range
+    check(np.zeros((2, 16385), np.uint8))                        # one pattern spread over two blocks of the sorter
+    check(np.arange(40000, dtype=np.uint32).view(np.uint8).reshape(-1, 4).T.copy())   # 40,000 distinct columns, three blocks
     with pytest.raises(Sb2Error):
-        compress_alignment(np.zeros((2, 16385), np.uint8))       # longer than the single-CTA sorter takes
+        compress_alignment(np.zeros((2, 0), np.uint8))           # no sites
 
 
 def test_simulated_locus_and_engine_round_trip():
