@@ -550,9 +550,24 @@ int do_walk(sb2_engine *e)
         ev = e->evPool[e->evUsed++];
         CUDA_TRY(e, cudaEventRecord(ev.first, e->stream));
     }
+    static const char *dbgTimesPath = getenv("SB2_DEBUG_WALK_TIMES");   // profiling only: per-tile %globaltimer stamps -> this file
+    static unsigned long long *dDbgTimes = nullptr;
+    static size_t dbgTiles = 0;
+    a.dbgTimes = nullptr;
+    if (dbgTimesPath) {
+        if (dbgTiles < (size_t)e->totalTiles) { if (dDbgTimes) cudaFree(dDbgTimes); cudaMalloc((void **)&dDbgTimes, 64 * (size_t)e->totalTiles); dbgTiles = (size_t)e->totalTiles; }
+        cudaMemsetAsync(dDbgTimes, 0, 64 * (size_t)e->totalTiles, e->stream);
+        a.dbgTimes = dDbgTimes;
+    }
     static const bool skipWalk = getenv("SB2_DEBUG_SKIP_WALK") != nullptr;   // timing experiments only
     if (e->totalTiles == 0) return SB2_OK;   // K-state likelihood-only loci only: nothing for the 4-state pruning kernel
     if (!skipWalk) CUDA_TRY(e, launch_treewalk(a, (int)e->totalTiles, e->cfg.exact_order != 0, e->stream));
+    if (dbgTimesPath && a.dbgTimes) {
+        std::vector<unsigned long long> h(8 * (size_t)e->totalTiles);
+        cudaStreamSynchronize(e->stream);
+        cudaMemcpy(h.data(), dDbgTimes, 64 * (size_t)e->totalTiles, cudaMemcpyDeviceToHost);
+        if (FILE *f = fopen(dbgTimesPath, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+    }
     e->launches++;
     if (e->cfg.profile) CUDA_TRY(e, cudaEventRecord(ev.second, e->stream));
     CUDA_TRY(e, cudaGetLastError());

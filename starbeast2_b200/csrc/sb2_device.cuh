@@ -202,6 +202,8 @@ struct WalkArgs {
     int32_t debugMaxOps;         // timing experiments only (SB2_DEBUG_MAX_OPS): walk at most this many ops per worker; < 0 = all
     const int32_t *laneOps;      // [nLoci][WALK_MAX_WORKERS + 1]
     int32_t ctasPerSM;           // > 0: cap on resident CTAs per SM (see engine.cu: walk_ctas_per_sm)
+    unsigned long long *dbgTimes; // profiling only (SB2_DEBUG_WALK_TIMES): [tile][8] %globaltimer stamps of warp 0 (start, staged, dependency met,
+                                 // walk begins, walk ends, CTA ends), else nullptr
 };
 
 

@@ -78,6 +78,10 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
 {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int tile = blockIdx.x;
+    auto stamp = [&](int i) {   // profiling only
+        if (A.dbgTimes && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); A.dbgTimes[(size_t)tile * 8 + i] = t; }
+    };
+    stamp(0);
     const int l = A.tileLocus[tile];
     const LocusDesc d = A.loci[l];
     const int C = NC ? NC : A.nCat, chunks = NC ? CH : A.chunksPerTile, depth = NC ? DEPTH : A.stackDepth;
@@ -126,7 +130,9 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
         }
     }
     // nOps / ops / opMats are k_prepare's outputs: they must not be touched before that grid has completed
+    stamp(1);
     cudaGridDependencySynchronize();
+    stamp(2);
     cudaTriggerProgrammaticLaunchCompletion();   // the (single-CTA) reduction kernel may queue up behind us already
     const Op *ops = A.ops + d.opBase;
     const double *matStream = A.opMats + ((size_t)d.opBase * C + c) * 32 + lane;   // + k * C*32: this lane's 8 bytes of op k's pair
@@ -204,6 +210,7 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
     cp_async_wait<MAT_RING - 2>();   // group 0 (tip states + op 0's matrices) has landed for this thread ...
     __syncthreads();                 // ... and for everybody else; the op schedule is visible too
 
+    stamp(3);
     for (int k = kBeg; k < kEnd; k++) {
         if (NW == 1 && (k & (OPS_BATCH - 1)) == OPS_BATCH / 2 && (k / OPS_BATCH + 1) * OPS_BATCH < nOps) {
             __syncthreads();                       // every warp has left the previous batch's half
@@ -311,6 +318,7 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
         }
     }
     cp_async_wait<0>();
+    stamp(4);
     __syncthreads();
 
     // root: integratePartials over categories, (+pInv on constant patterns), frequencies, log, pattern weight; then the sum
@@ -337,6 +345,7 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
             if (lane == 0 && ch < d.nChunks) A.chunkSum[d.chunkBase + ch] = contrib;
         }
     }
+    stamp(5);
 }
 
 template <bool EXACT, int R, int MINB, int NC, int CH, int DEPTH, int NW = 1>
