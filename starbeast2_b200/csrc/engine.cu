@@ -76,6 +76,7 @@ struct sb2_engine {
     double *dPartials = nullptr, *dMats = nullptr, *dOpMats = nullptr, *dPatLogL = nullptr, *dChunkSum = nullptr;
     int16_t *dCumExp = nullptr;
     Op *dOps = nullptr;
+    double *dMemo = nullptr;         // analytic closed forms, two-entry memo per species branch (ReduceArgs::memo)
     int32_t *dNOps = nullptr;
     // staged inputs: pinned host mirror + device copy
     LocusParams *hParams = nullptr, *dParams = nullptr;
@@ -258,6 +259,7 @@ ReduceArgs reduce_args(sb2_engine *e, bool coalOnly = false)
     r.nLoci = e->L; r.S = e->S; r.popKind = e->popKind; r.exact = e->cfg.exact_order;
     r.hostOut = e->hOutDev;
     r.hostWords = e->hWordsDev; r.hostTag = 0;
+    r.memo = e->dMemo;
     return r;
 }
 
@@ -941,6 +943,10 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
     if ((rc = dev_alloc(e, &e->dRedOwn, e->nRed))) return rc;
     e->dRed = e->dRedOwn;
     if ((rc = dev_alloc(e, &e->dOut, e->nOut))) return rc;
+    if (!getenv("SB2_NO_MEMO")) {   // A/B knob
+        if ((rc = dev_alloc(e, &e->dMemo, (size_t)MEMO_STRIDE * e->S))) return rc;
+        CUDA_TRY(e, cudaMemset(e->dMemo, 0xFF, sizeof(double) * MEMO_STRIDE * (size_t)e->S));   // keys that match nothing
+    }
     {   // result vector: host memory the kernels write directly (zero-copy), so a download is just a stream sync
         // (one extra slot behind the vector: the peer-exchange wait of the last evaluation, sb2_exchange_wait_us)
         cudaError_t st = cudaHostAlloc((void **)&e->hOut, sizeof(double) * (e->nOut + 1), cudaHostAllocMapped);

@@ -145,35 +145,38 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preCh
         // The three arrays are [locus][branch]: a warp reads whole rows (lanes = 32 consecutive branches: coalesced), warp w
         // the loci l = w (mod warps), several rows in flight; the warps' partial sums then meet in shared memory and are
         // added in warp order.  Fixed shape: deterministic, whatever runs before or after.
-        __shared__ double part[3][8][32];
+        __shared__ double part[3][8][64];
         const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;   // nw <= 8 (RED_THREADS / STEP_THREADS = 256)
-        for (int b0 = 0; b0 < S; b0 += 32) {
-            const int b = b0 + lane;
-            double q = 0.0, g = 0.0, r = 0.0;
-            if (b < S) {
-                int l = warp;
-                for (; l + 3 * nw < L; l += 4 * nw) {   // four rows in flight
-                    double vq[4], vg[4], vr[4];
+        for (int b0 = 0; b0 < S; b0 += 64) {   // two blocks of 32 branches per pass: twice the loads in flight per dependent step
+            const int bA = b0 + lane, bB = b0 + 32 + lane;
+            const bool hasA = bA < S, hasB = bB < S;
+            const int cA = hasA ? bA : 0, cB = hasB ? bB : 0;   // clamped: loads stay unconditional, results are masked
+            double qA = 0.0, gA = 0.0, rA = 0.0, qB = 0.0, gB = 0.0, rB = 0.0;
+            int l = warp;
+            for (; l + 3 * nw < L; l += 4 * nw) {   // four rows in flight
+                double vq[4], vg[4], vr[4], wq[4], wg[4], wr[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const size_t o = (size_t)(l + j * nw) * S + b;
-                        vq[j] = (double)__ldcg(A.cur.brK + o); vg[j] = __ldcg(A.cur.anG + o); vr[j] = __ldcg(A.cur.anR + o);
-                    }
+                for (int j = 0; j < 4; j++) {
+                    const size_t o = (size_t)(l + j * nw) * S;
+                    vq[j] = (double)__ldcg(A.cur.brK + o + cA); vg[j] = __ldcg(A.cur.anG + o + cA); vr[j] = __ldcg(A.cur.anR + o + cA);
+                    wq[j] = (double)__ldcg(A.cur.brK + o + cB); wg[j] = __ldcg(A.cur.anG + o + cB); wr[j] = __ldcg(A.cur.anR + o + cB);
+                }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { q += vq[j]; g += vg[j]; r += vr[j]; }
-                }
-                for (; l < L; l += nw) {
-                    const size_t o = (size_t)l * S + b;
-                    q += (double)__ldcg(A.cur.brK + o); g += __ldcg(A.cur.anG + o); r += __ldcg(A.cur.anR + o);
-                }
+                for (int j = 0; j < 4; j++) { qA += vq[j]; gA += vg[j]; rA += vr[j]; qB += wq[j]; gB += wg[j]; rB += wr[j]; }
             }
-            __syncthreads();   // the previous block of branches has been consumed
-            part[0][warp][lane] = q; part[1][warp][lane] = g; part[2][warp][lane] = r;
+            for (; l < L; l += nw) {
+                const size_t o = (size_t)l * S;
+                qA += (double)__ldcg(A.cur.brK + o + cA); gA += __ldcg(A.cur.anG + o + cA); rA += __ldcg(A.cur.anR + o + cA);
+                qB += (double)__ldcg(A.cur.brK + o + cB); gB += __ldcg(A.cur.anG + o + cB); rB += __ldcg(A.cur.anR + o + cB);
+            }
+            __syncthreads();   // the previous pair of blocks has been consumed
+            part[0][warp][lane] = qA; part[1][warp][lane] = gA; part[2][warp][lane] = rA;
+            part[0][warp][32 + lane] = qB; part[1][warp][32 + lane] = gB; part[2][warp][32 + lane] = rB;
             __syncthreads();
-            if (tid < 96) {
-                const int a = tid >> 5, bb = b0 + (tid & 31);
+            if (tid < 192) {
+                const int a = tid >> 6, bb = b0 + (tid & 63);
                 double sum = 0.0;
-                for (int w = 0; w < nw; w++) sum += part[a][w][tid & 31];
+                for (int w = 0; w < nw; w++) sum += part[a][w][tid & 63];
                 if (bb < S) A.red[3 + 3 * bb + a] = sum;
             }
         }
@@ -182,6 +185,7 @@ __device__ __forceinline__ void reduce_local_body(const ReduceArgs &A, int preCh
     }
 }
 
+constexpr int FINISH_SMEM_TERMS = 512;   // per-branch terms kept in shared memory for the final in-order sum (larger species trees: the rest from HBM)
 // sums3 (optional): the three leading entries of the reduce vector, already in registers (single-GPU, same CTA)
 __device__ __forceinline__ void finish_body(const ReduceArgs &A, const double *sums3 = nullptr)
 {
@@ -191,28 +195,74 @@ __device__ __forceinline__ void finish_body(const ReduceArgs &A, const double *s
     const double lik = sums3 ? sums3[1] : A.red[1];
     const bool incompatible = (sums3 ? sums3[2] : A.red[2]) > 0.0;
     if (A.popKind == 2) {
-        // one warp per species branch (no block barriers on this latency path); the per-branch terms are then added one by
-        // one in node-number order (MultispeciesCoalescent.java:194)
+        __shared__ double sterm[FINISH_SMEM_TERMS];   // per-branch terms for the final in-order sum (larger species trees: the rest from HBM)
+        __shared__ int smiss[FINISH_SMEM_TERMS];      // branches whose term has to be computed
+        __shared__ int s_nMiss;
         const double alpha = A.cur.hyper[0], beta = A.cur.hyper[1];
         const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-        for (int b = warp; b < S; b += nw) {
-            const long long q = (long long)(A.red[3 + 3 * b] + 0.5);
+        const bool useMemo = A.memo != nullptr && S <= FINISH_SMEM_TERMS;
+        if (tid == 0) s_nMiss = 0;
+        __syncthreads();
+        // Phase 1, one THREAD per branch: has this branch's term been computed for exactly these values before?  (keys compared as
+        // bit patterns.)  Every branch's loads are in flight together: ONE round trip for the whole species tree, where a warp
+        // per branch was one round trip per branch.
+        if (useMemo) {
+            const long long ka = __double_as_longlong(alpha), kb = __double_as_longlong(beta);
+            for (int b = tid; b < S; b += nt) {
+                double *m = A.memo + (size_t)MEMO_STRIDE * b;
+                const long long kq = __double_as_longlong(A.red[3 + 3 * b]), kg = __double_as_longlong(A.red[3 + 3 * b + 1]),
+                                kr = __double_as_longlong(A.red[3 + 3 * b + 2]);
+                int hit = -1;
+#pragma unroll
+                for (int en = 1; en >= 0; en--) {
+                    const double *k = m + 6 * en;
+                    if (__double_as_longlong(k[0]) == kq && __double_as_longlong(k[1]) == kg && __double_as_longlong(k[2]) == kr &&
+                        __double_as_longlong(k[3]) == ka && __double_as_longlong(k[4]) == kb) hit = en;
+                }
+                if (hit >= 0) {
+                    const double logP = m[6 * hit + 5];
+                    m[12] = (double)(1 - hit);   // the other entry is the next victim
+                    perBranch[b] = logP; sterm[b] = logP; host_put(A, 3 + 2 * L + b, logP);
+                } else {
+                    smiss[atomicAdd(&s_nMiss, 1)] = b;   // any order: every branch's term is computed independently
+                }
+            }
+            __syncthreads();
+        }
+        // Phase 2, one WARP per branch that missed (all of them without the memo); no block barriers inside
+        const int nWork = useMemo ? s_nMiss : S;
+        for (int i = warp; i < nWork; i += nw) {
+            const int b = useMemo ? smiss[i] : i;
+            const double qd = A.red[3 + 3 * b];
+            const long long q = (long long)(qd + 0.5);
             const double g = A.red[3 + 3 * b + 1], r = A.red[3 + 3 * b + 2];
             double lgr = 0.0;   // logGammaRatio, :227-230
             if (A.exact) {
-                if (lane == 0) for (long long i = 0; i < q; i++) lgr += log(alpha + (double)i);   // the reference's order
+                if (lane == 0) for (long long i2 = 0; i2 < q; i2++) lgr += log(alpha + (double)i2);   // the reference's order
             } else {
-                for (long long i = lane; i < q; i += 32) lgr += log(alpha + (double)i);
+                for (long long i2 = lane; i2 < q; i2 += 32) lgr += log(alpha + (double)i2);
                 for (int off = 16; off > 0; off >>= 1) lgr += __shfl_xor_sync(0xffffffffu, lgr, off);
             }
             const double branchLogR = -r;
-            // explicit roundings: this body is also inlined into k_treewalk, whose translation unit allows FMA contraction
+            // explicit roundings: the result must not depend on the translation unit's FMA contraction setting
             const double logP = __dadd_rn(__dsub_rn(__dadd_rn(branchLogR, __dmul_rn(alpha, log(beta))),
                                                     __dmul_rn(__dadd_rn(alpha, (double)q), log(__dadd_rn(beta, g)))), lgr);   // :232
-            if (lane == 0) { perBranch[b] = logP; host_put(A, 3 + 2 * L + b, logP); }
+            if (lane == 0) {
+                perBranch[b] = logP; host_put(A, 3 + 2 * L + b, logP);
+                if (b < FINISH_SMEM_TERMS) sterm[b] = logP;
+                if (useMemo) {   // into the entry that was not used last
+                    double *m = A.memo + (size_t)MEMO_STRIDE * b;
+                    const int v = (m[12] == 1.0) ? 1 : 0;
+                    double *k = m + 6 * v;
+                    k[0] = qd; k[1] = g; k[2] = r; k[3] = alpha; k[4] = beta; k[5] = logP;
+                    m[12] = (double)(1 - v);
+                }
+            }
         }
         __syncthreads();
-        if (tid == 0) for (int b = 0; b < S; b++) coal += perBranch[b];
+        // node-number order, one by one (MultispeciesCoalescent.java:194) -- from shared memory: read back from the result vector
+        // in HBM, the 47 dependent adds of C4 were 47 dependent L2 round trips
+        if (tid == 0) for (int b = 0; b < S; b++) coal += (b < FINISH_SMEM_TERMS) ? sterm[b] : perBranch[b];
     } else {
         for (int b = tid; b < S; b += nt) { perBranch[b] = 0.0; host_put(A, 3 + 2 * L + b, 0.0); }
     }

@@ -175,7 +175,14 @@ struct ReduceArgs {
     // drain on the host (the flag-in-data idea of the peer-memory all-reduce, pointed at the host).
     unsigned long long *hostWords;
     unsigned long long hostTag;
+    // Analytic mode: a two-entry memo per species branch of the closed form MultispeciesCoalescent.java:227-232, keyed by the VALUES
+    // it is a function of -- {q, gamma, logR, alpha, beta} -> term.  The reference caches a branch's term while nothing it
+    // depends on changes (MultispeciesCoalescent.java:165-195); a memo keyed by value gives the same saving and, being a pure
+    // function's cache, needs no store / restore bookkeeping: after a rejected proposal the restored state's key is simply the
+    // other entry.  16 doubles per branch: {key[5], term} x 2, next victim; nullptr = off.
+    double *memo;
 };
+constexpr int MEMO_STRIDE = 16;
 
 struct WalkArgs {
     const LocusDesc *loci;
