@@ -199,3 +199,43 @@ def test_shapes_beyond_the_cluster_fall_back_to_three_kernels():
     r = e.eval_posterior()
     assert e.launch_count() == 3
     close_to_oracle(r, pb)
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_analytic_closed_form_memo_never_changes_a_bit(fused):
+    """MultispeciesCoalescent.java:165-195 keeps a species branch's term while nothing it depends on changes; here the closed
+    form is memoised per branch by VALUE (two entries).  An engine with the memo and one without (SB2_NO_MEMO) must agree bit
+    for bit through proposals, rejections (the restored key is the other entry), acceptances and hyper-parameter moves."""
+    pb = synth.make_problem("C4", n_loci=12, n_sites=120, n_morph=0)
+    assert pb.pop_kind == POP_ANALYTIC
+    a = engine(pb, fused, SB2_NO_MEMO=None)
+    b = engine(pb, fused, SB2_NO_MEMO=1)
+    same_bits(a.eval_posterior(), b.eval_posterior())
+    rng = np.random.default_rng(11)
+    alpha, beta = pb.alpha, pb.beta
+    for step in range(24):
+        l = int(rng.integers(0, pb.n_loci))
+        loc = pb.loci[l]
+        new_tree, _ = synth.perturb_gene_tree(rng, loc.tree, loc.n_tips)
+        for e in (a, b):
+            e.store()
+            e.set_gene_tree(l, new_tree)
+        if step % 5 == 4:   # populationShape / populationMean move on top
+            alpha, beta = alpha * float(rng.uniform(0.8, 1.25)), beta * float(rng.uniform(0.8, 1.25))
+            for e in (a, b):
+                e.set_pop_model(pb.pop_kind, None, None, alpha, beta)
+        ra, rb = a.eval_posterior(), b.eval_posterior()
+        same_bits(ra, rb)
+        if step % 3 == 0:   # accept
+            loc.tree = new_tree
+            pb.alpha, pb.beta = alpha, beta
+            for e in (a, b):
+                e.accept()
+        else:               # reject: the state -- and the hyper-parameters -- go back
+            alpha, beta = pb.alpha, pb.beta
+            for e in (a, b):
+                e.restore()
+                e.set_pop_model(pb.pop_kind, None, None, alpha, beta)
+            same_bits(a.eval_posterior(), b.eval_posterior())
+    close_to_oracle(a.eval_posterior(), pb)
+    a.close(); b.close()
