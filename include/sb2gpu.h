@@ -159,7 +159,8 @@ SB2_API int sb2_store(sb2_engine *e);
 SB2_API int sb2_restore(sb2_engine *e);
 SB2_API int sb2_accept(sb2_engine *e);
 /* Marks every locus and model dirty so that the next eval recomputes everything from the device-resident state
- * (what BEAST's periodic from-scratch consistency check does; also the bench's "all nodes dirty" regime). */
+ * (what BEAST's periodic from-scratch consistency check does; also the bench's "all nodes dirty" regime).  Nothing cached
+ * counts: the memo of the analytic per-branch closed forms is bypassed (and refilled) by that evaluation too. */
 SB2_API int sb2_mark_all_dirty(sb2_engine *e);
 
 /* ---- read-back for the plugin classes' getters and for parity tests --------------------------------------- */

@@ -112,6 +112,7 @@ struct sb2_engine {
     // dirtiness
     std::vector<uint8_t> treeDirty, modelDirty, clockDirty;
     bool speciesDirty = true, catDirty = true, paramsDirty = true, explicitDirty = false, forceAll = true;
+    bool memoFlush = false;          // sb2_mark_all_dirty: the next closed forms are all recomputed (see ReduceArgs::memoFlush)
     bool needPrepare = true, walkPending = false, tilesValid = false, reduced = false;
     // lazy store(): the physical copy cur -> stored is owed until the next k_prepare, which does it for the few loci that
     // differ (`diffLoci`: changed since the blocks were last equal) -- or the host copies the whole block when everything differs
@@ -259,7 +260,7 @@ ReduceArgs reduce_args(sb2_engine *e, bool coalOnly = false)
     r.nLoci = e->L; r.S = e->S; r.popKind = e->popKind; r.exact = e->cfg.exact_order;
     r.hostOut = e->hOutDev;
     r.hostWords = e->hWordsDev; r.hostTag = 0;
-    r.memo = e->dMemo;
+    r.memo = e->dMemo; r.memoFlush = e->memoFlush ? 1 : 0; r.pad2 = 0;
     return r;
 }
 
@@ -468,6 +469,7 @@ int do_prepare(sb2_engine *e, bool allowFused = false, bool *didFused = nullptr)
             CUDA_TRY(e, cudaEventRecord(ev.first, st));
         }
         CUDA_TRY(e, launch_step(sa, nClusters, runCluster, st));
+        e->memoFlush = false;
         if (e->cfg.profile) CUDA_TRY(e, cudaEventRecord(ev.second, st));
     } else {
         CUDA_TRY(e, launch_prepare(a, e->maxNodes, st));
@@ -521,6 +523,7 @@ int launch_final(sb2_engine *e, const ReduceArgs &r)
     } else {
         CUDA_TRY(e, launch_reduce_finish(r, e->stream, &e->launches));
     }
+    e->memoFlush = false;
     return SB2_OK;
 }
 
@@ -1157,6 +1160,7 @@ int sb2_eval_end(sb2_engine *e, double *perLocusCoal, double *perLocusLik, doubl
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
     if (!e->reduced) return e->fail(SB2_ERR_STATE, "sb2_eval_end without sb2_eval_begin");
     CUDA_TRY(e, launch_finish(reduce_args(e), e->stream, &e->launches));
+    e->memoFlush = false;
     e->pollTag = 0;
     int rc = download(e);
     if (rc) return rc;
@@ -1374,7 +1378,7 @@ int sb2_mark_all_dirty(sb2_engine *e)
 {
     if (e) cudaSetDevice(e->cfg.device);   // several engines (one per GPU) may be driven by one host thread
     if (!e || !e->finalized) return e ? e->fail(SB2_ERR_STATE, "engine not finalized") : SB2_ERR_ARG;
-    e->forceAll = true; e->needPrepare = true;
+    e->forceAll = true; e->needPrepare = true; e->memoFlush = true;
     return SB2_OK;
 }
 

@@ -19,11 +19,12 @@
 namespace sb2 {
 
 constexpr int KS_THREADS = 128;
+constexpr int KS_SMEM_PATTERNS = 1024;   // pattern log-likelihoods kept in shared memory for the closing sum
 
 constexpr size_t KS_SCRATCH_SMEM_MAX = 96 * 1024;   // per-locus partials + exponents up to this size live in shared memory
 
 struct KsSmem {
-    size_t gH, gP, gL, gR, order, stack, mats, scr, total;
+    size_t gH, gP, gL, gR, order, stack, mats, scr, spl, total;
 };
 // scratchBytes: size of the shared-memory partials scratch (the largest locus that fits KS_SCRATCH_SMEM_MAX, see
 // kstate_scratch_bytes); the carve is the same for every K of one launch except for the two trailing regions
@@ -34,6 +35,7 @@ __host__ __device__ inline KsSmem ks_carve(int G, int C, int K, size_t scratchBy
     auto take = [&](size_t b) { size_t r = o; o += (b + 15) & ~size_t(15); return r; };
     m.gH = take(8ull * G); m.gP = take(4ull * G); m.gL = take(4ull * G); m.gR = take(4ull * G);
     m.order = take(4ull * G); m.stack = take(4ull * G);
+    m.spl = take(8ull * KS_SMEM_PATTERNS);   // pattern log-likelihoods for the closing sum
     m.scr = take(scratchBytes);
     m.mats = take(8ull * G * C * K * K);
     m.total = o;
@@ -117,6 +119,7 @@ __device__ __forceinline__ void kstate_locus(const KStateArgs &A, int l, const L
     double *scr = inSmem ? reinterpret_cast<double *>(smem + m.scr) : A.scratch + d.kBase;
     int32_t *scrE = inSmem ? reinterpret_cast<int32_t *>(smem + m.scr + 8 * K * nElem) : A.scratchExp + d.kBase / K;
     const double *props = A.catProps + d.catBase;
+    double *spl = reinterpret_cast<double *>(smem + m.spl);
     for (int p = tid; p < nPat; p += nt) {
         double acc[K];
         int E = 0;
@@ -183,21 +186,24 @@ __device__ __forceinline__ void kstate_locus(const KStateArgs &A, int l, const L
         double sum = 0.0;
 #pragma unroll
         for (int i = 0; i < K; i++) sum += freqs[i] * acc[i];
-        A.patLogL[d.patBase + p] = (E > -1000) ? log(ldexp(sum, E)) : (log(sum) + E * 0.6931471805599453);
+        const double lk = (E > -1000) ? log(ldexp(sum, E)) : (log(sum) + E * 0.6931471805599453);
+        A.patLogL[d.patBase + p] = lk;
+        if (p < KS_SMEM_PATTERNS) spl[p] = lk;   // the closing sum reads it back from shared memory, not through L2 one dependent round trip at a time
     }
     __syncthreads();
     if (tid == 0) {   // TreeLikelihood.calcLogP, with Alignment.getAscertainmentCorrection when patterns are excluded
-        const double *pl = A.patLogL + d.patBase;
+        const double *plG = A.patLogL + d.patBase;
+        auto pl = [&](int k) { return k < KS_SMEM_PATTERNS ? spl[k] : plG[k]; };
         const int32_t *w = A.weights + d.patBase;
         double logP = 0.0;
         if (d.nExcl > 0) {
             double excludeProb = 0.0, returnProb = 1.0;
-            for (int i = 0; i < d.nExcl; i++) excludeProb += exp(pl[A.excluded[d.exclBase + i]]);
+            for (int i = 0; i < d.nExcl; i++) excludeProb += exp(pl(A.excluded[d.exclBase + i]));
             returnProb -= excludeProb;
             const double corr = log(returnProb);
-            for (int k = 0; k < nPat; k++) logP += (pl[k] - corr) * w[k];
+            for (int k = 0; k < nPat; k++) logP += (pl(k) - corr) * w[k];
         } else {
-            for (int k = 0; k < nPat; k++) logP += pl[k] * w[k];
+            for (int k = 0; k < nPat; k++) logP += pl(k) * w[k];
         }
         A.cur.logL[l] = logP;
     }
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(KS_THREADS) k_kstate(KStateArgs A)
 cudaError_t launch_kstate(const KStateArgs &a, int nK, int maxK, cudaStream_t st)
 {
     const size_t smem = kstate_smem_bytes(a.maxNodes, a.maxCat, maxK, a.smemScratch);
-    static size_t configured[MAX_DEVICES] = {};
+    static size_t configured[MAX_DEVICES + 1] = {};
     cudaError_t rc = ensure_dynamic_smem(k_kstate, smem, configured);
     if (rc != cudaSuccess) return rc;
     k_kstate<<<nK, KS_THREADS, smem, st>>>(a);

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(PrepareArgs A, int max
 cudaError_t launch_prepare(const PrepareArgs &a, int maxNodes, cudaStream_t st)
 {
     const size_t smem = prepare_smem_bytes(maxNodes, a.S);
-    static size_t configured[MAX_DEVICES] = {};
+    static size_t configured[MAX_DEVICES + 1] = {};
     cudaError_t rc = ensure_dynamic_smem(k_prepare, smem, configured);
     if (rc != cudaSuccess) return rc;
     k_prepare<<<a.nLoci, PREP_THREADS, smem, st>>>(a, maxNodes);

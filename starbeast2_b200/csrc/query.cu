@@ -87,7 +87,7 @@ cudaError_t launch_tip_class_query(const QueryArgs &a, int nLoci, cudaStream_t s
 {
     const size_t smem = 8 * (size_t)a.maxNodes;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t configured[MAX_DEVICES] = {};
+    static size_t configured[MAX_DEVICES + 1] = {};
     cudaError_t rc = ensure_dynamic_smem(k_tip_class_query, smem, configured);
     if (rc != cudaSuccess) return rc;
     k_tip_class_query<<<nLoci, QUERY_THREADS, smem, st>>>(a);

@@ -200,7 +200,7 @@ __device__ __forceinline__ void finish_body(const ReduceArgs &A, const double *s
         __shared__ int s_nMiss;
         const double alpha = A.cur.hyper[0], beta = A.cur.hyper[1];
         const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-        const bool useMemo = A.memo != nullptr && S <= FINISH_SMEM_TERMS;
+        const bool useMemo = A.memo != nullptr && S <= FINISH_SMEM_TERMS;   // (branch numbers travel in 16 bits below)
         if (tid == 0) s_nMiss = 0;
         __syncthreads();
         // Phase 1, one THREAD per branch: has this branch's term been computed for exactly these values before?  (keys compared as
@@ -219,12 +219,16 @@ __device__ __forceinline__ void finish_body(const ReduceArgs &A, const double *s
                     if (__double_as_longlong(k[0]) == kq && __double_as_longlong(k[1]) == kg && __double_as_longlong(k[2]) == kr &&
                         __double_as_longlong(k[3]) == ka && __double_as_longlong(k[4]) == kb) hit = en;
                 }
-                if (hit >= 0) {
+                if (hit >= 0 && !A.memoFlush) {
                     const double logP = m[6 * hit + 5];
                     m[12] = (double)(1 - hit);   // the other entry is the next victim
                     perBranch[b] = logP; sterm[b] = logP; host_put(A, 3 + 2 * L + b, logP);
                 } else {
-                    smiss[atomicAdd(&s_nMiss, 1)] = b;   // any order: every branch's term is computed independently
+                    // to be computed (any order: every branch's term is independent); the entry it will be written to is chosen
+                    // here, where the memo's words are already in registers: the one that holds this key (forced recomputation),
+                    // else the one that was not used last
+                    const int v = hit >= 0 ? hit : ((m[12] == 1.0) ? 1 : 0);
+                    smiss[atomicAdd(&s_nMiss, 1)] = b | (v << 16);
                 }
             }
             __syncthreads();
@@ -232,7 +236,7 @@ __device__ __forceinline__ void finish_body(const ReduceArgs &A, const double *s
         // Phase 2, one WARP per branch that missed (all of them without the memo); no block barriers inside
         const int nWork = useMemo ? s_nMiss : S;
         for (int i = warp; i < nWork; i += nw) {
-            const int b = useMemo ? smiss[i] : i;
+            const int b = useMemo ? (smiss[i] & 0xffff) : i, victim = useMemo ? (smiss[i] >> 16) : 0;
             const double qd = A.red[3 + 3 * b];
             const long long q = (long long)(qd + 0.5);
             const double g = A.red[3 + 3 * b + 1], r = A.red[3 + 3 * b + 2];
@@ -250,12 +254,11 @@ __device__ __forceinline__ void finish_body(const ReduceArgs &A, const double *s
             if (lane == 0) {
                 perBranch[b] = logP; host_put(A, 3 + 2 * L + b, logP);
                 if (b < FINISH_SMEM_TERMS) sterm[b] = logP;
-                if (useMemo) {   // into the entry that was not used last
+                if (useMemo) {   // refill the entry chosen in phase 1
                     double *m = A.memo + (size_t)MEMO_STRIDE * b;
-                    const int v = (m[12] == 1.0) ? 1 : 0;
-                    double *k = m + 6 * v;
+                    double *k = m + 6 * victim;
                     k[0] = qd; k[1] = g; k[2] = r; k[3] = alpha; k[4] = beta; k[5] = logP;
-                    m[12] = (double)(1 - v);
+                    m[12] = (double)(1 - victim);
                 }
             }
         }

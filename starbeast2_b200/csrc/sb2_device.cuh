@@ -181,6 +181,8 @@ struct ReduceArgs {
     // function's cache, needs no store / restore bookkeeping: after a rejected proposal the restored state's key is simply the
     // other entry.  16 doubles per branch: {key[5], term} x 2, next victim; nullptr = off.
     double *memo;
+    int32_t memoFlush;   // 1: sb2_mark_all_dirty -- "recompute everything": no memo hit counts this time (entries are refilled)
+    int32_t pad2;
 };
 constexpr int MEMO_STRIDE = 16;
 
@@ -307,9 +309,18 @@ cudaError_t launch_reduce_finish(const ReduceArgs &a, cudaStream_t st, int64_t *
 // (INTEGRATION.md section 4), so the opt-in above 48 KB is cached per (kernel instantiation, device), never per process.
 constexpr int MAX_DEVICES = 64;
 template <typename K>
-inline cudaError_t ensure_dynamic_smem(K kernel, size_t smem, size_t (&configured)[MAX_DEVICES])
+inline cudaError_t ensure_dynamic_smem(K kernel, size_t smem, size_t (&configured)[MAX_DEVICES + 1])
 {
-    if (smem <= 48 * 1024) return cudaSuccess;
+    // the 48 KB a launch gets without opting in cover the kernel's STATIC shared memory too
+    // (cached behind the per-device entries of the call site's array, as bytes + 1: the template is instantiated per kernel
+    // TYPE, and kernels of one signature share it)
+    if (configured[MAX_DEVICES] == 0) {
+        cudaFuncAttributes fa;
+        const cudaError_t fst = cudaFuncGetAttributes(&fa, kernel);
+        if (fst != cudaSuccess) return fst;
+        configured[MAX_DEVICES] = fa.sharedSizeBytes + 1;
+    }
+    if (smem + (configured[MAX_DEVICES] - 1) <= 48 * 1024) return cudaSuccess;
     int dev = 0;
     cudaError_t st = cudaGetDevice(&dev);
     if (st != cudaSuccess) return st;

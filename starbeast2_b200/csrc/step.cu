@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) k_step(const __grid_constant_
 cudaError_t launch_step(const StepArgs &a, int nClusters, int clusterSize, cudaStream_t st)
 {
     const size_t smem = step_smem_bytes(a.maxNodes, a.prep.S, a.nCat, a.stackDepth, a.maxTips);
-    static size_t configured[MAX_DEVICES] = {};
+    static size_t configured[MAX_DEVICES + 1] = {};
     static bool nonPortable[MAX_DEVICES] = {};
     cudaError_t rc = ensure_dynamic_smem(k_step, smem, configured);
     if (rc != cudaSuccess) return rc;

@@ -353,7 +353,7 @@ static cudaError_t launch_one(const WalkArgs &a, int nTiles, size_t smem, int th
 {
     // resident CTAs per SM can be capped by padding the dynamic shared memory (WalkArgs::ctasPerSM, 0 = whatever fits)
     if (a.ctasPerSM > 0) smem = std::max(smem, (size_t)(227 * 1024 / a.ctasPerSM - 1024) & ~size_t(15));
-    static size_t configured[MAX_DEVICES] = {};
+    static size_t configured[MAX_DEVICES + 1] = {};
     cudaError_t rc = ensure_dynamic_smem(k_treewalk<EXACT, R, MINB, NC, CH, DEPTH, NW>, smem, configured);
     if (rc != cudaSuccess) return rc;
     cudaLaunchConfig_t cfg{};
