@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(NC ? 32 * NC * CH * NW : 256, MINB) k_treewalk
         if (A.dbgTimes && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); A.dbgTimes[(size_t)tile * 8 + i] = t; }
     };
     stamp(0);
+    if (A.dbgTimes && threadIdx.x == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); A.dbgTimes[(size_t)tile * 8 + 6] = sm; }
     const int l = A.tileLocus[tile];
     const LocusDesc d = A.loci[l];
     const int C = NC ? NC : A.nCat, chunks = NC ? CH : A.chunksPerTile, depth = NC ? DEPTH : A.stackDepth;
