@@ -18,13 +18,14 @@
 
 namespace sb2 {
 
-constexpr int KS_THREADS = 128;
+constexpr int KS_THREADS = 256;   // 32 groups of 8 lanes: the usual tens of characters take one pass of the walk
 constexpr int KS_SMEM_PATTERNS = 1024;   // pattern log-likelihoods kept in shared memory for the closing sum
+constexpr int KS_SMEM_TIP_BYTES = 16 * 1024;   // tip states staged in shared memory up to this size (a tip op's state byte is on the walk's critical path)
 
 constexpr size_t KS_SCRATCH_SMEM_MAX = 96 * 1024;   // per-locus partials + exponents up to this size live in shared memory
 
 struct KsSmem {
-    size_t gH, gP, gL, gR, order, stack, mats, scr, spl, total;
+    size_t gH, gP, gL, gR, order, stack, mats, scr, spl, tips, total;
 };
 // scratchBytes: size of the shared-memory partials scratch (the largest locus that fits KS_SCRATCH_SMEM_MAX, see
 // kstate_scratch_bytes); the carve is the same for every K of one launch except for the two trailing regions
@@ -36,6 +37,7 @@ __host__ __device__ inline KsSmem ks_carve(int G, int C, int K, size_t scratchBy
     m.gH = take(8ull * G); m.gP = take(4ull * G); m.gL = take(4ull * G); m.gR = take(4ull * G);
     m.order = take(4ull * G); m.stack = take(4ull * G);
     m.spl = take(8ull * KS_SMEM_PATTERNS);   // pattern log-likelihoods for the closing sum
+    m.tips = take(KS_SMEM_TIP_BYTES);        // the locus's tip states [tip][pattern] when they fit
     m.scr = take(scratchBytes);
     m.mats = take(8ull * G * C * K * K);
     m.total = o;
@@ -59,7 +61,14 @@ __device__ __forceinline__ void kstate_locus(const KStateArgs &A, int l, const L
     double *mats = reinterpret_cast<double *>(smem + m.mats);   // [node][category][K*K]
     __shared__ LocusParams prm;
     __shared__ int s_root;
+    // tip states: staged in shared memory when they fit (tens of tips x tens of characters) -- read from HBM inside the walk,
+    // every tip op was a dependent L2 round trip (8 of the kernel's 38 us); fetched in the same wave of loads as the tree
+    const uint8_t *gStates = A.tipStates + d.stateBase;
+    uint8_t *sStates = smem + m.tips;
+    const bool tipsInSmem = (size_t)nT * nPat <= KS_SMEM_TIP_BYTES;
     {
+        if (tipsInSmem)
+            for (int idx = tid; idx < nT * nPat; idx += nt) { const int t = idx / nPat, p = idx - t * nPat; sStates[idx] = gStates[(size_t)t * d.stateStride + p]; }
         constexpr int NP = (int)(sizeof(LocusParams) / 8);
         const double *src = reinterpret_cast<const double *>(&A.params[l]);
         double *dst = reinterpret_cast<double *>(&prm);
@@ -85,7 +94,9 @@ __device__ __forceinline__ void kstate_locus(const KStateArgs &A, int l, const L
     }
     // GeneralSubstitutionModel.getTransitionProbabilities per (branch, category): |V exp(d L) V^-1|
     const double *Eval = prm.subst, *Evec = prm.subst + K, *Ievc = prm.subst + K + KK, *freqs = prm.subst + K + 2 * KK;
-    for (int idx = tid; idx < G * C; idx += nt) {
+    // (warps 1.. : thread 0 is busy with the post-order meanwhile)
+    for (int idx = tid - 32; idx < G * C; idx += nt - 32) {
+        if (idx < 0) break;
         const int i = idx / C, c = idx - i * C;
         double *M = mats + (size_t)idx * KK;
         if (gP[i] < 0) { for (int q = 0; q < KK; q++) M[q] = 0.0; continue; }
@@ -111,85 +122,87 @@ __device__ __forceinline__ void kstate_locus(const KStateArgs &A, int l, const L
     }
     __syncthreads();
 
-    const uint8_t *states = A.tipStates + d.stateBase;
+    // tip states: staged in shared memory when they fit (tens of tips x tens of characters) -- read from HBM inside the walk,
+    // every tip op was a dependent L2 round trip
     // partials [internal][category][pattern][K] and exponents [internal][category][pattern]: in shared memory when the locus
     // fits (the usual case: tens of characters x tens of tips), else in the HBM scratch; only this thread touches its pattern's
     const size_t nElem = (size_t)nI * C * nPat;
     const bool inSmem = ks_locus_scratch(nI, C, nPat, K) <= A.smemScratch;
-    double *scr = inSmem ? reinterpret_cast<double *>(smem + m.scr) : A.scratch + d.kBase;
-    int32_t *scrE = inSmem ? reinterpret_cast<int32_t *>(smem + m.scr + 8 * K * nElem) : A.scratchExp + d.kBase / K;
     const double *props = A.catProps + d.catBase;
     double *spl = reinterpret_cast<double *>(smem + m.spl);
-    for (int p = tid; p < nPat; p += nt) {
-        double acc[K];
-        int E = 0;
-        for (int c = 0; c < C; c++) {
-            // one post-order pass for this (pattern, category)
-            for (int oi = 0; oi < nI; oi++) {
-                const int v = order[oi], c1 = gL[v], c2 = gR[v];
-                const double *m1 = mats + ((size_t)c1 * C + c) * KK, *m2 = mats + ((size_t)c2 * C + c) * KK;
-                double out[K];
-                int cum = 0;
+    // Eight lanes per pattern, lane i < K computes output state i: an op's K x K contraction is K chains of K terms side by side
+    // instead of one thread's K * K -- the walk is a chain of nInt dependent ops per pattern, and its latency, not its work, is
+    // what this kernel costs.  Same association per output state as a one-thread walk: not a bit changes.
+    auto walk = [&](double *scr, int32_t *scrE) {
+        const int grp = tid >> 3, i = tid & 7, nGrp = nt >> 3;
+        const bool lane_on = i < K;
+        const int ii = lane_on ? i : 0;
+        for (int p0 = 0; p0 < nPat; p0 += nGrp) {   // uniform trip count: every lane takes part in the shuffles
+            const int p = p0 + grp;
+            const bool on = p < nPat;
+            const int pp = on ? p : 0;
+            for (int c = 0; c < C; c++) {
+                // one post-order pass for this (pattern, category)
+                for (int oi = 0; oi < nI; oi++) {
+                    const int v = order[oi], c1 = gL[v], c2 = gR[v];
+                    double out = 1.0;
+                    int cum = 0;
 #pragma unroll
-                for (int side = 0; side < 2; side++) {
-                    const int ch = side ? c2 : c1;
-                    const double *M = side ? m2 : m1;
-                    if (ch < nT) {
-                        const int st = states[(size_t)ch * d.stateStride + p];
-#pragma unroll
-                        for (int i = 0; i < K; i++) {
-                            const double f = (st < K) ? M[i * K + st] : 1.0;    // gap / '?': factor 1
-                            out[i] = side ? out[i] * f : f;
-                        }
-                    } else {
-                        const size_t e = ((size_t)(ch - nT) * C + c) * nPat + p;
-                        double a[K];
-#pragma unroll
-                        for (int j = 0; j < K; j++) a[j] = scr[e * K + j];
-                        cum += scrE[e];
-#pragma unroll
-                        for (int i = 0; i < K; i++) {
+                    for (int side = 0; side < 2; side++) {
+                        const int ch = side ? c2 : c1;
+                        const double *M = mats + ((size_t)ch * C + c) * KK + ii * K;   // row ii of the child's matrix
+                        if (ch < nT) {
+                            const int st = tipsInSmem ? sStates[ch * nPat + pp] : gStates[(size_t)ch * d.stateStride + pp];
+                            const double f = (st < K) ? M[st] : 1.0;    // gap / '?': factor 1
+                            out = side ? out * f : f;
+                        } else {
+                            const size_t e = ((size_t)(ch - nT) * C + c) * nPat + pp;
+                            cum += scrE[e];
                             double sum = 0.0;
 #pragma unroll
-                            for (int j = 0; j < K; j++) sum += M[i * K + j] * a[j];
-                            out[i] = side ? out[i] * sum : sum;
+                            for (int j = 0; j < K; j++) sum += M[j] * scr[e * K + j];
+                            out = side ? out * sum : sum;
                         }
                     }
+                    // exact power-of-two rescale (partials are non-negative: the largest has the largest high word)
+                    int hmax = lane_on ? __double2hiint(out) : 0;
+#pragma unroll
+                    for (int off = 4; off > 0; off >>= 1) hmax = max(hmax, __shfl_xor_sync(0xffffffffu, hmax, off, 8));
+                    int field = hmax >> 20;
+                    if (field <= 0 || field > 1023) field = 1023;
+                    const double scale = __hiloint2double((2046 - field) << 20, 0);
+                    const size_t e = ((size_t)(v - nT) * C + c) * nPat + pp;
+                    if (on && lane_on) scr[e * K + i] = out * scale;
+                    if (on && i == 0) scrE[e] = cum + field - 1023;
+                    __syncwarp();   // the group's K values and the exponent are visible to its lanes before the parent reads them
                 }
-                // exact power-of-two rescale (partials are non-negative: the largest has the largest high word)
-                int hmax = 0;
+            }
+            // integratePartials over the categories at a common exponent, frequencies, log
+            const size_t r0 = (size_t)(root - nT) * C * nPat + pp;
+            int E = -2147483647;
+            for (int c = 0; c < C; c++) E = max(E, scrE[r0 + (size_t)c * nPat]);
+            double acc = 0.0;
+            for (int c = 0; c < C; c++) {
+                const size_t e = r0 + (size_t)c * nPat;
+                const int diff = scrE[e] - E;
+                const double f = (diff < -1022) ? 0.0 : __hiloint2double((1023 + diff) << 20, 0);
+                const double v = scr[e * K + ii] * f * props[c];
+                acc = (c == 0) ? v : acc + v;
+            }
+            const double term = freqs[ii] * acc;
+            double sum = 0.0;
 #pragma unroll
-                for (int i = 0; i < K; i++) hmax = max(hmax, __double2hiint(out[i]));
-                int field = hmax >> 20;
-                if (field <= 0 || field > 1023) field = 1023;
-                const double scale = __hiloint2double((2046 - field) << 20, 0);
-                const size_t e = ((size_t)(v - nT) * C + c) * nPat + p;
-#pragma unroll
-                for (int i = 0; i < K; i++) scr[e * K + i] = out[i] * scale;
-                scrE[e] = cum + field - 1023;
+            for (int s2 = 0; s2 < K; s2++) sum += __shfl_sync(0xffffffffu, term, (tid & 24) + s2);   // states in order, as a single thread adds them
+            if (on && i == 0) {
+                const double lk = (E > -1000) ? log(ldexp(sum, E)) : (log(sum) + E * 0.6931471805599453);
+                A.patLogL[d.patBase + p] = lk;
+                if (p < KS_SMEM_PATTERNS) spl[p] = lk;   // the closing sum reads it back from shared memory, not through L2
             }
         }
-        // integratePartials over the categories at a common exponent, frequencies, log
-        const size_t r0 = (size_t)(root - nT) * C * nPat + p;
-        E = -2147483647;
-        for (int c = 0; c < C; c++) E = max(E, scrE[r0 + (size_t)c * nPat]);
-        for (int c = 0; c < C; c++) {
-            const size_t e = r0 + (size_t)c * nPat;
-            const int diff = scrE[e] - E;
-            const double f = (diff < -1022) ? 0.0 : __hiloint2double((1023 + diff) << 20, 0);
-#pragma unroll
-            for (int i = 0; i < K; i++) {
-                const double v = scr[e * K + i] * f * props[c];
-                acc[i] = (c == 0) ? v : acc[i] + v;
-            }
-        }
-        double sum = 0.0;
-#pragma unroll
-        for (int i = 0; i < K; i++) sum += freqs[i] * acc[i];
-        const double lk = (E > -1000) ? log(ldexp(sum, E)) : (log(sum) + E * 0.6931471805599453);
-        A.patLogL[d.patBase + p] = lk;
-        if (p < KS_SMEM_PATTERNS) spl[p] = lk;   // the closing sum reads it back from shared memory, not through L2 one dependent round trip at a time
-    }
+    };
+    // two instantiations of the walk: the scratch in shared memory (LDS / STS) or in HBM -- one generic pointer would make every access generic
+    if (inSmem) walk(reinterpret_cast<double *>(smem + m.scr), reinterpret_cast<int32_t *>(smem + m.scr + 8 * K * nElem));
+    else walk(A.scratch + d.kBase, A.scratchExp + d.kBase / K);
     __syncthreads();
     if (tid == 0) {   // TreeLikelihood.calcLogP, with Alignment.getAscertainmentCorrection when patterns are excluded
         const double *plG = A.patLogL + d.patBase;
