@@ -299,10 +299,18 @@ __device__ __forceinline__ void xgpu_exchange_body(const ReduceArgs &A, const Co
     __syncthreads();
     unsigned long long waitT0 = 0;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(waitT0));
-    for (int i = tid; i < n; i += nt) {
-        double sum = 0.0;
-        const long long t0 = clock64();
-        for (int r = 0; r < nR; r++) {   // rank order: every rank adds the same numbers in the same order
+    // One thread per (element, rank) word pair: every rank's words are polled at the same time (one L2 round trip for all of
+    // them once they are there, instead of one per rank in turn); the ranks of an element sit in neighbouring lanes and are
+    // added in rank order by shuffles -- every rank adds the same numbers in the same order.
+    int nRp = 1;
+    while (nRp < nR) nRp <<= 1;          // lanes per element: a power of two <= COMM_MAX_RANKS (16), so groups never straddle a warp
+    const int lane = tid & 31;
+    for (int base = 0; base < n * nRp; base += nt) {   // uniform trip count: all lanes take part in the shuffles
+        const int p = base + tid, i = p / nRp, r = p - i * nRp;
+        const bool act = i < n && r < nR;
+        double v = 0.0;
+        if (act) {
+            const long long t0 = clock64();
             const volatile unsigned long long *src = Cm.peerSlots[Cm.rank] + (((size_t)half * COMM_MAX_RANKS + r) * n + i) * 2;
             unsigned long long w0, w1;
             for (;;) {
@@ -310,9 +318,13 @@ __device__ __forceinline__ void xgpu_exchange_body(const ReduceArgs &A, const Co
                 if ((w0 & 0xffffffff00000000ull) == tag && (w1 & 0xffffffff00000000ull) == tag) break;
                 if (clock64() - t0 > 4000000000ll) { s_poison = 1; w0 = w1 = 0; break; }   // ~2 s at 2 GHz: a peer is gone
             }
-            sum += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+            v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
         }
-        A.red[i] = sum;
+        __syncwarp();
+        const int g0 = lane & ~(nRp - 1);
+        double sum = __shfl_sync(0xffffffffu, v, g0);
+        for (int rr = 1; rr < nR; rr++) sum += __shfl_sync(0xffffffffu, v, g0 + rr);
+        if (act && r == 0) A.red[i] = sum;
     }
     __threadfence_block();
     __syncthreads();
