@@ -268,7 +268,10 @@ ReduceArgs reduce_args(sb2_engine *e, bool coalOnly = false)
 void arm_poll(sb2_engine *e, ReduceArgs &r)
 {
     e->pollTag = 0;
-    if (!e->pollOk || e->commConnected) return;
+    // (with peers connected too: the words are written after the exchange; a rank whose host has its result can be at most one
+    // evaluation ahead of a peer, which the exchange's alternating buffer halves already allow for)
+    static const bool pollUnderComm = getenv("SB2_NO_POLL_COMM") == nullptr;   // A/B knob
+    if (!e->pollOk || (e->commConnected && !pollUnderComm)) return;
     e->pollSeq++;
     e->pollTag = (0x80000000ull | (e->pollSeq & 0x7fffffffull)) << 32;
     r.hostTag = e->pollTag;
