@@ -76,6 +76,7 @@ struct sb2_engine {
     double *dPartials = nullptr, *dMats = nullptr, *dOpMats = nullptr, *dPatLogL = nullptr, *dChunkSum = nullptr;
     int16_t *dCumExp = nullptr;
     Op *dOps = nullptr;
+    unsigned long long *dDbgTimes = nullptr;   // SB2_DEBUG_WALK_TIMES: per-tile stamps of the pruning kernel (profiling only)
     double *dMemo = nullptr;         // analytic closed forms, two-entry memo per species branch (ReduceArgs::memo)
     int32_t *dNOps = nullptr;
     // staged inputs: pinned host mirror + device copy
@@ -559,13 +560,11 @@ int do_walk(sb2_engine *e)
         CUDA_TRY(e, cudaEventRecord(ev.first, e->stream));
     }
     static const char *dbgTimesPath = getenv("SB2_DEBUG_WALK_TIMES");   // profiling only: per-tile %globaltimer stamps -> this file
-    static unsigned long long *dDbgTimes = nullptr;
-    static size_t dbgTiles = 0;
     a.dbgTimes = nullptr;
-    if (dbgTimesPath) {
-        if (dbgTiles < (size_t)e->totalTiles) { if (dDbgTimes) cudaFree(dDbgTimes); cudaMalloc((void **)&dDbgTimes, 64 * (size_t)e->totalTiles); dbgTiles = (size_t)e->totalTiles; }
-        cudaMemsetAsync(dDbgTimes, 0, 64 * (size_t)e->totalTiles, e->stream);
-        a.dbgTimes = dDbgTimes;
+    if (dbgTimesPath && e->totalTiles > 0) {
+        if (!e->dDbgTimes) { int rc = dev_alloc(e, &e->dDbgTimes, 8 * (size_t)e->totalTiles); if (rc) return rc; }   // the engine's own: freed with it
+        CUDA_TRY(e, cudaMemsetAsync(e->dDbgTimes, 0, 64 * (size_t)e->totalTiles, e->stream));
+        a.dbgTimes = e->dDbgTimes;
     }
     static const bool skipWalk = getenv("SB2_DEBUG_SKIP_WALK") != nullptr;   // timing experiments only
     if (e->totalTiles == 0) return SB2_OK;   // K-state likelihood-only loci only: nothing for the 4-state pruning kernel
@@ -573,7 +572,7 @@ int do_walk(sb2_engine *e)
     if (dbgTimesPath && a.dbgTimes) {
         std::vector<unsigned long long> h(8 * (size_t)e->totalTiles);
         cudaStreamSynchronize(e->stream);
-        cudaMemcpy(h.data(), dDbgTimes, 64 * (size_t)e->totalTiles, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h.data(), e->dDbgTimes, 64 * (size_t)e->totalTiles, cudaMemcpyDeviceToHost);
         if (FILE *f = fopen(dbgTimesPath, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
     }
     e->launches++;
