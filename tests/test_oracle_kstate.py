@@ -163,3 +163,24 @@ def test_posterior_adds_the_morphological_partitions():
     extra = sum(oracle.tree_likelihood_k(m, pb.species) for m in pb.morph)
     assert r.likelihood == pytest.approx(r2.likelihood + extra, rel=1e-13)
     assert r.coalescent == r2.coalescent
+
+
+def test_morphological_partitions_travel_with_exactly_one_shard():
+    """Sharded runs (bench.py under torchrun, Engine.from_problem on a locus range): every partition of the C4 config belongs to
+    exactly one shard, in partition order, whatever the number of shards -- and the shards' oracle log-likelihoods add up to the
+    whole problem's."""
+    from starbeast2_b200 import synth
+    full = synth.make_problem("C4", n_loci=24, n_sites=40)
+    assert len(full.morph) == 4
+    want = oracle.posterior(full)
+    for world in (1, 2, 3, 8, 24):
+        cuts = [(24 * r) // world for r in range(world + 1)]
+        shards = [synth.make_problem("C4", n_loci=24, n_sites=40, locus_range=(a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
+        got = [m for sh in shards for m in sh.morph]
+        assert len(got) == 4 and all(np.array_equal(a.tip_states, b.tip_states) and a.n_states == b.n_states for a, b in zip(full.morph, got))
+        owners = [r for r, sh in enumerate(shards) for _ in sh.morph]
+        assert owners == sorted(owners)
+        if world >= 4:
+            assert max(owners.count(r) for r in set(owners)) == 1          # spread: no shard carries two of them
+        lik = sum(float(np.sum(oracle.posterior(sh).per_locus_lik)) for sh in shards)
+        assert lik == pytest.approx(want.likelihood, rel=1e-12)
