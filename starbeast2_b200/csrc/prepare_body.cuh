@@ -70,6 +70,11 @@ __host__ __device__ inline size_t prep_carve(PrepSmem *s, unsigned char *base, i
 }
 
 
+__device__ __forceinline__ void prep_st256(double *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 // One gene edge: climb from species branch b (edge starts at height lastH) to the branch that holds height hg.
 // Lineage counts: GeneTree.java:346.  Rate: StarBeastClock.java:60-70 sums r_j*occ_j over species node numbers j
 // ascending (zeros are no-ops), occ_j from GeneTree.java:345,354; reproduced by selecting the path's nodes in
@@ -671,9 +676,9 @@ __device__ __forceinline__ int prepare_locus(const PrepareArgs &A, int maxNodes,
             const double distance = (s.gH[par] - s.gH[i]) * jointBranchRate;
             if (substKind == 0) hky_matrix(tabs, distance, m);
             else eigen_matrix(prm->subst, distance, m);
-            if (owner) {
+            if (owner) {   // 256-bit stores: whole 32-byte sectors per lane (half as many store instructions as with 128-bit ones)
 #pragma unroll
-                for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(store + q) = make_double2(m[q], m[q + 1]);
+                for (int q = 0; q < 16; q += 4) prep_st256(store + q, m[q], m[q + 1], m[q + 2], m[q + 3]);
             }
         } else {
 #pragma unroll
@@ -683,8 +688,13 @@ __device__ __forceinline__ int prepare_locus(const PrepareArgs &A, int maxNodes,
             const int side = (s.gR[par] == i) ? 1 : 0;
             double *dst = FUSED ? F.smats + (((size_t)s.pos[par] * C + c) * 2 + side) * 16
                                 : A.opMats + (((size_t)(d.opBase + s.pos[par]) * C + c) * 2 + side) * 16;
+            if (FUSED) {   // shared memory
 #pragma unroll
-            for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(dst + q) = make_double2(m[q], m[q + 1]);
+                for (int q = 0; q < 16; q += 2) *reinterpret_cast<double2 *>(dst + q) = make_double2(m[q], m[q + 1]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; q += 4) prep_st256(dst + q, m[q], m[q + 1], m[q + 2], m[q + 3]);
+            }
         }
     }
     if (FUSED && matsByB) {   // this half is done: let the coalescent half know the schedule and the matrices are complete
