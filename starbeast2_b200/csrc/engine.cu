@@ -994,7 +994,7 @@ int sb2_finalize(sb2_engine *e, int32_t nSpeciesNodes, int32_t nSpeciesLeaves)
         for (auto &hl : e->loci) if (!hl.d.kStates) { maxPat = std::max(maxPat, hl.d.nPat); e->totalLanes += (int64_t)hl.d.nPat * hl.d.nCat; }
         e->fusedCluster = tilePat ? (maxPat + tilePat - 1) / tilePat : 0;
         e->fusedOk = tilePat > 0 && e->fusedCluster <= STEP_MAX_CLUSTER && e->workers == 1 &&
-                     step_smem_bytes(e->maxNodes, e->S, e->nCat, e->stackDepth, (e->maxNodes + 1) / 2) <= 227 * 1024;
+                     step_smem_bytes(e->maxNodes, e->S, e->nCat, e->stackDepth, (e->maxNodes + 1) / 2) <= STEP_DYNAMIC_SMEM_MAX;
         if (const char *v = getenv("SB2_FUSED")) e->fusedMode = atoi(v) ? 1 : 0;
         if (const char *v = getenv("SB2_FUSED_MAX_LANES")) e->fusedMaxLanes = atoll(v);
     }

@@ -220,6 +220,7 @@ struct WalkArgs {
 constexpr int STEP_THREADS = 256;       // == PREP_THREADS: the tree-shaped part is prepare_body.cuh's, warp-specialised in two halves
 constexpr int STEP_WARPS = STEP_THREADS / 32;
 constexpr int STEP_MAX_CLUSTER = 16;    // non-portable cluster size limit of sm_100
+constexpr size_t STEP_DYNAMIC_SMEM_MAX = (227 - 24) * 1024;   // k_step also holds ~20 KB of STATIC shared memory (reduction scratch, memo lists)
 constexpr int STEP_INLINE_TREE_MAX = 3072;   // bytes of gene tree (20 per node) that fit the kernel arguments next to the rest
 
 // Peer-memory all-reduce of the reduce vector (one process per GPU, NVLink / NVSwitch; see reduce.cu:k_reduce_xgpu)
